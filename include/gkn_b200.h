@@ -1,0 +1,124 @@
+/*
+ * gkn_b200.h — C ABI of libgkn_b200.so, the B200 (sm_100a) implementation of the graph-kernel
+ * neural-operator hot path of ramanathanlab/molecular_dynamics_neural_operator.
+ *
+ * The reference has no FFI of its own: its boundary is the PyTorch nn.Module surface
+ * (NNConv_old.forward graph_kernel.py:194-198, KernelNN.forward :277-309, construct_pairdata
+ * :362-393).  These entry points are what a binding for that path calls underneath that surface;
+ * INTEGRATION.md shows the ctypes stub.  Conventions:
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name says host;
+ *   - all tensors are dense row-major; "bf16" buffers hold raw 16-bit bfloat16 values;
+ *   - no allocation inside: the caller owns inputs, outputs and workspaces;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); calls are asynchronous,
+ *     re-entrant and keep no global mutable state besides caches keyed by device ordinal;
+ *   - return value 0 = success; non-zero = error, message via gkn_last_error() (thread-local);
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ *
+ * Edge layout ("destination-sorted CSR"): gkn_graph_prepare turns an arbitrary edge_index[2,E]
+ * into positions p = 0..E-1 ordered by destination node (ties: original edge order), with
+ * dst_ptr[N+1] row pointers.  All per-edge buffers below (h, msg, dxj, S) use that order.
+ */
+#ifndef GKN_B200_H_
+#define GKN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GKN_B200_VERSION 100 /* major*100 + minor */
+#define GKN_ERR_INVALID 1
+#define GKN_ERR_CUDA 2
+
+/* ---- housekeeping ---------------------------------------------------------------------- */
+int gkn_version(void);
+const char* gkn_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+long long gkn_launch_count(void);
+int gkn_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- graph metadata (replaces PyG propagate's implicit gather/scatter bookkeeping;
+ *      reference graph_kernel.py:198, dataset.py:41-45) ---------------------------------- */
+/* bytes of scratch gkn_graph_prepare needs for (N, E) */
+int64_t gkn_graph_prepare_workspace_bytes(int64_t N, int64_t E);
+/* edge_index: int64 [2,E] (row 0 = source j, row 1 = destination i, PyG source_to_target flow).
+ * Outputs (all int32 unless noted): perm[E] position -> original edge id; src_s[E], dst_s[E]
+ * endpoints in sorted order; dst_ptr[N+1]; inv_cnt float[N] = 1/max(in-degree,1);
+ * src_ptr[N+1] and src_perm[E]: sorted positions grouped by source node (ascending p).
+ * status: int32[1], set to non-zero on the device if an index is outside [0,N). */
+int gkn_graph_prepare(const int64_t* edge_index, int64_t N, int64_t E, int32_t* perm,
+                      int32_t* src_s, int32_t* dst_s, int32_t* dst_ptr, float* inv_cnt,
+                      int32_t* src_ptr, int32_t* src_perm, int32_t* status, void* workspace,
+                      int64_t workspace_bytes, void* stream);
+
+/* ---- radius graph (replaces construct_pairdata, reference graph_kernel.py:362-393:
+ *      scipy distance_matrix(float64) < threshold -> coo_matrix -> per-edge python loop) -- */
+int64_t gkn_radius_graph_workspace_bytes(int64_t F, int64_t N);
+/* Pass 1: pos float32 [F,N,3]; threshold as the float64 the reference compares against.
+ * Writes deg int32 [F*N] (neighbours of each atom inside its own frame, self included) and
+ * row_ptr int64 [F*N+1] (exclusive scan of deg); total edges = row_ptr[F*N]. */
+int gkn_radius_graph_count(const float* pos, int64_t F, int64_t N, double threshold, int32_t* deg,
+                           int64_t* row_ptr, void* workspace, int64_t workspace_bytes,
+                           void* stream);
+/* Pass 2 (same workspace, untouched since pass 1): edge_index int64 [2,E] with node ids offset by
+ * f*N (PyG batching, dataset.py:41-45), lexicographic (row, col) order; edge_attr float32 [E,6] =
+ * [pos[row], pos[col]].  E must equal row_ptr[F*N]. */
+int gkn_radius_graph_fill(const float* pos, int64_t F, int64_t N, double threshold,
+                          const int64_t* row_ptr, int64_t E, int64_t* edge_index, float* edge_attr,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- fused bilinear edge contraction (replaces NNConv_old.message, graph_kernel.py:200-202)
+ *   P[e, i*W+o] = sum_k h[e,k] * w3[i*W+o, k]  is never written to memory.
+ *   fwd: msg[e,o] = sum_i x[src[e], i] * P[e, i*W+o]
+ *   dx : dxj[e,i] = sum_o P[e, i*W+o] * g[dst[e], o]
+ * h [E,K], w3 [W*W,K] (= net.layers.4.weight); x, g [N,W] float32; msg, dxj [E,W] float32.
+ * bf16: tcgen05/TMEM tensor-core path (bf16 operands, fp32 accumulate), K % 64 == 0,
+ *       W in {32,64,128}.  f32: CUDA-core path with fp32 operands, any W % 16 == 0, K % 16 == 0. */
+int gkn_contract_fwd_bf16(const void* h_bf16, const void* w3_bf16, const int32_t* src,
+                          const float* x, float* msg, int64_t E, int32_t K, int32_t W,
+                          void* stream);
+int gkn_contract_dx_bf16(const void* h_bf16, const void* w3_bf16, const int32_t* dst,
+                         const float* g, float* dxj, int64_t E, int32_t K, int32_t W,
+                         void* stream);
+int gkn_contract_fwd_f32(const float* h, const float* w3, const int32_t* src, const float* x,
+                         float* msg, int64_t E, int32_t K, int32_t W, void* stream);
+int gkn_contract_dx_f32(const float* h, const float* w3, const int32_t* dst, const float* g,
+                        float* dxj, int64_t E, int32_t K, int32_t W, void* stream);
+
+/* ---- segmented mean / sums (replaces PyG aggregate(aggr="mean") + NNConv_old.update,
+ *      graph_kernel.py:204-209, and their autograd) --------------------------------------- */
+/* out[n,:] = act( inv_cnt[n] * sum_{p in [dst_ptr[n],dst_ptr[n+1])} (msg[p,:] + xb3[src_s[p],:])
+ *                 + xroot[n,:] + bias[:] )     xb3, xroot, bias may be NULL; relu != 0 => ReLU. */
+int gkn_scatter_mean_fwd(const float* msg, const int32_t* src_s, const int32_t* dst_ptr,
+                         const float* inv_cnt, const float* xb3, const float* xroot,
+                         const float* bias, float* out, int64_t N, int64_t E, int32_t W,
+                         int32_t relu, void* stream);
+/* dx[n,:] = addend[n,:] + sum_{q in [src_ptr[n],src_ptr[n+1])} (dxj[p,:] + gb3[dst_s[p],:]),
+ * p = src_perm[q].  gb3, addend may be NULL. */
+int gkn_scatter_src_sum(const float* dxj, const int32_t* src_ptr, const int32_t* src_perm,
+                        const int32_t* dst_s, const float* gb3, const float* addend, float* dx,
+                        int64_t N, int64_t E, int32_t W, void* stream);
+/* g[n,:] = gy[n,:] * (relu ? (y[n,:] > 0) : 1);  gn[n,:] = g[n,:] * inv_cnt[n] */
+int gkn_relu_grad_scale(const float* gy, const float* y, const float* inv_cnt, float* g, float* gn,
+                        int64_t N, int32_t W, int32_t relu, void* stream);
+
+/* ---- deferred weight-gradient operand --------------------------------------------------
+ * S[e-e0, i*W+o] = sum_a xs[a, src_s[e], i] * gs[a, dst_s[e], o]   for e in [e0, e1)
+ * (the gradient of the loss w.r.t. the per-edge kernel, summed over the A applications that share
+ * it, graph_kernel.py:271-273, :299-302).  xs, gs: float32 [A,N,W]; S: bf16 or float32
+ * [e1-e0, W*W].  Used by the staged (chunked) backward; the fused backward never stores S. */
+int gkn_edge_outer_sum(const float* xs, const float* gs, const int32_t* src_s,
+                       const int32_t* dst_s, void* S, int32_t out_is_bf16, int64_t e0, int64_t e1,
+                       int64_t N, int32_t A, int32_t W, void* stream);
+
+/* ---- casts ------------------------------------------------------------------------------ */
+/* out_bf16[i] = bf16_rn( relu ? max(in[i] + (bias ? bias[i % cols] : 0), 0) : in[i] + bias ) */
+int gkn_bias_act_cast_bf16(const float* in, const float* bias, void* out_bf16, int64_t rows,
+                           int64_t cols, int32_t relu, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* GKN_B200_H_ */

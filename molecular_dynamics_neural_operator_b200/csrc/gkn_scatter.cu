@@ -1,0 +1,366 @@
+// K2 / K2b / K6 — segmented reductions over destination-sorted edges, no global atomics.
+//
+// Replaces PyG's mean aggregation + NNConv_old.update (reference graph_kernel.py:198, :204-209:
+// scatter-add + count + clamp + divide, then "+ x @ root + bias") and the autograd of the gather
+// x_j = x[edge_index[0]].  Because gkn_graph_prepare orders edges by destination, every node owns
+// a contiguous run of message rows: one warp walks the run with float4 lanes across channels and
+// sub-warp groups across edges, then folds the groups with warp shuffles.  The summation order is
+// fixed (strided by group, then a shuffle tree), so results are run-to-run deterministic.
+#include <cuda_bf16.h>
+
+#include "gkn_internal.h"
+
+namespace gkn {
+
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+
+__device__ __forceinline__ float4 f4add(float4 a, float4 b) {
+    return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+
+__device__ __forceinline__ float4 f4shfl_xor(float4 a, int off) {
+    return make_float4(__shfl_xor_sync(0xffffffffu, a.x, off), __shfl_xor_sync(0xffffffffu, a.y, off),
+                       __shfl_xor_sync(0xffffffffu, a.z, off), __shfl_xor_sync(0xffffffffu, a.w, off));
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) {
+    return __ldg(reinterpret_cast<const float4*>(p));
+}
+
+// streaming (read-once) load that does not pollute L1
+__device__ __forceinline__ float4 ldg4_stream(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// out[n] = act(inv_cnt[n] * sum_{p in seg(n)} (msg[p] + xb3[src_s[p]]) + xroot[n] + bias)
+template <int W>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+scatter_mean_fwd_kernel(const float* __restrict__ msg, const int32_t* __restrict__ src_s,
+                        const int32_t* __restrict__ dst_ptr, const float* __restrict__ inv_cnt,
+                        const float* __restrict__ xb3, const float* __restrict__ xroot,
+                        const float* __restrict__ bias, float* __restrict__ out, int64_t N,
+                        int relu) {
+    constexpr int LPR = W / 4;     // lanes per row (float4 each)
+    constexpr int RPW = 32 / LPR;  // rows walked in parallel by one warp
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / LPR;
+    const int col = (lane % LPR) * 4;
+    const int64_t warp0 = int64_t(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int64_t nwarps = int64_t(gridDim.x) * kWarpsPerBlock;
+    for (int64_t n = warp0; n < N; n += nwarps) {
+        const int beg = dst_ptr[n], end = dst_ptr[n + 1];
+        float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+        int p = beg + sub;
+        for (; p + RPW < end; p += 2 * RPW) {
+            float4 m0 = ldg4_stream(msg + int64_t(p) * W + col);
+            float4 m1 = ldg4_stream(msg + int64_t(p + RPW) * W + col);
+            if (xb3 != nullptr) {
+                m0 = f4add(m0, ldg4(xb3 + int64_t(src_s[p]) * W + col));
+                m1 = f4add(m1, ldg4(xb3 + int64_t(src_s[p + RPW]) * W + col));
+            }
+            acc0 = f4add(acc0, m0);
+            acc1 = f4add(acc1, m1);
+        }
+        if (p < end) {
+            float4 m0 = ldg4_stream(msg + int64_t(p) * W + col);
+            if (xb3 != nullptr) m0 = f4add(m0, ldg4(xb3 + int64_t(src_s[p]) * W + col));
+            acc0 = f4add(acc0, m0);
+        }
+        float4 acc = f4add(acc0, acc1);
+#pragma unroll
+        for (int off = LPR; off < 32; off <<= 1) acc = f4add(acc, f4shfl_xor(acc, off));
+        if (sub == 0) {
+            const float s = inv_cnt[n];
+            float4 r = make_float4(acc.x * s, acc.y * s, acc.z * s, acc.w * s);
+            if (xroot != nullptr) r = f4add(r, ldg4(xroot + n * W + col));
+            if (bias != nullptr) r = f4add(r, ldg4(bias + col));
+            if (relu) {
+                r.x = fmaxf(r.x, 0.f);
+                r.y = fmaxf(r.y, 0.f);
+                r.z = fmaxf(r.z, 0.f);
+                r.w = fmaxf(r.w, 0.f);
+            }
+            *reinterpret_cast<float4*>(out + n * W + col) = r;
+        }
+    }
+}
+
+// dx[n] = addend[n] + sum_{q in srcseg(n)} (dxj[p] + gb3[dst_s[p]]),  p = src_perm[q]
+template <int W>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+scatter_src_sum_kernel(const float* __restrict__ dxj, const int32_t* __restrict__ src_ptr,
+                       const int32_t* __restrict__ src_perm, const int32_t* __restrict__ dst_s,
+                       const float* __restrict__ gb3, const float* __restrict__ addend,
+                       float* __restrict__ dx, int64_t N) {
+    constexpr int LPR = W / 4;
+    constexpr int RPW = 32 / LPR;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / LPR;
+    const int col = (lane % LPR) * 4;
+    const int64_t warp0 = int64_t(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int64_t nwarps = int64_t(gridDim.x) * kWarpsPerBlock;
+    for (int64_t n = warp0; n < N; n += nwarps) {
+        const int beg = src_ptr[n], end = src_ptr[n + 1];
+        float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+        int q = beg + sub;
+        for (; q + RPW < end; q += 2 * RPW) {
+            const int p0 = src_perm[q], p1 = src_perm[q + RPW];
+            float4 m0 = ldg4_stream(dxj + int64_t(p0) * W + col);
+            float4 m1 = ldg4_stream(dxj + int64_t(p1) * W + col);
+            if (gb3 != nullptr) {
+                m0 = f4add(m0, ldg4(gb3 + int64_t(dst_s[p0]) * W + col));
+                m1 = f4add(m1, ldg4(gb3 + int64_t(dst_s[p1]) * W + col));
+            }
+            acc0 = f4add(acc0, m0);
+            acc1 = f4add(acc1, m1);
+        }
+        if (q < end) {
+            const int p0 = src_perm[q];
+            float4 m0 = ldg4_stream(dxj + int64_t(p0) * W + col);
+            if (gb3 != nullptr) m0 = f4add(m0, ldg4(gb3 + int64_t(dst_s[p0]) * W + col));
+            acc0 = f4add(acc0, m0);
+        }
+        float4 acc = f4add(acc0, acc1);
+#pragma unroll
+        for (int off = LPR; off < 32; off <<= 1) acc = f4add(acc, f4shfl_xor(acc, off));
+        if (sub == 0) {
+            if (addend != nullptr) acc = f4add(acc, ldg4(addend + n * W + col));
+            *reinterpret_cast<float4*>(dx + n * W + col) = acc;
+        }
+    }
+}
+
+__global__ void relu_grad_scale_kernel(const float* __restrict__ gy, const float* __restrict__ y,
+                                       const float* __restrict__ inv_cnt, float* __restrict__ g,
+                                       float* __restrict__ gn, int64_t total4, int W4, int relu) {
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < total4; t += stride) {
+        float4 v = ldg4(gy + t * 4);
+        if (relu) {
+            const float4 yy = ldg4(y + t * 4);
+            v.x = yy.x > 0.f ? v.x : 0.f;
+            v.y = yy.y > 0.f ? v.y : 0.f;
+            v.z = yy.z > 0.f ? v.z : 0.f;
+            v.w = yy.w > 0.f ? v.w : 0.f;
+        }
+        const float s = inv_cnt[t / W4];
+        *reinterpret_cast<float4*>(g + t * 4) = v;
+        *reinterpret_cast<float4*>(gn + t * 4) = make_float4(v.x * s, v.y * s, v.z * s, v.w * s);
+    }
+}
+
+// S[e - e0, i*W + o] = sum_a xs[a, src_s[e], i] * gs[a, dst_s[e], o]; one block per edge (looped),
+// each thread a 4 x 4 patch of the W x W outer-product sum.
+template <int W, bool BF16>
+__global__ void __launch_bounds__(256)
+edge_outer_sum_kernel(const float* __restrict__ xs, const float* __restrict__ gs,
+                      const int32_t* __restrict__ src_s, const int32_t* __restrict__ dst_s,
+                      void* __restrict__ S, int64_t e0, int64_t e1, int64_t N, int A) {
+    extern __shared__ float sm[];  // X[A][W] then G[A][W]
+    float* X = sm;
+    float* G = sm + A * W;
+    constexpr int B4 = W / 4;
+    for (int64_t e = e0 + blockIdx.x; e < e1; e += gridDim.x) {
+        const int64_t s = src_s[e], d = dst_s[e];
+        __syncthreads();
+        for (int t = threadIdx.x; t < A * W; t += 256) {
+            const int a = t / W, c = t % W;
+            X[t] = xs[(int64_t(a) * N + s) * W + c];
+            G[t] = gs[(int64_t(a) * N + d) * W + c];
+        }
+        __syncthreads();
+        for (int item = threadIdx.x; item < B4 * B4; item += 256) {
+            const int ib = (item / B4) * 4, ob = (item % B4) * 4;
+            float acc[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+            for (int a = 0; a < A; ++a) {
+                const float4 xv = *reinterpret_cast<const float4*>(X + a * W + ib);
+                const float4 gv = *reinterpret_cast<const float4*>(G + a * W + ob);
+                const float xr[4] = {xv.x, xv.y, xv.z, xv.w};
+                const float gc[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(xr[r], gc[c], acc[r][c]);
+            }
+            const int64_t base = (e - e0) * int64_t(W) * W;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int64_t off = base + int64_t(ib + r) * W + ob;
+                if constexpr (BF16) {
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(acc[r][0], acc[r][1]);
+                    __nv_bfloat162 hi = __floats2bfloat162_rn(acc[r][2], acc[r][3]);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                    *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(S) + off) = pk;
+                } else {
+                    *reinterpret_cast<float4*>(static_cast<float*>(S) + off) =
+                        make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+                }
+            }
+        }
+    }
+}
+
+__global__ void bias_act_cast_bf16_kernel(const float* __restrict__ in,
+                                          const float* __restrict__ bias,
+                                          __nv_bfloat16* __restrict__ out, int64_t total4,
+                                          int64_t cols, int relu) {
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < total4; t += stride) {
+        float4 v = ldg4_stream(in + t * 4);
+        if (bias != nullptr) {
+            const float4 b = ldg4(bias + (t * 4) % cols);
+            v = f4add(v, b);
+        }
+        if (relu) {
+            v.x = fmaxf(v.x, 0.f);
+            v.y = fmaxf(v.y, 0.f);
+            v.z = fmaxf(v.z, 0.f);
+            v.w = fmaxf(v.w, 0.f);
+        }
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
+        __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(out + t * 4) = pk;
+    }
+}
+
+int node_grid(int64_t N) {
+    int sms = 148;
+    device_sm_count(&sms);
+    int64_t blocks = (N + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const int64_t cap = int64_t(sms) * 8;  // 8 resident blocks of 8 warps per SM
+    if (blocks > cap) blocks = cap;
+    return int(blocks < 1 ? 1 : blocks);
+}
+
+int elem_grid(int64_t total, int threads) {
+    int sms = 148;
+    device_sm_count(&sms);
+    int64_t blocks = (total + threads - 1) / threads;
+    const int64_t cap = int64_t(sms) * 8;
+    if (blocks > cap) blocks = cap;
+    return int(blocks < 1 ? 1 : blocks);
+}
+
+}  // namespace
+}  // namespace gkn
+
+extern "C" int gkn_scatter_mean_fwd(const float* msg, const int32_t* src_s, const int32_t* dst_ptr,
+                                    const float* inv_cnt, const float* xb3, const float* xroot,
+                                    const float* bias, float* out, int64_t N, int64_t E, int32_t W,
+                                    int32_t relu, void* stream) {
+    using namespace gkn;
+    (void)E;
+    if (N == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = node_grid(N);
+    const int threads = kWarpsPerBlock * 32;
+    switch (W) {
+        case 16: scatter_mean_fwd_kernel<16><<<grid, threads, 0, st>>>(msg, src_s, dst_ptr, inv_cnt, xb3, xroot, bias, out, N, relu); break;
+        case 32: scatter_mean_fwd_kernel<32><<<grid, threads, 0, st>>>(msg, src_s, dst_ptr, inv_cnt, xb3, xroot, bias, out, N, relu); break;
+        case 64: scatter_mean_fwd_kernel<64><<<grid, threads, 0, st>>>(msg, src_s, dst_ptr, inv_cnt, xb3, xroot, bias, out, N, relu); break;
+        case 128: scatter_mean_fwd_kernel<128><<<grid, threads, 0, st>>>(msg, src_s, dst_ptr, inv_cnt, xb3, xroot, bias, out, N, relu); break;
+        default: return set_error("gkn_scatter_mean_fwd: width must be 16, 32, 64 or 128");
+    }
+    GKN_CHECK_LAUNCH("scatter_mean_fwd launch");
+    return 0;
+}
+
+extern "C" int gkn_scatter_src_sum(const float* dxj, const int32_t* src_ptr,
+                                   const int32_t* src_perm, const int32_t* dst_s, const float* gb3,
+                                   const float* addend, float* dx, int64_t N, int64_t E, int32_t W,
+                                   void* stream) {
+    using namespace gkn;
+    (void)E;
+    if (N == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = node_grid(N);
+    const int threads = kWarpsPerBlock * 32;
+    switch (W) {
+        case 16: scatter_src_sum_kernel<16><<<grid, threads, 0, st>>>(dxj, src_ptr, src_perm, dst_s, gb3, addend, dx, N); break;
+        case 32: scatter_src_sum_kernel<32><<<grid, threads, 0, st>>>(dxj, src_ptr, src_perm, dst_s, gb3, addend, dx, N); break;
+        case 64: scatter_src_sum_kernel<64><<<grid, threads, 0, st>>>(dxj, src_ptr, src_perm, dst_s, gb3, addend, dx, N); break;
+        case 128: scatter_src_sum_kernel<128><<<grid, threads, 0, st>>>(dxj, src_ptr, src_perm, dst_s, gb3, addend, dx, N); break;
+        default: return set_error("gkn_scatter_src_sum: width must be 16, 32, 64 or 128");
+    }
+    GKN_CHECK_LAUNCH("scatter_src_sum launch");
+    return 0;
+}
+
+extern "C" int gkn_relu_grad_scale(const float* gy, const float* y, const float* inv_cnt, float* g,
+                                   float* gn, int64_t N, int32_t W, int32_t relu, void* stream) {
+    using namespace gkn;
+    if (N == 0) return 0;
+    if (W % 4 != 0) return set_error("gkn_relu_grad_scale: width must be a multiple of 4");
+    if (relu && y == nullptr) return set_error("gkn_relu_grad_scale: relu needs the layer output");
+    const int64_t total4 = N * W / 4;
+    relu_grad_scale_kernel<<<elem_grid(total4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        gy, y, inv_cnt, g, gn, total4, W / 4, relu);
+    GKN_CHECK_LAUNCH("relu_grad_scale launch");
+    return 0;
+}
+
+extern "C" int gkn_edge_outer_sum(const float* xs, const float* gs, const int32_t* src_s,
+                                  const int32_t* dst_s, void* S, int32_t out_is_bf16, int64_t e0,
+                                  int64_t e1, int64_t N, int32_t A, int32_t W, void* stream) {
+    using namespace gkn;
+    if (e1 <= e0) return 0;
+    if (A < 1 || A > 64) return set_error("gkn_edge_outer_sum: A must be in [1, 64]");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int sms = 148;
+    device_sm_count(&sms);
+    int64_t blocks = e1 - e0;
+    if (blocks > int64_t(sms) * 8) blocks = int64_t(sms) * 8;
+    const size_t smem = size_t(2) * A * W * sizeof(float);
+    const int grid = int(blocks);
+#define GKN_EOS(WW)                                                                              \
+    if (out_is_bf16)                                                                             \
+        edge_outer_sum_kernel<WW, true><<<grid, 256, smem, st>>>(xs, gs, src_s, dst_s, S, e0, e1, N, A); \
+    else                                                                                         \
+        edge_outer_sum_kernel<WW, false><<<grid, 256, smem, st>>>(xs, gs, src_s, dst_s, S, e0, e1, N, A);
+    switch (W) {
+        case 16: GKN_EOS(16) break;
+        case 32: GKN_EOS(32) break;
+        case 64: GKN_EOS(64) break;
+        case 128: {
+            // 2 * 64 * 128 * 4 = 64 KB > 48 KB default for large A
+            if (smem > 48 * 1024) {
+                cudaFuncSetAttribute(edge_outer_sum_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+                cudaFuncSetAttribute(edge_outer_sum_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            }
+            GKN_EOS(128)
+            break;
+        }
+        default: return set_error("gkn_edge_outer_sum: width must be 16, 32, 64 or 128");
+    }
+#undef GKN_EOS
+    GKN_CHECK_LAUNCH("edge_outer_sum launch");
+    return 0;
+}
+
+extern "C" int gkn_bias_act_cast_bf16(const float* in, const float* bias, void* out_bf16,
+                                      int64_t rows, int64_t cols, int32_t relu, void* stream) {
+    using namespace gkn;
+    if (rows == 0 || cols == 0) return 0;
+    if (cols % 4 != 0) return set_error("gkn_bias_act_cast_bf16: cols must be a multiple of 4");
+    const int64_t total4 = rows * cols / 4;
+    bias_act_cast_bf16_kernel<<<elem_grid(total4, 256), 256, 0,
+                                static_cast<cudaStream_t>(stream)>>>(
+        in, bias, static_cast<__nv_bfloat16*>(out_bf16), total4, cols, relu);
+    GKN_CHECK_LAUNCH("bias_act_cast_bf16 launch");
+    return 0;
+}

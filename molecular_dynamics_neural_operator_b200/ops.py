@@ -1,0 +1,244 @@
+"""Tensor-level wrappers over the C ABI (``include/gkn_b200.h``).
+
+PyTorch is used here only for device memory and streams: every function checks its arguments,
+allocates outputs with ``torch.empty`` and enqueues the CUDA kernels of libgkn_b200.so on the
+current stream.  CPU tensors are rejected — there is no fallback path.
+"""
+from __future__ import annotations
+
+from ctypes import c_void_p
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+
+
+def _stream() -> c_void_p:
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: torch.Tensor | None, dtype: torch.dtype | None = None, name: str = "tensor") -> c_void_p:
+    if t is None:
+        return c_void_p(0)
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: the GKN B200 kernels need CUDA tensors (no CPU fallback)")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    return c_void_p(t.data_ptr())
+
+
+@dataclass
+class GraphPlan:
+    """Destination-sorted CSR view of an edge list (see gkn_graph_prepare in gkn_b200.h)."""
+
+    num_nodes: int
+    num_edges: int
+    perm: torch.Tensor  # int32 [E]  sorted position -> original edge id
+    src: torch.Tensor  # int32 [E]  source node per sorted position
+    dst: torch.Tensor  # int32 [E]  destination node per sorted position
+    dst_ptr: torch.Tensor  # int32 [N+1]
+    inv_cnt: torch.Tensor  # float32 [N]  1 / max(in-degree, 1)
+    src_ptr: torch.Tensor  # int32 [N+1]
+    src_perm: torch.Tensor  # int32 [E]  sorted positions grouped by source node
+
+    @property
+    def perm_long(self) -> torch.Tensor:
+        if not hasattr(self, "_perm_long"):
+            self._perm_long = self.perm.long()
+        return self._perm_long
+
+
+def prepare_graph(edge_index: torch.Tensor, num_nodes: int, validate: bool = True) -> GraphPlan:
+    """Build the destination-sorted CSR metadata for ``edge_index`` (int64 [2, E])."""
+    if edge_index.dim() != 2 or edge_index.size(0) != 2:
+        raise ValueError(f"edge_index must have shape [2, E], got {tuple(edge_index.shape)}")
+    if edge_index.dtype != torch.int64:
+        raise TypeError(f"edge_index must be int64 (torch.long), got {edge_index.dtype}")
+    lib = _lib.load()
+    ei = edge_index.contiguous()
+    dev = ei.device
+    N, E = int(num_nodes), int(ei.size(1))
+    i32 = dict(dtype=torch.int32, device=dev)
+    perm = torch.empty(E, **i32)
+    src = torch.empty(E, **i32)
+    dst = torch.empty(E, **i32)
+    dst_ptr = torch.empty(N + 1, **i32)
+    src_ptr = torch.empty(N + 1, **i32)
+    src_perm = torch.empty(E, **i32)
+    inv_cnt = torch.empty(N, dtype=torch.float32, device=dev)
+    status = torch.zeros(1, **i32)
+    ws_bytes = int(lib.gkn_graph_prepare_workspace_bytes(N, E))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(
+            lib.gkn_graph_prepare(
+                _p(ei, torch.int64, "edge_index"), N, E, _p(perm), _p(src), _p(dst), _p(dst_ptr),
+                _p(inv_cnt), _p(src_ptr), _p(src_perm), _p(status), _p(ws), ws_bytes, _stream(),
+            ),
+            "gkn_graph_prepare",
+        )
+    if validate and int(status.item()) != 0:
+        raise ValueError(f"edge_index contains node ids outside [0, {N})")
+    return GraphPlan(N, E, perm, src, dst, dst_ptr, inv_cnt, src_ptr, src_perm)
+
+
+def radius_graph(pos: torch.Tensor, threshold: float) -> tuple[torch.Tensor, torch.Tensor]:
+    """Batched radius graph.  pos float32 [F, N, 3] -> (edge_index int64 [2, E], edge_attr [E, 6]).
+
+    Node ids of frame f are offset by f*N; edges are in (row, col) lexicographic order with
+    self loops, identical to scipy distance_matrix(float64) < threshold -> coo_matrix.
+    """
+    if pos.dim() == 2:
+        pos = pos.unsqueeze(0)
+    if pos.dim() != 3 or pos.size(-1) != 3:
+        raise ValueError(f"pos must have shape [F, N, 3], got {tuple(pos.shape)}")
+    lib = _lib.load()
+    pos = pos.contiguous()
+    dev = pos.device
+    F, N = int(pos.size(0)), int(pos.size(1))
+    ws_bytes = int(lib.gkn_radius_graph_workspace_bytes(F, N))
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    deg = torch.empty(F * N, dtype=torch.int32, device=dev)
+    row_ptr = torch.empty(F * N + 1, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(
+            lib.gkn_radius_graph_count(
+                _p(pos, torch.float32, "pos"), F, N, float(threshold), _p(deg), _p(row_ptr),
+                _p(ws), ws_bytes, _stream(),
+            ),
+            "gkn_radius_graph_count",
+        )
+        E = int(row_ptr[-1].item())  # output size is data dependent: one sync per build
+        edge_index = torch.empty((2, E), dtype=torch.int64, device=dev)
+        edge_attr = torch.empty((E, 6), dtype=torch.float32, device=dev)
+        _lib.check(
+            lib.gkn_radius_graph_fill(
+                _p(pos), F, N, float(threshold), _p(row_ptr), E, _p(edge_index), _p(edge_attr),
+                _p(ws), ws_bytes, _stream(),
+            ),
+            "gkn_radius_graph_fill",
+        )
+    return edge_index, edge_attr
+
+
+def _contract(kind: str, h, w3, idx, node, precision: str) -> torch.Tensor:
+    lib = _lib.load()
+    E, K = int(h.size(0)), int(h.size(1))
+    W = int(node.size(1))
+    if w3.shape != (W * W, K):
+        raise ValueError(f"w3 must be [{W * W}, {K}], got {tuple(w3.shape)}")
+    out = torch.empty((E, W), dtype=torch.float32, device=h.device)
+    if precision == "bf16":
+        fn = lib.gkn_contract_fwd_bf16 if kind == "fwd" else lib.gkn_contract_dx_bf16
+        dt = torch.bfloat16
+    elif precision == "fp32":
+        fn = lib.gkn_contract_fwd_f32 if kind == "fwd" else lib.gkn_contract_dx_f32
+        dt = torch.float32
+    else:
+        raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+    with torch.cuda.device(h.device):
+        _lib.check(
+            fn(_p(h, dt, "h"), _p(w3, dt, "w3"), _p(idx, torch.int32, "idx"),
+               _p(node, torch.float32, "node"), _p(out), E, K, W, _stream()),
+            f"gkn_contract_{kind}_{precision}",
+        )
+    return out
+
+
+def contract_fwd(h, w3, src, x, precision: str = "bf16") -> torch.Tensor:
+    """msg[e,o] = sum_i x[src[e],i] * sum_k h[e,k] w3[i*W+o,k]   (per-edge kernel never stored)."""
+    return _contract("fwd", h, w3, src, x, precision)
+
+
+def contract_dx(h, w3, dst, g, precision: str = "bf16") -> torch.Tensor:
+    """dxj[e,i] = sum_o (sum_k h[e,k] w3[i*W+o,k]) * g[dst[e],o]."""
+    return _contract("dx", h, w3, dst, g, precision)
+
+
+def scatter_mean(msg, plan: GraphPlan, xb3=None, xroot=None, bias=None, relu=False) -> torch.Tensor:
+    lib = _lib.load()
+    W = int(msg.size(1))
+    out = torch.empty((plan.num_nodes, W), dtype=torch.float32, device=msg.device)
+    f32 = torch.float32
+    with torch.cuda.device(msg.device):
+        _lib.check(
+            lib.gkn_scatter_mean_fwd(
+                _p(msg, f32, "msg"), _p(plan.src), _p(plan.dst_ptr), _p(plan.inv_cnt),
+                _p(xb3, f32, "xb3"), _p(xroot, f32, "xroot"), _p(bias, f32, "bias"), _p(out),
+                plan.num_nodes, plan.num_edges, W, int(bool(relu)), _stream(),
+            ),
+            "gkn_scatter_mean_fwd",
+        )
+    return out
+
+
+def scatter_src_sum(dxj, plan: GraphPlan, gb3=None, addend=None) -> torch.Tensor:
+    lib = _lib.load()
+    W = int(dxj.size(1))
+    out = torch.empty((plan.num_nodes, W), dtype=torch.float32, device=dxj.device)
+    f32 = torch.float32
+    with torch.cuda.device(dxj.device):
+        _lib.check(
+            lib.gkn_scatter_src_sum(
+                _p(dxj, f32, "dxj"), _p(plan.src_ptr), _p(plan.src_perm), _p(plan.dst),
+                _p(gb3, f32, "gb3"), _p(addend, f32, "addend"), _p(out),
+                plan.num_nodes, plan.num_edges, W, _stream(),
+            ),
+            "gkn_scatter_src_sum",
+        )
+    return out
+
+
+def relu_grad_scale(gy, y, inv_cnt, relu: bool) -> tuple[torch.Tensor, torch.Tensor]:
+    lib = _lib.load()
+    N, W = int(gy.size(0)), int(gy.size(1))
+    g = torch.empty_like(gy)
+    gn = torch.empty_like(gy)
+    f32 = torch.float32
+    with torch.cuda.device(gy.device):
+        _lib.check(
+            lib.gkn_relu_grad_scale(
+                _p(gy, f32, "gy"), _p(y if relu else None, f32, "y"), _p(inv_cnt, f32, "inv_cnt"),
+                _p(g), _p(gn), N, W, int(bool(relu)), _stream(),
+            ),
+            "gkn_relu_grad_scale",
+        )
+    return g, gn
+
+
+def edge_outer_sum(xs, gs, plan: GraphPlan, e0: int, e1: int, out_dtype=torch.bfloat16) -> torch.Tensor:
+    """S[e-e0, i*W+o] = sum_a xs[a, src[e], i] * gs[a, dst[e], o] for sorted positions [e0, e1)."""
+    lib = _lib.load()
+    A, N, W = (int(s) for s in xs.shape)
+    if gs.shape != xs.shape:
+        raise ValueError("xs and gs must have the same [A, N, W] shape")
+    if out_dtype not in (torch.bfloat16, torch.float32):
+        raise TypeError("out_dtype must be bfloat16 or float32")
+    S = torch.empty((e1 - e0, W * W), dtype=out_dtype, device=xs.device)
+    with torch.cuda.device(xs.device):
+        _lib.check(
+            lib.gkn_edge_outer_sum(
+                _p(xs, torch.float32, "xs"), _p(gs, torch.float32, "gs"), _p(plan.src),
+                _p(plan.dst), _p(S), int(out_dtype == torch.bfloat16), e0, e1, N, A, W, _stream(),
+            ),
+            "gkn_edge_outer_sum",
+        )
+    return S
+
+
+def bias_act_cast_bf16(x, bias=None, relu=False) -> torch.Tensor:
+    lib = _lib.load()
+    rows, cols = int(x.size(0)), int(x.size(1))
+    out = torch.empty((rows, cols), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(
+            lib.gkn_bias_act_cast_bf16(
+                _p(x, torch.float32, "x"), _p(bias, torch.float32, "bias"), _p(out), rows, cols,
+                int(bool(relu)), _stream(),
+            ),
+            "gkn_bias_act_cast_bf16",
+        )
+    return out
