@@ -1,0 +1,445 @@
+#!/usr/bin/env python
+"""GKN training throughput on B200 — the benchmark contract of this repo.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): BBA all-atom-sized frames (504 atoms, 8 A radius graph,
+~57k directed edges/frame), KernelNN width 64, kernel_width 1024, depth 6 (12 NNConv
+applications), window 10, bf16 tensor-core contraction with fp32 accumulation.  One step = one
+pass of the hot path over one batch of synthetic frames per GPU: radius-graph build from
+coordinates -> forward -> LpLoss -> backward -> (gradient all-reduce) -> Adam.
+
+One JSON line is printed by rank 0:
+  value     frames/s over all GPUs with the step's coordinates already resident in HBM
+  e2e       same metric through the public API with HOST (pinned) coordinates: H2D copy of the
+            step's window, graph build, train step and a D2H read of the loss inside the timing
+  roofline  the dominant kernel (fused tcgen05 edge contraction): executed FLOP per launch
+            (= algorithmic 2*E*K*w^2) / CUDA-event duration, measured live in the timed region,
+            against the measured sustained bf16 peak (MEASURED_PEAKS.json)
+  cpu_baseline  the CPU restatement of the reference (oracle/) timed on this box's host cores
+`--impl reference` times that CPU restatement alone (all host threads) with the same metric/config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "gkn_train_frames_per_s"
+UNIT = "frames/s"
+WORKLOAD = "bba_allatom"
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d.get("hbm_gbs"), "bf16_tflops": d.get("bf16_tflops"),
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained"), "source": "measured"}
+    # fallback stated in /opt/skills/guides/B200_PROFILING.md
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+            "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines: list[str] = []
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-i", str(self.gpu_index), "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_info():
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return world, rank, local
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference (oracle) training step — used by cpu_baseline and --impl reference ONLY
+# ------------------------------------------------------------------------------------------------
+class CpuReference:
+    """fp32 CPU restatement of the reference's training step on this path: SciPy radius graph
+    (graph_kernel.py:362-393), KernelNN forward with the materialised [E,w,w] kernel
+    (:194-209, :277-309), LpLoss.rel (:105-119), backward, Adam (:541)."""
+
+    def __init__(self, wl, threads: int, seed: int = 0):
+        from oracle import gkn_oracle as orc
+        from molecular_dynamics_neural_operator_b200.graph_kernel import KernelNN
+
+        self.orc = orc
+        self.wl = wl
+        torch.set_num_threads(threads)
+        self.threads = threads
+        torch.manual_seed(seed)
+        # the module is used here only as a parameter container with the reference's init
+        model = KernelNN(wl.width, wl.ker_width, wl.depth, 6, in_width=7, out_width=3,
+                         window_size=wl.window, num_residues=wl.num_atoms, precision="fp32")
+        self.sd = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+        for k in list(self.sd):
+            if k.startswith("conv2.net."):
+                self.sd[k] = self.sd["conv1.net." + k[len("conv2.net."):]]
+        uniq = {id(v): v for v in self.sd.values()}
+        self.opt = torch.optim.Adam(list(uniq.values()), lr=0.01, weight_decay=5e-4)
+
+    def calibrate_gflops(self) -> float:
+        a = torch.randn(2048, 1024)
+        b = torch.randn(1024, 2048)
+        torch.mm(a, b)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            torch.mm(a, b)
+        dt = (time.perf_counter() - t0) / 3
+        return 2 * 2048 * 1024 * 2048 / dt / 1e9
+
+    def pick_atoms(self, target_seconds: float, edges_per_frame: float) -> int:
+        """Number of atoms of a frame (a slab along x, same density) whose training step should
+        take about `target_seconds` on this host."""
+        wl = self.wl
+        gflops = self.calibrate_gflops()
+        A = 2 * wl.depth
+        flop_frame = A * 3 * 2.0 * edges_per_frame * wl.ker_width * wl.width ** 2 * 1.4
+        sec_frame = flop_frame / (gflops * 1e9)
+        # cap the sample at a quarter frame: the reference formulation keeps several [E,w,w]
+        # fp32 tensors per application alive for backward (~35 GB for a full frame)
+        frac = min(0.25, target_seconds / sec_frame)
+        return max(32, int(wl.num_atoms * frac))
+
+    def step(self, x_window: np.ndarray, y: np.ndarray, aa: np.ndarray, n_atoms: int):
+        """One training step on the sub-frame made of the n_atoms atoms with the smallest x.
+        Returns (seconds, edges)."""
+        from types import SimpleNamespace
+
+        wl, orc = self.wl, self.orc
+        t0 = time.perf_counter()
+        keep = np.sort(np.argsort(x_window[0, 0, :, 0], kind="stable")[:n_atoms])
+        xw = x_window[:, :, keep]
+        B, W = xw.shape[0], xw.shape[1]
+        ei, ea = orc.radius_graph_batched(xw[:, 0], wl.cutoff)
+        data = SimpleNamespace(
+            x_aminoacid=torch.from_numpy(np.tile(aa[keep], B)),
+            x_position=torch.from_numpy(xw.reshape(B * W, n_atoms, 3)),
+            edge_index=torch.from_numpy(ei), edge_attr=torch.from_numpy(ea))
+        yt = torch.from_numpy(y[:, keep].reshape(B, -1))
+        self.opt.zero_grad(set_to_none=True)
+        out = orc.kernelnn_forward(self.sd, data, wl.depth, wl.window, n_atoms)
+        loss = orc.lp_loss_rel(out.view(B, -1), yt, size_average=False)
+        loss.backward()
+        self.opt.step()
+        return time.perf_counter() - t0, ei.shape[1]
+
+
+def run_reference_arm(args, wl, edges_per_frame):
+    """`--impl reference`: the CPU restatement of the reference, all host threads, bounded sample
+    per step.  Rank 0 only."""
+    from molecular_dynamics_neural_operator_b200 import synthetic as syn
+
+    world, rank, _ = dist_info()
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    ref = CpuReference(wl, threads)
+    n_atoms = ref.pick_atoms(args.cpu_seconds_per_step, edges_per_frame)
+    traj = syn.trajectory(wl, wl.window + 2 + args.steps + args.warmup, seed=0)
+    aa = syn.residue_ids(wl)
+    times, edges = [], []
+    for i in range(args.warmup + args.steps):
+        xw, y = syn.window_batch(traj, [i], wl.window)
+        dt, e = ref.step(xw, y, aa, n_atoms)
+        if i >= args.warmup:
+            times.append(dt)
+            edges.append(e)
+    total = sum(times)
+    frames = sum(edges) / edges_per_frame  # frame-equivalents processed (cost is linear in E)
+    value = frames / total
+    sample = (f"{n_atoms}/{wl.num_atoms} atoms of one frame per step (x-slab, same density), "
+              f"{int(np.mean(edges))} edges vs {int(edges_per_frame)} per full frame; "
+              f"frames/s = edge-fraction / step time")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": bench_config(wl, 1, edges_per_frame),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def bench_config(wl, frames_per_gpu, edges_per_frame):
+    return {
+        "workload": (f"{WORKLOAD}: {wl.num_atoms}-atom frames, {wl.cutoff} A radius graph "
+                     f"(~{int(edges_per_frame)} directed edges/frame incl. self loops), KernelNN "
+                     f"width {wl.width} kernel_width {wl.ker_width} depth {wl.depth} "
+                     f"({2 * wl.depth} NNConv applications), window {wl.window}; step = graph "
+                     f"build + fwd + LpLoss + bwd + Adam"),
+        "frames_per_gpu_per_step": frames_per_gpu,
+        "parallelism": "frames sharded over GPUs, bucketed NCCL gradient all-reduce",
+        "l2_policy": "per-step working set (h_e alone ~0.9 GB at 8 frames) exceeds the 126 MB L2; "
+                     "each step uses a different batch of frames",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200_arm(args, wl):
+    import torch.distributed as dist
+
+    from molecular_dynamics_neural_operator_b200 import _lib, ops
+    from molecular_dynamics_neural_operator_b200 import synthetic as syn
+    from molecular_dynamics_neural_operator_b200.graph_kernel import KernelNN
+    from molecular_dynamics_neural_operator_b200.train import Trainer, broadcast_parameters
+
+    world, rank, local = dist_info()
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback); "
+                           "use --impl reference for the CPU baseline")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    B = args.frames_per_gpu
+    pool = args.pool
+    torch.manual_seed(0)
+    model = KernelNN(wl.width, wl.ker_width, wl.depth, 6, in_width=7, out_width=3,
+                     window_size=wl.window, num_residues=wl.num_atoms, precision="bf16").to(dev)
+    broadcast_parameters(model)
+    trainer = Trainer(model, lr=0.01, weight_decay=5e-4)
+
+    # synthetic trajectory; rank r takes frames r, r+world, ... of every global batch
+    n_frames = wl.window + 1 + pool * B * world
+    traj = syn.trajectory(wl, n_frames, seed=0)
+    aa = torch.from_numpy(syn.residue_ids(wl)).to(dev)
+    host_x, host_y = [], []
+    for b in range(pool):
+        starts = [b * B * world + rank + world * j for j in range(B)]
+        xw, y = syn.window_batch(traj, starts, wl.window)
+        host_x.append(torch.from_numpy(xw).pin_memory())
+        host_y.append(torch.from_numpy(y).pin_memory())
+    dev_x = [t.to(dev) for t in host_x]
+    dev_y = [t.to(dev) for t in host_y]
+    h2d_bytes = host_x[0].numel() * 4 + host_y[0].numel() * 4
+
+    edge_counts = []
+
+    def step_resident(i):
+        batch = syn.make_batch(dev_x[i % pool], aa, dev_y[i % pool], wl.cutoff)
+        edge_counts.append(batch.edge_index.size(1))
+        return trainer.step(batch, B)
+
+    def step_e2e(i):
+        x = host_x[i % pool].to(dev, non_blocking=True)
+        y = host_y[i % pool].to(dev, non_blocking=True)
+        batch = syn.make_batch(x, aa, y, wl.cutoff)
+        loss = trainer.step(batch, B)
+        return float(loss.item())  # D2H read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(steps):
+            fn(i)
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for i in range(args.warmup):
+        step_resident(i)
+    for i in range(max(1, args.warmup // 2)):
+        step_e2e(i)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    edge_counts.clear()
+    ops.KERNEL_TIMER.enable("contract")
+    launches0 = _lib.launch_count()
+    ms_total = timed(step_resident, args.steps)
+    launches = _lib.launch_count() - launches0
+    timer = ops.KERNEL_TIMER.collect()
+    ops.KERNEL_TIMER.disable()
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if sampler else None
+
+    frames_total = B * world * args.steps
+    value = frames_total / (ms_total * 1e-3)
+    e2e_value = frames_total / (ms_e2e * 1e-3)
+    edges_per_frame = float(np.mean(edge_counts)) / B
+    peaks = measured_peaks()
+
+    # dominant kernel: the fused contraction (forward + dx launches share one mainloop)
+    roofline = None
+    if timer["count"]:
+        flop_per_launch = 2.0 * (edges_per_frame * B) * wl.ker_width * wl.width ** 2
+        avg_ms = timer["ms"] / timer["count"]
+        achieved = flop_per_launch / (avg_ms * 1e-3) / 1e12
+        peak = peaks["bf16_tflops_sustained"]
+        traffic = None
+        tp = ROOT / "profiles" / "contract_traffic.json"
+        if tp.exists():
+            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak, "traffic": traffic,
+                    "kernel": "contract_tc_kernel (fwd+dx)", "launches": timer["count"],
+                    "avg_launch_ms": avg_ms, "flop_per_launch": flop_per_launch,
+                    "share_of_step": timer["ms"] / ms_total,
+                    "peak_source": f"{peaks['source']} sustained bf16 (kernel timed inside a long step)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    A = 2 * wl.depth
+    unit_flop = 2.0 * edges_per_frame * wl.ker_width * wl.width ** 2
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": bench_config(wl, B, edges_per_frame),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roofline,
+        "edges_per_s": value * edges_per_frame,
+        "flops": {
+            "algorithmic_train_flop_per_frame": 4 * A * unit_flop,
+            "executed_contraction_flop_per_frame": (2 * A - 1 + 2) * unit_flop,
+            "note": "backward defers dW3/dh to one pass over S (2 units instead of 2 per "
+                    "application) and skips dx of the first application; tensor-core utilisation "
+                    "must be read from roofline/ncu, not from algorithmic FLOP / time",
+            "algorithmic_tflops": value * 4 * A * unit_flop / 1e12 / world,
+        },
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        ref = CpuReference(wl, threads)
+        n_atoms = ref.pick_atoms(args.cpu_seconds_per_step, edges_per_frame)
+        xw, y = syn.window_batch(traj, [0], wl.window)
+        aa_np = syn.residue_ids(wl)
+        ref.step(xw, y, aa_np, max(32, n_atoms // 4))  # warm-up
+        dt, e = ref.step(xw, y, aa_np, n_atoms)
+        line["cpu_baseline"] = {
+            "value": (e / edges_per_frame) / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": (f"1 step on {n_atoms}/{wl.num_atoms} atoms of one frame (x-slab, same "
+                       f"density): {e} edges vs {int(edges_per_frame)} per full frame, {dt:.1f} s; "
+                       f"frames/s = edge-fraction / step time"),
+        }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames-per-gpu", type=int, default=8)
+    ap.add_argument("--pool", type=int, default=4, help="distinct batches cycled through")
+    ap.add_argument("--cpu-seconds-per-step", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+
+    from molecular_dynamics_neural_operator_b200 import synthetic as syn
+
+    wl = syn.WORKLOADS[WORKLOAD]
+    if args.impl == "reference":
+        # edges/frame of the synthetic workload, from the same generator (SciPy on one frame)
+        from oracle import gkn_oracle as orc
+
+        ei, _ = orc.radius_graph_batched(syn.trajectory(wl, 1, seed=0), wl.cutoff)
+        run_reference_arm(args, wl, float(ei.shape[1]))
+    else:
+        run_b200_arm(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,114 +1,139 @@
-"""Autograd glue for the graph-kernel layer: one ``torch.autograd.Function`` for the whole stack of
-NNConv applications that share an edge MLP (reference graph_kernel.py:271-273, :299-302).
+"""Autograd glue for the graph-kernel layer: ONE ``torch.autograd.Function`` for the edge MLP plus
+the whole stack of NNConv applications that share it (reference graph_kernel.py:271-273, :299-302).
 
-Why one Function for the stack and not one per layer: the edge hidden state ``h_e`` (output of
-net.layers.0-.3), the last-layer weight W3/b3 and the graph are identical for all 2*depth
-applications, so
+Why one Function and not one per layer: the edge hidden state ``h_e`` (output of net.layers.0-.3),
+the last-layer weight W3/b3 and the graph are identical for all 2*depth applications, so
 
-* forward computes ``h_e`` once and each application is two kernels: the fused tcgen05 contraction
-  (``msg``) and the segmented mean (+ root, bias, ReLU);
+* forward computes ``h_e`` once; each application is then two kernels: the fused tcgen05
+  contraction (``msg``) and the segmented mean (+ root, bias, ReLU);
 * backward recomputes the per-edge kernel flash-style for ``dx`` (one contraction per application)
   and DEFERS the gradients of the shared operands: with
       S_e[i,o] = sum_a x^(a-1)[src e, i] * gn^(a)[dst e, o]
-  (the loss gradient w.r.t. the per-edge kernel summed over applications) a single pass gives
+  (the loss gradient w.r.t. the per-edge kernel, summed over applications) a single pass gives
       dW3 = S^T h_e,   db3 = sum_e S_e,   dh_e = S W3
-  i.e. 2 GEMM units instead of 2 per application.
+  i.e. 2 GEMM units instead of 2 per application, and ``dh_e`` is consumed chunk by chunk by the
+  backward of layers .0-.3 without ever being stored for all edges.
 
-Everything E-sized that is saved for backward is ``h_e`` itself; per application only the node
-tensors ``x^(a)`` ([N, w]) are kept.
+Everything E-sized that is kept for backward is ``h_e`` and the layer-0 activation (bf16 in bf16
+mode); per application only the node tensors ``x^(a)`` ([N, w]) are saved.
+
+Precision modes
+  "bf16": layer 0 in fp32 (fan-in 6); layer 2, the fused contraction and the weight-gradient
+          GEMMs take bf16 operands and accumulate in fp32 (fp32 outputs, ``out_dtype``).
+  "fp32": everything in fp32 on CUDA cores / cuBLAS SGEMM (parity mode, 1e-5).
+The dense GEMMs of layers .0-.3 and of the staged weight gradients are plain library GEMMs
+(cuBLAS through torch); the graph-kernel contraction itself is libgkn_b200.so.
 """
 from __future__ import annotations
 
 import torch
-import torch.nn.functional as F
 
 from . import ops
 from .ops import GraphPlan
 
-# rows of S materialised at a time by the staged weight-gradient path (see _deferred_grads)
+# rows of S materialised at a time by the staged weight-gradient path (see _edge_grads)
 _S_CHUNK_EDGES = 16384
 
 
-def edge_hidden(net, edge_attr_sorted: torch.Tensor, precision: str) -> torch.Tensor:
-    """h_e = relu(layers.2(relu(layers.0(edge_attr))))  (reference graph_kernel.py:239-242).
+def _mm32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a @ b with an fp32 result (fp32 accumulation for bf16 operands)."""
+    if a.dtype == torch.bfloat16:
+        return torch.mm(a, b, out_dtype=torch.float32)
+    return torch.mm(a, b)
 
-    These two layers are ordinary dense GEMMs executed once per forward (cuBLAS through torch).
-    bf16 mode: layer 0 in fp32 (fan-in 6), layer 2 with bf16 operands / fp32 accumulation, result
-    kept in bf16 — exactly the A operand the tensor-core contraction consumes.
-    """
-    l0, l2 = net.layers[0], net.layers[2]
-    h1 = F.relu(F.linear(edge_attr_sorted, l0.weight, l0.bias))
+
+def _edge_hidden(ea, w1, b1, w2, b2, precision):
+    """h1 = relu(ea W1^T + b1), h = relu(h1 W2^T + b2)   (reference graph_kernel.py:239-242)."""
+    z1 = torch.mm(ea, w1.t())
     if precision == "bf16":
-        h = F.relu(F.linear(h1.to(torch.bfloat16), l2.weight.to(torch.bfloat16),
-                            l2.bias.to(torch.bfloat16)))
+        h1 = ops.bias_act_cast_bf16(z1, b1, relu=True)
+        del z1
+        z2 = _mm32(h1, w2.to(torch.bfloat16).t())
+        h = ops.bias_act_cast_bf16(z2, b2, relu=True)
     else:
-        h = F.relu(F.linear(h1, l2.weight, l2.bias))
-    return h.contiguous()
+        h1 = torch.relu_(z1.add_(b1))
+        h = torch.relu_(torch.addmm(b2, h1, w2.t()))
+    return h1, h
 
 
-def _deferred_grads(xs, gns, plan: GraphPlan, h, w3q, need_h: bool, need_w: bool, precision: str):
-    """dh_e, dW3, db3 from the per-application node tensors (see module docstring).
+def _edge_grads(xs, gns, plan: GraphPlan, ea, h1, h, w1, w2, w3q, need_ea: bool, precision: str):
+    """Gradients of everything edge-sized from the per-application node tensors: W3, b3 and,
+    through dh_e, layers .0-.3 (W2, b2, W1, b1, optionally edge_attr).
 
     Staged implementation: S is produced for a bounded chunk of edges at a time by
-    gkn_edge_outer_sum and multiplied with library GEMMs.  (The fused tcgen05 kernels that never
-    store S replace this path; it is kept as the fp32 route and cross-check.)
+    gkn_edge_outer_sum and multiplied with library GEMMs; dh_e only ever exists for one chunk.
     """
     E, K = h.shape
     WW = w3q.shape[0]
     dev = h.device
-    dh = torch.empty_like(h) if need_h else None
-    dw3 = torch.zeros((WW, K), dtype=torch.float32, device=dev) if need_w else None
-    db3 = torch.zeros(WW, dtype=torch.float32, device=dev) if need_w else None
-    s_dtype = torch.bfloat16 if precision == "bf16" else torch.float32
+    f32 = dict(dtype=torch.float32, device=dev)
+    dw3 = torch.zeros((WW, K), **f32)
+    db3 = torch.zeros(WW, **f32)
+    dw2 = torch.zeros((K, K), **f32)
+    db2 = torch.zeros(K, **f32)
+    dw1 = torch.zeros((K, ea.size(1)), **f32)
+    db1 = torch.zeros(K, **f32)
+    dea = torch.empty_like(ea) if need_ea else None
+    bf16 = precision == "bf16"
+    s_dtype = torch.bfloat16 if bf16 else torch.float32
+    w2q = w2.to(torch.bfloat16) if bf16 else w2
     for e0 in range(0, E, _S_CHUNK_EDGES):
         e1 = min(E, e0 + _S_CHUNK_EDGES)
+        hc, h1c = h[e0:e1], h1[e0:e1]
         S = ops.edge_outer_sum(xs, gns, plan, e0, e1, s_dtype)
-        if need_h:
-            torch.mm(S, w3q, out=dh[e0:e1])
-        if need_w:
-            dw3 += torch.mm(S.t(), h[e0:e1]).float()
-            db3 += S.sum(0, dtype=torch.float32)
-    return dh, dw3, db3
+        dw3 += _mm32(S.t(), hc)
+        db3 += S.sum(0, dtype=torch.float32)
+        dz2 = _mm32(S, w3q)  # dh_e for this chunk, fp32
+        del S
+        dz2.mul_(hc > 0)
+        db2 += dz2.sum(0)
+        dz2q = dz2.to(torch.bfloat16) if bf16 else dz2
+        dw2 += _mm32(dz2q.t(), h1c)
+        dz1 = _mm32(dz2q, w2q)
+        dz1.mul_(h1c > 0)
+        db1 += dz1.sum(0)
+        dw1 += torch.mm(dz1.t(), ea[e0:e1])
+        if need_ea:
+            torch.mm(dz1, w1, out=dea[e0:e1])
+    return dw3, db3, dw2, db2, dw1, db1, dea
 
 
-class _ConvStack(torch.autograd.Function):
+class _GKNStack(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x0, h, w3, b3, root1, bias1, root2, bias2, plan, schedule, relu, precision):
+    def forward(ctx, x0, ea, w1, b1, w2, b2, w3, b3, root1, bias1, root2, bias2, plan, schedule,
+                relu, precision):
         W = x0.size(1)
-        if precision == "bf16":
-            w3q = w3.detach().to(torch.bfloat16).contiguous()
-        else:
-            w3q = w3.detach().contiguous()
-        B3 = b3.detach().view(W, W)
-        roots = (root1.detach(), root2.detach() if root2 is not None else None)
-        biases = (bias1.detach(), bias2.detach() if bias2 is not None else None)
-        x = x0.detach().contiguous()
-        hq = h.detach()
+        det = lambda t: None if t is None else t.detach()  # noqa: E731
+        x0, ea, w1, b1, w2, b2, w3, b3 = map(det, (x0, ea, w1, b1, w2, b2, w3, b3))
+        h1, h = _edge_hidden(ea.contiguous(), w1, b1.contiguous(), w2, b2.contiguous(), precision)
+        w3q = (w3.to(torch.bfloat16) if precision == "bf16" else w3).contiguous()
+        B3 = b3.view(W, W)
+        roots = (det(root1), det(root2))
+        biases = (det(bias1), det(bias2))
+        x = x0.contiguous()
         xs = [x]
         for c in schedule:
             xroot = torch.mm(x, roots[c])
             xb3 = torch.mm(x, B3)
-            msg = ops.contract_fwd(hq, w3q, plan.src, x, precision)
+            msg = ops.contract_fwd(h, w3q, plan.src, x, precision)
             x = ops.scatter_mean(msg, plan, xb3=xb3, xroot=xroot, bias=biases[c].contiguous(),
                                  relu=relu)
             xs.append(x)
-        ctx.plan = plan
-        ctx.schedule = schedule
-        ctx.relu = relu
-        ctx.precision = precision
+        ctx.plan, ctx.schedule, ctx.relu, ctx.precision = plan, schedule, relu, precision
         ctx.has2 = root2 is not None
-        ctx.save_for_backward(hq, w3q, B3, roots[0], roots[1] if ctx.has2 else roots[0], *xs)
+        ctx.save_for_backward(ea, h1, h, w1, w2, w3q, B3, roots[0],
+                              roots[1] if ctx.has2 else roots[0], *xs)
         return x
 
     @staticmethod
     def backward(ctx, gout):
-        hq, w3q, B3, r1, r2, *xs = ctx.saved_tensors
+        ea, h1, h, w1, w2, w3q, B3, r1, r2, *xs = ctx.saved_tensors
         plan, schedule, relu, precision = ctx.plan, ctx.schedule, ctx.relu, ctx.precision
         roots = (r1, r2)
         A = len(schedule)
         W = xs[0].size(1)
-        need_x0, need_h, need_w3 = ctx.needs_input_grad[0], ctx.needs_input_grad[1], (
-            ctx.needs_input_grad[2] or ctx.needs_input_grad[3])
+        need = ctx.needs_input_grad
+        need_x0, need_ea, need_edge = need[0], need[1], any(need[1:8])
         droot = [torch.zeros_like(r1), torch.zeros_like(r2)]
         dbias = [torch.zeros(W, dtype=torch.float32, device=gout.device) for _ in range(2)]
         gns = [None] * A
@@ -121,27 +146,32 @@ class _ConvStack(torch.autograd.Function):
             dbias[c] += g.sum(0)
             gns[a] = gn
             if a > 0 or need_x0:
-                dxj = ops.contract_dx(hq, w3q, plan.dst, gn, precision)
+                dxj = ops.contract_dx(h, w3q, plan.dst, gn, precision)
                 gb3 = torch.mm(gn, B3.t())
                 addend = torch.mm(g, roots[c].t())
                 gx = ops.scatter_src_sum(dxj, plan, gb3=gb3, addend=addend)
             else:
                 gx = None
-        dh = dw3 = db3 = None
-        if need_h or need_w3:
-            dh, dw3, db3 = _deferred_grads(torch.stack(xs[:A]), torch.stack(gns), plan, hq, w3q,
-                                           need_h, need_w3, precision)
-        return (gx if need_x0 else None, dh, dw3, db3, droot[0], dbias[0],
+        dw3 = db3 = dw2 = db2 = dw1 = db1 = dea = None
+        if need_edge:
+            dw3, db3, dw2, db2, dw1, db1, dea = _edge_grads(
+                torch.stack(xs[:A]), torch.stack(gns), plan, ea, h1, h, w1, w2, w3q, need_ea,
+                precision)
+        return (gx if need_x0 else None, dea, dw1, db1, dw2, db2, dw3, db3, droot[0], dbias[0],
                 droot[1] if ctx.has2 else None, dbias[1] if ctx.has2 else None,
                 None, None, None, None)
 
 
-def conv_stack(x0, h, w3, b3, root1, bias1, root2, bias2, plan: GraphPlan, schedule, relu: bool,
-               precision: str = "bf16") -> torch.Tensor:
-    """Apply ``len(schedule)`` NNConv layers that share (h, w3, b3); ``schedule[a]`` picks the
-    (root, bias) pair (0 or 1) of application a; ``relu`` applies F.relu after every application
-    (reference graph_kernel.py:299-302)."""
-    if x0.dtype != torch.float32:
-        raise TypeError(f"node features must be float32, got {x0.dtype}")
-    return _ConvStack.apply(x0, h, w3, b3, root1, bias1, root2, bias2, plan, tuple(schedule),
-                            bool(relu), precision)
+def gkn_stack(x0, edge_attr_sorted, net, root1, bias1, root2, bias2, plan: GraphPlan, schedule,
+              relu: bool, precision: str = "bf16") -> torch.Tensor:
+    """Edge MLP + ``len(schedule)`` NNConv applications sharing it.
+
+    ``edge_attr_sorted`` is edge_attr in the plan's destination-sorted order; ``net`` is the
+    DenseNet([ker_in, K, K, w*w], ReLU); ``schedule[a]`` picks the (root, bias) pair (0 or 1) of
+    application a; ``relu`` applies F.relu after every application (graph_kernel.py:299-302)."""
+    if x0.dtype != torch.float32 or edge_attr_sorted.dtype != torch.float32:
+        raise TypeError("node features and edge attributes must be float32")
+    l0, l2, l4 = net.layers[0], net.layers[2], net.layers[4]
+    return _GKNStack.apply(x0, edge_attr_sorted, l0.weight, l0.bias, l2.weight, l2.bias, l4.weight,
+                           l4.bias, root1, bias1, root2, bias2, plan, tuple(schedule), bool(relu),
+                           precision)

@@ -14,8 +14,37 @@ import torch
 from . import _lib
 
 
+class _KernelTimer:
+    """Optional CUDA-event timing of the contraction launches on their own stream (bench.py's
+    live roofline measurement).  Disabled by default: zero overhead on the normal path."""
+
+    def __init__(self):
+        self.enabled = False
+        self.events: list = []
+
+    def enable(self, tag: str = "contract"):
+        self.enabled = True
+        self.events = []
+
+    def disable(self):
+        self.enabled = False
+
+    def collect(self) -> dict:
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in self.events)
+        return {"count": len(self.events), "ms": ms}
+
+
+KERNEL_TIMER = _KernelTimer()
+
+
 def _stream() -> c_void_p:
     return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: the GKN B200 kernels need CUDA tensors (no CPU fallback)")
 
 
 def _p(t: torch.Tensor | None, dtype: torch.dtype | None = None, name: str = "tensor") -> c_void_p:
@@ -57,6 +86,7 @@ def prepare_graph(edge_index: torch.Tensor, num_nodes: int, validate: bool = Tru
         raise ValueError(f"edge_index must have shape [2, E], got {tuple(edge_index.shape)}")
     if edge_index.dtype != torch.int64:
         raise TypeError(f"edge_index must be int64 (torch.long), got {edge_index.dtype}")
+    _require_cuda(edge_index, "edge_index")
     lib = _lib.load()
     ei = edge_index.contiguous()
     dev = ei.device
@@ -95,6 +125,7 @@ def radius_graph(pos: torch.Tensor, threshold: float) -> tuple[torch.Tensor, tor
         pos = pos.unsqueeze(0)
     if pos.dim() != 3 or pos.size(-1) != 3:
         raise ValueError(f"pos must have shape [F, N, 3], got {tuple(pos.shape)}")
+    _require_cuda(pos, "pos")
     lib = _lib.load()
     pos = pos.contiguous()
     dev = pos.device
@@ -125,6 +156,7 @@ def radius_graph(pos: torch.Tensor, threshold: float) -> tuple[torch.Tensor, tor
 
 
 def _contract(kind: str, h, w3, idx, node, precision: str) -> torch.Tensor:
+    _require_cuda(h, "h")
     lib = _lib.load()
     E, K = int(h.size(0)), int(h.size(1))
     W = int(node.size(1))
@@ -140,11 +172,18 @@ def _contract(kind: str, h, w3, idx, node, precision: str) -> torch.Tensor:
     else:
         raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
     with torch.cuda.device(h.device):
+        if KERNEL_TIMER.enabled:
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev0.record()
         _lib.check(
             fn(_p(h, dt, "h"), _p(w3, dt, "w3"), _p(idx, torch.int32, "idx"),
                _p(node, torch.float32, "node"), _p(out), E, K, W, _stream()),
             f"gkn_contract_{kind}_{precision}",
         )
+        if KERNEL_TIMER.enabled:
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev1.record()
+            KERNEL_TIMER.events.append((ev0, ev1))
     return out
 
 

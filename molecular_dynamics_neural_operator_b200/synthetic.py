@@ -1,0 +1,102 @@
+"""Seeded synthetic MD trajectories of the shapes BASELINE.json names, and the
+device-side feeder that turns a window of coordinates into the ``PairData`` batch the model
+consumes (the role of ContactMapDataset.__getitem__ + DataListLoader + Batch, reference
+dataset.py:180-227, with the per-frame radius graph built on the GPU instead of read from HDF5).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import ops
+from .dataset import PairData
+
+
+@dataclass(frozen=True)
+class Workload:
+    name: str
+    num_atoms: int
+    width: int
+    ker_width: int
+    depth: int
+    cutoff: float
+    window: int
+    box: float  # cube edge (uniform workloads) or 0 for the chain
+
+
+# the configs of BASELINE.json / SURVEY.md §8
+WORKLOADS = {
+    "bba_ca": Workload("bba_ca", 28, 32, 1024, 4, 8.0, 10, 0.0),
+    "bba_allatom": Workload("bba_allatom", 504, 64, 1024, 6, 8.0, 10, 17.1),
+    "synthetic_10k": Workload("synthetic_10k", 10000, 64, 1024, 6, 4.2, 10, 46.4),
+    "synthetic_100k": Workload("synthetic_100k", 100000, 128, 1024, 8, 4.2, 10, 100.0),
+}
+
+
+def chain_positions(rng: np.random.Generator, n: int, bond: float = 3.8) -> np.ndarray:
+    """Compact persistent random walk standing in for a C-alpha trace (bond 3.8 A)."""
+    pos = np.zeros((n, 3))
+    d = rng.normal(size=3)
+    d /= np.linalg.norm(d)
+    for i in range(1, n):
+        # new direction: previous direction bent by ~70 degrees, biased back toward the centroid
+        r = rng.normal(size=3)
+        r -= r.dot(d) * d
+        r /= np.linalg.norm(r)
+        ang = np.deg2rad(rng.uniform(55, 85))
+        nd = np.cos(ang) * d + np.sin(ang) * r
+        back = pos[:i].mean(0) - pos[i - 1]
+        nb = np.linalg.norm(back)
+        if nb > 1e-9:
+            nd = nd + 0.35 * back / nb
+        d = nd / np.linalg.norm(nd)
+        pos[i] = pos[i - 1] + bond * d
+    return pos
+
+
+def trajectory(workload: Workload, num_frames: int, seed: int = 0, jitter: float = 0.2) -> np.ndarray:
+    """float32 [num_frames, N, 3]: a fixed base configuration plus per-frame Gaussian jitter
+    (MD-like temporal coherence), ``numpy.random.default_rng(seed)``."""
+    rng = np.random.default_rng(seed)
+    n = workload.num_atoms
+    if workload.box > 0:
+        base = rng.random((n, 3)) * workload.box
+    else:
+        base = chain_positions(rng, n)
+    frames = base[None] + jitter * rng.normal(size=(num_frames, n, 3))
+    return frames.astype(np.float32)
+
+
+def residue_ids(workload: Workload, seed: int = 0) -> np.ndarray:
+    rng = np.random.default_rng(seed + 1)
+    return rng.integers(0, 20, size=workload.num_atoms).astype(np.int64)
+
+
+def window_batch(traj: np.ndarray, starts, window: int, horizon: int = 1):
+    """Host-side slicing only (what the reference Dataset does, dataset.py:180-204):
+    returns x_position [B, W, N, 3] and y [B, N, 3] as float32 numpy arrays."""
+    xs = np.stack([traj[s:s + window] for s in starts])
+    ys = np.stack([traj[s + window + horizon - 1] for s in starts])
+    return xs, ys
+
+
+def make_batch(x_window: torch.Tensor, aminoacid: torch.Tensor, y: torch.Tensor | None,
+               cutoff: float, graph_frame: int = 0) -> PairData:
+    """Device-side feeder.  x_window [B, W, N, 3] (device), aminoacid [N] int64, y [B, N, 3].
+
+    Graph and edge attributes come from window frame ``graph_frame`` of every sample: 0 (the
+    first frame) at training time as in dataset.py:189-201, -1 (the last) in rollout as in
+    graph_kernel.py:363-379.  Equivalent to collate([PairData(...) for each sample])."""
+    B, W, N, _ = x_window.shape
+    frames = x_window[:, graph_frame].contiguous()
+    edge_index, edge_attr = ops.radius_graph(frames, cutoff)
+    data = PairData(
+        x_aminoacid=aminoacid.repeat(B),
+        x_position=x_window.reshape(B * W, N, 3),
+        y=None if y is None else y.reshape(B * N, 3),
+        edge_attr=edge_attr,
+        edge_index=edge_index,
+    )
+    return data

@@ -1,0 +1,154 @@
+"""Training step and frame-parallel data parallelism for the GKN model.
+
+The reference trains through ``torch_geometric.nn.DataParallel`` (reference graph_kernel.py:528,
+:454): one process, parameters re-broadcast every iteration, outputs gathered to GPU 0.  Here the
+path shards the way it naturally does — trajectory frames are independent graphs — with one
+process per GPU: every rank holds the parameters, runs its own frames and the only exchange is a
+gradient all-reduce.  The loss is a SUM over frames (``LpLoss(size_average=False)``, :547), so
+summing gradients across ranks reproduces the single-process gradient with no rescaling.
+
+``GradReducer`` buckets that all-reduce and launches each bucket as soon as autograd has produced
+all of its gradients (post-accumulate hooks), on a side stream, so communication overlaps the rest
+of backward.  Buckets follow gradient-ready order: ``fc2`` first, then the conv stack's
+``root/bias`` and the shared ``W3/b3`` (final when the stack's backward returns), then the edge
+MLP's ``W2, b2, W1, b1`` and finally ``fc1/emb/lstm``.  Works with NCCL (GPU) and gloo (CPU tests).
+"""
+from __future__ import annotations
+
+from typing import Iterable, Optional
+
+import torch
+import torch.distributed as dist
+
+from .graph_kernel import LpLoss
+
+
+class GradReducer:
+    """Bucketed, backward-overlapped gradient all-reduce (sum) over flat contiguous buffers."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 8 << 20,
+                 process_group=None):
+        self.group = process_group
+        self.params = [p for p in params if p.requires_grad]
+        # reverse registration order ~ order in which autograd finishes gradients
+        order = list(reversed(self.params))
+        self.buckets: list[list[torch.nn.Parameter]] = []
+        cur, cur_bytes = [], 0
+        for p in order:
+            nbytes = p.numel() * p.element_size()
+            if cur and cur_bytes + nbytes > bucket_bytes:
+                self.buckets.append(cur)
+                cur, cur_bytes = [], 0
+            cur.append(p)
+            cur_bytes += nbytes
+        if cur:
+            self.buckets.append(cur)
+        self.flat: list[torch.Tensor] = []
+        self.bucket_of: dict[int, int] = {}
+        for b, ps in enumerate(self.buckets):
+            n = sum(p.numel() for p in ps)
+            flat = torch.zeros(n, dtype=ps[0].dtype, device=ps[0].device)
+            off = 0
+            for p in ps:
+                # gradients live inside the bucket buffer (no pack/unpack copies)
+                p.grad = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+                self.bucket_of[id(p)] = b
+            self.flat.append(flat)
+        self.pending = [0] * len(self.buckets)
+        self.works: list = []
+        self.cuda = self.params[0].is_cuda if self.params else False
+        self.comm_stream = torch.cuda.Stream() if self.cuda else None
+        self.handles = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params]
+        self.enabled = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+        self.reset()
+
+    def reset(self):
+        self.pending = [len(ps) for ps in self.buckets]
+        self.works = []
+
+    def zero_grad(self):
+        for flat in self.flat:
+            flat.zero_()
+        self.reset()
+
+    def _launch(self, b: int):
+        if not self.enabled:
+            return
+        flat = self.flat[b]
+        if self.cuda:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                w = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        else:
+            w = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self.works.append(w)
+
+    def _hook(self, p: torch.nn.Parameter):
+        b = self.bucket_of[id(p)]
+        self.pending[b] -= 1
+        if self.pending[b] == 0:
+            self._launch(b)
+
+    def finish(self):
+        """Call after backward: flush buckets whose hooks did not all fire (unused parameters)
+        and wait for the reductions."""
+        for b, left in enumerate(self.pending):
+            if left > 0:
+                self._launch(b)
+                self.pending[b] = 0
+        for w in self.works:
+            w.wait()
+        if self.cuda:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        self.works = []
+
+    def close(self):
+        for h in self.handles:
+            h.remove()
+
+
+def unique_parameters(model: torch.nn.Module) -> list[torch.nn.Parameter]:
+    """Parameters once each (conv2.net aliases conv1.net, reference graph_kernel.py:271-273)."""
+    return list(model.parameters())  # nn.Module.parameters() already de-duplicates shared tensors
+
+
+class Trainer:
+    """One optimisation step of the reference's training loop (graph_kernel.py:445-474):
+    zero_grad -> model(batch) -> LpLoss.rel (sum over frames) -> backward -> Adam step,
+    with the gradient all-reduce when torch.distributed is initialised."""
+
+    def __init__(self, model: torch.nn.Module, lr: float = 0.01, weight_decay: float = 5e-4,
+                 scheduler_step: int = 50, scheduler_gamma: float = 0.8,
+                 bucket_bytes: int = 8 << 20, process_group=None):
+        self.model = model
+        params = unique_parameters(model)
+        self.reducer = GradReducer(params, bucket_bytes, process_group)
+        # reference: Adam(lr, weight_decay) + StepLR (graph_kernel.py:541-546)
+        self.optimizer = torch.optim.Adam(params, lr=lr, weight_decay=weight_decay,
+                                          fused=params[0].is_cuda)
+        self.scheduler = torch.optim.lr_scheduler.StepLR(self.optimizer, step_size=scheduler_step,
+                                                         gamma=scheduler_gamma)
+        self.loss_fn = LpLoss(size_average=False)
+
+    def step(self, batch, num_frames: int) -> torch.Tensor:
+        self.reducer.zero_grad()
+        out = self.model(batch)
+        loss = self.loss_fn(out.view(num_frames, -1), batch.y.view(num_frames, -1))
+        loss.backward()
+        self.reducer.finish()
+        self.optimizer.step()
+        return loss.detach()
+
+
+def shard_frames(num_frames: int, rank: int, world: int) -> range:
+    """Frames r, r+world, r+2*world, ... of a global batch go to rank r."""
+    return range(rank, num_frames, world)
+
+
+def broadcast_parameters(model: torch.nn.Module, src: int = 0, process_group=None) -> None:
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1:
+        for p in unique_parameters(model):
+            dist.broadcast(p.data, src=src, group=process_group)
+        for b in model.buffers():
+            dist.broadcast(b.data, src=src, group=process_group)

@@ -105,16 +105,22 @@ def lstm_window(x_position, sd: dict, window_size: int, num_residues: int) -> to
     reshaped to [B, W, R, 3], swapped to [W, B, R, 3]; each window step feeds [B, R, 3] to
     nn.LSTM(3, 3) as (seq_len=B, batch=R) with the hidden state carried across window steps."""
     dt = x_position.dtype
-    lstm = torch.nn.LSTM(3, 3).to(dt)
-    with torch.no_grad():
-        for k in ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0"):
-            getattr(lstm, k).copy_(sd["lstm." + k])
+    w_ih, w_hh = sd["lstm.weight_ih_l0"], sd["lstm.weight_hh_l0"]
+    b_ih, b_hh = sd["lstm.bias_ih_l0"], sd["lstm.bias_hh_l0"]
     x = x_position.reshape(-1, window_size, num_residues, 3)
     x = torch.swapaxes(x, 0, 1)
-    hidden = (torch.zeros(1, num_residues, 3, dtype=dt), torch.zeros(1, num_residues, 3, dtype=dt))
+    h = torch.zeros(num_residues, 3, dtype=dt)
+    c = torch.zeros(num_residues, 3, dtype=dt)
     out = None
-    for i in x:
-        out, hidden = lstm(i, hidden)
+    for i in x:  # i: [B, R, 3] consumed by nn.LSTM as (seq_len=B, batch=R, input=3)
+        steps = []
+        for t in range(i.size(0)):  # nn.LSTM cell, gate order (i, f, g, o)
+            gates = F.linear(i[t], w_ih, b_ih) + F.linear(h, w_hh, b_hh)
+            gi, gf, gg, go = gates.chunk(4, dim=1)
+            c = torch.sigmoid(gf) * c + torch.sigmoid(gi) * torch.tanh(gg)
+            h = torch.sigmoid(go) * torch.tanh(c)
+            steps.append(h)
+        out = torch.stack(steps)  # [B, R, 3]; (h, c) carry over to the next window step
     return F.linear(out, sd["lstm_fc.weight"], sd["lstm_fc.bias"])  # :288
 
 

@@ -1,0 +1,275 @@
+"""Generate golden vectors by EXECUTING THE REFERENCE'S OWN SOURCE in this container.
+
+    python tests/golden/make_golden.py          # needs /root/reference; writes tests/golden/*.npz
+
+The reference (``/root/reference/graph_kernel.py``, ``dataset.py``) cannot be imported as-is here:
+torch_geometric, h5py, matplotlib, imageio and mdlearn are not installed.  This
+script registers minimal stand-ins for those THIRD-PARTY modules in ``sys.modules`` and then
+imports the reference unchanged, so that the reference's own code is what runs:
+
+    NNConv_old.__init__/reset_parameters/forward/message/update   graph_kernel.py:159-209
+    DenseNet                                                      graph_kernel.py:217-242
+    KernelNN.__init__/forward (LSTM quirk, shared kernel, loop)   graph_kernel.py:245-309
+    LpLoss.rel                                                    graph_kernel.py:105-119
+    construct_pairdata (real SciPy distance_matrix / coo_matrix)  graph_kernel.py:362-393
+    PairData                                                      dataset.py:21-53
+
+What is NOT the reference here is torch_geometric itself; its stand-in restates the documented
+behaviour the reference relies on:
+    MessagePassing.propagate(edge_index, x=..., pseudo=...): x_j = x[edge_index[0]];
+        out = message(x_j, pseudo); aggregate at edge_index[1] over dim_size = x.size(0) with
+        'mean' = sum / clamp(count, min=1) (or 'add'); return update(out, x=x)
+    inits.reset(m): reset_parameters() on m, else recurse over children
+    inits.uniform(size, t): t ~ U(-1/sqrt(size), 1/sqrt(size))
+    data.Data: attribute bag with .to()
+Two reference lines cannot run on a CPU-only box and are neutralised, not rewritten:
+``.cuda()`` at graph_kernel.py:281-282 (patched to identity) and the module-level ``args`` global
+read at :279-281 (set to a Namespace).
+
+The GPU box has no /root/reference, so the vectors are committed; tests only read the .npz files.
+"""
+from __future__ import annotations
+
+import argparse
+import math
+import sys
+import types
+import warnings
+from pathlib import Path
+
+import numpy as np
+import torch
+
+HERE = Path(__file__).resolve().parent
+REFERENCE = Path("/root/reference")
+
+
+# ------------------------------------------------------------------------------------------------
+# third-party stand-ins
+# ------------------------------------------------------------------------------------------------
+def install_stubs():
+    def mod(name):
+        m = types.ModuleType(name)
+        sys.modules[name] = m
+        return m
+
+    tg = mod("torch_geometric")
+    tg_data = mod("torch_geometric.data")
+    tg_loader = mod("torch_geometric.loader")
+    tg_nn = mod("torch_geometric.nn")
+    tg_conv = mod("torch_geometric.nn.conv")
+    tg_inits = mod("torch_geometric.nn.inits")
+    tg_typing = mod("torch_geometric.typing")
+    tg.data, tg.loader, tg.nn, tg.typing = tg_data, tg_loader, tg_nn, tg_typing
+    tg_nn.conv, tg_nn.inits = tg_conv, tg_inits
+
+    class Data:
+        def __init__(self, *a, **k):
+            pass
+
+        def to(self, device, *a, **k):
+            for k_, v in list(self.__dict__.items()):
+                if torch.is_tensor(v):
+                    setattr(self, k_, v.to(device))
+            return self
+
+        def __inc__(self, key, value, *a, **k):
+            return 0
+
+    class MessagePassing(torch.nn.Module):
+        def __init__(self, aggr="add", flow="source_to_target", node_dim=-2, **kwargs):
+            super().__init__()
+            self.aggr = aggr
+            assert flow == "source_to_target" and node_dim == -2
+
+        def propagate(self, edge_index, x, pseudo):
+            x_j = x.index_select(0, edge_index[0])
+            msg = self.message(x_j, pseudo)
+            n = x.size(0)
+            out = torch.zeros((n, msg.size(1)), dtype=msg.dtype).index_add_(0, edge_index[1], msg)
+            if self.aggr == "mean":
+                cnt = torch.zeros(n, dtype=msg.dtype).index_add_(
+                    0, edge_index[1], torch.ones(edge_index.size(1), dtype=msg.dtype))
+                out = out / cnt.clamp(min=1).unsqueeze(1)
+            elif self.aggr != "add":
+                raise NotImplementedError(self.aggr)
+            return self.update(out, x=x)
+
+    def reset(value):
+        if hasattr(value, "reset_parameters"):
+            value.reset_parameters()
+        else:
+            for child in value.children() if hasattr(value, "children") else []:
+                reset(child)
+
+    def uniform(size, value):
+        if isinstance(value, torch.Tensor):
+            bound = 1.0 / math.sqrt(size)
+            value.data.uniform_(-bound, bound)
+
+    class _Dummy:
+        def __init__(self, *a, **k):
+            raise RuntimeError("stub")
+
+    tg_data.Data = Data
+    tg_data.DataLoader = _Dummy
+    tg_loader.DataListLoader = _Dummy
+    tg_nn.DataParallel = _Dummy
+    tg_conv.MessagePassing = MessagePassing
+    tg_inits.reset, tg_inits.uniform = reset, uniform
+    tg_typing.OptTensor = "OptTensor"
+
+    for name in ("h5py", "imageio", "mdlearn", "mdlearn.utils", "matplotlib", "matplotlib.pyplot",
+                 "wandb"):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:  # noqa: BLE001
+                mod(name)
+    sys.modules["mdlearn.utils"].log_latent_visualization = lambda *a, **k: None
+    if not hasattr(sys.modules["matplotlib"], "pyplot"):
+        sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+
+
+def import_reference():
+    install_stubs()
+    sys.path.insert(0, str(REFERENCE))
+    warnings.simplefilter("ignore")
+    import graph_kernel as ref  # noqa: PLC0415  (the reference, unmodified)
+
+    return ref
+
+
+# ------------------------------------------------------------------------------------------------
+# deterministic inputs
+# ------------------------------------------------------------------------------------------------
+def chain(rng, n, bond=3.8):
+    pos = np.zeros((n, 3))
+    for i in range(1, n):
+        d = rng.normal(size=3)
+        pos[i] = pos[i - 1] + bond * d / np.linalg.norm(d)
+    return pos
+
+
+def to_np(sd):
+    return {k: v.detach().cpu().numpy() for k, v in sd.items()}
+
+
+def gen_nnconv(ref, name, w, K, n, thr, seed, aggr="mean", grad_row_stride=1):
+    torch.manual_seed(seed)
+    rng = np.random.default_rng(seed)
+    pos = (chain(rng, n) + rng.normal(size=(n, 3)) * 0.1).astype(np.float32)
+    data = ref.construct_pairdata(pos[None], torch.zeros(n, dtype=torch.long), threshold=thr)
+    net = ref.DenseNet([6, K, K, w * w], torch.nn.ReLU)
+    conv = ref.NNConv_old(w, w, net, aggr=aggr)
+    sd32 = {k: v.clone() for k, v in conv.state_dict().items()}  # fp32-representable weights
+    conv = conv.double()
+    x = torch.randn(n, w, dtype=torch.float32).double().requires_grad_(True)
+    ea = data.edge_attr.double()
+    out = conv(x, data.edge_index, ea)
+    gout = torch.randn(out.shape, dtype=torch.float32).double()
+    out.backward(gout)
+    arrays = {f"sd.{k}": v for k, v in to_np(sd32).items()}
+    arrays.update(
+        pos=pos, threshold=np.float64(thr), edge_index=data.edge_index.numpy(),
+        edge_attr=data.edge_attr.numpy(), x=x.detach().numpy().astype(np.float32),
+        gout=gout.numpy().astype(np.float32), out=out.detach().numpy(), grad_x=x.grad.numpy(),
+    )
+    for k, p in conv.named_parameters():
+        g = p.grad.numpy()
+        if k == "net.layers.4.weight" and grad_row_stride > 1:
+            g = g[::grad_row_stride]  # keep the fixture small: every n-th row of dW3
+        arrays[f"grad.{k}"] = g
+    arrays["grad_row_stride"] = np.int64(grad_row_stride)
+    np.savez_compressed(HERE / f"{name}.npz", **arrays)
+    print(name, "N", n, "E", data.edge_index.shape[1], "out", out.shape)
+
+
+def gen_kernelnn(ref, name, w, K, depth, B, W, R, thr, seed):
+    torch.manual_seed(seed)
+    rng = np.random.default_rng(seed)
+    ref.args = argparse.Namespace(window_size=W, num_residues=R, batch_size=B)
+    base = chain(rng, R)
+    traj = (base[None] + 0.3 * rng.normal(size=(B + W + 1, R, 3))).astype(np.float32)
+    aa = torch.from_numpy(rng.integers(0, 20, size=R).astype(np.int64))
+    samples = []
+    for b in range(B):
+        win = traj[b:b + W]
+        # training-time convention (dataset.py:189-201): graph + edge_attr from the FIRST window
+        # frame; built with the reference's own construct_pairdata on that frame
+        g = ref.construct_pairdata(win[:1], aa, threshold=thr)
+        samples.append(dict(x_position=torch.from_numpy(win), edge_index=g.edge_index,
+                            edge_attr=g.edge_attr, y=torch.from_numpy(traj[b + W])))
+    # PyG batching: concat, edge_index offset by num_nodes (dataset.py:41-45)
+    batch = ref.PairData(
+        x_aminoacid=aa.repeat(B),
+        x_position=torch.cat([s["x_position"] for s in samples]).double(),
+        y=torch.cat([s["y"] for s in samples]).double(),
+        edge_attr=torch.cat([s["edge_attr"] for s in samples]).double(),
+        edge_index=torch.cat([s["edge_index"] + i * R for i, s in enumerate(samples)], dim=1),
+    )
+    model = ref.KernelNN(w, K, depth, 6, in_width=7, out_width=3)
+    sd32 = {k: v.clone() for k, v in model.state_dict().items()}
+    model = model.double()
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self  # graph_kernel.py:281-282 on a CPU-only box
+    torch.set_default_dtype(torch.float64)  # so the torch.zeros hidden state at :281 is float64
+    try:
+        out, latent = model(batch, return_latent=True)
+    finally:
+        torch.Tensor.cuda = orig_cuda
+        torch.set_default_dtype(torch.float32)
+    loss_fn = ref.LpLoss(size_average=False)
+    loss = loss_fn(out.view(B, -1), batch.y.view(B, -1))
+    loss.backward()
+    arrays = {f"sd.{k}": v for k, v in to_np(sd32).items()}
+    arrays.update(
+        traj=traj, aminoacid=aa.numpy(), threshold=np.float64(thr), depth=np.int64(depth),
+        window=np.int64(W), num_residues=np.int64(R), batch=np.int64(B),
+        edge_index=batch.edge_index.numpy(), edge_attr=batch.edge_attr.numpy().astype(np.float32),
+        out=out.detach().numpy(), latent=latent.detach().numpy(), loss=loss.detach().numpy(),
+    )
+    seen = set()
+    for k, p in model.named_parameters():  # shared kernel appears once (conv1.net.*)
+        if id(p) in seen:
+            continue
+        seen.add(id(p))
+        arrays[f"grad.{k}"] = p.grad.numpy()
+    np.savez_compressed(HERE / f"{name}.npz", **arrays)
+    print(name, "N", B * R, "E", batch.edge_index.shape[1], "loss", float(loss))
+
+
+def gen_pairdata(ref, name, n, W, L, thr, seed):
+    rng = np.random.default_rng(seed)
+    xp = (rng.random((W, n, 3)) * L).astype(np.float32)
+    data = ref.construct_pairdata(xp, torch.zeros(n, dtype=torch.long), threshold=thr)
+    np.savez_compressed(HERE / f"{name}.npz", x_position=xp, threshold=np.float64(thr),
+                        edge_index=data.edge_index.numpy(), edge_attr=data.edge_attr.numpy())
+    print(name, "N", n, "E", data.edge_index.shape[1])
+
+
+def gen_lploss(ref, name, seed):
+    torch.manual_seed(seed)
+    x = torch.randn(5, 84, dtype=torch.float64)
+    y = torch.randn(5, 84, dtype=torch.float64)
+    np.savez_compressed(
+        HERE / f"{name}.npz", x=x.numpy(), y=y.numpy(),
+        rel_sum=ref.LpLoss(size_average=False)(x, y).numpy(),
+        rel_mean=ref.LpLoss(size_average=True)(x, y).numpy(),
+    )
+
+
+def main():
+    ref = import_reference()
+    gen_nnconv(ref, "nnconv_w16_k64", w=16, K=64, n=28, thr=8.0, seed=1)
+    gen_nnconv(ref, "nnconv_w32_k64", w=32, K=64, n=40, thr=8.0, seed=2)
+    gen_nnconv(ref, "nnconv_w64_k64_isolated", w=64, K=64, n=20, thr=3.0, seed=3, grad_row_stride=16)
+    gen_kernelnn(ref, "kernelnn_w16_k64_d2", w=16, K=64, depth=2, B=2, W=3, R=12, thr=8.0, seed=4)
+    gen_kernelnn(ref, "kernelnn_w32_k64_d1", w=32, K=64, depth=1, B=3, W=2, R=10, thr=6.0, seed=5)
+    gen_pairdata(ref, "pairdata_n28", n=28, W=3, L=20.0, thr=8.0, seed=6)
+    gen_pairdata(ref, "pairdata_n300", n=300, W=1, L=20.0, thr=4.2, seed=7)
+    gen_lploss(ref, "lploss", seed=8)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,106 @@
+"""GPU parity of the radius-graph build and the CSR prepare: bit-exact against the reference's
+golden vectors and the SciPy oracle; structural properties at full size."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["pairdata_n28", "pairdata_n300"])
+def test_construct_pairdata_bit_exact_vs_reference_golden(name):
+    from molecular_dynamics_neural_operator_b200.graph_kernel import construct_pairdata
+
+    g = load_golden(name)
+    n = g["x_position"].shape[1]
+    data = construct_pairdata(g["x_position"], torch.zeros(n, dtype=torch.long), float(g["threshold"]))
+    assert data.edge_index.dtype == torch.int64 and data.edge_attr.dtype == torch.float32
+    assert np.array_equal(data.edge_index.cpu().numpy(), g["edge_index"])
+    assert np.array_equal(data.edge_attr.cpu().numpy(), g["edge_attr"])
+    assert data.x_position.shape == g["x_position"].shape
+
+
+@pytest.mark.parametrize("F,N,L,thr", [(1, 1, 1.0, 8.0), (1, 28, 20.0, 8.0), (5, 100, 12.0, 4.2),
+                                        (2, 504, 17.1, 8.0), (3, 64, 300.0, 4.2), (1, 3000, 31.0, 4.2),
+                                        (2, 50, 5.0, 0.5), (1, 40, 10.0, 1000.0)])
+def test_radius_graph_bit_exact_vs_scipy_oracle(F, N, L, thr):
+    from molecular_dynamics_neural_operator_b200 import ops
+    from oracle import gkn_oracle as orc
+
+    rng = np.random.default_rng(F * 1000 + N)
+    pos = (rng.random((F, N, 3)) * L - L / 3).astype(np.float32)
+    ei_ref, ea_ref = orc.radius_graph_batched(pos, thr)
+    ei, ea = ops.radius_graph(torch.from_numpy(pos).cuda(), thr)
+    assert np.array_equal(ei.cpu().numpy(), ei_ref)
+    assert np.array_equal(ea.cpu().numpy(), ea_ref)
+
+
+def test_radius_graph_boundary_pairs_use_the_float64_predicate():
+    """Pairs sitting exactly at / one ulp around the cutoff, and duplicated atoms."""
+    from molecular_dynamics_neural_operator_b200 import ops
+    from oracle import gkn_oracle as orc
+
+    thr = 4.2
+    base = np.zeros((8, 3), dtype=np.float32)
+    base[1] = [4.2, 0, 0]
+    base[2] = [np.nextafter(np.float32(4.2), np.float32(0)), 0, 0]
+    base[3] = [np.nextafter(np.float32(4.2), np.float32(9)), 0, 0]
+    base[4] = [3.0, 2.9393876, 0]  # |d| ~ 4.2
+    base[5] = [0, 0, 0]  # duplicate of atom 0
+    base[6] = [2.4248712, 2.4248712, 2.4248712]
+    base[7] = [-4.2, 0, 0]
+    ei_ref, ea_ref = orc.radius_graph_batched(base[None], thr)
+    ei, ea = ops.radius_graph(torch.from_numpy(base[None]).cuda(), thr)
+    assert np.array_equal(ei.cpu().numpy(), ei_ref) and np.array_equal(ea.cpu().numpy(), ea_ref)
+
+
+def test_radius_graph_full_size_properties_and_kdtree_oracle():
+    """BASELINE config 3 (10k atoms, 4.2 A): equals the kd-tree oracle; symmetric, sorted, self loops."""
+    from molecular_dynamics_neural_operator_b200 import ops
+    from molecular_dynamics_neural_operator_b200 import synthetic as syn
+    from oracle import gkn_oracle as orc
+
+    wl = syn.WORKLOADS["synthetic_10k"]
+    pos = syn.trajectory(wl, 2, seed=1)
+    ei, ea = ops.radius_graph(torch.from_numpy(pos).cuda(), wl.cutoff)
+    ei_np = ei.cpu().numpy()
+    N = wl.num_atoms
+    refs = [orc.radius_graph_kdtree(pos[f], wl.cutoff) for f in range(2)]
+    ei_ref = np.concatenate([r[0] + f * N for f, r in enumerate(refs)], axis=1)
+    ea_ref = np.concatenate([r[1] for r in refs], axis=0)
+    assert np.array_equal(ei_np, ei_ref) and np.array_equal(ea.cpu().numpy(), ea_ref)
+    key = ei_np[0] * (2 * N) + ei_np[1]
+    assert np.all(np.diff(key) > 0)  # strictly increasing (row, col): sorted, no duplicates
+    rev = np.sort(ei_np[1] * (2 * N) + ei_np[0])
+    assert np.array_equal(rev, key)  # symmetric
+    assert np.count_nonzero(ei_np[0] == ei_np[1]) == 2 * N  # every self loop present
+    assert 250000 < ei_np.shape[1] // 2 < 340000  # ~291k edges / frame
+
+
+def test_prepare_graph_against_numpy_stable_sort():
+    from molecular_dynamics_neural_operator_b200 import ops
+
+    g = torch.Generator().manual_seed(0)
+    for N, E in [(1, 0), (7, 1), (50, 700), (504, 57000), (4000, 100000)]:
+        ei = torch.stack([torch.randint(0, N, (E,), generator=g), torch.randint(0, N, (E,), generator=g)])
+        plan = ops.prepare_graph(ei.cuda(), N)
+        dst = ei[1].numpy()
+        order = np.argsort(dst, kind="stable")
+        assert np.array_equal(plan.perm.cpu().numpy(), order)
+        assert np.array_equal(plan.src.cpu().numpy(), ei[0].numpy()[order])
+        assert np.array_equal(plan.dst.cpu().numpy(), dst[order])
+        cnt = np.bincount(dst, minlength=N)
+        assert np.array_equal(plan.dst_ptr.cpu().numpy(), np.concatenate([[0], np.cumsum(cnt)]))
+        assert np.array_equal(plan.inv_cnt.cpu().numpy(), (1.0 / np.maximum(cnt, 1)).astype(np.float32))
+        s_sorted = ei[0].numpy()[order]
+        assert np.array_equal(plan.src_perm.cpu().numpy(), np.argsort(s_sorted, kind="stable"))
+
+
+def test_prepare_graph_rejects_out_of_range_ids():
+    from molecular_dynamics_neural_operator_b200 import ops
+
+    ei = torch.tensor([[0, 1, 5], [1, 0, 1]], dtype=torch.long).cuda()
+    with pytest.raises(ValueError, match="outside"):
+        ops.prepare_graph(ei, 3)
