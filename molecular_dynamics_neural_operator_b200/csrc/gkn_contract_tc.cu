@@ -290,9 +290,9 @@ int launch_contract(const CUtensorMap& tmap_h, const CUtensorMap& tmap_w, const 
     cudaError_t err =
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (err != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(contract_tc)", err);
-    constexpr int kChunks = (W * W) / kBlockN;
-    int64_t total_units = p.num_tiles * kChunks;
-    int grid = int(total_units < max_ctas ? total_units : max_ctas);
+    // grid <= num_tiles: every CTA then owns at least one tile's worth of units, so a tile is
+    // shared by at most two CTAs and its two partial sums combine order-independently.
+    int grid = int(p.num_tiles < max_ctas ? p.num_tiles : max_ctas);
     if (grid < 1) return 0;
     kern<<<grid, kThreads, kSmemBytes, stream>>>(tmap_h, tmap_w, p);
     err = cudaGetLastError();
