@@ -99,6 +99,20 @@ int gkn_scatter_mean_fwd(const float* msg, const int32_t* src_s, const int32_t* 
 int gkn_scatter_src_sum(const float* dxj, const int32_t* src_ptr, const int32_t* src_perm,
                         const int32_t* dst_s, const float* gb3, const float* addend, float* dx,
                         int64_t N, int64_t E, int32_t W, void* stream);
+/* Fused node update, one kernel for NNConv_old.update (graph_kernel.py:204-209, forward) and for
+ * its autograd (backward):
+ *   r[n]   = scale[n] * sum_{q in [seg_ptr[n],seg_ptr[n+1])} rows[p,:]      p = perm ? perm[q] : q
+ *   agg[n] = scale[n] * sum_q gnode[gidx[p],:]                  (written to agg_out if not NULL)
+ *   out[n] = act( r[n] + agg[n] @ M1 + nin[n] @ M2 + bias )     M1, M2: [W,W] row-major
+ * forward : rows=msg, perm=NULL, seg_ptr=dst_ptr, gidx=src_s, gnode=x, scale=inv_cnt,
+ *           M1 = layers.4.bias viewed [W,W], nin=x, M2=root, bias, relu
+ * backward: rows=dxj, perm=src_perm, seg_ptr=src_ptr, gidx=dst_s, gnode=gn, scale=NULL,
+ *           M1 = (b3 view)^T, nin=g, M2=root^T, bias=NULL, relu=0 */
+int gkn_segment_matvec(const float* rows, const int32_t* perm, const int32_t* seg_ptr,
+                       const int32_t* gidx, const float* gnode, const float* scale,
+                       const float* M1, const float* nin, const float* M2, const float* bias,
+                       float* out, float* agg_out, int64_t N, int32_t W, int32_t relu,
+                       void* stream);
 /* g[n,:] = gy[n,:] * (relu ? (y[n,:] > 0) : 1);  gn[n,:] = g[n,:] * inv_cnt[n] */
 int gkn_relu_grad_scale(const float* gy, const float* y, const float* inv_cnt, float* g, float* gn,
                         int64_t N, int32_t W, int32_t relu, void* stream);
@@ -116,6 +130,22 @@ int gkn_edge_outer_sum(const float* xs, const float* gs, const int32_t* src_s,
 /* out_bf16[i] = bf16_rn( relu ? max(in[i] + (bias ? bias[i % cols] : 0), 0) : in[i] + bias ) */
 int gkn_bias_act_cast_bf16(const float* in, const float* bias, void* out_bf16, int64_t rows,
                            int64_t cols, int32_t relu, void* stream);
+
+/* ---- edge-MLP layer .0 and the backward of "bias + ReLU" ----------------------------------
+ * gkn_edge_layer0: out[e,k] = relu(sum_j ea[e,j]*w1[k,j] + b1[k]), bf16 or fp32 (DenseNet
+ * layers.0 + ReLU, graph_kernel.py:239-242; kin must be 6 = edge_features, :328).
+ * gkn_mask_cast_colsum: out[r,c] = dz[r,c] * (act[r,c] > 0), cast to bf16 or kept fp32 (may alias
+ * dz when fp32); colsum[0,c] (+)= sum_r out[r,c] (bias gradient) and, when side != NULL
+ * (nside = 6), colsum[1+j,c] (+)= sum_r out[r,c]*side[r,j] (layer-.0 weight gradient, transposed).
+ * colsum is [(1+nside), cols]; deterministic two-pass reduction, no atomics.  act is the layer's
+ * saved post-ReLU activation (bf16 or fp32). */
+int gkn_edge_layer0(const float* ea, const float* w1, const float* b1, void* out,
+                    int32_t out_is_bf16, int64_t E, int32_t K, int32_t kin, void* stream);
+int64_t gkn_mask_cast_colsum_workspace_bytes(int64_t cols, int32_t nside);
+int gkn_mask_cast_colsum(const float* dz, const void* act, int32_t act_is_bf16, void* out,
+                         int32_t out_is_bf16, const float* side, int32_t nside, float* colsum,
+                         int32_t accumulate, int64_t rows, int64_t cols, void* workspace,
+                         int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

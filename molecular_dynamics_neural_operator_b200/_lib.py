@@ -37,12 +37,22 @@ SIGNATURES = {
         [P, P, P, P, P, P, P, P, c_int64, c_int64, c_int32, c_int32, P],
     ),
     "gkn_scatter_src_sum": (c_int, [P, P, P, P, P, P, P, c_int64, c_int64, c_int32, P]),
+    "gkn_segment_matvec": (
+        c_int,
+        [P, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int32, c_int32, P],
+    ),
     "gkn_relu_grad_scale": (c_int, [P, P, P, P, P, c_int64, c_int32, c_int32, P]),
     "gkn_edge_outer_sum": (
         c_int,
         [P, P, P, P, P, c_int32, c_int64, c_int64, c_int64, c_int32, c_int32, P],
     ),
     "gkn_bias_act_cast_bf16": (c_int, [P, P, P, c_int64, c_int64, c_int32, P]),
+    "gkn_edge_layer0": (c_int, [P, P, P, P, c_int32, c_int64, c_int32, c_int32, P]),
+    "gkn_mask_cast_colsum_workspace_bytes": (c_int64, [c_int64, c_int32]),
+    "gkn_mask_cast_colsum": (
+        c_int,
+        [P, P, c_int32, P, c_int32, P, c_int32, P, c_int32, c_int64, c_int64, P, c_int64, P],
+    ),
 }
 
 

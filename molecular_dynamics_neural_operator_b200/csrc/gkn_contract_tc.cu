@@ -73,10 +73,19 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tmap_h,
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    // contiguous unit range of this CTA
+    // Contiguous unit range of this CTA.  With many tiles per CTA the ranges are tile-aligned: all
+    // CTAs then walk the W3 column chunks in phase, so a chunk fetched by one CTA is an L2 hit for
+    // the others (matters when W3 is large, e.g. 32 MB at w=128), at a tail cost < 1/16.  With few
+    // tiles per CTA, units are split evenly instead (no tile-quantisation tail).
     const int64_t total_units = p.num_tiles * kChunks;
-    const int64_t u0 = (total_units * blockIdx.x) / gridDim.x;
-    const int64_t u1 = (total_units * (blockIdx.x + 1)) / gridDim.x;
+    int64_t u0, u1;
+    if (p.num_tiles >= int64_t(gridDim.x) * 16) {
+        u0 = ((p.num_tiles * blockIdx.x) / gridDim.x) * kChunks;
+        u1 = ((p.num_tiles * (blockIdx.x + 1)) / gridDim.x) * kChunks;
+    } else {
+        u0 = (total_units * blockIdx.x) / gridDim.x;
+        u1 = (total_units * (blockIdx.x + 1)) / gridDim.x;
+    }
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -231,7 +240,8 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tmap_h,
 
             const uint32_t as = it & 1u;
             const uint32_t aphase = (it >> 1) & 1u;
-            mbar_wait(tfull_bar(as), aphase);
+            // one lane polls; the other 31 park at the warp barrier instead of hammering smem
+            if (lane == 0) mbar_wait(tfull_bar(as), aphase);
             __syncwarp();
             tc_fence_after();
             const uint32_t tcol = tmem_base + lane_addr + as * kBlockN;

@@ -136,6 +136,93 @@ scatter_src_sum_kernel(const float* __restrict__ dxj, const int32_t* __restrict_
     }
 }
 
+// Fused node update (forward AND backward use the same kernel):
+//   r[n]   = scale[n] * sum_{q in seg(n)} rows[p]                    p = perm ? perm[q] : q
+//   agg[n] = scale[n] * sum_{q in seg(n)} gnode[gidx[p]]             (optionally written out)
+//   out[n] = act( r[n] + agg[n] @ M1 + nin[n] @ M2 + bias )
+// forward : rows=msg, gidx=src, gnode=x, scale=1/deg, M1=B3 (b3 viewed [w,w]), nin=x, M2=root
+//           => NNConv_old.update with the layers.4 bias folded in (graph_kernel.py:200-209)
+// backward: rows=dxj, perm=src_perm, gidx=dst, gnode=gn, M1=B3^T, nin=g, M2=root^T, no scale/bias
+// The two w x w products are done per node inside the warp (operands from a per-warp smem row,
+// matrices through the read-only path), so no separate tiny GEMM launches are needed.
+template <int W>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+segment_matvec_kernel(const float* __restrict__ rows, const int32_t* __restrict__ perm,
+                      const int32_t* __restrict__ seg_ptr, const int32_t* __restrict__ gidx,
+                      const float* __restrict__ gnode, const float* __restrict__ scale,
+                      const float* __restrict__ M1, const float* __restrict__ nin,
+                      const float* __restrict__ M2, const float* __restrict__ bias,
+                      float* __restrict__ out, float* __restrict__ agg_out, int64_t N, int relu) {
+    constexpr int LPR = W / 4;
+    constexpr int RPW = 32 / LPR;
+    constexpr int CPL = W >= 32 ? W / 32 : 1;  // output columns per lane in the matvec phase
+    __shared__ float s_r[kWarpsPerBlock][W];
+    __shared__ float s_g[kWarpsPerBlock][W];
+    __shared__ float s_n[kWarpsPerBlock][W];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int sub = lane / LPR;
+    const int col = (lane % LPR) * 4;
+    const int64_t warp0 = int64_t(blockIdx.x) * kWarpsPerBlock + wib;
+    const int64_t nwarps = int64_t(gridDim.x) * kWarpsPerBlock;
+    for (int64_t n = warp0; n < N; n += nwarps) {
+        const int beg = seg_ptr[n], end = seg_ptr[n + 1];
+        float4 ar0 = make_float4(0.f, 0.f, 0.f, 0.f), ar1 = ar0, ag0 = ar0, ag1 = ar0;
+        int q = beg + sub;
+        for (; q + RPW < end; q += 2 * RPW) {
+            const int p0 = perm ? perm[q] : q;
+            const int p1 = perm ? perm[q + RPW] : q + RPW;
+            const float4 r0 = ldg4_stream(rows + int64_t(p0) * W + col);
+            const float4 r1 = ldg4_stream(rows + int64_t(p1) * W + col);
+            const float4 g0 = ldg4(gnode + int64_t(gidx[p0]) * W + col);
+            const float4 g1 = ldg4(gnode + int64_t(gidx[p1]) * W + col);
+            ar0 = f4add(ar0, r0);
+            ar1 = f4add(ar1, r1);
+            ag0 = f4add(ag0, g0);
+            ag1 = f4add(ag1, g1);
+        }
+        if (q < end) {
+            const int p0 = perm ? perm[q] : q;
+            ar0 = f4add(ar0, ldg4_stream(rows + int64_t(p0) * W + col));
+            ag0 = f4add(ag0, ldg4(gnode + int64_t(gidx[p0]) * W + col));
+        }
+        float4 ar = f4add(ar0, ar1), ag = f4add(ag0, ag1);
+#pragma unroll
+        for (int off = LPR; off < 32; off <<= 1) {
+            ar = f4add(ar, f4shfl_xor(ar, off));
+            ag = f4add(ag, f4shfl_xor(ag, off));
+        }
+        if (sub == 0) {
+            const float sc = scale ? scale[n] : 1.f;
+            ar = make_float4(ar.x * sc, ar.y * sc, ar.z * sc, ar.w * sc);
+            ag = make_float4(ag.x * sc, ag.y * sc, ag.z * sc, ag.w * sc);
+            *reinterpret_cast<float4*>(&s_r[wib][col]) = ar;
+            *reinterpret_cast<float4*>(&s_g[wib][col]) = ag;
+            *reinterpret_cast<float4*>(&s_n[wib][col]) = ldg4(nin + n * W + col);
+            if (agg_out) *reinterpret_cast<float4*>(agg_out + n * W + col) = ag;
+        }
+        __syncwarp();
+        const int c0 = lane * CPL;
+        if (c0 < W) {
+            float o[CPL];
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) o[k] = s_r[wib][c0 + k] + (bias ? __ldg(bias + c0 + k) : 0.f);
+#pragma unroll 4
+            for (int i = 0; i < W; ++i) {
+                const float a = s_g[wib][i], b = s_n[wib][i];
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) {
+                    o[k] = fmaf(a, __ldg(M1 + i * W + c0 + k), o[k]);
+                    o[k] = fmaf(b, __ldg(M2 + i * W + c0 + k), o[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) out[n * W + c0 + k] = relu ? fmaxf(o[k], 0.f) : o[k];
+        }
+        __syncwarp();
+    }
+}
+
 __global__ void relu_grad_scale_kernel(const float* __restrict__ gy, const float* __restrict__ y,
                                        const float* __restrict__ inv_cnt, float* __restrict__ g,
                                        float* __restrict__ gn, int64_t total4, int W4, int relu) {
@@ -235,6 +322,169 @@ __global__ void bias_act_cast_bf16_kernel(const float* __restrict__ in,
         pk.x = *reinterpret_cast<uint32_t*>(&lo);
         pk.y = *reinterpret_cast<uint32_t*>(&hi);
         *reinterpret_cast<uint2*>(out + t * 4) = pk;
+    }
+}
+
+// dz_out[r,c] = dz[r,c] * (act[r,c] > 0)  (cast to OUT type), and per-block column partial sums
+// partial[b, c] = sum over the block's rows; a second kernel folds the partials in a fixed order
+// (deterministic bias gradient without atomics).  One thread owns 4 adjacent columns.
+template <typename ACT>
+__device__ __forceinline__ void load_act4(const ACT* p, float (&a)[4]) {
+    if constexpr (sizeof(ACT) == 2) {
+        const uint2 raw = *reinterpret_cast<const uint2*>(p);
+        const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
+        const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+        a[0] = __low2float(lo);
+        a[1] = __high2float(lo);
+        a[2] = __low2float(hi);
+        a[3] = __high2float(hi);
+    } else {
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        a[0] = t.x;
+        a[1] = t.y;
+        a[2] = t.z;
+        a[3] = t.w;
+    }
+}
+
+// `out` may alias `dz` (fp32 in place): every element is read and written by the same thread.
+// NSIDE > 0 additionally accumulates partial[b, 1+j, c] = sum_r out[r,c] * side[r,j] (j < NSIDE):
+// with side = edge_attr this is the layer-0 weight gradient, produced in the same pass.
+template <typename ACT, typename OUT, int NSIDE>
+__global__ void __launch_bounds__(256)
+mask_cast_colsum_kernel(const float* dz, const ACT* __restrict__ act, OUT* out,
+                        const float* __restrict__ side, float* __restrict__ partial, int64_t rows,
+                        int cols) {
+    constexpr int U = 4;  // rows in flight per thread
+    constexpr int kMaxSideRows = 256;
+    __shared__ float s_side[NSIDE > 0 ? kMaxSideRows * NSIDE : 1];
+    const int64_t rows_per_block = (rows + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = int64_t(blockIdx.x) * rows_per_block;
+    const int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+    float* pbase = partial + int64_t(blockIdx.x) * (1 + NSIDE) * cols;
+    const bool side_in_smem = NSIDE > 0 && (r1 - r0) <= kMaxSideRows;
+    if (NSIDE > 0) {
+        if (side_in_smem) {
+            for (int t = threadIdx.x; t < int(r1 - r0) * NSIDE; t += 256) {
+                s_side[t] = side[r0 * NSIDE + t];
+            }
+        }
+        __syncthreads();
+    }
+    for (int c = threadIdx.x * 4; c < cols; c += 256 * 4) {
+        float4 acc[1 + NSIDE];
+#pragma unroll
+        for (int j = 0; j <= NSIDE; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int64_t rb = r0; rb < r1; rb += U) {
+            float4 v[U];
+            float a[U][4];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t r = rb + u;
+                if (r < r1) {
+                    v[u] = *reinterpret_cast<const float4*>(dz + r * cols + c);
+                    load_act4(act + r * cols + c, a[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t r = rb + u;
+                if (r >= r1) break;
+                float4 w = v[u];
+                w.x = a[u][0] > 0.f ? w.x : 0.f;
+                w.y = a[u][1] > 0.f ? w.y : 0.f;
+                w.z = a[u][2] > 0.f ? w.z : 0.f;
+                w.w = a[u][3] > 0.f ? w.w : 0.f;
+                acc[0] = f4add(acc[0], w);
+#pragma unroll
+                for (int j = 0; j < NSIDE; ++j) {
+                    const float sj = side_in_smem ? s_side[int(r - r0) * NSIDE + j]
+                                                  : __ldg(side + r * NSIDE + j);
+                    acc[1 + j].x = fmaf(w.x, sj, acc[1 + j].x);
+                    acc[1 + j].y = fmaf(w.y, sj, acc[1 + j].y);
+                    acc[1 + j].z = fmaf(w.z, sj, acc[1 + j].z);
+                    acc[1 + j].w = fmaf(w.w, sj, acc[1 + j].w);
+                }
+                const int64_t off = r * cols + c;
+                if constexpr (sizeof(OUT) == 2) {
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(w.x, w.y);
+                    __nv_bfloat162 hi = __floats2bfloat162_rn(w.z, w.w);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                    *reinterpret_cast<uint2*>(out + off) = pk;
+                } else {
+                    *reinterpret_cast<float4*>(out + off) = w;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j <= NSIDE; ++j) {
+            *reinterpret_cast<float4*>(pbase + int64_t(j) * cols + c) = acc[j];
+        }
+    }
+}
+
+// colsum[j, c] (+)= sum_b partial[b, j, c]; 32 columns x 8 block-groups per CTA, fixed fold order.
+__global__ void __launch_bounds__(256)
+colsum_fold_kernel(const float* __restrict__ partial, float* __restrict__ colsum, int nblocks,
+                   int planes, int cols, int accumulate) {
+    __shared__ float sm[8][33];
+    const int cx = threadIdx.x & 31, by = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cx;
+    const int j = blockIdx.y;
+    float s = 0.f;
+    if (c < cols) {
+        for (int b = by; b < nblocks; b += 8) s += partial[(int64_t(b) * planes + j) * cols + c];
+    }
+    sm[by][cx] = s;
+    __syncthreads();
+    if (by == 0 && c < cols) {
+        float t = accumulate ? colsum[int64_t(j) * cols + c] : 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sm[k][cx];
+        colsum[int64_t(j) * cols + c] = t;
+    }
+}
+
+// h1[e,k] = relu(sum_j ea[e,j] * w1[k,j] + b1[k])   (DenseNet layers.0 + ReLU, fan-in KIN <= 8;
+// reference graph_kernel.py:239-242), written straight in the dtype layer .2 consumes.
+template <typename OUT, int KIN>
+__global__ void __launch_bounds__(256)
+edge_layer0_kernel(const float* __restrict__ ea, const float* __restrict__ w1,
+                   const float* __restrict__ b1, OUT* __restrict__ out, int64_t E, int K) {
+    const int64_t stride = gridDim.x;
+    for (int c = threadIdx.x * 4; c < K; c += 256 * 4) {
+        float w[4][KIN], b[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            b[k] = b1[c + k];
+#pragma unroll
+            for (int j = 0; j < KIN; ++j) w[k][j] = w1[(c + k) * KIN + j];
+        }
+        for (int64_t e = blockIdx.x; e < E; e += stride) {
+            float x[KIN];
+#pragma unroll
+            for (int j = 0; j < KIN; ++j) x[j] = __ldg(ea + e * KIN + j);
+            float o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float acc = b[k];
+#pragma unroll
+                for (int j = 0; j < KIN; ++j) acc = fmaf(x[j], w[k][j], acc);
+                o[k] = fmaxf(acc, 0.f);
+            }
+            if constexpr (sizeof(OUT) == 2) {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]);
+                __nv_bfloat162 hi = __floats2bfloat162_rn(o[2], o[3]);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(out + e * K + c) = pk;
+            } else {
+                *reinterpret_cast<float4*>(out + e * K + c) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
     }
 }
 
@@ -362,5 +612,114 @@ extern "C" int gkn_bias_act_cast_bf16(const float* in, const float* bias, void* 
                                 static_cast<cudaStream_t>(stream)>>>(
         in, bias, static_cast<__nv_bfloat16*>(out_bf16), total4, cols, relu);
     GKN_CHECK_LAUNCH("bias_act_cast_bf16 launch");
+    return 0;
+}
+
+extern "C" int64_t gkn_mask_cast_colsum_workspace_bytes(int64_t cols, int32_t nside) {
+    int sms = 148;
+    gkn::device_sm_count(&sms);
+    return int64_t(sms) * 4 * (1 + nside) * cols * int64_t(sizeof(float));
+}
+
+namespace gkn {
+namespace {
+template <typename ACT, typename OUT>
+void launch_mask(int nside, int grid, cudaStream_t st, const float* dz, const ACT* act, OUT* out,
+                 const float* side, float* partial, int64_t rows, int cols) {
+    if (nside == 0) {
+        mask_cast_colsum_kernel<ACT, OUT, 0><<<grid, 256, 0, st>>>(dz, act, out, side, partial, rows, cols);
+    } else {
+        mask_cast_colsum_kernel<ACT, OUT, 6><<<grid, 256, 0, st>>>(dz, act, out, side, partial, rows, cols);
+    }
+}
+}  // namespace
+}  // namespace gkn
+
+extern "C" int gkn_mask_cast_colsum(const float* dz, const void* act, int32_t act_is_bf16,
+                                    void* out, int32_t out_is_bf16, const float* side,
+                                    int32_t nside, float* colsum, int32_t accumulate, int64_t rows,
+                                    int64_t cols, void* workspace, int64_t workspace_bytes,
+                                    void* stream) {
+    using namespace gkn;
+    if (rows == 0 || cols == 0) return 0;
+    if (cols % 4 != 0 || cols > (1 << 20)) {
+        return set_error("gkn_mask_cast_colsum: cols must be a multiple of 4");
+    }
+    if (nside != 0 && nside != 6) {
+        return set_error("gkn_mask_cast_colsum: side width must be 0 or 6 (edge_features)");
+    }
+    if (nside != 0 && side == nullptr) return set_error("gkn_mask_cast_colsum: side is NULL");
+    int sms = 148;
+    device_sm_count(&sms);
+    int64_t nblocks = int64_t(sms) * 4;
+    if (nblocks > rows) nblocks = rows;
+    if (workspace_bytes < nblocks * (1 + nside) * cols * int64_t(sizeof(float))) {
+        return set_error("gkn_mask_cast_colsum: workspace too small");
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* partial = static_cast<float*>(workspace);
+    const int grid = int(nblocks);
+    const int c = int(cols);
+    using bf = __nv_bfloat16;
+    if (act_is_bf16 && out_is_bf16) {
+        launch_mask<bf, bf>(nside, grid, st, dz, static_cast<const bf*>(act), static_cast<bf*>(out), side, partial, rows, c);
+    } else if (act_is_bf16) {
+        launch_mask<bf, float>(nside, grid, st, dz, static_cast<const bf*>(act), static_cast<float*>(out), side, partial, rows, c);
+    } else if (out_is_bf16) {
+        launch_mask<float, bf>(nside, grid, st, dz, static_cast<const float*>(act), static_cast<bf*>(out), side, partial, rows, c);
+    } else {
+        launch_mask<float, float>(nside, grid, st, dz, static_cast<const float*>(act), static_cast<float*>(out), side, partial, rows, c);
+    }
+    GKN_CHECK_LAUNCH("mask_cast_colsum launch");
+    const dim3 fgrid((c + 31) / 32, 1 + nside);
+    colsum_fold_kernel<<<fgrid, 256, 0, st>>>(partial, colsum, grid, 1 + nside, c, accumulate);
+    GKN_CHECK_LAUNCH("colsum_fold launch");
+    return 0;
+}
+
+extern "C" int gkn_edge_layer0(const float* ea, const float* w1, const float* b1, void* out,
+                               int32_t out_is_bf16, int64_t E, int32_t K, int32_t kin,
+                               void* stream) {
+    using namespace gkn;
+    if (E == 0) return 0;
+    if (kin != 6) return set_error("gkn_edge_layer0: edge feature width must be 6");
+    if (K % 4 != 0) return set_error("gkn_edge_layer0: K must be a multiple of 4");
+    int sms = 148;
+    device_sm_count(&sms);
+    int64_t blocks = int64_t(sms) * 8;
+    if (blocks > E) blocks = E;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (out_is_bf16) {
+        edge_layer0_kernel<__nv_bfloat16, 6><<<int(blocks), 256, 0, st>>>(
+            ea, w1, b1, static_cast<__nv_bfloat16*>(out), E, K);
+    } else {
+        edge_layer0_kernel<float, 6><<<int(blocks), 256, 0, st>>>(ea, w1, b1, static_cast<float*>(out), E, K);
+    }
+    GKN_CHECK_LAUNCH("edge_layer0 launch");
+    return 0;
+}
+
+extern "C" int gkn_segment_matvec(const float* rows, const int32_t* perm, const int32_t* seg_ptr,
+                                  const int32_t* gidx, const float* gnode, const float* scale,
+                                  const float* M1, const float* nin, const float* M2,
+                                  const float* bias, float* out, float* agg_out, int64_t N,
+                                  int32_t W, int32_t relu, void* stream) {
+    using namespace gkn;
+    if (N == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = node_grid(N);
+    const int threads = kWarpsPerBlock * 32;
+#define GKN_SMV(WW)                                                                              \
+    segment_matvec_kernel<WW><<<grid, threads, 0, st>>>(rows, perm, seg_ptr, gidx, gnode, scale, \
+                                                        M1, nin, M2, bias, out, agg_out, N, relu)
+    switch (W) {
+        case 16: GKN_SMV(16); break;
+        case 32: GKN_SMV(32); break;
+        case 64: GKN_SMV(64); break;
+        case 128: GKN_SMV(128); break;
+        default: return set_error("gkn_segment_matvec: width must be 16, 32, 64 or 128");
+    }
+#undef GKN_SMV
+    GKN_CHECK_LAUNCH("segment_matvec launch");
     return 0;
 }

@@ -42,37 +42,42 @@ def _mm32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return torch.mm(a, b)
 
 
+def _addmm32(acc: torch.Tensor, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """acc + a @ b with fp32 accumulation/result; the addition rides in the GEMM epilogue."""
+    if a.dtype == torch.bfloat16:
+        return torch.addmm(acc, a, b, out_dtype=torch.float32)
+    return acc.addmm_(a, b)
+
+
 def _edge_hidden(ea, w1, b1, w2, b2, precision):
-    """h1 = relu(ea W1^T + b1), h = relu(h1 W2^T + b2)   (reference graph_kernel.py:239-242)."""
-    z1 = torch.mm(ea, w1.t())
+    """h1 = relu(ea W1^T + b1), h = relu(h1 W2^T + b2)   (reference graph_kernel.py:239-242).
+    Layer .0 (fan-in 6) is one streaming kernel that writes the operand dtype of layer .2
+    directly; layer .2 is a library GEMM with the bias + ReLU epilogue fused (cuBLASLt)."""
     if precision == "bf16":
-        h1 = ops.bias_act_cast_bf16(z1, b1, relu=True)
-        del z1
-        z2 = _mm32(h1, w2.to(torch.bfloat16).t())
-        h = ops.bias_act_cast_bf16(z2, b2, relu=True)
+        h1 = ops.edge_layer0(ea, w1.contiguous(), b1, torch.bfloat16)
+        h = torch._addmm_activation(b2.to(torch.bfloat16), h1, w2.to(torch.bfloat16).t())
     else:
-        h1 = torch.relu_(z1.add_(b1))
-        h = torch.relu_(torch.addmm(b2, h1, w2.t()))
-    return h1, h
+        h1 = ops.edge_layer0(ea, w1.contiguous(), b1, torch.float32)
+        h = torch._addmm_activation(b2, h1, w2.t())
+    return h1, h.contiguous()
 
 
 def _edge_grads(xs, gns, plan: GraphPlan, ea, h1, h, w1, w2, w3q, need_ea: bool, precision: str):
-    """Gradients of everything edge-sized from the per-application node tensors: W3, b3 and,
-    through dh_e, layers .0-.3 (W2, b2, W1, b1, optionally edge_attr).
+    """Gradients of everything edge-sized from the per-application node tensors: W3 and, through
+    dh_e, layers .0-.3 (W2, b2, W1, b1, optionally edge_attr).  (b3 is a node-level product.)
 
     Staged implementation: S is produced for a bounded chunk of edges at a time by
     gkn_edge_outer_sum and multiplied with library GEMMs; dh_e only ever exists for one chunk.
     """
     E, K = h.shape
     WW = w3q.shape[0]
+    kin = ea.size(1)
     dev = h.device
     f32 = dict(dtype=torch.float32, device=dev)
     dw3 = torch.zeros((WW, K), **f32)
-    db3 = torch.zeros(WW, **f32)
     dw2 = torch.zeros((K, K), **f32)
     db2 = torch.zeros(K, **f32)
-    dw1 = torch.zeros((K, ea.size(1)), **f32)
-    db1 = torch.zeros(K, **f32)
+    cs1 = torch.zeros((1 + kin, K), **f32)  # row 0: db1, rows 1..: dW1^T
     dea = torch.empty_like(ea) if need_ea else None
     bf16 = precision == "bf16"
     s_dtype = torch.bfloat16 if bf16 else torch.float32
@@ -81,21 +86,18 @@ def _edge_grads(xs, gns, plan: GraphPlan, ea, h1, h, w1, w2, w3q, need_ea: bool,
         e1 = min(E, e0 + _S_CHUNK_EDGES)
         hc, h1c = h[e0:e1], h1[e0:e1]
         S = ops.edge_outer_sum(xs, gns, plan, e0, e1, s_dtype)
-        dw3 += _mm32(S.t(), hc)
-        db3 += S.sum(0, dtype=torch.float32)
+        dw3 = _addmm32(dw3, S.t(), hc)
         dz2 = _mm32(S, w3q)  # dh_e for this chunk, fp32
         del S
-        dz2.mul_(hc > 0)
-        db2 += dz2.sum(0)
-        dz2q = dz2.to(torch.bfloat16) if bf16 else dz2
-        dw2 += _mm32(dz2q.t(), h1c)
+        # backward of "+ b2, ReLU": mask, bias gradient and bf16 hand-off in one pass
+        dz2q = ops.mask_cast_colsum(dz2, hc, db2, s_dtype)
+        dw2 = _addmm32(dw2, dz2q.t(), h1c)
         dz1 = _mm32(dz2q, w2q)
-        dz1.mul_(h1c > 0)
-        db1 += dz1.sum(0)
-        dw1 += torch.mm(dz1.t(), ea[e0:e1])
+        # backward of "+ b1, ReLU" and of layer .0 itself: db1 and dW1 = dz1^T edge_attr
+        dz1 = ops.mask_cast_colsum(dz1, h1c, cs1, torch.float32, side=ea[e0:e1])
         if need_ea:
             torch.mm(dz1, w1, out=dea[e0:e1])
-    return dw3, db3, dw2, db2, dw1, db1, dea
+    return dw3, dw2, db2, cs1[1:].t().contiguous(), cs1[0].contiguous(), dea
 
 
 class _GKNStack(torch.autograd.Function):
@@ -111,52 +113,70 @@ class _GKNStack(torch.autograd.Function):
         roots = (det(root1), det(root2))
         biases = (det(bias1), det(bias2))
         x = x0.contiguous()
-        xs = [x]
+        xs, aggs = [x], []
+        want_agg = any(ctx.needs_input_grad)
+        B3c = B3.contiguous()
         for c in schedule:
-            xroot = torch.mm(x, roots[c])
-            xb3 = torch.mm(x, B3)
             msg = ops.contract_fwd(h, w3q, plan.src, x, precision)
-            x = ops.scatter_mean(msg, plan, xb3=xb3, xroot=xroot, bias=biases[c].contiguous(),
-                                 relu=relu)
+            # mean over incoming edges + (mean x_j) @ B3 + x @ root + bias (+ ReLU), one kernel
+            x_new, agg = ops.segment_matvec(msg, None, plan.dst_ptr, plan.src, x, plan.inv_cnt, B3c,
+                                            x, roots[c].contiguous(), biases[c].contiguous(), relu,
+                                            want_agg=want_agg)
+            if want_agg:
+                aggs.append(agg)
+            x = x_new
             xs.append(x)
         ctx.plan, ctx.schedule, ctx.relu, ctx.precision = plan, schedule, relu, precision
         ctx.has2 = root2 is not None
-        ctx.save_for_backward(ea, h1, h, w1, w2, w3q, B3, roots[0],
-                              roots[1] if ctx.has2 else roots[0], *xs)
+        ctx.n_apps = len(schedule)
+        ctx.save_for_backward(ea, h1, h, w1, w2, w3q, B3c, roots[0],
+                              roots[1] if ctx.has2 else roots[0], *xs, *aggs)
         return x
 
     @staticmethod
     def backward(ctx, gout):
-        ea, h1, h, w1, w2, w3q, B3, r1, r2, *xs = ctx.saved_tensors
+        ea, h1, h, w1, w2, w3q, B3, r1, r2, *rest = ctx.saved_tensors
         plan, schedule, relu, precision = ctx.plan, ctx.schedule, ctx.relu, ctx.precision
+        A = ctx.n_apps
+        xs, aggs = rest[:A + 1], rest[A + 1:]
         roots = (r1, r2)
-        A = len(schedule)
+        rootsT = (r1.t().contiguous(), r2.t().contiguous())
+        B3T = B3.t().contiguous()
         W = xs[0].size(1)
         need = ctx.needs_input_grad
         need_x0, need_ea, need_edge = need[0], need[1], any(need[1:8])
-        droot = [torch.zeros_like(r1), torch.zeros_like(r2)]
-        dbias = [torch.zeros(W, dtype=torch.float32, device=gout.device) for _ in range(2)]
-        gns = [None] * A
+        gs, gns = [None] * A, [None] * A
         gx = gout.contiguous().float()
         for a in range(A - 1, -1, -1):
             c = schedule[a]
-            xin, y = xs[a], xs[a + 1]
-            g, gn = ops.relu_grad_scale(gx, y, plan.inv_cnt, relu)
-            droot[c].addmm_(xin.t(), g)
-            dbias[c] += g.sum(0)
-            gns[a] = gn
+            g, gn = ops.relu_grad_scale(gx, xs[a + 1], plan.inv_cnt, relu)
+            gs[a], gns[a] = g, gn
             if a > 0 or need_x0:
                 dxj = ops.contract_dx(h, w3q, plan.dst, gn, precision)
-                gb3 = torch.mm(gn, B3.t())
-                addend = torch.mm(g, roots[c].t())
-                gx = ops.scatter_src_sum(dxj, plan, gb3=gb3, addend=addend)
+                # scatter dx_j onto sources + (sum gn[dst]) @ B3^T + g @ root^T, one kernel
+                gx, _ = ops.segment_matvec(dxj, plan.src_perm, plan.src_ptr, plan.dst, gn, None,
+                                           B3T, g, rootsT[c], None, False)
             else:
                 gx = None
+        # node-level parameter gradients, batched over applications
+        G = torch.stack(gs)  # [A, N, W]
+        X = torch.stack(xs[:A])
+        droot, dbias = [None, None], [None, None]
+        for c in (0, 1):
+            idx = [a for a in range(A) if schedule[a] == c]
+            if idx:
+                Gc, Xc = G[idx].reshape(-1, W), X[idx].reshape(-1, W)
+                droot[c] = torch.mm(Xc.t(), Gc)
+                dbias[c] = Gc.sum(0)
+            else:
+                droot[c] = torch.zeros_like(roots[c])
+                dbias[c] = torch.zeros(W, dtype=torch.float32, device=gout.device)
         dw3 = db3 = dw2 = db2 = dw1 = db1 = dea = None
         if need_edge:
-            dw3, db3, dw2, db2, dw1, db1, dea = _edge_grads(
-                torch.stack(xs[:A]), torch.stack(gns), plan, ea, h1, h, w1, w2, w3q, need_ea,
-                precision)
+            # db3[i*W+o] = sum_e x_j[e,i] gn[dst e,o] = sum_n (mean-scaled agg)[n,i] g[n,o]
+            db3 = torch.mm(torch.stack(list(aggs)).reshape(-1, W).t(), G.reshape(-1, W)).reshape(-1)
+            dw3, dw2, db2, dw1, db1, dea = _edge_grads(
+                X, torch.stack(gns), plan, ea, h1, h, w1, w2, w3q, need_ea, precision)
         return (gx if need_x0 else None, dea, dw1, db1, dw2, db2, dw3, db3, droot[0], dbias[0],
                 droot[1] if ctx.has2 else None, dbias[1] if ctx.has2 else None,
                 None, None, None, None)

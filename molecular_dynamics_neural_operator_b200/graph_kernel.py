@@ -208,14 +208,18 @@ class KernelNN(torch.nn.Module):
         Reference graph_kernel.py:278-298, including its quirk that each window step feeds
         [B, R, 3] to nn.LSTM as (seq_len=B, batch=R) with the hidden state carried across steps."""
         x = data.x_position.reshape(-1, self.window_size, self.num_residues, 3)
-        x = torch.swapaxes(x, 0, 1)
+        x = torch.swapaxes(x, 0, 1)  # [W, B, R, 3]
+        n_batch = x.size(1)
         hidden = (torch.zeros(1, self.num_residues, 3, device=x.device, dtype=x.dtype),
                   torch.zeros(1, self.num_residues, 3, device=x.device, dtype=x.dtype))
-        # native (non-cuDNN) LSTM kernels: cuDNN would run this 3 -> 3 LSTM and its backward in
-        # TF32 (cudnn.allow_tf32 defaults to True), which breaks the 1e-5 fp32 parity bar
-        with torch.backends.cudnn.flags(enabled=False):
-            for i in x:
-                x, hidden = self.lstm(i, hidden)
+        # The reference loops `for i in x: x, hidden = self.lstm(i, hidden)` (:283-284): W calls on
+        # [B, R, 3] sequences with the state carried over.  That is exactly ONE pass over the
+        # concatenated sequence of length W*B, whose last B outputs are the loop's final `x`.
+        # fp32 mode uses the native kernels: cuDNN would run this 3 -> 3 LSTM and its backward in
+        # TF32 (cudnn.allow_tf32 defaults to True), which breaks the 1e-5 parity bar.
+        with torch.backends.cudnn.flags(enabled=self.precision != "fp32"):
+            seq, hidden = self.lstm(x.reshape(-1, self.num_residues, 3), hidden)
+        x = seq[-n_batch:]
         x = self.lstm_fc(x)
         emb = self.emb(data.x_aminoacid)
         x = x.reshape(emb.shape[0], -1)

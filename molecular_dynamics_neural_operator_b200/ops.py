@@ -281,3 +281,75 @@ def bias_act_cast_bf16(x, bias=None, relu=False) -> torch.Tensor:
             "gkn_bias_act_cast_bf16",
         )
     return out
+
+
+_COLSUM_WS: dict = {}
+
+
+def mask_cast_colsum(dz, act, colsum, out_dtype, side=None, accumulate: bool = True) -> torch.Tensor:
+    """out = dz * (act > 0) in ``out_dtype`` (bf16 / fp32); colsum[0] (+)= out.sum(0) and, with
+    ``side`` [rows, 6], colsum[1+j] (+)= (out * side[:, j:j+1]).sum(0).  ``colsum`` is
+    [(1 + nside), cols] (or [cols] without side).  One pass over dz, deterministic reduction."""
+    lib = _lib.load()
+    rows, cols = int(dz.size(0)), int(dz.size(1))
+    nside = 0 if side is None else int(side.size(1))
+    if colsum.numel() != (1 + nside) * cols:
+        raise ValueError("colsum must have (1 + nside) * cols elements")
+    key = (dz.device, cols, nside)
+    ws = _COLSUM_WS.get(key)
+    if ws is None:
+        ws = torch.empty(int(lib.gkn_mask_cast_colsum_workspace_bytes(cols, nside)),
+                         dtype=torch.uint8, device=dz.device)
+        _COLSUM_WS[key] = ws
+    out = dz if out_dtype == torch.float32 else torch.empty((rows, cols), dtype=out_dtype,
+                                                            device=dz.device)
+    with torch.cuda.device(dz.device):
+        _lib.check(
+            lib.gkn_mask_cast_colsum(
+                _p(dz, torch.float32, "dz"), _p(act, None, "act"), int(act.dtype == torch.bfloat16),
+                _p(out), int(out_dtype == torch.bfloat16), _p(side, torch.float32, "side"), nside,
+                _p(colsum, torch.float32, "colsum"), int(bool(accumulate)), rows, cols, _p(ws),
+                ws.numel(), _stream(),
+            ),
+            "gkn_mask_cast_colsum",
+        )
+    return out
+
+
+def edge_layer0(ea, w1, b1, out_dtype) -> torch.Tensor:
+    """relu(ea @ w1.T + b1) written directly as bf16 / fp32 [E, K] (gkn_edge_layer0)."""
+    lib = _lib.load()
+    _require_cuda(ea, "edge_attr")
+    E, kin = int(ea.size(0)), int(ea.size(1))
+    K = int(w1.size(0))
+    out = torch.empty((E, K), dtype=out_dtype, device=ea.device)
+    with torch.cuda.device(ea.device):
+        _lib.check(
+            lib.gkn_edge_layer0(_p(ea, torch.float32, "edge_attr"), _p(w1, torch.float32, "w1"),
+                                _p(b1, torch.float32, "b1"), _p(out),
+                                int(out_dtype == torch.bfloat16), E, K, kin, _stream()),
+            "gkn_edge_layer0",
+        )
+    return out
+
+
+def segment_matvec(rows, perm, seg_ptr, gidx, gnode, scale, M1, nin, M2, bias, relu: bool,
+                   want_agg: bool = False):
+    """out[n] = act(scale*sum rows[p] + (scale*sum gnode[gidx[p]]) @ M1 + nin[n] @ M2 + bias).
+    See gkn_segment_matvec in gkn_b200.h.  Returns (out, agg or None)."""
+    lib = _lib.load()
+    N, W = int(nin.size(0)), int(nin.size(1))
+    f32, i32 = torch.float32, torch.int32
+    out = torch.empty((N, W), dtype=f32, device=nin.device)
+    agg = torch.empty((N, W), dtype=f32, device=nin.device) if want_agg else None
+    with torch.cuda.device(nin.device):
+        _lib.check(
+            lib.gkn_segment_matvec(
+                _p(rows, f32, "rows"), _p(perm, i32, "perm"), _p(seg_ptr, i32, "seg_ptr"),
+                _p(gidx, i32, "gidx"), _p(gnode, f32, "gnode"), _p(scale, f32, "scale"),
+                _p(M1, f32, "M1"), _p(nin, f32, "nin"), _p(M2, f32, "M2"), _p(bias, f32, "bias"),
+                _p(out), _p(agg), N, W, int(bool(relu)), _stream(),
+            ),
+            "gkn_segment_matvec",
+        )
+    return out, agg

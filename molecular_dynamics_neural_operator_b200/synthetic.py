@@ -83,12 +83,14 @@ def window_batch(traj: np.ndarray, starts, window: int, horizon: int = 1):
 
 
 def make_batch(x_window: torch.Tensor, aminoacid: torch.Tensor, y: torch.Tensor | None,
-               cutoff: float, graph_frame: int = 0) -> PairData:
+               cutoff: float, graph_frame: int = 0, prepare: bool = False) -> PairData:
     """Device-side feeder.  x_window [B, W, N, 3] (device), aminoacid [N] int64, y [B, N, 3].
 
     Graph and edge attributes come from window frame ``graph_frame`` of every sample: 0 (the
     first frame) at training time as in dataset.py:189-201, -1 (the last) in rollout as in
-    graph_kernel.py:363-379.  Equivalent to collate([PairData(...) for each sample])."""
+    graph_kernel.py:363-379.  Equivalent to collate([PairData(...) for each sample]).
+    ``prepare=True`` also builds the destination-sorted CSR plan and attaches it to the batch
+    (``KernelNN.forward`` picks it up), so both happen off the training stream when prefetched."""
     B, W, N, _ = x_window.shape
     frames = x_window[:, graph_frame].contiguous()
     edge_index, edge_attr = ops.radius_graph(frames, cutoff)
@@ -99,4 +101,45 @@ def make_batch(x_window: torch.Tensor, aminoacid: torch.Tensor, y: torch.Tensor 
         edge_attr=edge_attr,
         edge_index=edge_index,
     )
+    if prepare:
+        data._gkn_plan = ops.prepare_graph(edge_index, B * N)
     return data
+
+
+class BatchPrefetcher:
+    """Builds the NEXT step's batch on a side CUDA stream while the current step computes.
+
+    The radius-graph build has a data-dependent output size (one host read of the edge count);
+    done on the training stream that read would drain the whole queue every step.  Here the
+    optional H2D copy, graph build and CSR prepare run on their own stream and the training
+    stream only waits on an event."""
+
+    def __init__(self, device):
+        self.device = device
+        self.stream = torch.cuda.Stream(device=device)
+        self._pending = None
+        self._event = None
+
+    def submit(self, build_fn) -> None:
+        main = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.stream):
+            batch = build_fn()
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        # tensors were allocated on the side stream but will be consumed on the training stream
+        tensors = [getattr(batch, f) for f in PairData._FIELDS]
+        plan = getattr(batch, "_gkn_plan", None)
+        if plan is not None:
+            tensors += [plan.perm, plan.src, plan.dst, plan.dst_ptr, plan.inv_cnt, plan.src_ptr,
+                        plan.src_perm]
+        for t in tensors:
+            if t is not None and t.is_cuda:
+                t.record_stream(main)
+        self._pending, self._event = batch, ev
+
+    def get(self) -> PairData:
+        if self._pending is None:
+            raise RuntimeError("BatchPrefetcher.get() called before submit()")
+        torch.cuda.current_stream(self.device).wait_event(self._event)
+        batch, self._pending = self._pending, None
+        return batch

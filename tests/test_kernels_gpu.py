@@ -116,3 +116,86 @@ def test_launch_counter_counts_library_kernels():
     n0 = _lib.launch_count()
     ops.bias_act_cast_bf16(torch.randn(8, 64, device=DEV))
     assert _lib.launch_count() == n0 + 1
+
+
+@pytest.mark.parametrize("act_dt,out_dt", [(torch.bfloat16, torch.bfloat16), (torch.bfloat16, torch.float32),
+                                           (torch.float32, torch.float32), (torch.float32, torch.bfloat16)])
+def test_mask_cast_colsum(act_dt, out_dt):
+    from molecular_dynamics_neural_operator_b200 import ops
+
+    g = torch.Generator().manual_seed(3)
+    for rows, cols in [(1, 64), (37, 128), (5000, 1024)]:
+        dz = torch.randn(rows, cols, generator=g)
+        act = torch.relu(torch.randn(rows, cols, generator=g)).to(act_dt)
+        colsum = torch.full((cols,), 0.5)
+        ref = dz * (act.float() > 0)
+        cs = colsum.to(DEV)
+        out = ops.mask_cast_colsum(dz.to(DEV), act.to(DEV), cs, out_dt, accumulate=True)
+        assert torch.equal(out.cpu(), ref.to(out_dt))
+        assert torch.allclose(cs.cpu(), 0.5 + ref.sum(0), rtol=1e-5, atol=1e-4)
+        cs2 = torch.full((cols,), 7.0, device=DEV)
+        ops.mask_cast_colsum(dz.to(DEV), act.to(DEV), cs2, out_dt, accumulate=False)
+        assert torch.allclose(cs2.cpu(), ref.sum(0), rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("N,E,W", [(50, 700, 64), (504, 20000, 64), (300, 5000, 32), (100, 3000, 128),
+                                   (40, 100, 16), (10, 0, 64)])
+def test_segment_matvec_forward_and_backward_forms(N, E, W):
+    from molecular_dynamics_neural_operator_b200 import ops
+
+    ei = rand_graph(N, E, 11 * N + E)
+    plan = ops.prepare_graph(ei.to(DEV), N)
+    g = torch.Generator().manual_seed(5)
+    rows = torch.randn(E, W, generator=g)
+    x, nin = torch.randn(N, W, generator=g), torch.randn(N, W, generator=g)
+    M1, M2 = torch.randn(W, W, generator=g) / W ** 0.5, torch.randn(W, W, generator=g) / W ** 0.5
+    bias = torch.randn(W, generator=g)
+    order = plan.perm.cpu().long()
+    src_s, dst_s = ei[0][order], ei[1][order]
+    inv = plan.inv_cnt.cpu().double()[:, None]
+    # forward form
+    r = torch.zeros(N, W, dtype=torch.float64).index_add_(0, dst_s, rows.double()) * inv
+    agg = torch.zeros(N, W, dtype=torch.float64).index_add_(0, dst_s, x.double()[src_s]) * inv
+    ref = torch.relu(r + agg @ M1.double() + nin.double() @ M2.double() + bias.double())
+    out, agg_out = ops.segment_matvec(rows.to(DEV), None, plan.dst_ptr, plan.src, x.to(DEV), plan.inv_cnt,
+                                      M1.to(DEV), nin.to(DEV), M2.to(DEV), bias.to(DEV), True, want_agg=True)
+    assert (out.cpu().double() - ref).abs().max().item() <= 2e-5
+    assert (agg_out.cpu().double() - agg).abs().max().item() <= 2e-5
+    # backward form: rows are in sorted-position order, summed per SOURCE node through src_perm
+    r = torch.zeros(N, W, dtype=torch.float64).index_add_(0, src_s, rows.double())
+    agg = torch.zeros(N, W, dtype=torch.float64).index_add_(0, src_s, x.double()[dst_s])
+    ref = r + agg @ M1.double() + nin.double() @ M2.double()
+    out, none = ops.segment_matvec(rows.to(DEV), plan.src_perm, plan.src_ptr, plan.dst, x.to(DEV), None,
+                                   M1.to(DEV), nin.to(DEV), M2.to(DEV), None, False)
+    assert none is None
+    assert (out.cpu().double() - ref).abs().max().item() <= 2e-4
+
+
+def test_mask_cast_colsum_side_sums_give_layer0_weight_gradient():
+    from molecular_dynamics_neural_operator_b200 import ops
+
+    g = torch.Generator().manual_seed(4)
+    rows, cols = 3000, 256
+    dz = torch.randn(rows, cols, generator=g)
+    act = torch.relu(torch.randn(rows, cols, generator=g)).bfloat16()
+    side = torch.randn(rows, 6, generator=g) * 10
+    cs = torch.zeros(7, cols, device=DEV)
+    out = ops.mask_cast_colsum(dz.to(DEV), act.to(DEV), cs, torch.float32, side=side.to(DEV))
+    ref = (dz * (act.float() > 0)).double()
+    assert torch.equal(out.cpu().double(), ref)
+    assert torch.allclose(cs[0].cpu().double(), ref.sum(0), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(cs[1:].cpu().double(), side.double().t() @ ref, rtol=1e-5, atol=1e-2)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_edge_layer0(dt):
+    from molecular_dynamics_neural_operator_b200 import ops
+
+    g = torch.Generator().manual_seed(6)
+    for E, K in [(1, 64), (777, 128), (5000, 1024)]:
+        ea = torch.randn(E, 6, generator=g) * 5
+        w1, b1 = torch.randn(K, 6, generator=g), torch.randn(K, generator=g)
+        out = ops.edge_layer0(ea.to(DEV), w1.to(DEV), b1.to(DEV), dt)
+        ref = torch.relu(ea.double() @ w1.double().t() + b1.double())
+        tol = 1e-5 if dt == torch.float32 else 2.0 ** -8
+        assert ((out.cpu().double() - ref).abs() / (ref.abs() + 1)).max().item() <= tol
