@@ -52,6 +52,14 @@ int gkn_graph_prepare(const int64_t* edge_index, int64_t N, int64_t E, int32_t* 
                       int32_t* src_ptr, int32_t* src_perm, int32_t* status, void* workspace,
                       int64_t workspace_bytes, void* stream);
 
+/* Fast path for symmetric graphs already in (row, col) order with CSR row pointers - exactly what
+ * gkn_radius_graph_fill emits.  No sorting: position p <-> (dst = row[p], src = col[p]);
+ * rev[p] = position of the reverse edge, which is at once `perm` and `src_perm` of the general
+ * plan; ptr32 = row_ptr as int32 (= dst_ptr = src_ptr).  status != 0: graph was not symmetric. */
+int gkn_plan_from_csr(const int64_t* edge_index, const int64_t* row_ptr, int64_t N, int64_t E,
+                      int32_t* rev, int32_t* src_s, int32_t* dst_s, int32_t* ptr32, float* inv_cnt,
+                      int32_t* status, void* stream);
+
 /* ---- radius graph (replaces construct_pairdata, reference graph_kernel.py:362-393:
  *      scipy distance_matrix(float64) < threshold -> coo_matrix -> per-edge python loop) -- */
 int64_t gkn_radius_graph_workspace_bytes(int64_t F, int64_t N);

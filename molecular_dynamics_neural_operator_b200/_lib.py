@@ -22,6 +22,7 @@ SIGNATURES = {
     "gkn_device_info": (c_int, [ctypes.POINTER(c_int)] * 3),
     "gkn_graph_prepare_workspace_bytes": (c_int64, [c_int64, c_int64]),
     "gkn_graph_prepare": (c_int, [P, c_int64, c_int64, P, P, P, P, P, P, P, P, P, c_int64, P]),
+    "gkn_plan_from_csr": (c_int, [P, P, c_int64, c_int64, P, P, P, P, P, P, P]),
     "gkn_radius_graph_workspace_bytes": (c_int64, [c_int64, c_int64]),
     "gkn_radius_graph_count": (c_int, [P, c_int64, c_int64, c_double, P, P, P, c_int64, P]),
     "gkn_radius_graph_fill": (

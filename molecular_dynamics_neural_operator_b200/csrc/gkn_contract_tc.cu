@@ -75,11 +75,11 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tmap_h,
 
     // Contiguous unit range of this CTA.  With many tiles per CTA the ranges are tile-aligned: all
     // CTAs then walk the W3 column chunks in phase, so a chunk fetched by one CTA is an L2 hit for
-    // the others (matters when W3 is large, e.g. 32 MB at w=128), at a tail cost < 1/16.  With few
+    // the others (matters when W3 is large, e.g. 32 MB at w=128), at a tail cost < 1/64.  With few
     // tiles per CTA, units are split evenly instead (no tile-quantisation tail).
     const int64_t total_units = p.num_tiles * kChunks;
     int64_t u0, u1;
-    if (p.num_tiles >= int64_t(gridDim.x) * 16) {
+    if (p.num_tiles >= int64_t(gridDim.x) * 64) {
         u0 = ((p.num_tiles * blockIdx.x) / gridDim.x) * kChunks;
         u1 = ((p.num_tiles * (blockIdx.x + 1)) / gridDim.x) * kChunks;
     } else {

@@ -15,6 +15,9 @@
 // reduce at edge_index[1]; reference graph_kernel.py:198).  Atomics appear only in the counting
 // sort's histogram/placement; every run is then put into a canonical (ascending) order so
 // results never depend on atomic arrival order.
+#include <cmath>
+#include <limits>
+
 #include "gkn_internal.h"
 
 namespace gkn {
@@ -30,7 +33,8 @@ template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(kScanThreads)
 exclusive_scan_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int64_t n,
                       int64_t in_stride, int64_t out_stride) {
-    // one block per segment (blockIdx.x), segment length n; writes n+1 values
+    // one block per segment (blockIdx.x), segment length n; writes n+1 values; 4 items / thread
+    constexpr int IT = 4;
     in += int64_t(blockIdx.x) * in_stride;
     out += int64_t(blockIdx.x) * out_stride;
     __shared__ TOut warp_tot[32];
@@ -38,10 +42,15 @@ exclusive_scan_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int64_
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int64_t base = 0; base < n; base += kScanThreads) {
-        const int64_t i = base + threadIdx.x;
-        const TOut v = i < n ? TOut(in[i]) : TOut(0);
-        TOut incl = v;
+    for (int64_t base = 0; base < n; base += kScanThreads * IT) {
+        const int64_t i0 = base + int64_t(threadIdx.x) * IT;
+        TOut v[IT], tsum = 0;
+#pragma unroll
+        for (int k = 0; k < IT; ++k) {
+            v[k] = i0 + k < n ? TOut(in[i0 + k]) : TOut(0);
+            tsum += v[k];
+        }
+        TOut incl = tsum;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
             const TOut t = __shfl_up_sync(0xffffffffu, incl, off);
@@ -60,8 +69,12 @@ exclusive_scan_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int64_
         }
         __syncthreads();
         const TOut carry = carry_s;
-        const TOut warp_excl = warp == 0 ? TOut(0) : warp_tot[warp - 1];
-        if (i < n) out[i] = carry + warp_excl + incl - v;
+        TOut run = carry + (warp == 0 ? TOut(0) : warp_tot[warp - 1]) + incl - tsum;
+#pragma unroll
+        for (int k = 0; k < IT; ++k) {
+            if (i0 + k < n) out[i0 + k] = run;
+            run += v[k];
+        }
         __syncthreads();
         if (threadIdx.x == 0) carry_s = carry + warp_tot[31];
         __syncthreads();
@@ -158,6 +171,41 @@ __global__ void prep_canon_src_kernel(int64_t N, const int32_t* __restrict__ src
     }
 }
 
+// Symmetric, (row, col)-sorted graphs (what the radius-graph kernel emits) need no sorting at all:
+// the destination-sorted order has the same CSR structure, position p <-> (dst = row[p],
+// src = col[p]), and the only non-trivial array is the position of every edge's reverse edge.
+__global__ void plan_from_csr_kernel(const int64_t* __restrict__ ei, const int64_t* __restrict__ row_ptr,
+                                     int64_t N, int64_t E, int32_t* __restrict__ rev,
+                                     int32_t* __restrict__ src_s, int32_t* __restrict__ dst_s,
+                                     int32_t* __restrict__ ptr32, float* __restrict__ inv_cnt,
+                                     int32_t* __restrict__ status) {
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    const int64_t t0 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    for (int64_t n = t0; n <= N; n += stride) {
+        ptr32[n] = int32_t(row_ptr[n]);
+        if (n < N) {
+            const int64_t c = row_ptr[n + 1] - row_ptr[n];
+            inv_cnt[n] = 1.0f / float(c < 1 ? 1 : c);
+        }
+    }
+    for (int64_t e = t0; e < E; e += stride) {
+        const int64_t r = ei[e], c = ei[E + e];
+        src_s[e] = int32_t(c);
+        dst_s[e] = int32_t(r);
+        int64_t lo = row_ptr[c], hi = row_ptr[c + 1];  // find r among the columns of row c
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (ei[E + mid] < r) lo = mid + 1; else hi = mid;
+        }
+        if (lo < row_ptr[c + 1] && ei[E + lo] == r) {
+            rev[e] = int32_t(lo);
+        } else {
+            rev[e] = 0;
+            atomicOr(status, 1);  // not symmetric / not sorted
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // radius graph
 // ------------------------------------------------------------------------------------------------
@@ -175,6 +223,9 @@ struct RadiusWs {
     int32_t* cell_start;   // [F, C+1]
     int32_t* atom_cell;    // [F*N]
     float4* sorted_pos;    // [F*N]  xyz + original atom index (bit-cast) in cell order
+    int64_t* block_sums;   // [nblk]     row-pointer scan: per-block sums
+    int64_t* block_offs;   // [nblk + 1] and their exclusive scan
+    int64_t nblk;
     int64_t C;             // cells reserved per frame
     int64_t bytes;
 };
@@ -193,12 +244,15 @@ inline RadiusWs carve_radius_ws(void* base, int64_t F, int64_t N) {
     w.cell_start = reinterpret_cast<int32_t*>(take(F * (w.C + 1) * 4));
     w.atom_cell = reinterpret_cast<int32_t*>(take(F * N * 4));
     w.sorted_pos = reinterpret_cast<float4*>(take(F * N * 16));
+    w.nblk = (F * N + 4095) / 4096;
+    w.block_sums = reinterpret_cast<int64_t*>(take(w.nblk * 8));
+    w.block_offs = reinterpret_cast<int64_t*>(take((w.nblk + 1) * 8));
     w.bytes = off;
     return w;
 }
 
 // one block per frame: bounding box, then pick a cell edge >= cutoff whose grid fits in C cells
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 rg_frame_setup_kernel(const float* __restrict__ pos, int64_t N, double threshold, int64_t C,
                       FrameMeta* __restrict__ meta) {
     const int64_t f = blockIdx.x;
@@ -212,14 +266,14 @@ rg_frame_setup_kernel(const float* __restrict__ pos, int64_t N, double threshold
             mx[d] = fmaxf(mx[d], v);
         }
     }
-    __shared__ float smn[3][256], smx[3][256];
+    __shared__ float smn[3][1024], smx[3][1024];
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
         smn[d][threadIdx.x] = mn[d];
         smx[d][threadIdx.x] = mx[d];
     }
     __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
+    for (int s = 512; s > 0; s >>= 1) {
         if (threadIdx.x < s) {
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
@@ -298,91 +352,367 @@ __global__ void rg_place_kernel(const float* __restrict__ pos, int64_t F, int64_
     }
 }
 
-// exact reference predicate: float32 -> float64 promotion, ((dx^2 + dy^2) + dz^2), sqrt, strict <
-__device__ __forceinline__ bool within(double xi, double yi, double zi, float4 pj, double thr) {
+// Exact reference predicate without the square root.  SciPy evaluates, after promoting float32
+// coordinates to float64,  fl(sqrt(fl(fl(dx*dx + dy*dy) + dz*dz))) < threshold.  Correctly
+// rounded sqrt is monotone, so this equals  d2 <= d2_max  with d2_max the LARGEST double whose
+// rounded square root is still below the threshold; exact_d2_bound() finds it on the host by
+// stepping ulps around threshold^2.  d2 itself is formed with the same operations in the same
+// order and no FMA contraction.
+__device__ __forceinline__ bool within(double xi, double yi, double zi, float4 pj, double d2_max) {
     const double dx = __dsub_rn(double(pj.x), xi);
     const double dy = __dsub_rn(double(pj.y), yi);
     const double dz = __dsub_rn(double(pj.z), zi);
     const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-    return __dsqrt_rn(d2) < thr;
+    return d2 <= d2_max;
 }
 
-// One warp per atom.  FILL=false: count neighbours.  FILL=true: write the sorted row.
+// One warp handles one atom straight from global memory (sparse cells, and the general path for
+// any cell occupancy).  The nine (x, y) neighbour columns are contiguous z-runs of the cell-sorted
+// array; lanes 0..8 fetch their bounds in parallel and the runs are then walked as ONE flat
+// candidate range, two independent coalesced chunks of 32 per step.
+// FILL=false: count neighbours.  FILL=true: hits are parked in a per-warp smem buffer, ranked by
+// atom index and written as the sorted row (coordinates of both endpoints come from the buffer);
+// rows longer than the buffer use the row's own output slots as scratch instead.
+constexpr int kHitCap = 256;  // per-warp hit buffer (float4)
+
 template <bool FILL>
-__global__ void __launch_bounds__(256)
-rg_neighbor_kernel(const float* __restrict__ pos, int64_t F, int64_t N, int64_t C, double thr,
-                   const FrameMeta* __restrict__ meta, const int32_t* __restrict__ cell_start,
-                   const float4* __restrict__ sorted_pos, int32_t* __restrict__ deg,
-                   const int64_t* __restrict__ row_ptr, int64_t E, int64_t* __restrict__ edge_index,
-                   float* __restrict__ edge_attr) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp0 = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
-    const int64_t total = F * N;
-    for (int64_t g = warp0; g < total; g += nwarps) {
-        const int64_t f = g / N;
-        const FrameMeta m = meta[f];
-        const float px = pos[g * 3], py = pos[g * 3 + 1], pz = pos[g * 3 + 2];
-        const double xi = px, yi = py, zi = pz;
-        int cx, cy, cz;
-        cell_of(m, px, py, pz, cx, cy, cz);
-        const int32_t* cs = cell_start + f * (C + 1);
-        const float4* sp = sorted_pos + f * N;
-        const int64_t beg = FILL ? row_ptr[g] : 0;
-        int64_t* scratch = FILL ? edge_index + beg : nullptr;  // row-id slots double as scratch
-        int count = 0;
-        for (int ax = max(cx - 1, 0); ax <= min(cx + 1, m.nx - 1); ++ax) {
-            for (int ay = max(cy - 1, 0); ay <= min(cy + 1, m.ny - 1); ++ay) {
-                // cells (ax, ay, z0..z1) are contiguous in the cell-sorted array
-                const int z0 = max(cz - 1, 0), z1 = min(cz + 1, m.nz - 1);
-                const int c0 = (ax * m.ny + ay) * m.nz + z0;
-                const int c1 = (ax * m.ny + ay) * m.nz + z1;
-                const int jb = cs[c0], je = cs[c1 + 1];
-                for (int base = jb; base < je; base += 32) {  // warp-uniform trip count
-                    const int j = base + lane;
-                    bool hit = false;
-                    float4 pj = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (j < je) {
-                        pj = sp[j];
-                        hit = within(xi, yi, zi, pj, thr);
-                    }
-                    const unsigned mask = __ballot_sync(0xffffffffu, hit);
-                    if (FILL && hit) {
-                        const int slot = count + __popc(mask & ((1u << lane) - 1u));
-                        scratch[slot] = int64_t(__float_as_int(pj.w));
-                    }
-                    count += __popc(mask);
-                }
-            }
-        }
-        if (!FILL) {
-            if (lane == 0) deg[g] = count;
-        } else {
-            __syncwarp();
-            // rank-count sort of the (distinct) neighbour ids into the column slots
-            int64_t* cols = edge_index + E + beg;
-            const int64_t node0 = f * N;
-            for (int j = lane; j < count; j += 32) {
-                const int64_t v = scratch[j];
-                int rank = 0;
-                for (int k = 0; k < count; ++k) rank += (scratch[k] < v) ? 1 : 0;
-                cols[rank] = node0 + v;
-            }
-            __syncwarp();
-            for (int j = lane; j < count; j += 32) {
-                scratch[j] = g;  // row id (already offset by f*N)
-                const int64_t c = cols[j];
-                float* ea = edge_attr + (beg + j) * 6;
-                ea[0] = px;
-                ea[1] = py;
-                ea[2] = pz;
-                ea[3] = pos[c * 3];
-                ea[4] = pos[c * 3 + 1];
-                ea[5] = pos[c * 3 + 2];
-            }
-            __syncwarp();
+__device__ __forceinline__ void rg_atom_warp(float4 pi, int64_t node0, int cx, int cy, int cz,
+                                             const FrameMeta& m, int lane,
+                                             float4* __restrict__ hitbuf,
+                                             const float* __restrict__ pos, double d2_max,
+                                             const int32_t* __restrict__ cs,
+                                             const float4* __restrict__ sp,
+                                             int32_t* __restrict__ deg,
+                                             const int64_t* __restrict__ row_ptr, int64_t E,
+                                             int64_t* __restrict__ edge_index,
+                                             float* __restrict__ edge_attr) {
+    // the atom's cell (cx, cy, cz) is the centre cell of the calling CTA: nothing to recompute
+    const int64_t g = node0 + __float_as_int(pi.w);
+    const float px = pi.x, py = pi.y, pz = pi.z;
+    const double xi = px, yi = py, zi = pz;
+    int jb = 0, je = 0;
+    if (lane < 9) {
+        const int ax = cx - 1 + lane / 3, ay = cy - 1 + lane % 3;
+        if (ax >= 0 && ax < m.nx && ay >= 0 && ay < m.ny) {
+            const int z0 = max(cz - 1, 0), z1 = min(cz + 1, m.nz - 1);
+            jb = cs[(ax * m.ny + ay) * m.nz + z0];
+            je = cs[(ax * m.ny + ay) * m.nz + z1 + 1];
         }
     }
+    const int len = je - jb;
+    int incl = len;
+#pragma unroll
+    for (int off = 1; off < 16; off <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 15);
+    const int excl = incl - len;
+    int rb[9], ro[9];
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+        rb[r] = __shfl_sync(0xffffffffu, jb, r);
+        ro[r] = __shfl_sync(0xffffffffu, excl, r);
+    }
+    auto candidate = [&](int t) -> float4 {
+        int bsel = rb[0], osel = ro[0];
+#pragma unroll
+        for (int r = 1; r < 9; ++r) {
+            if (t >= ro[r]) {
+                bsel = rb[r];
+                osel = ro[r];
+            }
+        }
+        return sp[bsel + (t - osel)];
+    };
+    const int64_t beg = FILL ? row_ptr[g] : 0;
+    // rows are sized by the count pass: deg is exact, so the buffer decision is warp-uniform
+    const bool in_smem = FILL && (row_ptr[g + 1] - beg) <= kHitCap;
+    int64_t* scratch = FILL ? edge_index + beg : nullptr;  // row-id slots double as scratch
+    int count = 0;
+    for (int base = 0; base < total; base += 64) {  // warp-uniform trip count
+        const int t0 = base + lane, t1 = base + 32 + lane;
+        float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
+        if (t0 < total) p0 = candidate(t0);
+        if (t1 < total) p1 = candidate(t1);
+        const bool h0 = t0 < total && within(xi, yi, zi, p0, d2_max);
+        const bool h1 = t1 < total && within(xi, yi, zi, p1, d2_max);
+        const unsigned m0 = __ballot_sync(0xffffffffu, h0);
+        const unsigned m1 = __ballot_sync(0xffffffffu, h1);
+        if (FILL) {
+            const unsigned below = (1u << lane) - 1u;
+            const int s0 = count + __popc(m0 & below);
+            const int s1 = count + __popc(m0) + __popc(m1 & below);
+            if (in_smem) {
+                if (h0) hitbuf[s0] = p0;
+                if (h1) hitbuf[s1] = p1;
+            } else {
+                if (h0) scratch[s0] = int64_t(__float_as_int(p0.w));
+                if (h1) scratch[s1] = int64_t(__float_as_int(p1.w));
+            }
+        }
+        count += __popc(m0) + __popc(m1);
+    }
+    if (!FILL) {
+        if (lane == 0) deg[g] = count;
+        return;
+    }
+    __syncwarp();
+    if (in_smem) {
+        for (int j = lane; j < count; j += 32) {
+            const float4 pj = hitbuf[j];
+            const int v = __float_as_int(pj.w);
+            int rank = 0;
+            for (int k = 0; k < count; ++k) rank += (__float_as_int(hitbuf[k].w) < v) ? 1 : 0;
+            const int64_t slot = beg + rank;
+            edge_index[slot] = g;
+            edge_index[E + slot] = node0 + v;
+            float2* ea = reinterpret_cast<float2*>(edge_attr + slot * 6);
+            ea[0] = make_float2(px, py);
+            ea[1] = make_float2(pz, pj.x);
+            ea[2] = make_float2(pj.y, pj.z);
+        }
+        __syncwarp();
+        return;
+    }
+    // long row: rank-count sort of the (distinct) neighbour ids through the output slots
+    int64_t* cols = edge_index + E + beg;
+    for (int j = lane; j < count; j += 32) {
+        const int64_t v = scratch[j];
+        int rank = 0;
+        for (int k = 0; k < count; ++k) rank += (scratch[k] < v) ? 1 : 0;
+        cols[rank] = node0 + v;
+    }
+    __syncwarp();
+    for (int j = lane; j < count; j += 32) {
+        scratch[j] = g;  // row id (already offset by f*N)
+        const int64_t c = cols[j];
+        float* ea = edge_attr + (beg + j) * 6;
+        ea[0] = px;
+        ea[1] = py;
+        ea[2] = pz;
+        ea[3] = pos[c * 3];
+        ea[4] = pos[c * 3 + 1];
+        ea[5] = pos[c * 3 + 2];
+    }
+    __syncwarp();
+}
+
+// One CTA per (frame, cell): the atoms of the 27 surrounding cells are staged in shared memory
+// once (coalesced float4 loads of the cell-sorted array) and shared by every atom of the centre
+// cell.  For FILL the staged list is first sorted by atom index (bitonic, in smem), so each atom's
+// hits come out in ascending column order and are written directly - no per-row sort, and both
+// endpoints' coordinates for edge_attr come from smem.  Cells whose neighbourhood exceeds the
+// staging capacity fall back to the per-atom global path.
+constexpr int kRgCap = 2048;  // staged candidates (float4) = 32 KB
+constexpr int kRgThreads = 256;
+constexpr int kRgDenseMin = 24;  // centre-cell atoms from which staging + sorting pays off
+
+template <bool FILL>
+__global__ void __launch_bounds__(kRgThreads)
+rg_cell_kernel(const float* __restrict__ pos, int64_t F, int64_t N, int64_t C, double d2_max,
+               const FrameMeta* __restrict__ meta, const int32_t* __restrict__ cell_start,
+               const float4* __restrict__ sorted_pos, int32_t* __restrict__ deg,
+               const int64_t* __restrict__ row_ptr, int64_t E, int64_t* __restrict__ edge_index,
+               float* __restrict__ edge_attr) {
+    __shared__ float4 s_cand[kRgCap];
+    __shared__ int s_run_beg[9], s_run_off[10];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t f = blockIdx.y;
+    const FrameMeta m = meta[f];
+    const int32_t* cs = cell_start + f * (C + 1);
+    const float4* sp = sorted_pos + f * N;
+    const int64_t node0 = f * N;
+    for (int c = blockIdx.x; c < m.ncell; c += gridDim.x) {
+        const int ib = cs[c], ie = cs[c + 1];
+        if (ib == ie) continue;  // empty centre cell (block-uniform)
+        const int cz = c % m.nz, cy = (c / m.nz) % m.ny, cx = c / (m.nz * m.ny);
+        if (ie - ib < kRgDenseMin) {
+            // sparse centre cell: staging + sorting would cost more than it saves
+            __syncthreads();  // s_cand is about to be reused as per-warp hit buffers
+            for (int i = ib + warp; i < ie; i += kRgThreads / 32) {
+                rg_atom_warp<FILL>(sp[i], node0, cx, cy, cz, m, lane, s_cand + warp * kHitCap, pos,
+                                   d2_max, cs, sp, deg, row_ptr, E, edge_index, edge_attr);
+            }
+            continue;
+        }
+        __syncthreads();  // previous item's smem no longer in use
+        if (threadIdx.x < 9) {
+            const int r = threadIdx.x;
+            const int ax = cx - 1 + r / 3, ay = cy - 1 + r % 3;
+            int jb = 0, je = 0;
+            if (ax >= 0 && ax < m.nx && ay >= 0 && ay < m.ny) {
+                const int z0 = max(cz - 1, 0), z1 = min(cz + 1, m.nz - 1);
+                jb = cs[(ax * m.ny + ay) * m.nz + z0];
+                je = cs[(ax * m.ny + ay) * m.nz + z1 + 1];
+            }
+            s_run_beg[r] = jb;
+            s_run_off[r + 1] = je - jb;  // lengths first, prefix-summed below
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int off = 0;
+            for (int r = 0; r < 9; ++r) {
+                const int len = s_run_off[r + 1];
+                s_run_off[r] = off;
+                off += len;
+            }
+            s_run_off[9] = off;
+        }
+        __syncthreads();
+        const int ncand = s_run_off[9];
+        if (ncand > kRgCap) {
+            // oversize neighbourhood: per-atom path straight from global memory
+            __syncthreads();
+            for (int i = ib + warp; i < ie; i += kRgThreads / 32) {
+                rg_atom_warp<FILL>(sp[i], node0, cx, cy, cz, m, lane, s_cand + warp * kHitCap, pos,
+                                   d2_max, cs, sp, deg, row_ptr, E, edge_index, edge_attr);
+            }
+            continue;
+        }
+        for (int r = 0; r < 9; ++r) {
+            const int len = s_run_off[r + 1] - s_run_off[r];
+            for (int t = threadIdx.x; t < len; t += kRgThreads) {
+                s_cand[s_run_off[r] + t] = sp[s_run_beg[r] + t];
+            }
+        }
+        int P = ncand;
+        if (FILL) {
+            P = 32;
+            while (P < ncand) P <<= 1;
+            for (int t = ncand + threadIdx.x; t < P; t += kRgThreads) {
+                s_cand[t] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7fffffff));
+            }
+            __syncthreads();
+            for (int k = 2; k <= P; k <<= 1) {
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int t = threadIdx.x; t < P; t += kRgThreads) {
+                        const int u = t ^ j;
+                        if (u > t) {
+                            const float4 a = s_cand[t], b = s_cand[u];
+                            const bool asc = (t & k) == 0;
+                            if ((__float_as_int(a.w) > __float_as_int(b.w)) == asc) {
+                                s_cand[t] = b;
+                                s_cand[u] = a;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+        } else {
+            __syncthreads();
+        }
+        for (int i = ib + warp; i < ie; i += kRgThreads / 32) {
+            const float4 pi = sp[i];
+            const double xi = pi.x, yi = pi.y, zi = pi.z;
+            const int64_t g = node0 + __float_as_int(pi.w);
+            const int64_t beg = FILL ? row_ptr[g] : 0;
+            int count = 0;
+            for (int base = 0; base < ncand; base += 32) {
+                const int j = base + lane;
+                bool hit = false;
+                float4 pj = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j < ncand) {
+                    pj = s_cand[j];
+                    hit = within(xi, yi, zi, pj, d2_max);
+                }
+                const unsigned mask = __ballot_sync(0xffffffffu, hit);
+                if (FILL && hit) {
+                    const int64_t slot = beg + count + __popc(mask & ((1u << lane) - 1u));
+                    edge_index[slot] = g;
+                    edge_index[E + slot] = node0 + __float_as_int(pj.w);
+                    float2* ea = reinterpret_cast<float2*>(edge_attr + slot * 6);
+                    ea[0] = make_float2(pi.x, pi.y);
+                    ea[1] = make_float2(pi.z, pj.x);
+                    ea[2] = make_float2(pj.y, pj.z);
+                }
+                count += __popc(mask);
+            }
+            if (!FILL && lane == 0) deg[g] = count;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-block exclusive scan (int32 -> int64) for the row pointers: block sums, scan of the sums
+// (single block), then per-block scan + offset
+// ------------------------------------------------------------------------------------------------
+constexpr int kScanItems = 4;
+constexpr int kScanChunk = kScanThreads * kScanItems;
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_block_sums_kernel(const int32_t* __restrict__ in, int64_t n, int64_t* __restrict__ sums) {
+    __shared__ int64_t sm[32];
+    const int64_t base = int64_t(blockIdx.x) * kScanChunk;
+    int64_t v = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        const int64_t i = base + int64_t(threadIdx.x) * kScanItems + k;
+        if (i < n) v += in[i];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int64_t t = sm[threadIdx.x];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+        if (threadIdx.x == 0) sums[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_apply_kernel(const int32_t* __restrict__ in, int64_t n, const int64_t* __restrict__ offs,
+                  int64_t* __restrict__ out) {
+    __shared__ int64_t warp_tot[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t base = int64_t(blockIdx.x) * kScanChunk + int64_t(threadIdx.x) * kScanItems;
+    int64_t v[kScanItems], tsum = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        v[k] = base + k < n ? in[base + k] : 0;
+        tsum += v[k];
+    }
+    int64_t incl = tsum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int64_t t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int64_t wv = warp_tot[lane];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int64_t t = __shfl_up_sync(0xffffffffu, wv, off);
+            if (lane >= off) wv += t;
+        }
+        warp_tot[lane] = wv;
+    }
+    __syncthreads();
+    int64_t run = offs[blockIdx.x] + (warp == 0 ? 0 : warp_tot[warp - 1]) + incl - tsum;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = offs[gridDim.x];
+}
+
+// largest double d2 with fl(sqrt(d2)) < thr  (see `within`); -1 if no distance qualifies
+double exact_d2_bound(double thr) {
+    if (!(thr > 0.0)) return -1.0;  // also NaN
+    if (std::isinf(thr)) return std::numeric_limits<double>::max();
+    double t = thr * thr;
+    if (std::isinf(t)) t = std::numeric_limits<double>::max();
+    while (t > 0.0 && std::sqrt(t) >= thr) t = std::nextafter(t, -1.0);
+    while (std::sqrt(std::nextafter(t, std::numeric_limits<double>::infinity())) < thr) {
+        t = std::nextafter(t, std::numeric_limits<double>::infinity());
+    }
+    return std::sqrt(t) < thr ? t : -1.0;
 }
 
 int grid_for(int64_t total, int threads, int per_sm) {
@@ -462,6 +792,7 @@ extern "C" int gkn_radius_graph_count(const float* pos, int64_t F, int64_t N, do
     using namespace gkn;
     if (F < 0 || N < 0) return set_error("gkn_radius_graph_count: negative size");
     if (N >= (int64_t(1) << 30)) return set_error("gkn_radius_graph_count: N too large");
+    if (F > 65535) return set_error("gkn_radius_graph_count: at most 65535 frames per call");
     RadiusWs w = carve_radius_ws(workspace, F, N);
     if (workspace_bytes < w.bytes) return set_error("gkn_radius_graph_count: workspace too small");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -473,7 +804,7 @@ extern "C" int gkn_radius_graph_count(const float* pos, int64_t F, int64_t N, do
     }
     cudaError_t err = cudaMemsetAsync(w.cell_count, 0, size_t(F) * (w.C + 1) * 4, st);
     if (err != cudaSuccess) return set_cuda_error("cudaMemsetAsync(cell_count)", err);
-    rg_frame_setup_kernel<<<unsigned(F), 256, 0, st>>>(pos, N, threshold, w.C, w.meta);
+    rg_frame_setup_kernel<<<unsigned(F), 1024, 0, st>>>(pos, N, threshold, w.C, w.meta);
     GKN_CHECK_LAUNCH("rg_frame_setup");
     const int ag = grid_for(total, 256, 8);
     rg_assign_kernel<<<ag, 256, 0, st>>>(pos, F, N, w.C, w.meta, w.atom_cell, w.cell_count);
@@ -486,11 +817,21 @@ extern "C" int gkn_radius_graph_count(const float* pos, int64_t F, int64_t N, do
     rg_place_kernel<<<ag, 256, 0, st>>>(pos, F, N, w.C, w.atom_cell, w.cell_start, w.cell_count,
                                         w.sorted_pos);
     GKN_CHECK_LAUNCH("rg_place");
-    const int wg = grid_for(total * 32, 256, 8);
-    rg_neighbor_kernel<false><<<wg, 256, 0, st>>>(pos, F, N, w.C, threshold, w.meta, w.cell_start,
-                                                  w.sorted_pos, deg, nullptr, 0, nullptr, nullptr);
+    int sms = 148;
+    device_sm_count(&sms);
+    int64_t cgx = (int64_t(sms) * 16 + F - 1) / F;  // CTAs per frame striding over its cells
+    if (cgx > w.C) cgx = w.C;
+    const dim3 cg(unsigned(cgx < 1 ? 1 : cgx), unsigned(F));
+    rg_cell_kernel<false><<<cg, kRgThreads, 0, st>>>(pos, F, N, w.C, exact_d2_bound(threshold), w.meta,
+                                                         w.cell_start, w.sorted_pos, deg, nullptr,
+                                                         0, nullptr, nullptr);
     GKN_CHECK_LAUNCH("rg_count");
-    exclusive_scan_kernel<int32_t, int64_t><<<1, kScanThreads, 0, st>>>(deg, row_ptr, total, 0, 0);
+    scan_block_sums_kernel<<<unsigned(w.nblk), kScanThreads, 0, st>>>(deg, total, w.block_sums);
+    GKN_CHECK_LAUNCH("rg_scan_sums");
+    exclusive_scan_kernel<int64_t, int64_t>
+        <<<1, kScanThreads, 0, st>>>(w.block_sums, w.block_offs, w.nblk, 0, 0);
+    GKN_CHECK_LAUNCH("rg_scan_offs");
+    scan_apply_kernel<<<unsigned(w.nblk), kScanThreads, 0, st>>>(deg, total, w.block_offs, row_ptr);
     GKN_CHECK_LAUNCH("rg_scan_rows");
     return 0;
 }
@@ -506,10 +847,33 @@ extern "C" int gkn_radius_graph_fill(const float* pos, int64_t F, int64_t N, dou
     const int64_t total = F * N;
     if (total == 0 || E == 0) return 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int wg = grid_for(total * 32, 256, 8);
-    rg_neighbor_kernel<true><<<wg, 256, 0, st>>>(pos, F, N, w.C, threshold, w.meta, w.cell_start,
-                                                 w.sorted_pos, nullptr, row_ptr, E, edge_index,
-                                                 edge_attr);
+    int sms = 148;
+    device_sm_count(&sms);
+    int64_t cgx = (int64_t(sms) * 16 + F - 1) / F;
+    if (cgx > w.C) cgx = w.C;
+    const dim3 cg(unsigned(cgx < 1 ? 1 : cgx), unsigned(F));
+    rg_cell_kernel<true><<<cg, kRgThreads, 0, st>>>(pos, F, N, w.C, exact_d2_bound(threshold), w.meta,
+                                                        w.cell_start, w.sorted_pos, nullptr,
+                                                        row_ptr, E, edge_index, edge_attr);
     GKN_CHECK_LAUNCH("rg_fill");
+    return 0;
+}
+
+extern "C" int gkn_plan_from_csr(const int64_t* edge_index, const int64_t* row_ptr, int64_t N,
+                                 int64_t E, int32_t* rev, int32_t* src_s, int32_t* dst_s,
+                                 int32_t* ptr32, float* inv_cnt, int32_t* status, void* stream) {
+    using namespace gkn;
+    if (N < 0 || E < 0) return set_error("gkn_plan_from_csr: negative size");
+    if (N >= (int64_t(1) << 31) || E >= (int64_t(1) << 31)) {
+        return set_error("gkn_plan_from_csr: N and E must fit in int32");
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t err = cudaMemsetAsync(status, 0, 4, st);
+    if (err != cudaSuccess) return set_cuda_error("cudaMemsetAsync(status)", err);
+    const int64_t work = E > N + 1 ? E : N + 1;
+    plan_from_csr_kernel<<<grid_for(work, 256, 8), 256, 0, st>>>(edge_index, row_ptr, N, E, rev,
+                                                                src_s, dst_s, ptr32, inv_cnt,
+                                                                status);
+    GKN_CHECK_LAUNCH("plan_from_csr");
     return 0;
 }

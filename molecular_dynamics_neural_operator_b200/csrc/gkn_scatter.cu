@@ -145,7 +145,23 @@ scatter_src_sum_kernel(const float* __restrict__ dxj, const int32_t* __restrict_
 // backward: rows=dxj, perm=src_perm, gidx=dst, gnode=gn, M1=B3^T, nin=g, M2=root^T, no scale/bias
 // The two w x w products are done per node inside the warp (operands from a per-warp smem row,
 // matrices through the read-only path), so no separate tiny GEMM launches are needed.
-template <int W>
+template <int CPL>
+__device__ __forceinline__ void ldg_vec(const float* p, float (&v)[CPL]) {
+    if constexpr (CPL == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else if constexpr (CPL == 2) {
+        const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+        v[0] = t.x; v[1] = t.y;
+    } else {
+        v[0] = __ldg(p);
+    }
+}
+
+// A warp handles NB nodes per round: their segment sums are parked in per-warp smem rows, then the
+// two w x w products are done for all NB nodes together so every matrix element fetched (vector
+// loads through the read-only path) is reused NB times from registers.
+template <int W, int NB>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 segment_matvec_kernel(const float* __restrict__ rows, const int32_t* __restrict__ perm,
                       const int32_t* __restrict__ seg_ptr, const int32_t* __restrict__ gidx,
@@ -156,68 +172,100 @@ segment_matvec_kernel(const float* __restrict__ rows, const int32_t* __restrict_
     constexpr int LPR = W / 4;
     constexpr int RPW = 32 / LPR;
     constexpr int CPL = W >= 32 ? W / 32 : 1;  // output columns per lane in the matvec phase
-    __shared__ float s_r[kWarpsPerBlock][W];
-    __shared__ float s_g[kWarpsPerBlock][W];
-    __shared__ float s_n[kWarpsPerBlock][W];
+    __shared__ __align__(16) float s_r[kWarpsPerBlock][NB][W];
+    __shared__ __align__(16) float s_g[kWarpsPerBlock][NB][W];
+    __shared__ __align__(16) float s_n[kWarpsPerBlock][NB][W];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int sub = lane / LPR;
     const int col = (lane % LPR) * 4;
     const int64_t warp0 = int64_t(blockIdx.x) * kWarpsPerBlock + wib;
     const int64_t nwarps = int64_t(gridDim.x) * kWarpsPerBlock;
-    for (int64_t n = warp0; n < N; n += nwarps) {
-        const int beg = seg_ptr[n], end = seg_ptr[n + 1];
-        float4 ar0 = make_float4(0.f, 0.f, 0.f, 0.f), ar1 = ar0, ag0 = ar0, ag1 = ar0;
-        int q = beg + sub;
-        for (; q + RPW < end; q += 2 * RPW) {
-            const int p0 = perm ? perm[q] : q;
-            const int p1 = perm ? perm[q + RPW] : q + RPW;
-            const float4 r0 = ldg4_stream(rows + int64_t(p0) * W + col);
-            const float4 r1 = ldg4_stream(rows + int64_t(p1) * W + col);
-            const float4 g0 = ldg4(gnode + int64_t(gidx[p0]) * W + col);
-            const float4 g1 = ldg4(gnode + int64_t(gidx[p1]) * W + col);
-            ar0 = f4add(ar0, r0);
-            ar1 = f4add(ar1, r1);
-            ag0 = f4add(ag0, g0);
-            ag1 = f4add(ag1, g1);
-        }
-        if (q < end) {
-            const int p0 = perm ? perm[q] : q;
-            ar0 = f4add(ar0, ldg4_stream(rows + int64_t(p0) * W + col));
-            ag0 = f4add(ag0, ldg4(gnode + int64_t(gidx[p0]) * W + col));
-        }
-        float4 ar = f4add(ar0, ar1), ag = f4add(ag0, ag1);
+    const int64_t rounds = (N + NB - 1) / NB;
+    for (int64_t rd = warp0; rd < rounds; rd += nwarps) {
+        const int64_t n0 = rd * NB;
+#pragma unroll 1
+        for (int nb = 0; nb < NB; ++nb) {
+            const int64_t n = n0 + nb;
+            if (n >= N) break;
+            const int beg = seg_ptr[n], end = seg_ptr[n + 1];
+            float4 ar0 = make_float4(0.f, 0.f, 0.f, 0.f), ar1 = ar0, ag0 = ar0, ag1 = ar0;
+            int q = beg + sub;
+            // 4 rows in flight per lane: indices first, then the 8 dependent row loads
+            for (; q + 3 * RPW < end; q += 4 * RPW) {
+                int pp[4], ii[4];
 #pragma unroll
-        for (int off = LPR; off < 32; off <<= 1) {
-            ar = f4add(ar, f4shfl_xor(ar, off));
-            ag = f4add(ag, f4shfl_xor(ag, off));
-        }
-        if (sub == 0) {
-            const float sc = scale ? scale[n] : 1.f;
-            ar = make_float4(ar.x * sc, ar.y * sc, ar.z * sc, ar.w * sc);
-            ag = make_float4(ag.x * sc, ag.y * sc, ag.z * sc, ag.w * sc);
-            *reinterpret_cast<float4*>(&s_r[wib][col]) = ar;
-            *reinterpret_cast<float4*>(&s_g[wib][col]) = ag;
-            *reinterpret_cast<float4*>(&s_n[wib][col]) = ldg4(nin + n * W + col);
-            if (agg_out) *reinterpret_cast<float4*>(agg_out + n * W + col) = ag;
+                for (int u = 0; u < 4; ++u) pp[u] = perm ? perm[q + u * RPW] : q + u * RPW;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) ii[u] = gidx[pp[u]];
+                float4 rr[4], gg[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    rr[u] = ldg4_stream(rows + int64_t(pp[u]) * W + col);
+                    gg[u] = ldg4(gnode + int64_t(ii[u]) * W + col);
+                }
+                ar0 = f4add(ar0, f4add(rr[0], rr[2]));
+                ar1 = f4add(ar1, f4add(rr[1], rr[3]));
+                ag0 = f4add(ag0, f4add(gg[0], gg[2]));
+                ag1 = f4add(ag1, f4add(gg[1], gg[3]));
+            }
+            for (; q < end; q += RPW) {
+                const int p0 = perm ? perm[q] : q;
+                ar0 = f4add(ar0, ldg4_stream(rows + int64_t(p0) * W + col));
+                ag0 = f4add(ag0, ldg4(gnode + int64_t(gidx[p0]) * W + col));
+            }
+            float4 ar = f4add(ar0, ar1), ag = f4add(ag0, ag1);
+#pragma unroll
+            for (int off = LPR; off < 32; off <<= 1) {
+                ar = f4add(ar, f4shfl_xor(ar, off));
+                ag = f4add(ag, f4shfl_xor(ag, off));
+            }
+            if (sub == 0) {
+                const float sc = scale ? scale[n] : 1.f;
+                ar = make_float4(ar.x * sc, ar.y * sc, ar.z * sc, ar.w * sc);
+                ag = make_float4(ag.x * sc, ag.y * sc, ag.z * sc, ag.w * sc);
+                *reinterpret_cast<float4*>(&s_r[wib][nb][col]) = ar;
+                *reinterpret_cast<float4*>(&s_g[wib][nb][col]) = ag;
+                *reinterpret_cast<float4*>(&s_n[wib][nb][col]) = ldg4(nin + n * W + col);
+                if (agg_out) *reinterpret_cast<float4*>(agg_out + n * W + col) = ag;
+            }
         }
         __syncwarp();
         const int c0 = lane * CPL;
         if (c0 < W) {
-            float o[CPL];
+            const int nvalid = int(N - n0 < NB ? N - n0 : NB);
+            float o[NB][CPL];
+            float bv[CPL];
 #pragma unroll
-            for (int k = 0; k < CPL; ++k) o[k] = s_r[wib][c0 + k] + (bias ? __ldg(bias + c0 + k) : 0.f);
+            for (int k = 0; k < CPL; ++k) bv[k] = bias ? __ldg(bias + c0 + k) : 0.f;
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) o[nb][k] = nb < nvalid ? s_r[wib][nb][c0 + k] + bv[k] : 0.f;
 #pragma unroll 4
             for (int i = 0; i < W; ++i) {
-                const float a = s_g[wib][i], b = s_n[wib][i];
+                float m1[CPL], m2[CPL];
+                ldg_vec<CPL>(M1 + i * W + c0, m1);
+                ldg_vec<CPL>(M2 + i * W + c0, m2);
 #pragma unroll
-                for (int k = 0; k < CPL; ++k) {
-                    o[k] = fmaf(a, __ldg(M1 + i * W + c0 + k), o[k]);
-                    o[k] = fmaf(b, __ldg(M2 + i * W + c0 + k), o[k]);
+                for (int nb = 0; nb < NB; ++nb) {
+                    const float a = s_g[wib][nb][i], b = s_n[wib][nb][i];
+#pragma unroll
+                    for (int k = 0; k < CPL; ++k) {
+                        o[nb][k] = fmaf(a, m1[k], o[nb][k]);
+                        o[nb][k] = fmaf(b, m2[k], o[nb][k]);
+                    }
                 }
             }
 #pragma unroll
-            for (int k = 0; k < CPL; ++k) out[n * W + c0 + k] = relu ? fmaxf(o[k], 0.f) : o[k];
+            for (int nb = 0; nb < NB; ++nb) {
+                if (nb < nvalid) {
+#pragma unroll
+                    for (int k = 0; k < CPL; ++k) {
+                        out[(n0 + nb) * W + c0 + k] = relu ? fmaxf(o[nb][k], 0.f) : o[nb][k];
+                    }
+                }
+            }
         }
         __syncwarp();
     }
@@ -709,14 +757,18 @@ extern "C" int gkn_segment_matvec(const float* rows, const int32_t* perm, const 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int grid = node_grid(N);
     const int threads = kWarpsPerBlock * 32;
-#define GKN_SMV(WW)                                                                              \
-    segment_matvec_kernel<WW><<<grid, threads, 0, st>>>(rows, perm, seg_ptr, gidx, gnode, scale, \
-                                                        M1, nin, M2, bias, out, agg_out, N, relu)
+    // many nodes: 4 (2 at w=128) nodes per warp round so matrix loads are reused; few nodes:
+    // one node per warp keeps every SM busy with the (latency-bound) segment walks
+    const bool batch_nodes = N >= int64_t(grid) * kWarpsPerBlock * 8;
+#define GKN_SMV(WW, NBB)                                                                         \
+    segment_matvec_kernel<WW, NBB><<<grid, threads, 0, st>>>(rows, perm, seg_ptr, gidx, gnode,   \
+                                                             scale, M1, nin, M2, bias, out,      \
+                                                             agg_out, N, relu)
     switch (W) {
-        case 16: GKN_SMV(16); break;
-        case 32: GKN_SMV(32); break;
-        case 64: GKN_SMV(64); break;
-        case 128: GKN_SMV(128); break;
+        case 16: if (batch_nodes) GKN_SMV(16, 4); else GKN_SMV(16, 1); break;
+        case 32: if (batch_nodes) GKN_SMV(32, 4); else GKN_SMV(32, 1); break;
+        case 64: if (batch_nodes) GKN_SMV(64, 4); else GKN_SMV(64, 1); break;
+        case 128: if (batch_nodes) GKN_SMV(128, 2); else GKN_SMV(128, 1); break;
         default: return set_error("gkn_segment_matvec: width must be 16, 32, 64 or 128");
     }
 #undef GKN_SMV

@@ -115,8 +115,35 @@ def prepare_graph(edge_index: torch.Tensor, num_nodes: int, validate: bool = Tru
     return GraphPlan(N, E, perm, src, dst, dst_ptr, inv_cnt, src_ptr, src_perm)
 
 
-def radius_graph(pos: torch.Tensor, threshold: float) -> tuple[torch.Tensor, torch.Tensor]:
-    """Batched radius graph.  pos float32 [F, N, 3] -> (edge_index int64 [2, E], edge_attr [E, 6]).
+def plan_from_csr(edge_index: torch.Tensor, row_ptr: torch.Tensor, num_nodes: int,
+                  validate: bool = True) -> GraphPlan:
+    """GraphPlan of a symmetric (row, col)-sorted graph with int64 row pointers — the output of
+    ``radius_graph(..., return_row_ptr=True)`` — without any sorting (gkn_plan_from_csr)."""
+    _require_cuda(edge_index, "edge_index")
+    lib = _lib.load()
+    ei = edge_index.contiguous()
+    dev = ei.device
+    N, E = int(num_nodes), int(ei.size(1))
+    i32 = dict(dtype=torch.int32, device=dev)
+    rev, src, dst = torch.empty(E, **i32), torch.empty(E, **i32), torch.empty(E, **i32)
+    ptr32 = torch.empty(N + 1, **i32)
+    inv_cnt = torch.empty(N, dtype=torch.float32, device=dev)
+    status = torch.zeros(1, **i32)
+    with torch.cuda.device(dev):
+        _lib.check(
+            lib.gkn_plan_from_csr(_p(ei, torch.int64, "edge_index"), _p(row_ptr, torch.int64, "row_ptr"),
+                                  N, E, _p(rev), _p(src), _p(dst), _p(ptr32), _p(inv_cnt),
+                                  _p(status), _stream()),
+            "gkn_plan_from_csr",
+        )
+    if validate and int(status.item()) != 0:
+        raise ValueError("plan_from_csr: edge_index is not a symmetric (row, col)-sorted graph")
+    return GraphPlan(N, E, rev, src, dst, ptr32, inv_cnt, ptr32, rev)
+
+
+def radius_graph(pos: torch.Tensor, threshold: float, return_row_ptr: bool = False):
+    """Batched radius graph.  pos float32 [F, N, 3] -> (edge_index int64 [2, E], edge_attr [E, 6])
+    (and the int64 CSR row pointers [F*N + 1] with ``return_row_ptr``).
 
     Node ids of frame f are offset by f*N; edges are in (row, col) lexicographic order with
     self loops, identical to scipy distance_matrix(float64) < threshold -> coo_matrix.
@@ -152,6 +179,8 @@ def radius_graph(pos: torch.Tensor, threshold: float) -> tuple[torch.Tensor, tor
             ),
             "gkn_radius_graph_fill",
         )
+    if return_row_ptr:
+        return edge_index, edge_attr, row_ptr
     return edge_index, edge_attr
 
 

@@ -93,7 +93,7 @@ def make_batch(x_window: torch.Tensor, aminoacid: torch.Tensor, y: torch.Tensor 
     (``KernelNN.forward`` picks it up), so both happen off the training stream when prefetched."""
     B, W, N, _ = x_window.shape
     frames = x_window[:, graph_frame].contiguous()
-    edge_index, edge_attr = ops.radius_graph(frames, cutoff)
+    edge_index, edge_attr, row_ptr = ops.radius_graph(frames, cutoff, return_row_ptr=True)
     data = PairData(
         x_aminoacid=aminoacid.repeat(B),
         x_position=x_window.reshape(B * W, N, 3),
@@ -102,7 +102,8 @@ def make_batch(x_window: torch.Tensor, aminoacid: torch.Tensor, y: torch.Tensor 
         edge_index=edge_index,
     )
     if prepare:
-        data._gkn_plan = ops.prepare_graph(edge_index, B * N)
+        # radius graphs are symmetric and (row, col)-sorted: no sorting needed for the CSR plan
+        data._gkn_plan = ops.plan_from_csr(edge_index, row_ptr, B * N, validate=False)
     return data
 
 

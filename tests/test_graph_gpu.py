@@ -24,7 +24,9 @@ def test_construct_pairdata_bit_exact_vs_reference_golden(name):
 
 @pytest.mark.parametrize("F,N,L,thr", [(1, 1, 1.0, 8.0), (1, 28, 20.0, 8.0), (5, 100, 12.0, 4.2),
                                         (2, 504, 17.1, 8.0), (3, 64, 300.0, 4.2), (1, 3000, 31.0, 4.2),
-                                        (2, 50, 5.0, 0.5), (1, 40, 10.0, 1000.0)])
+                                        (2, 50, 5.0, 0.5), (1, 40, 10.0, 1000.0),
+                                        (1, 2300, 5.0, 9.0),   # > 2048 staged candidates: per-atom fallback
+                                        (3, 700, 9.0, 3.0)])
 def test_radius_graph_bit_exact_vs_scipy_oracle(F, N, L, thr):
     from molecular_dynamics_neural_operator_b200 import ops
     from oracle import gkn_oracle as orc
@@ -104,3 +106,19 @@ def test_prepare_graph_rejects_out_of_range_ids():
     ei = torch.tensor([[0, 1, 5], [1, 0, 1]], dtype=torch.long).cuda()
     with pytest.raises(ValueError, match="outside"):
         ops.prepare_graph(ei, 3)
+
+
+def test_plan_from_csr_equals_general_prepare_on_radius_graphs():
+    from molecular_dynamics_neural_operator_b200 import ops
+
+    rng = np.random.default_rng(3)
+    for F, N, L, thr in [(1, 1, 1.0, 2.0), (3, 200, 14.0, 4.2), (2, 504, 17.1, 8.0)]:
+        pos = torch.from_numpy((rng.random((F, N, 3)) * L).astype(np.float32)).cuda()
+        ei, ea, row_ptr = ops.radius_graph(pos, thr, return_row_ptr=True)
+        fast = ops.plan_from_csr(ei, row_ptr, F * N)
+        ref = ops.prepare_graph(ei, F * N)
+        for name in ("perm", "src", "dst", "dst_ptr", "inv_cnt", "src_ptr", "src_perm"):
+            assert torch.equal(getattr(fast, name), getattr(ref, name)), name
+    bad = torch.tensor([[0, 1, 1], [1, 0, 2]], dtype=torch.long).cuda()  # 1->2 has no reverse
+    with pytest.raises(ValueError, match="symmetric"):
+        ops.plan_from_csr(bad, torch.tensor([0, 1, 3, 3], dtype=torch.long).cuda(), 3)

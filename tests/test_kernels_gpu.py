@@ -139,7 +139,8 @@ def test_mask_cast_colsum(act_dt, out_dt):
 
 
 @pytest.mark.parametrize("N,E,W", [(50, 700, 64), (504, 20000, 64), (300, 5000, 32), (100, 3000, 128),
-                                   (40, 100, 16), (10, 0, 64)])
+                                   (40, 100, 16), (10, 0, 64),
+                                   (80001, 200000, 64), (80001, 150000, 128), (80001, 100000, 32)])  # batched-node path
 def test_segment_matvec_forward_and_backward_forms(N, E, W):
     from molecular_dynamics_neural_operator_b200 import ops
 
