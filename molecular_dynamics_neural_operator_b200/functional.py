@@ -31,8 +31,13 @@ import torch
 from . import ops
 from .ops import GraphPlan
 
-# rows of S materialised at a time by the staged weight-gradient path (see _edge_grads)
-_S_CHUNK_EDGES = 16384
+import os
+
+# Edges per chunk of the staged weight-gradient pass (see _edge_grads): S for one chunk is
+# chunk * w*w bf16 values (134 MB at 16384 edges, w = 64).  Measured on B200 (bench workload,
+# ms/step): 16384 -> 72.9, 8192 -> 88.2, 4096 -> 84.3, 2048 -> 91.3; smaller chunks lose more in
+# GEMM efficiency and dW3 accumulate traffic than they gain in L2 residency.
+_S_CHUNK_EDGES = int(os.environ.get("GKN_S_CHUNK_EDGES", "16384"))
 
 
 def _mm32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
