@@ -267,6 +267,9 @@ def run_b200_arm(args, wl):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # keep stdout to the single JSON line (NCCL_DEBUG=VERSION/INFO prints to stdout)
+        if os.environ.get("GKN_BENCH_KEEP_NCCL_DEBUG") is None:
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
 

@@ -12,16 +12,26 @@
 // so P never reaches HBM (flash-style recompute in backward).  The b3 bias term of layers.4 is a
 // node-level product and is applied by the scatter kernels, not here.
 //
-// Structure (one persistent CTA per SM, 192 threads):
-//   warp 0      TMA producer: h_e tile [128 x 64] + W3 chunk tile [256 x 64] per k-block, 4 stages,
-//               128-byte swizzle, completion on full[] mbarriers.
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=256, K=16 per MMA);
-//               tcgen05.commit releases smem stages (empty[]) and publishes accumulators (tfull[]).
-//   warps 2..5  epilogue: 128 threads = 128 accumulator rows (edges); two TMEM accumulator stages
-//               (2 x 256 columns) so the contraction of chunk c overlaps the MMAs of chunk c+1.
-// Work unit = (edge tile, column chunk).  Units are split evenly over CTAs (contiguous ranges), so
-// there is no tile-quantisation tail; a tile shared by two CTAs is combined with fp32 reductions
-// onto the zero-initialised output (at most two addends per element => order-independent).
+// Structure (one persistent CTA per SM, 192 threads; CTAs run as PAIRS, cluster of 2):
+//   warp 0      TMA producer: per k-block its own h_e tile [128 x 64] and HALF of the W3 chunk tile
+//               ([128 x 64] of the 256 rows), 6 stages of 32 KB, 128-byte swizzle; both CTAs'
+//               bytes complete on the leader's full[] mbarrier.
+//   warp 1      TMEM allocator; in the leader CTA, the single-thread issuer of
+//               tcgen05.mma.cta_group::2 (M = 256 edges across the pair, N = 256, K = 16 per MMA);
+//               multicast tcgen05.commit releases smem stages (empty[]) and publishes
+//               accumulators (tfull[]) in both CTAs.
+//   warps 2..5  epilogue: 128 threads = this CTA's 128 accumulator rows (edges); two TMEM
+//               accumulator stages (2 x 256 columns) so the contraction of chunk c overlaps the
+//               MMAs of chunk c+1; the peer's warps release a stage by a remote mbarrier arrive.
+// Pairing cuts operand bytes per flop by a third (measured: tensor pipe 91 % of peak cycles,
+// 1.6 PFLOP/s isolated, 2.0 PFLOP/s inside the training step where the lower power draw buys
+// clock).  GKN_CONTRACT_CTA_GROUP=1 selects the single-CTA variant (4 stages of 48 KB).
+// Work unit = (tile group, column chunk).  Units are split evenly over CTA pairs (contiguous
+// ranges), so there is no tile-quantisation tail; a tile shared by two pairs is combined with fp32
+// reductions onto the zero-initialised output (at most two addends per element =>
+// order-independent).
+#include <stdlib.h>
+
 #include "gkn_internal.h"
 #include "gkn_ptx.cuh"
 
@@ -29,17 +39,26 @@ namespace gkn {
 
 namespace {
 
-constexpr int kBlockM = 128;
-constexpr int kBlockN = 256;
+constexpr int kBlockM = 128;  // accumulator rows (edges) per CTA
+constexpr int kBlockN = 256;  // accumulator columns per MMA
 constexpr int kBlockK = 64;
 constexpr int kUmmaK = 16;
-constexpr int kStages = 4;
 constexpr int kThreads = 192;
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
-constexpr int kBBytes = kBlockN * kBlockK * 2;  // 32 KB
-constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kTmemCols = 512;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+
+// CG = 1: one CTA per 128-edge tile, B tile = 256 rows.  CG = 2: a CTA pair (cluster of 2) shares one
+// tcgen05.mma.cta_group::2 over 256 edges x 256 columns: each CTA stages its own 128 edge rows
+// and HALF of the W3 chunk (128 rows), so operand bytes per flop drop by a third and the freed
+// smem deepens the pipeline (6 stages of 32 KB instead of 4 of 48 KB).
+template <int CG>
+struct Cfg {
+    static constexpr int kBRows = kBlockN / CG;
+    static constexpr int kBBytes = kBRows * kBlockK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = CG == 1 ? 4 : 6;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
 
 enum { MODE_FWD = 0, MODE_DX = 1 };
 
@@ -52,10 +71,13 @@ struct ContractParams {
     int64_t num_tiles;     // ceil(E / 128)
 };
 
-template <int W, int MODE>
+template <int W, int MODE, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 contract_tc_kernel(const __grid_constant__ CUtensorMap tmap_h,
                    const __grid_constant__ CUtensorMap tmap_w, const ContractParams p) {
+    using C = Cfg<CG>;
+    constexpr int kStages = C::kStages;
+    constexpr int kStageBytes = C::kStageBytes;
     constexpr int kChunks = (W * W) / kBlockN;  // column chunks per edge tile
     constexpr int kIPerChunk = kBlockN / W;      // i-values covered by one chunk
     static_assert((W * W) % kBlockN == 0 && kBlockN % W == 0 && W % 32 == 0, "unsupported width");
@@ -72,19 +94,24 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tmap_h,
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;  // 0 = leader of the pair
+    const int64_t group = blockIdx.x / CG;                   // CTA (pair) index
+    const int64_t ngroups = gridDim.x / CG;
 
-    // Contiguous unit range of this CTA.  With many tiles per CTA the ranges are tile-aligned: all
-    // CTAs then walk the W3 column chunks in phase, so a chunk fetched by one CTA is an L2 hit for
-    // the others (matters when W3 is large, e.g. 32 MB at w=128), at a tail cost < 1/64.  With few
-    // tiles per CTA, units are split evenly instead (no tile-quantisation tail).
-    const int64_t total_units = p.num_tiles * kChunks;
+    // Contiguous unit range of this CTA (pair); unit = (tile group, column chunk), a tile group
+    // being CG consecutive 128-edge tiles.  With many tile groups per CTA the ranges are
+    // group-aligned: all CTAs then walk the W3 column chunks in phase, so a chunk fetched by one
+    // CTA is an L2 hit for the others (matters when W3 is large, e.g. 32 MB at w=128), at a tail
+    // cost < 1/64.  Otherwise units are split evenly (no tile-quantisation tail).
+    const int64_t num_tgroups = (p.num_tiles + CG - 1) / CG;
+    const int64_t total_units = num_tgroups * kChunks;
     int64_t u0, u1;
-    if (p.num_tiles >= int64_t(gridDim.x) * 64) {
-        u0 = ((p.num_tiles * blockIdx.x) / gridDim.x) * kChunks;
-        u1 = ((p.num_tiles * (blockIdx.x + 1)) / gridDim.x) * kChunks;
+    if (num_tgroups >= ngroups * 64) {
+        u0 = ((num_tgroups * group) / ngroups) * kChunks;
+        u1 = ((num_tgroups * (group + 1)) / ngroups) * kChunks;
     } else {
-        u0 = (total_units * blockIdx.x) / gridDim.x;
-        u1 = (total_units * (blockIdx.x + 1)) / gridDim.x;
+        u0 = (total_units * group) / ngroups;
+        u1 = (total_units * (group + 1)) / ngroups;
     }
 
     if (threadIdx.x == 0) {
@@ -94,7 +121,7 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tmap_h,
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+            mbar_init(tempty_bar(s), 4 * CG);  // one arrive per epilogue warp of every CTA
         }
         fence_mbar_init();
     }
@@ -103,30 +130,48 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tmap_h,
         tma_prefetch_desc(&tmap_w);
     }
     if (warp == 1) {
-        tmem_alloc(tmem_ptr_smem, kTmemCols);
-        tmem_relinquish();
+        if constexpr (CG == 2) {
+            tmem_alloc_pair(tmem_ptr_smem, kTmemCols);
+            tmem_relinquish_pair();
+        } else {
+            tmem_alloc(tmem_ptr_smem, kTmemCols);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) {
+        cluster_sync_all();  // peer barriers are initialised before any remote arrive / TMA signal
+    } else {
+        __syncthreads();
+    }
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer (every CTA loads its own operands) ==============
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
             for (int64_t u = u0; u < u1; ++u) {
-                const int32_t tile = int32_t(u / kChunks);
+                const int32_t tile = int32_t(u / kChunks) * CG + int32_t(rank);
                 const int32_t chunk = int32_t(u % kChunks);
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
-                    mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
                     const uint32_t sa = smem_base + stage * kStageBytes;
-                    tma_load_2d(sa, &tmap_h, full_bar(stage), kb * kBlockK, tile * kBlockM);
-                    tma_load_2d(sa + kABytes, &tmap_w, full_bar(stage), kb * kBlockK,
-                                chunk * kBlockN);
+                    if constexpr (CG == 2) {
+                        // both CTAs' bytes complete on the leader's barrier; only it arms it
+                        if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * kStageBytes);
+                        tma_load_2d_pair(sa, &tmap_h, full_bar(stage), kb * kBlockK,
+                                         tile * kBlockM);
+                        tma_load_2d_pair(sa + kABytes, &tmap_w, full_bar(stage), kb * kBlockK,
+                                         chunk * kBlockN + int32_t(rank) * C::kBRows);
+                    } else {
+                        mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
+                        tma_load_2d(sa, &tmap_h, full_bar(stage), kb * kBlockK, tile * kBlockM);
+                        tma_load_2d(sa + kABytes, &tmap_w, full_bar(stage), kb * kBlockK,
+                                    chunk * kBlockN);
+                    }
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1u;
@@ -135,9 +180,9 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tmap_h,
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, kBlockN, 0, 0);
+        // ===================== MMA issuer (leader CTA only when paired) =====================
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(kBlockM * CG, kBlockN, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
             uint32_t it = 0;
@@ -156,16 +201,32 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tmap_h,
 #pragma unroll
                     for (int k = 0; k < kBlockK / kUmmaK; ++k) {
                         // advance 16 bf16 (= 32 B) along K inside the 128-byte swizzle atom
-                        umma_bf16_ss(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k),
-                                     idesc, (kb | k) != 0 ? 1u : 0u);
+                        const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+                        if constexpr (CG == 2) {
+                            umma_bf16_ss_pair(tmem_d, adesc + uint64_t(2 * k),
+                                              bdesc + uint64_t(2 * k), idesc, acc);
+                        } else {
+                            umma_bf16_ss(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k),
+                                         idesc, acc);
+                        }
                     }
-                    umma_commit(empty_bar(stage));  // smem stage reusable once these MMAs retire
+                    // smem stage reusable (in both CTAs) once these MMAs retire
+                    if constexpr (CG == 2) {
+                        umma_commit_pair(empty_bar(stage), 3);
+                    } else {
+                        umma_commit(empty_bar(stage));
+                    }
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1u;
                     }
                 }
-                umma_commit(tfull_bar(as));  // accumulator chunk complete
+                // accumulator chunk complete (each CTA's epilogue reads its own 128 rows)
+                if constexpr (CG == 2) {
+                    umma_commit_pair(tfull_bar(as), 3);
+                } else {
+                    umma_commit(tfull_bar(as));
+                }
             }
         }
     } else {
@@ -201,7 +262,7 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tmap_h,
 
         uint32_t it = 0;
         for (int64_t u = u0; u < u1; ++u, ++it) {
-            const int32_t tile = int32_t(u / kChunks);
+            const int32_t tile = int32_t(u / kChunks) * CG + int32_t(rank);
             const int32_t chunk = int32_t(u % kChunks);
             if (tile != cur_tile) {
                 flush_fwd();
@@ -264,7 +325,14 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tmap_h,
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(as));
+            if (lane == 0) {
+                // the accumulator stage is free once every epilogue warp of the pair has read it
+                if (CG == 2 && rank != 0) {
+                    mbar_arrive_remote(tempty_bar(as), 0);
+                } else {
+                    mbar_arrive(tempty_bar(as));
+                }
+            }
 
             if constexpr (MODE == MODE_DX) {
                 if (valid) {
@@ -286,29 +354,61 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tmap_h,
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) {
+        cluster_sync_all();  // the peer may still signal this CTA's barriers / read its smem
+    } else {
+        __syncthreads();
+    }
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        if constexpr (CG == 2) {
+            tmem_dealloc_pair(tmem_base, kTmemCols);
+        } else {
+            tmem_dealloc(tmem_base, kTmemCols);
+        }
     }
 }
 
-template <int W, int MODE>
+template <int W, int MODE, int CG>
 int launch_contract(const CUtensorMap& tmap_h, const CUtensorMap& tmap_w, const ContractParams& p,
                     int max_ctas, cudaStream_t stream) {
-    auto kern = contract_tc_kernel<W, MODE>;
-    cudaError_t err =
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    auto kern = contract_tc_kernel<W, MODE, CG>;
+    constexpr int smem = Cfg<CG>::kSmemBytes;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (err != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(contract_tc)", err);
-    // grid <= num_tiles: every CTA then owns at least one tile's worth of units, so a tile is
-    // shared by at most two CTAs and its two partial sums combine order-independently.
-    int grid = int(p.num_tiles < max_ctas ? p.num_tiles : max_ctas);
-    if (grid < 1) return 0;
-    kern<<<grid, kThreads, kSmemBytes, stream>>>(tmap_h, tmap_w, p);
-    err = cudaGetLastError();
+    // grid <= number of tile groups: every CTA (pair) then owns at least one tile group's worth of
+    // units, so a tile is shared by at most two of them and its two partial sums combine
+    // order-independently.
+    const int64_t num_tgroups = (p.num_tiles + CG - 1) / CG;
+    int64_t groups = max_ctas / CG;
+    if (groups > num_tgroups) groups = num_tgroups;
+    if (groups < 1) return 0;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(unsigned(groups * CG));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    err = cudaLaunchKernelEx(&cfg, kern, tmap_h, tmap_w, p);
     if (err != cudaSuccess) return set_cuda_error("contract_tc launch", err);
     count_launch();
     return 0;
+}
+
+// CTA pairing: on by default; GKN_CONTRACT_CTA_GROUP=1 selects the single-CTA kernel
+int contract_cta_group() {
+    static int cached = 0;
+    if (cached == 0) {
+        const char* v = getenv("GKN_CONTRACT_CTA_GROUP");
+        cached = (v != nullptr && v[0] == '1') ? 1 : 2;
+    }
+    return cached;
 }
 
 template <int MODE>
@@ -322,14 +422,15 @@ int contract_dispatch(const void* h_bf16, const void* w3_bf16, const int32_t* id
     if (W != 32 && W != 64 && W != 128) {
         return set_error("gkn_contract_*_bf16: width must be 32, 64 or 128");
     }
-    if (E >= (int64_t(1) << 31) - kBlockM) {
+    if (E >= (int64_t(1) << 31) - 2 * kBlockM) {
         return set_error("gkn_contract_*_bf16: too many edges for one launch (>= 2^31)");
     }
+    const int cg = contract_cta_group();
     CUtensorMap tmap_h, tmap_w;
     int rc = make_tensor_map_bf16_2d(&tmap_h, h_bf16, uint64_t(K), uint64_t(E), kBlockK, kBlockM);
     if (rc) return rc;
     rc = make_tensor_map_bf16_2d(&tmap_w, w3_bf16, uint64_t(K), uint64_t(W) * uint64_t(W), kBlockK,
-                                 kBlockN);
+                                 kBlockN / cg);
     if (rc) return rc;
     ContractParams p;
     p.idx = idx;
@@ -346,11 +447,15 @@ int contract_dispatch(const void* h_bf16, const void* w3_bf16, const int32_t* id
         cudaError_t err = cudaMemsetAsync(out, 0, size_t(E) * W * sizeof(float), stream);
         if (err != cudaSuccess) return set_cuda_error("cudaMemsetAsync(msg)", err);
     }
+#define GKN_LAUNCH(WW)                                                                  \
+    return cg == 2 ? launch_contract<WW, MODE, 2>(tmap_h, tmap_w, p, sms, stream)       \
+                   : launch_contract<WW, MODE, 1>(tmap_h, tmap_w, p, sms, stream)
     switch (W) {
-        case 32: return launch_contract<32, MODE>(tmap_h, tmap_w, p, sms, stream);
-        case 64: return launch_contract<64, MODE>(tmap_h, tmap_w, p, sms, stream);
-        default: return launch_contract<128, MODE>(tmap_h, tmap_w, p, sms, stream);
+        case 32: GKN_LAUNCH(32);
+        case 64: GKN_LAUNCH(64);
+        default: GKN_LAUNCH(128);
     }
+#undef GKN_LAUNCH
 }
 
 }  // namespace
