@@ -237,7 +237,7 @@ def run_reference_arm(args, wl, edges_per_frame):
 
 def bench_config(wl, frames_per_gpu, edges_per_frame):
     return {
-        "workload": (f"{WORKLOAD}: {wl.num_atoms}-atom frames, {wl.cutoff} A radius graph "
+        "workload": (f"{wl.name}: {wl.num_atoms}-atom frames, {wl.cutoff} A radius graph "
                      f"(~{int(edges_per_frame)} directed edges/frame incl. self loops), KernelNN "
                      f"width {wl.width} kernel_width {wl.ker_width} depth {wl.depth} "
                      f"({2 * wl.depth} NNConv applications), window {wl.window}; step = graph "
@@ -399,6 +399,9 @@ def run_b200_arm(args, wl):
             traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak, "traffic": traffic,
+                    # context for frac > 1: the sustained cuBLAS figure was taken at ~1.35 GHz under
+                    # the power cap; inside this step the contraction runs at a higher clock
+                    "peak_burst": peaks["bf16_tflops"], "frac_burst": achieved / peaks["bf16_tflops"],
                     "kernel": "contract_tc_kernel (fwd+dx)", "launches": timer["count"],
                     "avg_launch_ms": avg_ms, "flop_per_launch": flop_per_launch,
                     "share_of_step": timer["ms"] / ms_total,
@@ -407,6 +410,11 @@ def run_b200_arm(args, wl):
                                    f"{ms_total / args.steps:.1f} ms clean)",
                     "peak_source": f"{peaks['source']} sustained bf16 (kernel timed inside a long step)"}
 
+    if roofline and clocks and clocks.get("sm_mhz"):
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        hw_peak = sms * 8192 * clocks["sm_mhz"] * 1e6 / 1e12  # 4096 bf16 MAC/clk/SM
+        roofline["hw_peak_at_sampled_clock"] = hw_peak
+        roofline["frac_hw_at_sampled_clock"] = roofline["achieved"] / hw_peak
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -464,13 +472,14 @@ def main():
     ap.add_argument("--cpu-seconds-per-step", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timer", action="store_true", help="(diagnostic) no per-launch events")
+    ap.add_argument("--workload", default=WORKLOAD, help="(diagnostic) another BASELINE.json shape")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3  # timing rule: at least 3 warm-up steps
 
     from molecular_dynamics_neural_operator_b200 import synthetic as syn
 
-    wl = syn.WORKLOADS[WORKLOAD]
+    wl = syn.WORKLOADS[args.workload]
     if args.impl == "reference":
         # edges/frame of the synthetic workload, from the same generator (SciPy on one frame)
         from oracle import gkn_oracle as orc
