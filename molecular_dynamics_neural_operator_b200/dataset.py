@@ -71,3 +71,86 @@ def collate(batch: Sequence[PairData]) -> PairData:
     edge_index = torch.cat([d.edge_index + o for d, o in zip(batch, offs)], dim=1)
     return PairData(x_aminoacid=cat("x_aminoacid"), x_position=cat("x_position"), y=cat("y"),
                     edge_attr=cat("edge_attr"), edge_index=edge_index)
+
+
+class ContactMapDataset(torch.utils.data.Dataset):
+    """Mirror of the reference's dataset (dataset.py:56-227): pre-computed ragged contact maps
+    (``contact_map``: per frame a flat ``[rows..., cols...]`` int array), positions
+    (``point_cloud`` ``[F, 3, R]``, transposed to ``[F, R, 3]``, dataset.py:159), ``rmsd`` and
+    ``amino_acids``.  Same constructor names and ``__getitem__`` contract; differences:
+
+    * ``.npz`` files are read natively; ``.h5`` files (or a directory of them) need ``h5py``,
+      which is optional here (ImportError with a clear message if absent);
+    * ``edge_attr = [pos[idx, i], pos[idx, j]]`` is built with one vectorised gather instead of
+      the per-edge Python loop (dataset.py:194-201) — identical values.
+    """
+
+    def __init__(self, path, edge_index_dset_name: str = "contact_map",
+                 edge_attr_dset_name: str = "point_cloud",
+                 node_feature_dset_name: Optional[str] = "amino_acids",
+                 node_feature: str = "amino_acid_onehot", constant_num_node_features: int = 20,
+                 window_size: int = 1, horizon: int = 1, node_feature_dset_path: str = None):
+        import glob
+
+        import numpy as np
+
+        self._constant_num_node_features = constant_num_node_features
+        self.window_size = window_size
+        self.horizon = horizon
+        path = str(path)
+
+        def read(fname):
+            if fname.endswith(".npz"):
+                with np.load(fname, allow_pickle=True) as z:
+                    return {k: z[k] for k in z.files}
+            try:
+                import h5py  # noqa: PLC0415
+            except ImportError as exc:  # pragma: no cover - h5py is absent in this image
+                raise ImportError("reading .h5 trajectories needs h5py; convert to .npz with the "
+                                  "same dataset names or install h5py") from exc
+            with h5py.File(fname, "r", libver="latest", swmr=False) as f:
+                return {k: np.array(f[k][...]) for k in f.keys()}
+
+        if path.endswith(".h5") or path.endswith(".npz"):
+            files = [path]
+        else:
+            files = sorted(glob.glob(path + "/*.h5") + glob.glob(path + "/*.npz"))
+        edge_indices, edge_attrs, rmsd, node_feats = [], [], [], None
+        for fname in files:
+            d = read(fname)
+            edge_indices.extend(list(d[edge_index_dset_name]))
+            edge_attrs.extend(list(d[edge_attr_dset_name]))
+            rmsd.extend(list(d["rmsd"]) if "rmsd" in d else [])
+            if node_feature_dset_name is not None and node_feature_dset_name in d:
+                node_feats = d[node_feature_dset_name]
+        if node_feature_dset_path is not None and node_feature_dset_name is not None:
+            node_feats = read(str(node_feature_dset_path))[node_feature_dset_name]
+        if node_feats is None:
+            raise ValueError(f"no '{node_feature_dset_name}' dataset found under {path}")
+        self.edge_indices = edge_indices
+        self.rmsd_values = rmsd
+        if len(self.edge_indices) - self.window_size - self.horizon + 1 < 0:
+            raise ValueError("The sum of window_size and horizon is longer than the input data")
+        # positions in order (N, num_nodes, 3)                                   dataset.py:159
+        self.edge_attrs = np.transpose(np.asarray(edge_attrs), [0, 2, 1])
+        self.x_aminoacid = torch.from_numpy(np.asarray(node_feats)).to(torch.long)
+
+    def __len__(self):
+        return len(self.edge_indices) - self.window_size - self.horizon + 1
+
+    def __getitem__(self, idx) -> PairData:
+        import numpy as np
+
+        pred_idx = idx + self.window_size + self.horizon - 1
+        x_position = self.edge_attrs[idx:idx + self.window_size]
+        edge_index = np.asarray(self.edge_indices[idx]).reshape(2, -1)
+        pos = self.edge_attrs[idx]  # FIRST window frame, as in the reference (dataset.py:197)
+        edge_attr = np.concatenate([pos[edge_index[0]], pos[edge_index[1]]], axis=1)
+        y = self.edge_attrs[pred_idx]
+        return PairData(
+            x_aminoacid=self.x_aminoacid,
+            x_position=torch.from_numpy(np.ascontiguousarray(x_position)).to(torch.float32),
+            y=torch.from_numpy(np.ascontiguousarray(y)).to(torch.float32),
+            edge_attr=torch.from_numpy(edge_attr.reshape(-1, 6)).to(torch.float32),
+            edge_index=torch.from_numpy(edge_index).to(torch.long),
+        )

@@ -152,3 +152,59 @@ def broadcast_parameters(model: torch.nn.Module, src: int = 0, process_group=Non
             dist.broadcast(p.data, src=src, group=process_group)
         for b in model.buffers():
             dist.broadcast(b.data, src=src, group=process_group)
+
+
+# --------------------------------------------------------------------------------------------
+# Epoch loops and checkpoints with the reference's layout (graph_kernel.py:445-493, :631-639)
+# --------------------------------------------------------------------------------------------
+def train_epoch(trainer: Trainer, batches, frames_per_batch: int):
+    """`train` of the reference (graph_kernel.py:445-474) over an iterable of batched PairData."""
+    trainer.model.train()
+    total, n = 0.0, 0
+    for batch in batches:
+        total += float(trainer.step(batch, frames_per_batch))
+        n += 1
+    return total / max(n, 1)
+
+
+@torch.no_grad()
+def validate(model: torch.nn.Module, batches, frames_per_batch: int):
+    """`validate` of the reference (graph_kernel.py:477-493): mean LpLoss and MSE."""
+    model.eval()
+    loss_fn = LpLoss(size_average=False)
+    mse_fn = torch.nn.MSELoss()
+    tot_loss, tot_mse, n = 0.0, 0.0, 0
+    for batch in batches:
+        out = model(batch)
+        tot_loss += float(loss_fn(out.view(frames_per_batch, -1), batch.y.view(frames_per_batch, -1)))
+        tot_mse += float(mse_fn(out, batch.y))
+        n += 1
+    return tot_loss / max(n, 1), tot_mse / max(n, 1)
+
+
+def save_checkpoint(path, epoch: int, trainer: Trainer, dataparallel_prefix: bool = True) -> None:
+    """Same dictionary the reference writes (graph_kernel.py:631-639).  The reference saves a
+    DataParallel-wrapped model, so its keys carry a ``module.`` prefix; keep that by default so
+    the reference's notebook can load the file."""
+    sd = trainer.model.state_dict()
+    if dataparallel_prefix:
+        sd = {"module." + k: v for k, v in sd.items()}
+    torch.save({"epoch": epoch, "model_state_dict": sd,
+                "optimizer_state_dict": trainer.optimizer.state_dict(),
+                "scheduler_state_dict": trainer.scheduler.state_dict()}, path)
+
+
+def load_checkpoint(path, model: torch.nn.Module, trainer: Optional[Trainer] = None,
+                    map_location=None) -> int:
+    """Load a checkpoint written by the reference or by save_checkpoint (with or without the
+    ``module.`` prefix).  Returns the stored epoch."""
+    ckpt = torch.load(path, map_location=map_location, weights_only=False)
+    sd = {(k[len("module."):] if k.startswith("module.") else k): v
+          for k, v in ckpt["model_state_dict"].items()}
+    model.load_state_dict(sd)
+    if trainer is not None:
+        if "optimizer_state_dict" in ckpt:
+            trainer.optimizer.load_state_dict(ckpt["optimizer_state_dict"])
+        if "scheduler_state_dict" in ckpt:
+            trainer.scheduler.load_state_dict(ckpt["scheduler_state_dict"])
+    return int(ckpt.get("epoch", 0))

@@ -78,3 +78,57 @@ def test_synthetic_workloads_have_the_survey_sizes():
     xs, ys = syn.window_batch(traj[:, :10], [0], 2)
     assert xs.shape == (1, 2, 10, 3) and ys.shape == (1, 10, 3)
     assert np.array_equal(ys[0], traj[2, :10])
+
+
+def _write_npz(path, frames=9, R=7, seed=0):
+    rng = np.random.default_rng(seed)
+    pc = rng.normal(size=(frames, 3, R)).astype(np.float32)  # [F, 3, R] as in the reference files
+    cms = np.empty(frames, dtype=object)
+    for f in range(frames):
+        e = int(rng.integers(3, 12))
+        cms[f] = np.concatenate([rng.integers(0, R, e), rng.integers(0, R, e)]).astype(np.int64)
+    np.savez(path, contact_map=cms, point_cloud=pc, rmsd=rng.random(frames).astype(np.float32),
+             amino_acids=rng.integers(0, 20, R).astype(np.int64))
+    return pc, cms
+
+
+def test_contact_map_dataset_follows_the_reference_getitem(tmp_path):
+    from molecular_dynamics_neural_operator_b200.dataset import ContactMapDataset
+
+    pc, cms = _write_npz(tmp_path / "traj.npz")
+    W, H = 3, 2
+    ds = ContactMapDataset(str(tmp_path / "traj.npz"), window_size=W, horizon=H)
+    assert len(ds) == len(cms) - W - H + 1
+    pos = np.transpose(pc, [0, 2, 1])
+    for idx in (0, 2, len(ds) - 1):
+        d = ds[idx]
+        ei = cms[idx].reshape(2, -1)
+        # literal restatement of dataset.py:180-204 (per-edge python loop)
+        ea = np.array([np.concatenate((pos[idx, i, :], pos[idx, j, :])).flatten()
+                       for i, j in zip(ei[0], ei[1])])
+        assert torch.equal(d.edge_index, torch.from_numpy(ei))
+        assert np.array_equal(d.edge_attr.numpy(), ea.astype(np.float32))
+        assert np.array_equal(d.x_position.numpy(), pos[idx:idx + W])
+        assert np.array_equal(d.y.numpy(), pos[idx + W + H - 1])
+        assert d.x_aminoacid.dtype == torch.long and d.num_nodes == 7
+    with pytest.raises(ValueError):
+        ContactMapDataset(str(tmp_path / "traj.npz"), window_size=20, horizon=1)
+    # a directory of files is concatenated in sorted order (dataset.py:133-143)
+    _write_npz(tmp_path / "traj2.npz", seed=1)
+    assert len(ContactMapDataset(str(tmp_path), window_size=1, horizon=1)) == 18 - 1
+
+
+def test_checkpoint_roundtrip_uses_the_reference_layout(tmp_path):
+    from molecular_dynamics_neural_operator_b200.train import Trainer, load_checkpoint, save_checkpoint
+
+    model = KernelNN(16, 64, 1, 6, in_width=7, out_width=3, window_size=2, num_residues=5)
+    trainer = Trainer(model)
+    save_checkpoint(tmp_path / "best.pt", 7, trainer)
+    ckpt = torch.load(tmp_path / "best.pt", weights_only=False)
+    assert set(ckpt) == {"epoch", "model_state_dict", "optimizer_state_dict", "scheduler_state_dict"}
+    assert all(k.startswith("module.") for k in ckpt["model_state_dict"])  # graph_kernel.py:528, :635
+    assert "module.conv2.net.layers.4.weight" in ckpt["model_state_dict"]
+    model2 = KernelNN(16, 64, 1, 6, in_width=7, out_width=3, window_size=2, num_residues=5)
+    assert load_checkpoint(tmp_path / "best.pt", model2, Trainer(model2)) == 7
+    for a, b in zip(model.parameters(), model2.parameters()):
+        assert torch.equal(a, b)

@@ -44,3 +44,37 @@ def test_cuda_extension_is_loaded_in_tree():
     _lib.load()
     maps = open("/proc/self/maps").read()
     assert "libgkn_b200.so" in maps
+
+
+def test_dataset_fed_batch_with_arbitrary_contact_maps_matches_oracle(tmp_path):
+    """Pre-computed (non-symmetric, unsorted, duplicate-carrying) contact maps through the
+    reference's feeder path: ContactMapDataset -> collate -> KernelNN (general CSR prepare)."""
+    from types import SimpleNamespace
+
+    import numpy as np
+
+    from molecular_dynamics_neural_operator_b200.dataset import ContactMapDataset, collate
+    from molecular_dynamics_neural_operator_b200.graph_kernel import KernelNN
+    from oracle import gkn_oracle as orc
+
+    rng = np.random.default_rng(0)
+    F, R, W = 8, 11, 3
+    pc = rng.normal(size=(F, 3, R)).astype(np.float32) * 4
+    cms = np.empty(F, dtype=object)
+    for f in range(F):
+        e = int(rng.integers(20, 40))
+        cms[f] = np.concatenate([rng.integers(0, R, e), rng.integers(0, R - 2, e)]).astype(np.int64)
+    np.savez(tmp_path / "t.npz", contact_map=cms, point_cloud=pc, rmsd=np.zeros(F, np.float32),
+             amino_acids=rng.integers(0, 20, R).astype(np.int64))
+    ds = ContactMapDataset(str(tmp_path / "t.npz"), window_size=W, horizon=1)
+    batch = collate([ds[0], ds[1], ds[2]])
+    torch.manual_seed(0)
+    model = KernelNN(32, 64, 2, 6, in_width=7, out_width=3, window_size=W, num_residues=R,
+                     precision="fp32").cuda()
+    out = model(batch.to("cuda"))
+    sd = {k: v.detach().cpu().double() for k, v in model.state_dict().items()}
+    data = SimpleNamespace(x_aminoacid=batch.x_aminoacid, x_position=batch.x_position.double(),
+                           edge_index=batch.edge_index, edge_attr=batch.edge_attr.double())
+    ref = orc.kernelnn_forward(sd, data, 2, W, R)
+    err = float((out.detach().cpu().double() - ref).abs().max() / ref.abs().max())
+    assert err <= 1e-5  # nodes R-2, R-1 never receive messages: mean over zero edges -> 0
