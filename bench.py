@@ -32,8 +32,11 @@ import threading
 import time
 from pathlib import Path
 
-import numpy as np
-import torch
+# per-step edge counts vary: grow allocator segments in place instead of re-cudaMalloc-ing
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))

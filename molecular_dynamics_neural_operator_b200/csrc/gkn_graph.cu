@@ -290,17 +290,30 @@ rg_frame_setup_kernel(const float* __restrict__ pos, int64_t N, double threshold
         m.minz = smn[2][0];
         const double ext[3] = {double(smx[0][0]) - m.minx, double(smx[1][0]) - m.miny,
                                double(smx[2][0]) - m.minz};
-        // cell edge strictly above the cutoff so that |d| < threshold implies adjacent cells
+        // cell edge strictly above the cutoff so that |d| < threshold implies adjacent cells;
+        // grown until the grid fits the C reserved cells.  All in double so that huge or
+        // non-finite coordinates (e.g. a diverged rollout) cannot overflow the cell counts:
+        // non-finite extents fall back to a single cell (the predicate then rejects NaN/Inf).
         double cell = fmax(threshold, 1e-30) * 1.0001;
-        int64_t nx, ny, nz;
-        for (;;) {
-            nx = int64_t(floor(ext[0] / cell)) + 1;
-            ny = int64_t(floor(ext[1] / cell)) + 1;
-            nz = int64_t(floor(ext[2] / cell)) + 1;
-            if (nx * ny * nz <= C) break;
-            cell *= 1.26;
+        int64_t nx = 1, ny = 1, nz = 1;
+        const bool finite = isfinite(ext[0]) && isfinite(ext[1]) && isfinite(ext[2]) &&
+                            isfinite(cell) && N > 0;
+        if (finite) {
+            for (;;) {
+                const double dx = floor(ext[0] / cell) + 1.0, dy = floor(ext[1] / cell) + 1.0,
+                             dz = floor(ext[2] / cell) + 1.0;
+                if (dx * dy * dz <= double(C)) {
+                    nx = int64_t(dx);
+                    ny = int64_t(dy);
+                    nz = int64_t(dz);
+                    break;
+                }
+                cell *= 1.26;
+            }
+        } else {
+            cell = 1.0;
+            m.minx = m.miny = m.minz = 0.0;
         }
-        if (N == 0) nx = ny = nz = 1;
         m.inv_cell = 1.0 / cell;
         m.nx = int32_t(nx);
         m.ny = int32_t(ny);

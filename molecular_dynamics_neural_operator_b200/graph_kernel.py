@@ -261,9 +261,13 @@ def construct_pairdata(x_position, x_aminoacid, threshold: float = 8.0,
     if device is None:
         device = x_position.device if x_position.is_cuda else torch.device("cuda")
     x_position = x_position.to(device)
-    edge_index, edge_attr = ops.radius_graph(x_position[-1:], threshold)
-    return PairData(x_aminoacid=x_aminoacid.to(device) if x_aminoacid is not None else None,
+    edge_index, edge_attr, row_ptr = ops.radius_graph(x_position[-1:], threshold,
+                                                      return_row_ptr=True)
+    data = PairData(x_aminoacid=x_aminoacid.to(device) if x_aminoacid is not None else None,
                     x_position=x_position, edge_attr=edge_attr, edge_index=edge_index)
+    # the radius graph is symmetric and (row, col)-sorted: its CSR plan needs no sorting
+    data._gkn_plan = ops.plan_from_csr(edge_index, row_ptr, x_position.size(1), validate=False)
+    return data
 
 
 def recursive_propagation(model, dataset, device, num_steps: int, starting_points: list,

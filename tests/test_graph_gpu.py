@@ -122,3 +122,29 @@ def test_plan_from_csr_equals_general_prepare_on_radius_graphs():
     bad = torch.tensor([[0, 1, 1], [1, 0, 2]], dtype=torch.long).cuda()  # 1->2 has no reverse
     with pytest.raises(ValueError, match="symmetric"):
         ops.plan_from_csr(bad, torch.tensor([0, 1, 3, 3], dtype=torch.long).cuda(), 3)
+
+
+def test_radius_graph_survives_nan_inf_and_huge_coordinates():
+    """A diverged rollout can feed garbage positions: the build must not crash and must still
+    agree with SciPy (NaN / Inf distances fail the strict comparison, so those atoms are isolated
+    - not even a self loop)."""
+    import warnings
+
+    from molecular_dynamics_neural_operator_b200 import ops
+    from oracle import gkn_oracle as orc
+
+    rng = np.random.default_rng(9)
+    pos = (rng.random((2, 60, 3)) * 10).astype(np.float32)
+    pos[0, 3] = np.nan
+    pos[0, 7, 1] = np.inf
+    pos[1, 5] = [1e30, -1e30, 1e30]
+    pos[1, 6] = [3e38, 0, 0]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ei_ref, ea_ref = orc.radius_graph_batched(pos, 4.2)
+    ei, ea = ops.radius_graph(torch.from_numpy(pos).cuda(), 4.2)
+    assert np.array_equal(ei.cpu().numpy(), ei_ref)
+    assert np.array_equal(ea.cpu().numpy(), ea_ref, equal_nan=True)
+    allnan = np.full((1, 10, 3), np.nan, dtype=np.float32)
+    ei, ea = ops.radius_graph(torch.from_numpy(allnan).cuda(), 4.2)
+    assert ei.shape == (2, 0)
