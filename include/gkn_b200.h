@@ -142,18 +142,18 @@ int gkn_bias_act_cast_bf16(const float* in, const float* bias, void* out_bf16, i
 /* ---- edge-MLP layer .0 and the backward of "bias + ReLU" ----------------------------------
  * gkn_edge_layer0: out[e,k] = relu(sum_j ea[e,j]*w1[k,j] + b1[k]), bf16 or fp32 (DenseNet
  * layers.0 + ReLU, graph_kernel.py:239-242; kin must be 6 = edge_features, :328).
- * gkn_mask_cast_colsum: out[r,c] = dz[r,c] * (act[r,c] > 0), cast to bf16 or kept fp32 (may alias
- * dz when fp32); colsum[0,c] (+)= sum_r out[r,c] (bias gradient) and, when side != NULL
+ * gkn_mask_cast_colsum: out[r,c] = dz[r,c] * (act[r,c] > 0); dz fp32 or bf16 (bf16 dz needs bf16
+ * act/out), out cast to bf16 or kept fp32 (may alias dz when dtypes match); colsum[0,c] (+)= sum_r out[r,c] (bias gradient) and, when side != NULL
  * (nside = 6), colsum[1+j,c] (+)= sum_r out[r,c]*side[r,j] (layer-.0 weight gradient, transposed).
  * colsum is [(1+nside), cols]; deterministic two-pass reduction, no atomics.  act is the layer's
  * saved post-ReLU activation (bf16 or fp32). */
 int gkn_edge_layer0(const float* ea, const float* w1, const float* b1, void* out,
                     int32_t out_is_bf16, int64_t E, int32_t K, int32_t kin, void* stream);
 int64_t gkn_mask_cast_colsum_workspace_bytes(int64_t cols, int32_t nside);
-int gkn_mask_cast_colsum(const float* dz, const void* act, int32_t act_is_bf16, void* out,
-                         int32_t out_is_bf16, const float* side, int32_t nside, float* colsum,
-                         int32_t accumulate, int64_t rows, int64_t cols, void* workspace,
-                         int64_t workspace_bytes, void* stream);
+int gkn_mask_cast_colsum(const void* dz, int32_t dz_is_bf16, const void* act, int32_t act_is_bf16,
+                         void* out, int32_t out_is_bf16, const float* side, int32_t nside,
+                         float* colsum, int32_t accumulate, int64_t rows, int64_t cols,
+                         void* workspace, int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

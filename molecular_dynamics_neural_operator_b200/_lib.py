@@ -52,7 +52,7 @@ SIGNATURES = {
     "gkn_mask_cast_colsum_workspace_bytes": (c_int64, [c_int64, c_int32]),
     "gkn_mask_cast_colsum": (
         c_int,
-        [P, P, c_int32, P, c_int32, P, c_int32, P, c_int32, c_int64, c_int64, P, c_int64, P],
+        [P, c_int32, P, c_int32, P, c_int32, P, c_int32, P, c_int32, c_int64, c_int64, P, c_int64, P],
     ),
 }
 

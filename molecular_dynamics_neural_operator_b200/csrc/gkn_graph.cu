@@ -647,6 +647,53 @@ rg_cell_kernel(const float* __restrict__ pos, int64_t F, int64_t N, int64_t C, d
     }
 }
 
+// Small frames (N <= kRgCap atoms, e.g. the 28-residue and 504-atom BBA graphs): no cell list at
+// all.  A CTA stages the whole frame's coordinates in shared memory in ATOM-INDEX order (coalesced
+// loads straight from `pos`), so every row's hits come out in ascending column order for free;
+// each warp owns one atom at a time.  blockIdx.y = frame, blockIdx.x strides over 8-atom groups.
+template <bool FILL>
+__global__ void __launch_bounds__(kRgThreads)
+rg_small_kernel(const float* __restrict__ pos, int64_t N, double d2_max, int32_t* __restrict__ deg,
+                const int64_t* __restrict__ row_ptr, int64_t E, int64_t* __restrict__ edge_index,
+                float* __restrict__ edge_attr) {
+    __shared__ float s_xyz[kRgCap * 3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t f = blockIdx.y;
+    const int n = int(N);
+    const float* p = pos + f * N * 3;
+    for (int t = threadIdx.x; t < n * 3; t += kRgThreads) s_xyz[t] = p[t];
+    __syncthreads();
+    const int64_t node0 = f * N;
+    for (int i = blockIdx.x * (kRgThreads / 32) + warp; i < n; i += gridDim.x * (kRgThreads / 32)) {
+        const float px = s_xyz[i * 3], py = s_xyz[i * 3 + 1], pz = s_xyz[i * 3 + 2];
+        const double xi = px, yi = py, zi = pz;
+        const int64_t g = node0 + i;
+        const int64_t beg = FILL ? row_ptr[g] : 0;
+        int count = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int j = base + lane;
+            bool hit = false;
+            float4 pj = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < n) {
+                pj = make_float4(s_xyz[j * 3], s_xyz[j * 3 + 1], s_xyz[j * 3 + 2], 0.f);
+                hit = within(xi, yi, zi, pj, d2_max);
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, hit);
+            if (FILL && hit) {
+                const int64_t slot = beg + count + __popc(mask & ((1u << lane) - 1u));
+                edge_index[slot] = g;
+                edge_index[E + slot] = node0 + j;
+                float2* ea = reinterpret_cast<float2*>(edge_attr + slot * 6);
+                ea[0] = make_float2(px, py);
+                ea[1] = make_float2(pz, pj.x);
+                ea[2] = make_float2(pj.y, pj.z);
+            }
+            count += __popc(mask);
+        }
+        if (!FILL && lane == 0) deg[g] = count;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // multi-block exclusive scan (int32 -> int64) for the row pointers: block sums, scan of the sums
 // (single block), then per-block scan + offset
@@ -815,30 +862,41 @@ extern "C" int gkn_radius_graph_count(const float* pos, int64_t F, int64_t N, do
         if (err != cudaSuccess) return set_cuda_error("cudaMemsetAsync(row_ptr)", err);
         return 0;
     }
-    cudaError_t err = cudaMemsetAsync(w.cell_count, 0, size_t(F) * (w.C + 1) * 4, st);
-    if (err != cudaSuccess) return set_cuda_error("cudaMemsetAsync(cell_count)", err);
-    rg_frame_setup_kernel<<<unsigned(F), 1024, 0, st>>>(pos, N, threshold, w.C, w.meta);
-    GKN_CHECK_LAUNCH("rg_frame_setup");
-    const int ag = grid_for(total, 256, 8);
-    rg_assign_kernel<<<ag, 256, 0, st>>>(pos, F, N, w.C, w.meta, w.atom_cell, w.cell_count);
-    GKN_CHECK_LAUNCH("rg_assign");
-    exclusive_scan_kernel<int32_t, int32_t>
-        <<<unsigned(F), kScanThreads, 0, st>>>(w.cell_count, w.cell_start, w.C, w.C + 1, w.C + 1);
-    GKN_CHECK_LAUNCH("rg_scan_cells");
-    err = cudaMemsetAsync(w.cell_count, 0, size_t(F) * (w.C + 1) * 4, st);
-    if (err != cudaSuccess) return set_cuda_error("cudaMemsetAsync(cell cursor)", err);
-    rg_place_kernel<<<ag, 256, 0, st>>>(pos, F, N, w.C, w.atom_cell, w.cell_start, w.cell_count,
-                                        w.sorted_pos);
-    GKN_CHECK_LAUNCH("rg_place");
     int sms = 148;
     device_sm_count(&sms);
-    int64_t cgx = (int64_t(sms) * 16 + F - 1) / F;  // CTAs per frame striding over its cells
-    if (cgx > w.C) cgx = w.C;
-    const dim3 cg(unsigned(cgx < 1 ? 1 : cgx), unsigned(F));
-    rg_cell_kernel<false><<<cg, kRgThreads, 0, st>>>(pos, F, N, w.C, exact_d2_bound(threshold), w.meta,
-                                                         w.cell_start, w.sorted_pos, deg, nullptr,
-                                                         0, nullptr, nullptr);
-    GKN_CHECK_LAUNCH("rg_count");
+    if (N <= kRgCap) {
+        // small frames: all-pairs from shared memory, no cell list
+        int64_t gx = (N + 7) / 8;
+        const int64_t want = (int64_t(sms) * 8 + F - 1) / F;
+        if (gx > want) gx = want;
+        const dim3 sg(unsigned(gx < 1 ? 1 : gx), unsigned(F));
+        rg_small_kernel<false><<<sg, kRgThreads, 0, st>>>(pos, N, exact_d2_bound(threshold), deg,
+                                                         nullptr, 0, nullptr, nullptr);
+        GKN_CHECK_LAUNCH("rg_small_count");
+    } else {
+        cudaError_t err = cudaMemsetAsync(w.cell_count, 0, size_t(F) * (w.C + 1) * 4, st);
+        if (err != cudaSuccess) return set_cuda_error("cudaMemsetAsync(cell_count)", err);
+        rg_frame_setup_kernel<<<unsigned(F), 1024, 0, st>>>(pos, N, threshold, w.C, w.meta);
+        GKN_CHECK_LAUNCH("rg_frame_setup");
+        const int ag = grid_for(total, 256, 8);
+        rg_assign_kernel<<<ag, 256, 0, st>>>(pos, F, N, w.C, w.meta, w.atom_cell, w.cell_count);
+        GKN_CHECK_LAUNCH("rg_assign");
+        exclusive_scan_kernel<int32_t, int32_t><<<unsigned(F), kScanThreads, 0, st>>>(
+            w.cell_count, w.cell_start, w.C, w.C + 1, w.C + 1);
+        GKN_CHECK_LAUNCH("rg_scan_cells");
+        err = cudaMemsetAsync(w.cell_count, 0, size_t(F) * (w.C + 1) * 4, st);
+        if (err != cudaSuccess) return set_cuda_error("cudaMemsetAsync(cell cursor)", err);
+        rg_place_kernel<<<ag, 256, 0, st>>>(pos, F, N, w.C, w.atom_cell, w.cell_start,
+                                            w.cell_count, w.sorted_pos);
+        GKN_CHECK_LAUNCH("rg_place");
+        int64_t cgx = (int64_t(sms) * 16 + F - 1) / F;  // CTAs per frame striding over its cells
+        if (cgx > w.C) cgx = w.C;
+        const dim3 cg(unsigned(cgx < 1 ? 1 : cgx), unsigned(F));
+        rg_cell_kernel<false><<<cg, kRgThreads, 0, st>>>(pos, F, N, w.C, exact_d2_bound(threshold),
+                                                        w.meta, w.cell_start, w.sorted_pos, deg,
+                                                        nullptr, 0, nullptr, nullptr);
+        GKN_CHECK_LAUNCH("rg_count");
+    }
     scan_block_sums_kernel<<<unsigned(w.nblk), kScanThreads, 0, st>>>(deg, total, w.block_sums);
     GKN_CHECK_LAUNCH("rg_scan_sums");
     exclusive_scan_kernel<int64_t, int64_t>
@@ -862,12 +920,21 @@ extern "C" int gkn_radius_graph_fill(const float* pos, int64_t F, int64_t N, dou
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int sms = 148;
     device_sm_count(&sms);
-    int64_t cgx = (int64_t(sms) * 16 + F - 1) / F;
-    if (cgx > w.C) cgx = w.C;
-    const dim3 cg(unsigned(cgx < 1 ? 1 : cgx), unsigned(F));
-    rg_cell_kernel<true><<<cg, kRgThreads, 0, st>>>(pos, F, N, w.C, exact_d2_bound(threshold), w.meta,
-                                                        w.cell_start, w.sorted_pos, nullptr,
+    if (N <= kRgCap) {
+        int64_t gx = (N + 7) / 8;
+        const int64_t want = (int64_t(sms) * 8 + F - 1) / F;
+        if (gx > want) gx = want;
+        const dim3 sg(unsigned(gx < 1 ? 1 : gx), unsigned(F));
+        rg_small_kernel<true><<<sg, kRgThreads, 0, st>>>(pos, N, exact_d2_bound(threshold), nullptr,
                                                         row_ptr, E, edge_index, edge_attr);
+    } else {
+        int64_t cgx = (int64_t(sms) * 16 + F - 1) / F;
+        if (cgx > w.C) cgx = w.C;
+        const dim3 cg(unsigned(cgx < 1 ? 1 : cgx), unsigned(F));
+        rg_cell_kernel<true><<<cg, kRgThreads, 0, st>>>(pos, F, N, w.C, exact_d2_bound(threshold),
+                                                       w.meta, w.cell_start, w.sorted_pos, nullptr,
+                                                       row_ptr, E, edge_index, edge_attr);
+    }
     GKN_CHECK_LAUNCH("rg_fill");
     return 0;
 }

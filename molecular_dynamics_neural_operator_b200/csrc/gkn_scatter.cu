@@ -398,9 +398,9 @@ __device__ __forceinline__ void load_act4(const ACT* p, float (&a)[4]) {
 // `out` may alias `dz` (fp32 in place): every element is read and written by the same thread.
 // NSIDE > 0 additionally accumulates partial[b, 1+j, c] = sum_r out[r,c] * side[r,j] (j < NSIDE):
 // with side = edge_attr this is the layer-0 weight gradient, produced in the same pass.
-template <typename ACT, typename OUT, int NSIDE>
+template <typename DZ, typename ACT, typename OUT, int NSIDE>
 __global__ void __launch_bounds__(256)
-mask_cast_colsum_kernel(const float* dz, const ACT* __restrict__ act, OUT* out,
+mask_cast_colsum_kernel(const DZ* dz, const ACT* __restrict__ act, OUT* out,
                         const float* __restrict__ side, float* __restrict__ partial, int64_t rows,
                         int cols) {
     constexpr int U = 4;  // rows in flight per thread
@@ -424,13 +424,13 @@ mask_cast_colsum_kernel(const float* dz, const ACT* __restrict__ act, OUT* out,
 #pragma unroll
         for (int j = 0; j <= NSIDE; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int64_t rb = r0; rb < r1; rb += U) {
-            float4 v[U];
+            float v4[U][4];
             float a[U][4];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int64_t r = rb + u;
                 if (r < r1) {
-                    v[u] = *reinterpret_cast<const float4*>(dz + r * cols + c);
+                    load_act4(dz + r * cols + c, v4[u]);
                     load_act4(act + r * cols + c, a[u]);
                 }
             }
@@ -438,7 +438,7 @@ mask_cast_colsum_kernel(const float* dz, const ACT* __restrict__ act, OUT* out,
             for (int u = 0; u < U; ++u) {
                 const int64_t r = rb + u;
                 if (r >= r1) break;
-                float4 w = v[u];
+                float4 w = make_float4(v4[u][0], v4[u][1], v4[u][2], v4[u][3]);
                 w.x = a[u][0] > 0.f ? w.x : 0.f;
                 w.y = a[u][1] > 0.f ? w.y : 0.f;
                 w.z = a[u][2] > 0.f ? w.z : 0.f;
@@ -671,23 +671,23 @@ extern "C" int64_t gkn_mask_cast_colsum_workspace_bytes(int64_t cols, int32_t ns
 
 namespace gkn {
 namespace {
-template <typename ACT, typename OUT>
-void launch_mask(int nside, int grid, cudaStream_t st, const float* dz, const ACT* act, OUT* out,
+template <typename DZ, typename ACT, typename OUT>
+void launch_mask(int nside, int grid, cudaStream_t st, const DZ* dz, const ACT* act, OUT* out,
                  const float* side, float* partial, int64_t rows, int cols) {
     if (nside == 0) {
-        mask_cast_colsum_kernel<ACT, OUT, 0><<<grid, 256, 0, st>>>(dz, act, out, side, partial, rows, cols);
+        mask_cast_colsum_kernel<DZ, ACT, OUT, 0><<<grid, 256, 0, st>>>(dz, act, out, side, partial, rows, cols);
     } else {
-        mask_cast_colsum_kernel<ACT, OUT, 6><<<grid, 256, 0, st>>>(dz, act, out, side, partial, rows, cols);
+        mask_cast_colsum_kernel<DZ, ACT, OUT, 6><<<grid, 256, 0, st>>>(dz, act, out, side, partial, rows, cols);
     }
 }
 }  // namespace
 }  // namespace gkn
 
-extern "C" int gkn_mask_cast_colsum(const float* dz, const void* act, int32_t act_is_bf16,
-                                    void* out, int32_t out_is_bf16, const float* side,
-                                    int32_t nside, float* colsum, int32_t accumulate, int64_t rows,
-                                    int64_t cols, void* workspace, int64_t workspace_bytes,
-                                    void* stream) {
+extern "C" int gkn_mask_cast_colsum(const void* dz, int32_t dz_is_bf16, const void* act,
+                                    int32_t act_is_bf16, void* out, int32_t out_is_bf16,
+                                    const float* side, int32_t nside, float* colsum,
+                                    int32_t accumulate, int64_t rows, int64_t cols,
+                                    void* workspace, int64_t workspace_bytes, void* stream) {
     using namespace gkn;
     if (rows == 0 || cols == 0) return 0;
     if (cols % 4 != 0 || cols > (1 << 20)) {
@@ -697,6 +697,9 @@ extern "C" int gkn_mask_cast_colsum(const float* dz, const void* act, int32_t ac
         return set_error("gkn_mask_cast_colsum: side width must be 0 or 6 (edge_features)");
     }
     if (nside != 0 && side == nullptr) return set_error("gkn_mask_cast_colsum: side is NULL");
+    if (dz_is_bf16 && !(act_is_bf16 && out_is_bf16)) {
+        return set_error("gkn_mask_cast_colsum: bf16 dz requires bf16 act and bf16 out");
+    }
     int sms = 148;
     device_sm_count(&sms);
     int64_t nblocks = int64_t(sms) * 4;
@@ -709,14 +712,17 @@ extern "C" int gkn_mask_cast_colsum(const float* dz, const void* act, int32_t ac
     const int grid = int(nblocks);
     const int c = int(cols);
     using bf = __nv_bfloat16;
-    if (act_is_bf16 && out_is_bf16) {
-        launch_mask<bf, bf>(nside, grid, st, dz, static_cast<const bf*>(act), static_cast<bf*>(out), side, partial, rows, c);
+    const float* dzf = static_cast<const float*>(dz);
+    if (dz_is_bf16) {
+        launch_mask<bf, bf, bf>(nside, grid, st, static_cast<const bf*>(dz), static_cast<const bf*>(act), static_cast<bf*>(out), side, partial, rows, c);
+    } else if (act_is_bf16 && out_is_bf16) {
+        launch_mask<float, bf, bf>(nside, grid, st, dzf, static_cast<const bf*>(act), static_cast<bf*>(out), side, partial, rows, c);
     } else if (act_is_bf16) {
-        launch_mask<bf, float>(nside, grid, st, dz, static_cast<const bf*>(act), static_cast<float*>(out), side, partial, rows, c);
+        launch_mask<float, bf, float>(nside, grid, st, dzf, static_cast<const bf*>(act), static_cast<float*>(out), side, partial, rows, c);
     } else if (out_is_bf16) {
-        launch_mask<float, bf>(nside, grid, st, dz, static_cast<const float*>(act), static_cast<bf*>(out), side, partial, rows, c);
+        launch_mask<float, float, bf>(nside, grid, st, dzf, static_cast<const float*>(act), static_cast<bf*>(out), side, partial, rows, c);
     } else {
-        launch_mask<float, float>(nside, grid, st, dz, static_cast<const float*>(act), static_cast<float*>(out), side, partial, rows, c);
+        launch_mask<float, float, float>(nside, grid, st, dzf, static_cast<const float*>(act), static_cast<float*>(out), side, partial, rows, c);
     }
     GKN_CHECK_LAUNCH("mask_cast_colsum launch");
     const dim3 fgrid((c + 31) / 32, 1 + nside);

@@ -92,9 +92,12 @@ def _edge_grads(xs, gns, plan: GraphPlan, ea, h1, h, w1, w2, w3q, need_ea: bool,
         hc, h1c = h[e0:e1], h1[e0:e1]
         S = ops.edge_outer_sum(xs, gns, plan, e0, e1, s_dtype)
         dw3 = _addmm32(dw3, S.t(), hc)
-        dz2 = _mm32(S, w3q)  # dh_e for this chunk, fp32
+        # dh_e for this chunk.  bf16 mode: the GEMM rounds its fp32 accumulators to bf16 itself
+        # (rounding before or after the 0/1 ReLU mask is the same), halving the traffic of the
+        # mask pass below.
+        dz2 = torch.mm(S, w3q)
         del S
-        # backward of "+ b2, ReLU": mask, bias gradient and bf16 hand-off in one pass
+        # backward of "+ b2, ReLU": mask, bias gradient and operand hand-off in one pass
         dz2q = ops.mask_cast_colsum(dz2, hc, db2, s_dtype)
         dw2 = _addmm32(dw2, dz2q.t(), h1c)
         dz1 = _mm32(dz2q, w2q)
@@ -170,16 +173,16 @@ class _GKNStack(torch.autograd.Function):
         for c in (0, 1):
             idx = [a for a in range(A) if schedule[a] == c]
             if idx:
-                Gc, Xc = G[idx].reshape(-1, W), X[idx].reshape(-1, W)
-                droot[c] = torch.mm(Xc.t(), Gc)
-                dbias[c] = Gc.sum(0)
+                # batched over applications (a [w, A*N] @ [A*N, w] product would run on one CTA)
+                droot[c] = torch.bmm(X[idx].transpose(1, 2), G[idx]).sum(0)
+                dbias[c] = G[idx].sum((0, 1))
             else:
                 droot[c] = torch.zeros_like(roots[c])
                 dbias[c] = torch.zeros(W, dtype=torch.float32, device=gout.device)
         dw3 = db3 = dw2 = db2 = dw1 = db1 = dea = None
         if need_edge:
             # db3[i*W+o] = sum_e x_j[e,i] gn[dst e,o] = sum_n (mean-scaled agg)[n,i] g[n,o]
-            db3 = torch.mm(torch.stack(list(aggs)).reshape(-1, W).t(), G.reshape(-1, W)).reshape(-1)
+            db3 = torch.bmm(torch.stack(list(aggs)).transpose(1, 2), G).sum(0).reshape(-1)
             dw3, dw2, db2, dw1, db1, dea = _edge_grads(
                 X, torch.stack(gns), plan, ea, h1, h, w1, w2, w3q, need_ea, precision)
         return (gx if need_x0 else None, dea, dw1, db1, dw2, db2, dw3, db3, droot[0], dbias[0],

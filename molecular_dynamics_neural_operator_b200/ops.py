@@ -330,15 +330,15 @@ def mask_cast_colsum(dz, act, colsum, out_dtype, side=None, accumulate: bool = T
         ws = torch.empty(int(lib.gkn_mask_cast_colsum_workspace_bytes(cols, nside)),
                          dtype=torch.uint8, device=dz.device)
         _COLSUM_WS[key] = ws
-    out = dz if out_dtype == torch.float32 else torch.empty((rows, cols), dtype=out_dtype,
-                                                            device=dz.device)
+    out = dz if out_dtype == dz.dtype else torch.empty((rows, cols), dtype=out_dtype,
+                                                      device=dz.device)
     with torch.cuda.device(dz.device):
         _lib.check(
             lib.gkn_mask_cast_colsum(
-                _p(dz, torch.float32, "dz"), _p(act, None, "act"), int(act.dtype == torch.bfloat16),
-                _p(out), int(out_dtype == torch.bfloat16), _p(side, torch.float32, "side"), nside,
-                _p(colsum, torch.float32, "colsum"), int(bool(accumulate)), rows, cols, _p(ws),
-                ws.numel(), _stream(),
+                _p(dz, None, "dz"), int(dz.dtype == torch.bfloat16), _p(act, None, "act"),
+                int(act.dtype == torch.bfloat16), _p(out), int(out_dtype == torch.bfloat16),
+                _p(side, torch.float32, "side"), nside, _p(colsum, torch.float32, "colsum"),
+                int(bool(accumulate)), rows, cols, _p(ws), ws.numel(), _stream(),
             ),
             "gkn_mask_cast_colsum",
         )

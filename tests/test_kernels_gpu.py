@@ -200,3 +200,18 @@ def test_edge_layer0(dt):
         ref = torch.relu(ea.double() @ w1.double().t() + b1.double())
         tol = 1e-5 if dt == torch.float32 else 2.0 ** -8
         assert ((out.cpu().double() - ref).abs() / (ref.abs() + 1)).max().item() <= tol
+
+
+def test_mask_cast_colsum_bf16_input_in_place():
+    from molecular_dynamics_neural_operator_b200 import ops
+
+    g = torch.Generator().manual_seed(8)
+    dz = torch.randn(4000, 512, generator=g).bfloat16()
+    act = torch.relu(torch.randn(4000, 512, generator=g)).bfloat16()
+    cs = torch.zeros(512, device=DEV)
+    d = dz.to(DEV)
+    out = ops.mask_cast_colsum(d, act.to(DEV), cs, torch.bfloat16)
+    ref = dz.float() * (act.float() > 0)
+    assert out.data_ptr() == d.data_ptr()  # same dtype: masked in place
+    assert torch.equal(out.cpu().float(), ref)
+    assert torch.allclose(cs.cpu(), ref.sum(0), rtol=1e-4, atol=1e-2)
