@@ -371,12 +371,24 @@ __global__ void rg_place_kernel(const float* __restrict__ pos, int64_t F, int64_
 // rounded square root is still below the threshold; exact_d2_bound() finds it on the host by
 // stepping ulps around threshold^2.  d2 itself is formed with the same operations in the same
 // order and no FMA contraction.
-__device__ __forceinline__ bool within(double xi, double yi, double zi, float4 pj, double d2_max) {
+struct D2Bound {
+    double d2_max;  // exact: hit  <=>  d2 (float64, reference operation order) <= d2_max
+    float lo, hi;   // fp32 screen: d2f < lo => certainly a hit, d2f > hi => certainly a miss
+};
+
+__device__ __forceinline__ bool within(double xi, double yi, double zi, float4 pj, const D2Bound& b) {
+    // fp32 screen first: the float32 squared distance is within a few ulps (< 2^-21 relative) of
+    // the float64 one, so only pairs inside a 4e-6-wide band around the cutoff need float64.
+    // NaNs fail both comparisons and fall through to the exact test, which rejects them.
+    const float fx = pj.x - float(xi), fy = pj.y - float(yi), fz = pj.z - float(zi);
+    const float d2f = fmaf(fz, fz, fmaf(fy, fy, fx * fx));
+    if (d2f < b.lo) return true;
+    if (d2f > b.hi) return false;
     const double dx = __dsub_rn(double(pj.x), xi);
     const double dy = __dsub_rn(double(pj.y), yi);
     const double dz = __dsub_rn(double(pj.z), zi);
     const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-    return d2 <= d2_max;
+    return d2 <= b.d2_max;
 }
 
 // One warp handles one atom straight from global memory (sparse cells, and the general path for
@@ -392,7 +404,7 @@ template <bool FILL>
 __device__ __forceinline__ void rg_atom_warp(float4 pi, int64_t node0, int cx, int cy, int cz,
                                              const FrameMeta& m, int lane,
                                              float4* __restrict__ hitbuf,
-                                             const float* __restrict__ pos, double d2_max,
+                                             const float* __restrict__ pos, const D2Bound& d2_max,
                                              const int32_t* __restrict__ cs,
                                              const float4* __restrict__ sp,
                                              int32_t* __restrict__ deg,
@@ -523,7 +535,7 @@ constexpr int kRgDenseMin = 24;  // centre-cell atoms from which staging + sorti
 
 template <bool FILL>
 __global__ void __launch_bounds__(kRgThreads)
-rg_cell_kernel(const float* __restrict__ pos, int64_t F, int64_t N, int64_t C, double d2_max,
+rg_cell_kernel(const float* __restrict__ pos, int64_t F, int64_t N, int64_t C, D2Bound d2_max,
                const FrameMeta* __restrict__ meta, const int32_t* __restrict__ cell_start,
                const float4* __restrict__ sorted_pos, int32_t* __restrict__ deg,
                const int64_t* __restrict__ row_ptr, int64_t E, int64_t* __restrict__ edge_index,
@@ -653,7 +665,7 @@ rg_cell_kernel(const float* __restrict__ pos, int64_t F, int64_t N, int64_t C, d
 // each warp owns one atom at a time.  blockIdx.y = frame, blockIdx.x strides over 8-atom groups.
 template <bool FILL>
 __global__ void __launch_bounds__(kRgThreads)
-rg_small_kernel(const float* __restrict__ pos, int64_t N, double d2_max, int32_t* __restrict__ deg,
+rg_small_kernel(const float* __restrict__ pos, int64_t N, D2Bound d2_max, int32_t* __restrict__ deg,
                 const int64_t* __restrict__ row_ptr, int64_t E, int64_t* __restrict__ edge_index,
                 float* __restrict__ edge_attr) {
     __shared__ float s_xyz[kRgCap * 3];
@@ -762,17 +774,36 @@ scan_apply_kernel(const int32_t* __restrict__ in, int64_t n, const int64_t* __re
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = offs[gridDim.x];
 }
 
-// largest double d2 with fl(sqrt(d2)) < thr  (see `within`); -1 if no distance qualifies
-double exact_d2_bound(double thr) {
-    if (!(thr > 0.0)) return -1.0;  // also NaN
-    if (std::isinf(thr)) return std::numeric_limits<double>::max();
-    double t = thr * thr;
-    if (std::isinf(t)) t = std::numeric_limits<double>::max();
-    while (t > 0.0 && std::sqrt(t) >= thr) t = std::nextafter(t, -1.0);
-    while (std::sqrt(std::nextafter(t, std::numeric_limits<double>::infinity())) < thr) {
-        t = std::nextafter(t, std::numeric_limits<double>::infinity());
+// largest double d2 with fl(sqrt(d2)) < thr  (see `within`); -1 if no distance qualifies; plus the
+// conservative float32 screening band around it
+D2Bound exact_d2_bound(double thr) {
+    D2Bound b;
+    b.d2_max = -1.0;
+    if (thr > 0.0) {  // false for NaN too
+        if (std::isinf(thr)) {
+            b.d2_max = std::numeric_limits<double>::max();
+        } else {
+            double t = thr * thr;
+            if (std::isinf(t)) t = std::numeric_limits<double>::max();
+            while (t > 0.0 && std::sqrt(t) >= thr) t = std::nextafter(t, -1.0);
+            while (std::sqrt(std::nextafter(t, std::numeric_limits<double>::infinity())) < thr) {
+                t = std::nextafter(t, std::numeric_limits<double>::infinity());
+            }
+            b.d2_max = std::sqrt(t) < thr ? t : -1.0;
+        }
     }
-    return std::sqrt(t) < thr ? t : -1.0;
+    if (b.d2_max < 0.0) {
+        b.lo = -1.0f;  // d2f >= 0 is never below it
+        b.hi = -1.0f;  // everything finite is above it => miss (NaN falls to the exact test)
+    } else {
+        const double lo = b.d2_max * (1.0 - 2e-6), hi = b.d2_max * (1.0 + 2e-6);
+        b.lo = std::nextafterf(float(lo), -1.0f);
+        if (double(b.lo) > lo) b.lo = std::nextafterf(b.lo, -1.0f);
+        b.hi = hi >= double(std::numeric_limits<float>::max())
+                   ? std::numeric_limits<float>::infinity()
+                   : std::nextafterf(float(hi), std::numeric_limits<float>::infinity());
+    }
+    return b;
 }
 
 int grid_for(int64_t total, int threads, int per_sm) {
