@@ -24,9 +24,20 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="synthetic_100k")
 ap.add_argument("--steps", type=int, default=4)
 ap.add_argument("--window", type=int, default=2)
+ap.add_argument("--sharded", action="store_true", help="shard the frame over the torchrun ranks")
 a = ap.parse_args()
 wl = syn.WORKLOADS[a.workload]
-dev = torch.device("cuda:0")
+world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+local = int(os.environ.get("LOCAL_RANK", "0"))
+dev = torch.device("cuda", local)
+torch.cuda.set_device(dev)
+if a.sharded:
+    import torch.distributed as dist
+
+    from molecular_dynamics_neural_operator_b200.sharded import kernelnn_forward_sharded
+
+    os.environ["NCCL_DEBUG"] = "WARN"
+    dist.init_process_group("nccl", device_id=dev)
 torch.manual_seed(0)
 model = KernelNN(wl.width, wl.ker_width, wl.depth, 6, in_width=7, out_width=3, window_size=a.window,
                  num_residues=wl.num_atoms, precision="bf16").to(dev).eval()
@@ -40,7 +51,7 @@ with torch.no_grad():
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        out = model(data, single_example=True)
+        out = kernelnn_forward_sharded(model, data) if a.sharded else model(data, single_example=True)
         # random-init weights: bound the predicted displacement so the rollout stays physical
         step_pos = data.x_position[-1] + 0.05 * torch.tanh(torch.nan_to_num(out))
         newpos = torch.cat([data.x_position[1:], step_pos[None]], dim=0)
@@ -51,7 +62,14 @@ with torch.no_grad():
 ms = e0.elapsed_time(e1) / a.steps
 A = 2 * wl.depth
 flop = A * 2.0 * (sum(edges[1:]) / max(a.steps, 1)) * wl.ker_width * wl.width ** 2
-print(json.dumps({"workload": wl.name, "atoms": wl.num_atoms, "width": wl.width, "depth": wl.depth,
+if a.sharded:
+    t = torch.tensor([ms], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+if rank == 0:
+  print(json.dumps({"workload": wl.name, "sharded_over_gpus": world if a.sharded else 1, "atoms": wl.num_atoms, "width": wl.width, "depth": wl.depth,
                   "edges_per_step": edges, "ms_per_rollout_step": ms, "steps_per_s": 1e3 / ms,
                   "contraction_tflops": flop / ms / 1e9,
                   "mem_gb": torch.cuda.max_memory_allocated() / 1e9}))
+if a.sharded:
+    dist.destroy_process_group()
