@@ -246,6 +246,7 @@ def bench_config(wl, frames_per_gpu, edges_per_frame):
                      f"({2 * wl.depth} NNConv applications), window {wl.window}; step = graph "
                      f"build + fwd + LpLoss + bwd + Adam"),
         "frames_per_gpu_per_step": frames_per_gpu,
+        "untimed_steps_before_timing": "max(8, warmup) resident + warmup//2 host-fed",
         "parallelism": "frames sharded over GPUs, bucketed NCCL gradient all-reduce",
         "l2_policy": "per-step working set (h_e alone ~0.9 GB at 8 frames) exceeds the 126 MB L2; "
                      "each step uses a different batch of frames",
@@ -277,7 +278,9 @@ def run_b200_arm(args, wl):
     _lib.load()
 
     B = args.frames_per_gpu
-    pool = args.pool
+    # every distinct batch (distinct edge count => distinct buffer sizes) must have been seen
+    # during warm-up, otherwise the caching allocator grows inside the timed region
+    pool = max(1, min(args.pool, args.warmup))
     torch.manual_seed(0)
     model = KernelNN(wl.width, wl.ker_width, wl.depth, 6, in_width=7, out_width=3,
                      window_size=wl.window, num_residues=wl.num_atoms, precision="bf16").to(dev)
@@ -315,7 +318,9 @@ def run_b200_arm(args, wl):
     def run_loop(build, steps, read_loss):
         """`steps` training steps; the next batch is built on a side stream while the current
         step runs.  read_loss: copy every step's loss to the host (read one step late so the
-        host never drains the training stream)."""
+        host never drains the training stream).  Both timed loops read the loss: it also paces the
+        host to one step ahead of the device, which measured steadier than a free-running host
+        (intermittent +10 % step times when the host queues two steps ahead)."""
         prefetch.submit(lambda: build(0))
         done: list = []
         for i in range(steps):
@@ -360,15 +365,23 @@ def run_b200_arm(args, wl):
             ms = float(t.item())
         return ms
 
-    run_loop(build_resident, args.warmup, False)
-    run_loop(build_e2e, max(1, args.warmup // 2), True)
-
+    # the clock sampler (an nvidia-smi process) starts BEFORE warm-up: its start-up talks to the
+    # driver and was seen to disturb the first timed steps; in steady state it samples every 200 ms
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+    # A cold process on a fresh box needs more than 3 steps to settle (lazy CUDA module loading,
+    # cuBLAS handles/heuristics, allocator growth, page cache): measured 107 frames/s with 3
+    # warm-up steps vs 124 with 10 in the FIRST process on a box.  Extra untimed settle steps are
+    # added in front of the W warm-up steps so that at least 8 steps precede the timed region.
+    settle = max(0, 8 - args.warmup)
+    run_loop(build_resident, settle + args.warmup, True)
+    run_loop(build_e2e, max(1, args.warmup // 2), True)
+    if sampler:
+        sampler.lines.clear()  # keep only samples taken during the timed loops
     edge_counts.clear()
     launches0 = _lib.launch_count()
-    ms_total = timed(build_resident, args.steps, False)
+    ms_total = timed(build_resident, args.steps, True)
     launches = _lib.launch_count() - launches0
     ms_e2e = timed(build_e2e, args.steps, True)
     # Per-launch CUDA events around the contraction cost ~0.15 ms each on this driver (measured:
@@ -378,7 +391,7 @@ def run_b200_arm(args, wl):
     ms_instr = None
     if not args.no_kernel_timer:
         ops.KERNEL_TIMER.enable("contract")
-        ms_instr = timed(build_resident, args.steps, False)
+        ms_instr = timed(build_resident, args.steps, True)
         timer = ops.KERNEL_TIMER.collect()
         ops.KERNEL_TIMER.disable()
     clocks = sampler.stop() if sampler else None

@@ -347,6 +347,110 @@ edge_outer_sum_kernel(const float* __restrict__ xs, const float* __restrict__ gs
     }
 }
 
+// bf16 variant of edge_outer_sum on the (legacy) warp-level tensor-core path: per edge
+// S_e = X_e^T G_e is a 64x16 @ 16x64 product (the A <= 16 applications are the reduction dim),
+// i.e. 4 x 8 mma.sync.m16n8k16 tiles.  One warp per edge; X_e / G_e rows are gathered, rounded to
+// bf16 and parked transposed in a per-warp smem patch ([channel][application], 32 B rows) so every
+// fragment register is one 32-bit load.  The n-tiles take G columns in the permuted order
+// o(nt, n) = 16*(n/2) + 2*nt + n%2, which makes each lane own 16 consecutive output columns of a
+// row: results leave as two 16-byte stores per row, full 128-byte lines per 4 lanes.
+// W = 64 only (the widths 32 / 128 keep the CUDA-core kernel above).
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4],
+                                               const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 "
+        "{%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__global__ void __launch_bounds__(256)
+edge_outer_sum_mma64_kernel(const float* __restrict__ xs, const float* __restrict__ gs,
+                            const int32_t* __restrict__ src_s, const int32_t* __restrict__ dst_s,
+                            __nv_bfloat16* __restrict__ S, int64_t e0, int64_t e1, int64_t N,
+                            int A) {
+    constexpr int W = 64, KP = 16, LD = KP + 8;  // 48-byte rows: conflict-free 32-bit loads
+    __shared__ __align__(16) __nv_bfloat16 sx[8][W][LD];
+    __shared__ __align__(16) __nv_bfloat16 sg[8][W][LD];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __nv_bfloat16(*X)[LD] = sx[warp];
+    __nv_bfloat16(*G)[LD] = sg[warp];
+    // zero the padded application slots once (A..15); they are never written again
+    for (int t = lane; t < W * KP; t += 32) {
+        const int ch = t / KP, a = t % KP;
+        if (a >= A) {
+            X[ch][a] = __float2bfloat16(0.f);
+            G[ch][a] = __float2bfloat16(0.f);
+        }
+    }
+    const int r = lane >> 2, q = lane & 3;
+    const int64_t wstride = int64_t(gridDim.x) * 8;
+    for (int64_t e = e0 + int64_t(blockIdx.x) * 8 + warp; e < e1; e += wstride) {
+        const int64_t s = src_s[e], d = dst_s[e];
+        __syncwarp();
+        // gather in groups of 4 applications: 8 independent row loads in flight per lane
+        for (int a0 = 0; a0 < A; a0 += 4) {
+            float2 xv[4], gv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int a = a0 + u < A ? a0 + u : A - 1;
+                xv[u] = __ldg(reinterpret_cast<const float2*>(xs + (int64_t(a) * N + s) * W) + lane);
+                gv[u] = __ldg(reinterpret_cast<const float2*>(gs + (int64_t(a) * N + d) * W) + lane);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int a = a0 + u;
+                if (a < A) {
+                    X[2 * lane][a] = __float2bfloat16(xv[u].x);
+                    X[2 * lane + 1][a] = __float2bfloat16(xv[u].y);
+                    G[2 * lane][a] = __float2bfloat16(gv[u].x);
+                    G[2 * lane + 1][a] = __float2bfloat16(gv[u].y);
+                }
+            }
+        }
+        __syncwarp();
+        // B fragments for the 8 n-tiles (reused by all 4 m-tiles)
+        uint32_t bf[8][2];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const int o = 16 * (r >> 1) + 2 * nt + (r & 1);
+            bf[nt][0] = *reinterpret_cast<const uint32_t*>(&G[o][2 * q]);
+            bf[nt][1] = *reinterpret_cast<const uint32_t*>(&G[o][2 * q + 8]);
+        }
+        __nv_bfloat16* out = S + (e - e0) * int64_t(W) * W;
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            uint32_t af[4];
+            af[0] = *reinterpret_cast<const uint32_t*>(&X[16 * mt + r][2 * q]);
+            af[1] = *reinterpret_cast<const uint32_t*>(&X[16 * mt + r + 8][2 * q]);
+            af[2] = *reinterpret_cast<const uint32_t*>(&X[16 * mt + r][2 * q + 8]);
+            af[3] = *reinterpret_cast<const uint32_t*>(&X[16 * mt + r + 8][2 * q + 8]);
+            float acc[8][4];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+                mma_bf16_16816(acc[nt], af, bf[nt]);
+            }
+            // lane (r, q) holds, for rows i = 16mt + r and i + 8, the 16 columns [16q, 16q+16):
+            // tile nt contributes columns 16q + 2nt + {0,1}
+            uint32_t lo[8], hi[8];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                __nv_bfloat162 t0 = __floats2bfloat162_rn(acc[nt][0], acc[nt][1]);
+                __nv_bfloat162 t1 = __floats2bfloat162_rn(acc[nt][2], acc[nt][3]);
+                lo[nt] = *reinterpret_cast<uint32_t*>(&t0);
+                hi[nt] = *reinterpret_cast<uint32_t*>(&t1);
+            }
+            uint4* p0 = reinterpret_cast<uint4*>(out + (16 * mt + r) * W + 16 * q);
+            uint4* p1 = reinterpret_cast<uint4*>(out + (16 * mt + r + 8) * W + 16 * q);
+            p0[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            p0[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            p1[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            p1[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+        }
+    }
+}
+
 __global__ void bias_act_cast_bf16_kernel(const float* __restrict__ in,
                                           const float* __restrict__ bias,
                                           __nv_bfloat16* __restrict__ out, int64_t total4,
@@ -623,6 +727,15 @@ extern "C" int gkn_edge_outer_sum(const float* xs, const float* gs, const int32_
     device_sm_count(&sms);
     int64_t blocks = e1 - e0;
     if (blocks > int64_t(sms) * 8) blocks = int64_t(sms) * 8;
+    if (out_is_bf16 && W == 64 && A <= 16) {
+        // tensor-core path: one warp per edge
+        int64_t b8 = (e1 - e0 + 7) / 8;
+        if (b8 > int64_t(sms) * 8) b8 = int64_t(sms) * 8;
+        edge_outer_sum_mma64_kernel<<<int(b8), 256, 0, st>>>(
+            xs, gs, src_s, dst_s, static_cast<__nv_bfloat16*>(S), e0, e1, N, A);
+        GKN_CHECK_LAUNCH("edge_outer_sum_mma launch");
+        return 0;
+    }
     const size_t smem = size_t(2) * A * W * sizeof(float);
     const int grid = int(blocks);
 #define GKN_EOS(WW)                                                                              \

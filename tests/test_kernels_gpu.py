@@ -97,7 +97,14 @@ def test_segmented_reductions(N, E, W):
         S = ops.edge_outer_sum(xs.to(DEV), gs.to(DEV), plan, e0, e1, torch.float32)
         assert (S.cpu().double() - refS.reshape(e1 - e0, -1)).abs().max().item() <= 1e-4
         Sb = ops.edge_outer_sum(xs.to(DEV), gs.to(DEV), plan, e0, e1, torch.bfloat16)
-        assert torch.equal(Sb.cpu(), S.cpu().bfloat16())  # same fp32 sum, one rounding
+        if W == 64:
+            # tensor-core path: operands rounded to bf16, fp32 accumulation, one output rounding
+            xq, gq = xs.bfloat16().double(), gs.bfloat16().double()
+            refq = torch.einsum("aei,aeo->eio", xq[:, src_s[e0:e1]], gq[:, dst_s[e0:e1]]).reshape(e1 - e0, -1)
+            err = (Sb.cpu().double() - refq).abs().max().item()
+            assert err <= 2.0 ** -8 * max(refq.abs().max().item(), 1.0)
+        else:
+            assert torch.equal(Sb.cpu(), S.cpu().bfloat16())  # same fp32 sum, one rounding
 
 
 def test_bias_act_cast_bf16_is_one_rounding():
