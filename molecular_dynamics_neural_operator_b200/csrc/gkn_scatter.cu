@@ -364,12 +364,13 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 edge_outer_sum_mma64_kernel(const float* __restrict__ xs, const float* __restrict__ gs,
                             const int32_t* __restrict__ src_s, const int32_t* __restrict__ dst_s,
                             __nv_bfloat16* __restrict__ S, int64_t e0, int64_t e1, int64_t N,
                             int A) {
-    constexpr int W = 64, KP = 16, LD = KP + 8;  // 48-byte rows: conflict-free 32-bit loads
+    constexpr int W = 64, KP = 16, LD = KP + 2;  // 36-byte rows (9 words, odd): the paired stores of
+                                                 // rows 2l / 2l+1 spread over 16 banks, loads over 32
     __shared__ __align__(16) __nv_bfloat16 sx[8][W][LD];
     __shared__ __align__(16) __nv_bfloat16 sg[8][W][LD];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -388,7 +389,8 @@ edge_outer_sum_mma64_kernel(const float* __restrict__ xs, const float* __restric
     for (int64_t e = e0 + int64_t(blockIdx.x) * 8 + warp; e < e1; e += wstride) {
         const int64_t s = src_s[e], d = dst_s[e];
         __syncwarp();
-        // gather in groups of 4 applications: 8 independent row loads in flight per lane
+        // gather in groups of 4 applications (8 independent row loads in flight per lane); two
+        // applications are packed per 32-bit smem store
         for (int a0 = 0; a0 < A; a0 += 4) {
             float2 xv[4], gv[4];
 #pragma unroll
@@ -398,13 +400,19 @@ edge_outer_sum_mma64_kernel(const float* __restrict__ xs, const float* __restric
                 gv[u] = __ldg(reinterpret_cast<const float2*>(gs + (int64_t(a) * N + d) * W) + lane);
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 4; u += 2) {
                 const int a = a0 + u;
                 if (a < A) {
-                    X[2 * lane][a] = __float2bfloat16(xv[u].x);
-                    X[2 * lane + 1][a] = __float2bfloat16(xv[u].y);
-                    G[2 * lane][a] = __float2bfloat16(gv[u].x);
-                    G[2 * lane + 1][a] = __float2bfloat16(gv[u].y);
+                    const bool two = a + 1 < A;  // odd A: the pad slot stays zero
+                    __nv_bfloat162 t;
+                    t = __floats2bfloat162_rn(xv[u].x, two ? xv[u + 1].x : 0.f);
+                    *reinterpret_cast<__nv_bfloat162*>(&X[2 * lane][a]) = t;
+                    t = __floats2bfloat162_rn(xv[u].y, two ? xv[u + 1].y : 0.f);
+                    *reinterpret_cast<__nv_bfloat162*>(&X[2 * lane + 1][a]) = t;
+                    t = __floats2bfloat162_rn(gv[u].x, two ? gv[u + 1].x : 0.f);
+                    *reinterpret_cast<__nv_bfloat162*>(&G[2 * lane][a]) = t;
+                    t = __floats2bfloat162_rn(gv[u].y, two ? gv[u + 1].y : 0.f);
+                    *reinterpret_cast<__nv_bfloat162*>(&G[2 * lane + 1][a]) = t;
                 }
             }
         }
