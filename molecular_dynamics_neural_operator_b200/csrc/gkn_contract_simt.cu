@@ -130,6 +130,9 @@ template <int MODE>
 int simt_dispatch(const float* h, const float* w3, const int32_t* idx, const float* node,
                   float* out, int64_t E, int32_t K, int32_t W, cudaStream_t stream) {
     if (E == 0) return 0;
+    if (E < 0 || h == nullptr || w3 == nullptr || idx == nullptr || node == nullptr || out == nullptr) {
+        return set_error("gkn_contract_*_f32: bad size or NULL pointer argument");
+    }
     if (K <= 0 || K % kKS != 0) return set_error("gkn_contract_*_f32: K must be a multiple of 16");
     const int64_t blocks = (E + kTE - 1) / kTE;
     if (blocks > 0x7fffffff) return set_error("gkn_contract_*_f32: too many edges");

@@ -416,6 +416,11 @@ int contract_dispatch(const void* h_bf16, const void* w3_bf16, const int32_t* id
                       const float* node, float* out, int64_t E, int32_t K, int32_t W,
                       cudaStream_t stream) {
     if (E == 0) return 0;
+    if (E < 0) return set_error("gkn_contract_*_bf16: negative edge count");
+    if (h_bf16 == nullptr || w3_bf16 == nullptr || idx == nullptr || node == nullptr ||
+        out == nullptr) {
+        return set_error("gkn_contract_*_bf16: NULL pointer argument");
+    }
     if (K <= 0 || K % kBlockK != 0) {
         return set_error("gkn_contract_*_bf16: kernel_width K must be a positive multiple of 64");
     }

@@ -882,6 +882,9 @@ extern "C" int gkn_radius_graph_count(const float* pos, int64_t F, int64_t N, do
                                       int64_t workspace_bytes, void* stream) {
     using namespace gkn;
     if (F < 0 || N < 0) return set_error("gkn_radius_graph_count: negative size");
+    if (pos == nullptr || deg == nullptr || row_ptr == nullptr || workspace == nullptr) {
+        return set_error("gkn_radius_graph_count: NULL pointer argument");
+    }
     if (N >= (int64_t(1) << 30)) return set_error("gkn_radius_graph_count: N too large");
     if (F > 65535) return set_error("gkn_radius_graph_count: at most 65535 frames per call");
     RadiusWs w = carve_radius_ws(workspace, F, N);
@@ -944,6 +947,10 @@ extern "C" int gkn_radius_graph_fill(const float* pos, int64_t F, int64_t N, dou
                                      void* stream) {
     using namespace gkn;
     if (F < 0 || N < 0 || E < 0) return set_error("gkn_radius_graph_fill: negative size");
+    if (pos == nullptr || row_ptr == nullptr || workspace == nullptr ||
+        (E > 0 && (edge_index == nullptr || edge_attr == nullptr))) {
+        return set_error("gkn_radius_graph_fill: NULL pointer argument");
+    }
     RadiusWs w = carve_radius_ws(workspace, F, N);
     if (workspace_bytes < w.bytes) return set_error("gkn_radius_graph_fill: workspace too small");
     const int64_t total = F * N;

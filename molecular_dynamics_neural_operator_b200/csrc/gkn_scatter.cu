@@ -881,6 +881,11 @@ extern "C" int gkn_segment_matvec(const float* rows, const int32_t* perm, const 
                                   int32_t W, int32_t relu, void* stream) {
     using namespace gkn;
     if (N == 0) return 0;
+    // rows / gidx may be NULL for a graph without edges (never dereferenced: all segments empty)
+    if (N < 0 || seg_ptr == nullptr || gnode == nullptr || M1 == nullptr || nin == nullptr ||
+        M2 == nullptr || out == nullptr) {
+        return set_error("gkn_segment_matvec: bad size or NULL pointer argument");
+    }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int grid = node_grid(N);
     const int threads = kWarpsPerBlock * 32;

@@ -312,9 +312,6 @@ def bias_act_cast_bf16(x, bias=None, relu=False) -> torch.Tensor:
     return out
 
 
-_COLSUM_WS: dict = {}
-
-
 def mask_cast_colsum(dz, act, colsum, out_dtype, side=None, accumulate: bool = True) -> torch.Tensor:
     """out = dz * (act > 0) in ``out_dtype`` (bf16 / fp32); colsum[0] (+)= out.sum(0) and, with
     ``side`` [rows, 6], colsum[1+j] (+)= (out * side[:, j:j+1]).sum(0).  ``colsum`` is
@@ -324,12 +321,9 @@ def mask_cast_colsum(dz, act, colsum, out_dtype, side=None, accumulate: bool = T
     nside = 0 if side is None else int(side.size(1))
     if colsum.numel() != (1 + nside) * cols:
         raise ValueError("colsum must have (1 + nside) * cols elements")
-    key = (dz.device, cols, nside)
-    ws = _COLSUM_WS.get(key)
-    if ws is None:
-        ws = torch.empty(int(lib.gkn_mask_cast_colsum_workspace_bytes(cols, nside)),
-                         dtype=torch.uint8, device=dz.device)
-        _COLSUM_WS[key] = ws
+    # per-call scratch from the caching allocator (stream-ordered, so safe on any stream)
+    ws = torch.empty(int(lib.gkn_mask_cast_colsum_workspace_bytes(cols, nside)), dtype=torch.uint8,
+                     device=dz.device)
     out = dz if out_dtype == dz.dtype else torch.empty((rows, cols), dtype=out_dtype,
                                                       device=dz.device)
     with torch.cuda.device(dz.device):

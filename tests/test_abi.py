@@ -54,3 +54,17 @@ def test_cpu_tensors_are_rejected_loudly():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.contract_fwd(torch.zeros(4, 64), torch.zeros(1024, 64), torch.zeros(4, dtype=torch.int32),
                          torch.zeros(3, 32), "fp32")
+
+
+def test_entry_points_reject_null_pointers_without_touching_the_gpu():
+    """Argument validation happens before any CUDA call, so it is testable on a CPU-only box."""
+    lib = _lib.load()
+    rc = lib.gkn_contract_fwd_bf16(None, None, None, None, None, 128, 64, 64, None)
+    assert rc != 0 and "NULL" in _lib.last_error()
+    rc = lib.gkn_contract_fwd_bf16(None, None, None, None, None, 0, 64, 64, None)
+    assert rc == 0  # empty edge set is a no-op
+    rc = lib.gkn_radius_graph_count(None, 1, 10, 8.0, None, None, None, 1 << 20, None)
+    assert rc != 0 and "NULL" in _lib.last_error()
+    rc = lib.gkn_segment_matvec(None, None, None, None, None, None, None, None, None, None, None, None,
+                                5, 64, 0, None)
+    assert rc != 0
