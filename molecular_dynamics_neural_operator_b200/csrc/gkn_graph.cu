@@ -225,6 +225,8 @@ struct RadiusWs {
     float4* sorted_pos;    // [F*N]  xyz + original atom index (bit-cast) in cell order
     int64_t* block_sums;   // [nblk]     row-pointer scan: per-block sums
     int64_t* block_offs;   // [nblk + 1] and their exclusive scan
+    uint32_t* hit_mask;    // small frames: [F*N, ceil(N/32)] hit bit matrix
+    int64_t* cta_edges;    // small frames: edge total of every pass-1 CTA
     int64_t nblk;
     int64_t C;             // cells reserved per frame
     int64_t bytes;
@@ -247,6 +249,9 @@ inline RadiusWs carve_radius_ws(void* base, int64_t F, int64_t N) {
     w.nblk = (F * N + 4095) / 4096;
     w.block_sums = reinterpret_cast<int64_t*>(take(w.nblk * 8));
     w.block_offs = reinterpret_cast<int64_t*>(take((w.nblk + 1) * 8));
+    const bool small = N <= 2048;  // kRgCap
+    w.hit_mask = reinterpret_cast<uint32_t*>(take(small ? F * N * ((N + 31) / 32) * 4 : 0));
+    w.cta_edges = reinterpret_cast<int64_t*>(take(small ? F * (N / 8 + 1) * 8 : 0));
     w.bytes = off;
     return w;
 }
@@ -659,50 +664,282 @@ rg_cell_kernel(const float* __restrict__ pos, int64_t F, int64_t N, int64_t C, D
     }
 }
 
-// Small frames (N <= kRgCap atoms, e.g. the 28-residue and 504-atom BBA graphs): no cell list at
-// all.  A CTA stages the whole frame's coordinates in shared memory in ATOM-INDEX order (coalesced
-// loads straight from `pos`), so every row's hits come out in ascending column order for free;
-// each warp owns one atom at a time.  blockIdx.y = frame, blockIdx.x strides over 8-atom groups.
-template <bool FILL>
-__global__ void __launch_bounds__(kRgThreads)
-rg_small_kernel(const float* __restrict__ pos, int64_t N, D2Bound d2_max, int32_t* __restrict__ deg,
-                const int64_t* __restrict__ row_ptr, int64_t E, int64_t* __restrict__ edge_index,
-                float* __restrict__ edge_attr) {
-    __shared__ float s_xyz[kRgCap * 3];
+// ------------------------------------------------------------------------------------------------
+// Small frames (N <= kRgCap atoms, e.g. the 28-residue and 504-atom BBA graphs): no cell list.
+// Pass 1 evaluates every pair ONCE and keeps the answer as a bit matrix (1 bit per pair, N^2/8
+// bytes per frame - 2 MB for 64 BBA frames, L2 resident); pass 2 is a pure streaming write of the
+// 40 bytes per edge, fully coalesced, driven by that bit matrix.
+//   rg_small_mask_kernel   CTA = (row slice, frame): the frame's coordinates are staged in smem as
+//                          float4; a warp keeps 32 candidate atoms in registers and sweeps the CTA's
+//                          rows (one broadcast LDS.128 + ~14 instructions per 32 pairs); the hit
+//                          words go to smem, then to `mask` (coalesced) with the row degrees and
+//                          the CTA's edge total.
+//   rg_small_rowptr_kernel same decomposition: CTA b adds the totals of CTAs < b and scans its own
+//                          <= 256 degrees -> row_ptr (int64).  No chained scan, no spinning.
+//   rg_small_fill_kernel   a warp expands a row's bit words into a column list in smem and streams
+//                          row ids, column ids and edge_attr with consecutive lanes on consecutive
+//                          addresses.  Columns come out ascending by construction.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSmThreads = 256;
+constexpr int kSmWarps = kSmThreads / 32;
+constexpr int kSmMaskWords = 4096;  // smem hit words per CTA in pass 1 (16 KB)
+constexpr int kSmFixCap = 256;      // hit words per CTA that may need the float64 predicate
+
+__device__ __forceinline__ bool within_exact(const float4& pi, const float4& pj, const D2Bound& b) {
+    const double dx = __dsub_rn(double(pj.x), double(pi.x));
+    const double dy = __dsub_rn(double(pj.y), double(pi.y));
+    const double dz = __dsub_rn(double(pj.z), double(pi.z));
+    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    return d2 <= b.d2_max;
+}
+
+__device__ __forceinline__ void stage_frame_float4(const float* __restrict__ p, int n,
+                                                   float4* __restrict__ s_p) {
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        s_p[t] = make_float4(p[t * 3], p[t * 3 + 1], p[t * 3 + 2], 0.f);
+    }
+}
+
+__global__ void __launch_bounds__(kSmThreads)
+rg_small_mask_kernel(const float* __restrict__ pos, int N, int rows_per, D2Bound b,
+                     int32_t* __restrict__ deg, uint32_t* __restrict__ mask,
+                     int64_t* __restrict__ partial) {
+    extern __shared__ float4 s_dyn[];
+    float4* s_p = s_dyn;                                        // [N]
+    uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_p + N);    // [rows_per, nws]
+    __shared__ int s_wsum[kSmWarps];
+    __shared__ int s_nfix;
+    __shared__ uint32_t s_fix[kSmFixCap];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nw = (N + 31) >> 5;
+    const int nws = (nw + 2 * kSmWarps - 1) / (2 * kSmWarps) * (2 * kSmWarps);  // padded row stride
+    const unsigned tail = (N & 31) ? (1u << (N & 31)) - 1u : 0xffffffffu;
     const int64_t f = blockIdx.y;
-    const int n = int(N);
-    const float* p = pos + f * N * 3;
-    for (int t = threadIdx.x; t < n * 3; t += kRgThreads) s_xyz[t] = p[t];
+    const int r0 = blockIdx.x * rows_per, r1 = min(N, r0 + rows_per);
+    if (threadIdx.x == 0) s_nfix = 0;
+    stage_frame_float4(pos + f * N * 3, N, s_p);
     __syncthreads();
-    const int64_t node0 = f * N;
-    for (int i = blockIdx.x * (kRgThreads / 32) + warp; i < n; i += gridDim.x * (kRgThreads / 32)) {
-        const float px = s_xyz[i * 3], py = s_xyz[i * 3 + 1], pz = s_xyz[i * 3 + 2];
-        const double xi = px, yi = py, zi = pz;
-        const int64_t g = node0 + i;
-        const int64_t beg = FILL ? row_ptr[g] : 0;
-        int count = 0;
-        for (int base = 0; base < n; base += 32) {
-            const int j = base + lane;
-            bool hit = false;
-            float4 pj = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (j < n) {
-                pj = make_float4(s_xyz[j * 3], s_xyz[j * 3 + 1], s_xyz[j * 3 + 2], 0.f);
-                hit = within(xi, yi, zi, pj, d2_max);
+    // Two column chunks (64 candidate atoms in registers) per sweep over the CTA's rows.  Lanes
+    // past the last atom re-test atom N-1 (their bits are cleared when the words leave smem), and
+    // all lanes store the warp-uniform hit word, so the sweep has no divergent code at all.
+    for (int c = warp; c < nw; c += 2 * kSmWarps) {
+        const int c2 = c + kSmWarps;  // < nws: lands in the row's padding when >= nw
+        const float4 pj = s_p[min(c * 32 + lane, N - 1)];
+        const float4 pk = s_p[min(c2 * 32 + lane, N - 1)];
+        uint32_t* wrow = s_mask + c;
+#pragma unroll 2
+        for (int i = r0; i < r1; ++i, wrow += nws) {
+            const float4 pi = s_p[i];
+            const float fx = pj.x - pi.x, fy = pj.y - pi.y, fz = pj.z - pi.z;
+            const float gx = pk.x - pi.x, gy = pk.y - pi.y, gz = pk.z - pi.z;
+            const float d2f = fmaf(fz, fz, fmaf(fy, fy, fx * fx));
+            const float d2g = fmaf(gz, gz, fmaf(gy, gy, gx * gx));
+            // fp32 screen: below `lo` certainly a hit, above `hi` certainly a miss; words with a
+            // pair in between (or a NaN, which fails both comparisons) are redone exactly below
+            const unsigned sure = __ballot_sync(0xffffffffu, d2f < b.lo);
+            const unsigned maybe = __ballot_sync(0xffffffffu, !(d2f > b.hi));
+            const unsigned sure2 = __ballot_sync(0xffffffffu, d2g < b.lo);
+            const unsigned maybe2 = __ballot_sync(0xffffffffu, !(d2g > b.hi));
+            wrow[0] = sure;
+            wrow[kSmWarps] = sure2;
+            if ((sure ^ maybe) | (sure2 ^ maybe2)) {  // warp-uniform, rare
+                if (lane == 0) {
+                    if (sure != maybe) {
+                        const int k = atomicAdd(&s_nfix, 1);
+                        if (k < kSmFixCap) s_fix[k] = uint32_t(i - r0) << 16 | uint32_t(c);
+                    }
+                    if (sure2 != maybe2 && c2 < nw) {
+                        const int k = atomicAdd(&s_nfix, 1);
+                        if (k < kSmFixCap) s_fix[k] = uint32_t(i - r0) << 16 | uint32_t(c2);
+                    }
+                }
             }
-            const unsigned mask = __ballot_sync(0xffffffffu, hit);
-            if (FILL && hit) {
-                const int64_t slot = beg + count + __popc(mask & ((1u << lane) - 1u));
-                edge_index[slot] = g;
-                edge_index[E + slot] = node0 + j;
-                float2* ea = reinterpret_cast<float2*>(edge_attr + slot * 6);
-                ea[0] = make_float2(px, py);
-                ea[1] = make_float2(pz, pj.x);
-                ea[2] = make_float2(pj.y, pj.z);
-            }
-            count += __popc(mask);
         }
-        if (!FILL && lane == 0) deg[g] = count;
+    }
+    __syncthreads();
+    const int nfix = s_nfix;
+    if (nfix > kSmFixCap) {
+        // pathological input (e.g. a lattice at exactly the cutoff spacing): everything in float64
+        for (int c = warp; c < nw; c += kSmWarps) {
+            const int j = c * 32 + lane;
+            const float4 pj = s_p[min(j, N - 1)];
+            for (int i = r0; i < r1; ++i) {
+                const unsigned m = __ballot_sync(0xffffffffu, j < N && within_exact(s_p[i], pj, b));
+                if (lane == 0) s_mask[(i - r0) * nws + c] = m;
+            }
+        }
+    } else {
+        for (int k = warp; k < nfix; k += kSmWarps) {
+            const int ir = int(s_fix[k] >> 16), c = int(s_fix[k] & 0xffffu);
+            const int j = c * 32 + lane;
+            const float4 pj = s_p[min(j, N - 1)];
+            const unsigned m = __ballot_sync(0xffffffffu, j < N && within_exact(s_p[r0 + ir], pj, b));
+            if (lane == 0) s_mask[ir * nws + c] = m;
+        }
+    }
+    __syncthreads();
+    int wsum = 0;
+    for (int i = r0 + warp; i < r1; i += kSmWarps) {
+        const int64_t g = f * N + i;
+        int cnt = 0;
+        for (int c = lane; c < nw; c += 32) {
+            const unsigned m = s_mask[(i - r0) * nws + c] & (c == nw - 1 ? tail : 0xffffffffu);
+            mask[g * nw + c] = m;
+            cnt += __popc(m);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+        if (lane == 0) deg[g] = cnt;
+        wsum += cnt;
+    }
+    if (lane == 0) s_wsum[warp] = wsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < kSmWarps; ++w) tot += s_wsum[w];
+        partial[int64_t(blockIdx.y) * gridDim.x + blockIdx.x] = tot;
+    }
+}
+
+__global__ void __launch_bounds__(kSmThreads)
+rg_small_rowptr_kernel(const int32_t* __restrict__ deg, const int64_t* __restrict__ partial, int N,
+                       int rows_per, int64_t* __restrict__ row_ptr) {
+    __shared__ int64_t s_red[kSmWarps];
+    __shared__ int s_wtot[kSmWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t bid = int64_t(blockIdx.y) * gridDim.x + blockIdx.x;
+    int64_t v = 0;
+    for (int64_t t = threadIdx.x; t < bid; t += kSmThreads) v += partial[t];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0) s_red[warp] = v;
+    const int r0 = blockIdx.x * rows_per, r1 = min(N, r0 + rows_per);
+    const int i = r0 + threadIdx.x;  // rows_per <= kSmThreads
+    const int64_t g = int64_t(blockIdx.y) * N + i;
+    const int d = i < r1 ? deg[g] : 0;
+    int incl = d;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
+    }
+    if (lane == 31) s_wtot[warp] = incl;
+    __syncthreads();
+    int64_t base = 0;
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kSmWarps; ++w) {
+        base += s_red[w];
+        if (w < warp) before += s_wtot[w];
+        total += s_wtot[w];
+    }
+    if (i < r1) row_ptr[g] = base + before + incl - d;
+    if (bid == int64_t(gridDim.x) * gridDim.y - 1 && threadIdx.x == 0) {
+        row_ptr[int64_t(gridDim.y) * N] = base + total;
+    }
+}
+
+// loads that must be ISSUED where they are written (software prefetch of the next row): volatile
+// asm keeps nvcc from sinking them to their first use
+__device__ __forceinline__ unsigned ld_nc_u32_here(const uint32_t* p) {
+    unsigned v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int64_t ld_nc_s64_here(const int64_t* p) {
+    long long v;
+    asm volatile("ld.global.nc.s64 %0, [%1];" : "=l"(v) : "l"(p));
+    return int64_t(v);
+}
+
+__global__ void __launch_bounds__(kSmThreads)
+rg_small_fill_kernel(const float* __restrict__ pos, int N, int rows_per, int col_cap,
+                     const uint32_t* __restrict__ mask, const int64_t* __restrict__ row_ptr,
+                     int64_t E, int64_t* __restrict__ edge_index, float* __restrict__ edge_attr) {
+    extern __shared__ float4 s_dyn[];
+    float4* s_p = s_dyn;  // [N]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float2* s_stage = reinterpret_cast<float2*>(s_p + N) + warp * 96;  // 32 edges x 6 floats
+    unsigned char* s_cols =
+        reinterpret_cast<unsigned char*>(reinterpret_cast<float2*>(s_p + N) + kSmWarps * 96) +
+        size_t(warp) * col_cap * 2;  // uint16 column list of the warp's current row
+    const int nw = (N + 31) >> 5;
+    const int64_t f = blockIdx.y;
+    const int64_t node0 = f * N;
+    const int r0 = blockIdx.x * rows_per, r1 = min(N, r0 + rows_per);
+    stage_frame_float4(pos + node0 * 3, N, s_p);
+    __syncthreads();
+    const unsigned below = (1u << lane) - 1u, mybit = 1u << lane;
+    // software pipeline: the next row's first 32 hit words and its row pointer are in flight
+    // while the current row is expanded and written
+    int i = r0 + warp;
+    unsigned wnext = 0u;
+    int64_t bnext = 0;
+    if (i < r1) {
+        if (lane < nw) wnext = mask[(node0 + i) * nw + lane];
+        bnext = row_ptr[node0 + i];
+    }
+    for (; i < r1; i += kSmWarps) {
+        const int64_t g = node0 + i;
+        const uint32_t* mrow = mask + g * nw;
+        unsigned wreg = wnext;
+        const int64_t beg = bnext;
+        if (i + kSmWarps < r1) {
+            if (lane < nw) wnext = ld_nc_u32_here(mask + (g + kSmWarps) * nw + lane);
+            bnext = ld_nc_s64_here(row_ptr + g + kSmWarps);
+        }
+        // 1. expand the row's hit words into an ascending column list (uint16) in smem
+        int d = 0;
+        for (int c0 = 0; c0 < nw; c0 += 32) {
+            if (c0 > 0) wreg = c0 + lane < nw ? mrow[c0 + lane] : 0u;
+            const int pc = __popc(wreg);
+            int incl = pc;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= off) incl += t;
+            }
+            const int excl2 = 2 * (d + incl - pc);  // byte offset of this word's first column
+            const int nn = min(32, nw - c0);
+            int col = c0 * 32 + lane;
+#pragma unroll 4
+            for (int cc = 0; cc < nn; ++cc, col += 32) {
+                const unsigned m = __shfl_sync(0xffffffffu, wreg, cc);
+                const int o = __shfl_sync(0xffffffffu, excl2, cc);
+                if (m & mybit) {
+                    *reinterpret_cast<uint16_t*>(s_cols + o + 2 * __popc(m & below)) = uint16_t(col);
+                }
+            }
+            d += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        __syncwarp();
+        // 2. stream the row: 32 edges per round; edge_attr goes through a 768-byte smem staging
+        //    buffer so that consecutive lanes store consecutive float2
+        int64_t* er = edge_index + beg;
+        int64_t* ec = edge_index + E + beg;
+        const float4 pi = s_p[i];
+        float2* ea = reinterpret_cast<float2*>(edge_attr + beg * 6);  // beg*24 bytes: 8-aligned
+        for (int e0 = 0; e0 < d; e0 += 32, ea += 96) {
+            const int e = e0 + lane;
+            if (e < d) {
+                const int col = reinterpret_cast<const uint16_t*>(s_cols)[e];
+                const float4 pj = s_p[col];
+                er[e] = g;
+                ec[e] = node0 + col;
+                s_stage[3 * lane] = make_float2(pi.x, pi.y);
+                s_stage[3 * lane + 1] = make_float2(pi.z, pj.x);
+                s_stage[3 * lane + 2] = make_float2(pj.y, pj.z);
+            }
+            __syncwarp();
+            const int n2 = 3 * min(32, d - e0);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int u = 32 * k + lane;
+                if (u < n2) ea[u] = s_stage[u];
+            }
+            __syncwarp();
+        }
     }
 }
 
@@ -772,6 +1009,30 @@ scan_apply_kernel(const int32_t* __restrict__ in, int64_t n, const int64_t* __re
         run += v[k];
     }
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = offs[gridDim.x];
+}
+
+// Row slices of the small-frame kernels: pass 1 (mask + row pointers) and pass 2 (fill).
+struct SmallSplit {
+    int rows_per, gx;
+};
+SmallSplit small_split(int64_t F, int64_t N, int sms, int ctas_per_sm, int min_rows, int max_rows) {
+    int64_t gx_want = (int64_t(sms) * ctas_per_sm + F - 1) / F;
+    if (gx_want < 1) gx_want = 1;
+    int64_t rows = (N + gx_want - 1) / gx_want;
+    if (rows < min_rows) rows = min_rows;
+    if (rows > max_rows) rows = max_rows;
+    if (rows > N) rows = N;
+    if (rows < 1) rows = 1;
+    SmallSplit sp;
+    sp.rows_per = int(rows);
+    sp.gx = int((N + rows - 1) / rows);
+    return sp;
+}
+SmallSplit small_split_pass1(int64_t F, int64_t N, int sms) {
+    const int nws = int(((N + 31) / 32 + 2 * kSmWarps - 1) / (2 * kSmWarps) * (2 * kSmWarps));
+    int max_rows = kSmMaskWords / (nws < 1 ? 1 : nws);
+    if (max_rows > kSmThreads) max_rows = kSmThreads;
+    return small_split(F, N, sms, 4, 8, max_rows);  // gx <= N/8 + 1 (cta_edges capacity)
 }
 
 // largest double d2 with fl(sqrt(d2)) < thr  (see `within`); -1 if no distance qualifies; plus the
@@ -899,14 +1160,21 @@ extern "C" int gkn_radius_graph_count(const float* pos, int64_t F, int64_t N, do
     int sms = 148;
     device_sm_count(&sms);
     if (N <= kRgCap) {
-        // small frames: all-pairs from shared memory, no cell list
-        int64_t gx = (N + 7) / 8;
-        const int64_t want = (int64_t(sms) * 8 + F - 1) / F;
-        if (gx > want) gx = want;
-        const dim3 sg(unsigned(gx < 1 ? 1 : gx), unsigned(F));
-        rg_small_kernel<false><<<sg, kRgThreads, 0, st>>>(pos, N, exact_d2_bound(threshold), deg,
-                                                         nullptr, 0, nullptr, nullptr);
-        GKN_CHECK_LAUNCH("rg_small_count");
+        // small frames: all-pairs from shared memory, no cell list; hits kept as a bit matrix
+        const SmallSplit sp = small_split_pass1(F, N, sms);
+        const int nws = int(((N + 31) / 32 + 2 * kSmWarps - 1) / (2 * kSmWarps) * (2 * kSmWarps));
+        const dim3 sg(unsigned(sp.gx), unsigned(F));
+        const size_t smem = size_t(N) * 16 + size_t(sp.rows_per) * nws * 4;
+        rg_small_mask_kernel<<<sg, kSmThreads, smem, st>>>(pos, int(N), sp.rows_per,
+                                                           exact_d2_bound(threshold), deg,
+                                                           w.hit_mask, w.cta_edges);
+        GKN_CHECK_LAUNCH("rg_small_mask");
+        if (int64_t(sp.gx) * F <= 4096) {
+            rg_small_rowptr_kernel<<<sg, kSmThreads, 0, st>>>(deg, w.cta_edges, int(N), sp.rows_per,
+                                                              row_ptr);
+            GKN_CHECK_LAUNCH("rg_small_rowptr");
+            return 0;
+        }
     } else {
         cudaError_t err = cudaMemsetAsync(w.cell_count, 0, size_t(F) * (w.C + 1) * 4, st);
         if (err != cudaSuccess) return set_cuda_error("cudaMemsetAsync(cell_count)", err);
@@ -959,12 +1227,18 @@ extern "C" int gkn_radius_graph_fill(const float* pos, int64_t F, int64_t N, dou
     int sms = 148;
     device_sm_count(&sms);
     if (N <= kRgCap) {
-        int64_t gx = (N + 7) / 8;
-        const int64_t want = (int64_t(sms) * 8 + F - 1) / F;
-        if (gx > want) gx = want;
-        const dim3 sg(unsigned(gx < 1 ? 1 : gx), unsigned(F));
-        rg_small_kernel<true><<<sg, kRgThreads, 0, st>>>(pos, N, exact_d2_bound(threshold), nullptr,
-                                                        row_ptr, E, edge_index, edge_attr);
+        const SmallSplit sp = small_split(F, N, sms, 6, 8, int(N));
+        const int col_cap = int((N + 7) / 8 * 8);
+        const size_t smem = size_t(N) * 16 + size_t(kSmWarps) * (96 * 8 + col_cap * 2);
+        if (smem > 48 * 1024) {
+            cudaError_t err = cudaFuncSetAttribute(
+                rg_small_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            if (err != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(rg_small_fill)", err);
+        }
+        const dim3 sg(unsigned(sp.gx), unsigned(F));
+        rg_small_fill_kernel<<<sg, kSmThreads, smem, st>>>(pos, int(N), sp.rows_per, col_cap,
+                                                           w.hit_mask, row_ptr, E, edge_index,
+                                                           edge_attr);
     } else {
         int64_t cgx = (int64_t(sms) * 16 + F - 1) / F;
         if (cgx > w.C) cgx = w.C;

@@ -37,11 +37,48 @@ def emit(**kw):
     print(json.dumps(kw), flush=True)
 
 
+def graph_pass_times(pos, thr, iters=10):
+    """Device time of the two passes of the radius-graph build through the C ABI with every buffer
+    preallocated (CUDA events on the launching stream; no allocation or host read in between)."""
+    from molecular_dynamics_neural_operator_b200 import _lib
+    lib = _lib.load()
+    F, N = int(pos.size(0)), int(pos.size(1))
+    ws_bytes = int(lib.gkn_radius_graph_workspace_bytes(F, N))
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    deg = torch.empty(F * N, dtype=torch.int32, device=dev)
+    row_ptr = torch.empty(F * N + 1, dtype=torch.int64, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    p = lambda t: t.data_ptr()  # noqa: E731
+
+    def count():
+        _lib.check(lib.gkn_radius_graph_count(p(pos), F, N, float(thr), p(deg), p(row_ptr), p(ws), ws_bytes, st),
+                   "count")
+    count()
+    E = int(row_ptr[-1].item())
+    ei = torch.empty((2, E), dtype=torch.int64, device=dev)
+    ea = torch.empty((E, 6), dtype=torch.float32, device=dev)
+
+    def fill():
+        _lib.check(lib.gkn_radius_graph_fill(p(pos), F, N, float(thr), p(row_ptr), E, p(ei), p(ea), p(ws),
+                                             ws_bytes, st), "fill")
+    def both():
+        count()
+        fill()
+    return timeit(count, iters), timeit(fill, iters), timeit(both, iters), E
+
+
 def bench_graph(name, frames):
     wl = syn.WORKLOADS[name]
     pos = torch.from_numpy(syn.trajectory(wl, frames, seed=0)).to(dev)
     ei, ea = ops.radius_graph(pos, wl.cutoff)
     E, N = ei.size(1), wl.num_atoms * frames
+    cms, fms, bms, E2 = graph_pass_times(pos, wl.cutoff)
+    assert E2 == E
+    nb = 12 * N + 40 * E
+    emit(kernel="radius_graph device time (count pass, fill pass, both back to back)", workload=name,
+         frames=frames, atoms=N, edges=E, count_ms=cms, fill_ms=fms, ms=bms, algorithmic_bytes=nb,
+         gbs=nb / bms / 1e6, frac_hbm=nb / bms / 1e6 / peaks["hbm_gbs"],
+         fill_frac_hbm=nb / fms / 1e6 / peaks["hbm_gbs"])
     ms = timeit(lambda: ops.radius_graph(pos, wl.cutoff), iters=5, warm=2)
     nbytes = 12 * N + 40 * E
     emit(kernel="radius_graph (count+fill, incl. host read of E)", workload=name, frames=frames, atoms=N, edges=E,
@@ -91,8 +128,15 @@ def bench_contract(name, frames, E, N):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--graph-only", action="store_true")
     a = ap.parse_args()
     print(json.dumps({"gpu": torch.cuda.get_device_name(0), "peaks": peaks}))
+    if a.graph_only:
+        for name, frames in (("bba_ca", 128), ("bba_allatom", 8), ("bba_allatom", 64), ("bba_allatom", 512),
+                             ("synthetic_10k", 16), ("synthetic_10k", 64), ("synthetic_100k", 1),
+                             ("synthetic_100k", 4)):
+            bench_graph(name, frames)
+        sys.exit(0)
     ei, ea, N, E = bench_graph("bba_allatom", 64)
     bench_node_update("bba_allatom", 64, ei, N, E)
     del ei, ea

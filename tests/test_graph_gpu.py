@@ -26,7 +26,8 @@ def test_construct_pairdata_bit_exact_vs_reference_golden(name):
                                         (2, 504, 17.1, 8.0), (3, 64, 300.0, 4.2), (1, 3000, 31.0, 4.2),
                                         (2, 50, 5.0, 0.5), (1, 40, 10.0, 1000.0),
                                         (1, 2300, 5.0, 9.0),   # > 2048 staged candidates: per-atom fallback
-                                        (3, 700, 9.0, 3.0)])
+                                        (3, 700, 9.0, 3.0), (2, 2048, 30.0, 4.2), (7, 33, 9.0, 4.2),
+                                        (300, 28, 14.0, 8.0), (1, 1999, 12.0, 8.0)])
 def test_radius_graph_bit_exact_vs_scipy_oracle(F, N, L, thr):
     from molecular_dynamics_neural_operator_b200 import ops
     from oracle import gkn_oracle as orc
@@ -55,6 +56,22 @@ def test_radius_graph_boundary_pairs_use_the_float64_predicate():
     base[7] = [-4.2, 0, 0]
     ei_ref, ea_ref = orc.radius_graph_batched(base[None], thr)
     ei, ea = ops.radius_graph(torch.from_numpy(base[None]).cuda(), thr)
+    assert np.array_equal(ei.cpu().numpy(), ei_ref) and np.array_equal(ea.cpu().numpy(), ea_ref)
+
+
+@pytest.mark.parametrize("n_side,thr", [(6, 1.0), (8, 2.0), (13, 1.0)])
+def test_radius_graph_lattice_at_exactly_the_cutoff_spacing(n_side, thr):
+    """Integer lattice with neighbours at exactly the cutoff: nearly every hit word is inside the
+    fp32 screening band, so the small-frame kernel's float64 fix-up list overflows and its
+    all-float64 path runs; the strict `<` must still exclude the distance == cutoff pairs."""
+    from molecular_dynamics_neural_operator_b200 import ops
+    from oracle import gkn_oracle as orc
+
+    g = np.arange(n_side, dtype=np.float32)
+    pos = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(1, -1, 3)
+    pos = np.concatenate([pos, pos[:, ::-1] + np.float32(100.0)], 0)  # second frame, other order
+    ei_ref, ea_ref = orc.radius_graph_batched(pos, thr)
+    ei, ea = ops.radius_graph(torch.from_numpy(np.ascontiguousarray(pos)).cuda(), thr)
     assert np.array_equal(ei.cpu().numpy(), ei_ref) and np.array_equal(ea.cpu().numpy(), ea_ref)
 
 
