@@ -225,6 +225,10 @@ struct RadiusWs {
     float4* sorted_pos;    // [F*N]  xyz + original atom index (bit-cast) in cell order
     int64_t* block_sums;   // [nblk]     row-pointer scan: per-block sums
     int64_t* block_offs;   // [nblk + 1] and their exclusive scan
+    int32_t* nbr;          // large frames: [F*N, kListCap] sorted neighbour lists of pass 1
+    int32_t* list_ok;      // large frames: [F*N] 1 = row has its list, 0 = pass 2 rebuilds it
+    int32_t* crowded_count;  // large frames: cells left to rg_crowded_kernel
+    int2* crowded_cells;     // [F * C] (frame, cell)
     uint32_t* hit_mask;    // small frames: [F*N, ceil(N/32)] hit bit matrix
     int64_t* cta_edges;    // small frames: edge total of every pass-1 CTA
     int64_t nblk;
@@ -250,6 +254,10 @@ inline RadiusWs carve_radius_ws(void* base, int64_t F, int64_t N) {
     w.block_sums = reinterpret_cast<int64_t*>(take(w.nblk * 8));
     w.block_offs = reinterpret_cast<int64_t*>(take((w.nblk + 1) * 8));
     const bool small = N <= 2048;  // kRgCap
+    w.nbr = reinterpret_cast<int32_t*>(take(small ? 0 : F * N * 64 * 4));  // kListCap
+    w.list_ok = reinterpret_cast<int32_t*>(take(small ? 0 : F * N * 4));
+    w.crowded_count = reinterpret_cast<int32_t*>(take(small ? 0 : 4));
+    w.crowded_cells = reinterpret_cast<int2*>(take(small ? 0 : F * w.C * 8));
     w.hit_mask = reinterpret_cast<uint32_t*>(take(small ? F * N * ((N + 31) / 32) * 4 : 0));
     w.cta_edges = reinterpret_cast<int64_t*>(take(small ? F * (N / 8 + 1) * 8 : 0));
     w.bytes = off;
@@ -259,8 +267,12 @@ inline RadiusWs carve_radius_ws(void* base, int64_t F, int64_t N) {
 // one block per frame: bounding box, then pick a cell edge >= cutoff whose grid fits in C cells
 __global__ void __launch_bounds__(1024)
 rg_frame_setup_kernel(const float* __restrict__ pos, int64_t N, double threshold, int64_t C,
-                      FrameMeta* __restrict__ meta) {
+                      FrameMeta* __restrict__ meta, int32_t* __restrict__ cell_count,
+                      int32_t* __restrict__ crowded_count) {
     const int64_t f = blockIdx.x;
+    // this frame's cell histogram and the crowded-cell worklist start from zero
+    for (int64_t t = threadIdx.x; t <= C; t += blockDim.x) cell_count[f * (C + 1) + t] = 0;
+    if (f == 0 && threadIdx.x == 0) *crowded_count = 0;
     const float* p = pos + f * N * 3;
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
@@ -364,7 +376,8 @@ __global__ void rg_place_kernel(const float* __restrict__ pos, int64_t F, int64_
     for (int64_t g = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; g < total; g += stride) {
         const int64_t f = g / N;
         const int c = atom_cell[g];
-        const int slot = cell_start[f * (C + 1) + c] + atomicAdd(cursor + f * (C + 1) + c, 1);
+        // the histogram doubles as the placement cursor, counted down to zero
+        const int slot = cell_start[f * (C + 1) + c] + atomicSub(cursor + f * (C + 1) + c, 1) - 1;
         sorted_pos[f * N + slot] =
             make_float4(pos[g * 3], pos[g * 3 + 1], pos[g * 3 + 2], __int_as_float(int(g - f * N)));
     }
@@ -394,6 +407,27 @@ __device__ __forceinline__ bool within(double xi, double yi, double zi, float4 p
     const double dz = __dsub_rn(double(pj.z), zi);
     const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
     return d2 <= b.d2_max;
+}
+
+__device__ __forceinline__ bool within_exact(const float4& pi, const float4& pj, const D2Bound& b) {
+    const double dx = __dsub_rn(double(pj.x), double(pi.x));
+    const double dy = __dsub_rn(double(pj.y), double(pi.y));
+    const double dz = __dsub_rn(double(pj.z), double(pi.z));
+    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    return d2 <= b.d2_max;
+}
+
+// loads that must be ISSUED where they are written (software prefetch of the next row): volatile
+// asm keeps nvcc from sinking them to their first use
+__device__ __forceinline__ unsigned ld_nc_u32_here(const uint32_t* p) {
+    unsigned v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int64_t ld_nc_s64_here(const int64_t* p) {
+    long long v;
+    asm volatile("ld.global.nc.s64 %0, [%1];" : "=l"(v) : "l"(p));
+    return int64_t(v);
 }
 
 // One warp handles one atom straight from global memory (sparse cells, and the general path for
@@ -457,7 +491,7 @@ __device__ __forceinline__ void rg_atom_warp(float4 pi, int64_t node0, int cx, i
     };
     const int64_t beg = FILL ? row_ptr[g] : 0;
     // rows are sized by the count pass: deg is exact, so the buffer decision is warp-uniform
-    const bool in_smem = FILL && (row_ptr[g + 1] - beg) <= kHitCap;
+    const bool in_smem = FILL && hitbuf != nullptr && (row_ptr[g + 1] - beg) <= kHitCap;
     int64_t* scratch = FILL ? edge_index + beg : nullptr;  // row-id slots double as scratch
     int count = 0;
     for (int base = 0; base < total; base += 64) {  // warp-uniform trip count
@@ -538,6 +572,128 @@ constexpr int kRgCap = 2048;  // staged candidates (float4) = 32 KB
 constexpr int kRgThreads = 256;
 constexpr int kRgDenseMin = 24;  // centre-cell atoms from which staging + sorting pays off
 
+// The CTA-cooperative treatment of ONE cell (see rg_cell_kernel): must be called by all threads of
+// the CTA with the same arguments.
+template <bool FILL>
+__device__ __forceinline__ void rg_cell_cta(int c, const FrameMeta& m, int64_t node0, int64_t N,
+                                            const D2Bound& d2_max, const float* __restrict__ pos,
+                                            const int32_t* __restrict__ cs,
+                                            const float4* __restrict__ sp, float4* s_cand,
+                                            int* s_run_beg, int* s_run_off,
+                                            int32_t* __restrict__ deg,
+                                            const int64_t* __restrict__ row_ptr, int64_t E,
+                                            int64_t* __restrict__ edge_index,
+                                            float* __restrict__ edge_attr) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ib = cs[c], ie = cs[c + 1];
+    if (ib == ie) return;  // empty centre cell (block-uniform)
+    const int cz = c % m.nz, cy = (c / m.nz) % m.ny, cx = c / (m.nz * m.ny);
+    if (ie - ib < kRgDenseMin) {
+        // sparse centre cell: staging + sorting would cost more than it saves
+        __syncthreads();  // s_cand is about to be reused as per-warp hit buffers
+        for (int i = ib + warp; i < ie; i += kRgThreads / 32) {
+            rg_atom_warp<FILL>(sp[i], node0, cx, cy, cz, m, lane, s_cand + warp * kHitCap, pos,
+                               d2_max, cs, sp, deg, row_ptr, E, edge_index, edge_attr);
+        }
+        return;
+    }
+    __syncthreads();  // previous item's smem no longer in use
+    if (threadIdx.x < 9) {
+        const int r = threadIdx.x;
+        const int ax = cx - 1 + r / 3, ay = cy - 1 + r % 3;
+        int jb = 0, je = 0;
+        if (ax >= 0 && ax < m.nx && ay >= 0 && ay < m.ny) {
+            const int z0 = max(cz - 1, 0), z1 = min(cz + 1, m.nz - 1);
+            jb = cs[(ax * m.ny + ay) * m.nz + z0];
+            je = cs[(ax * m.ny + ay) * m.nz + z1 + 1];
+        }
+        s_run_beg[r] = jb;
+        s_run_off[r + 1] = je - jb;  // lengths first, prefix-summed below
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int off = 0;
+        for (int r = 0; r < 9; ++r) {
+            const int len = s_run_off[r + 1];
+            s_run_off[r] = off;
+            off += len;
+        }
+        s_run_off[9] = off;
+    }
+    __syncthreads();
+    const int ncand = s_run_off[9];
+    if (ncand > kRgCap) {
+        // oversize neighbourhood: per-atom path straight from global memory
+        __syncthreads();
+        for (int i = ib + warp; i < ie; i += kRgThreads / 32) {
+            rg_atom_warp<FILL>(sp[i], node0, cx, cy, cz, m, lane, s_cand + warp * kHitCap, pos,
+                               d2_max, cs, sp, deg, row_ptr, E, edge_index, edge_attr);
+        }
+        return;
+    }
+    for (int r = 0; r < 9; ++r) {
+        const int len = s_run_off[r + 1] - s_run_off[r];
+        for (int t = threadIdx.x; t < len; t += kRgThreads) {
+            s_cand[s_run_off[r] + t] = sp[s_run_beg[r] + t];
+        }
+    }
+    int P = ncand;
+    if (FILL) {
+        P = 32;
+        while (P < ncand) P <<= 1;
+        for (int t = ncand + threadIdx.x; t < P; t += kRgThreads) {
+            s_cand[t] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7fffffff));
+        }
+        __syncthreads();
+        for (int k = 2; k <= P; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = threadIdx.x; t < P; t += kRgThreads) {
+                    const int u = t ^ j;
+                    if (u > t) {
+                        const float4 a = s_cand[t], b = s_cand[u];
+                        const bool asc = (t & k) == 0;
+                        if ((__float_as_int(a.w) > __float_as_int(b.w)) == asc) {
+                            s_cand[t] = b;
+                            s_cand[u] = a;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    } else {
+        __syncthreads();
+    }
+    for (int i = ib + warp; i < ie; i += kRgThreads / 32) {
+        const float4 pi = sp[i];
+        const double xi = pi.x, yi = pi.y, zi = pi.z;
+        const int64_t g = node0 + __float_as_int(pi.w);
+        const int64_t beg = FILL ? row_ptr[g] : 0;
+        int count = 0;
+        for (int base = 0; base < ncand; base += 32) {
+            const int j = base + lane;
+            bool hit = false;
+            float4 pj = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < ncand) {
+                pj = s_cand[j];
+                hit = within(xi, yi, zi, pj, d2_max);
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, hit);
+            if (FILL && hit) {
+                const int64_t slot = beg + count + __popc(mask & ((1u << lane) - 1u));
+                edge_index[slot] = g;
+                edge_index[E + slot] = node0 + __float_as_int(pj.w);
+                float2* ea = reinterpret_cast<float2*>(edge_attr + slot * 6);
+                ea[0] = make_float2(pi.x, pi.y);
+                ea[1] = make_float2(pi.z, pj.x);
+                ea[2] = make_float2(pj.y, pj.z);
+            }
+            count += __popc(mask);
+        }
+        if (!FILL && lane == 0) deg[g] = count;
+    }
+}
+
 template <bool FILL>
 __global__ void __launch_bounds__(kRgThreads)
 rg_cell_kernel(const float* __restrict__ pos, int64_t F, int64_t N, int64_t C, D2Bound d2_max,
@@ -547,119 +703,267 @@ rg_cell_kernel(const float* __restrict__ pos, int64_t F, int64_t N, int64_t C, D
                float* __restrict__ edge_attr) {
     __shared__ float4 s_cand[kRgCap];
     __shared__ int s_run_beg[9], s_run_off[10];
+    const int64_t f = blockIdx.y;
+    const FrameMeta m = meta[f];
+    const int32_t* cs = cell_start + f * (C + 1);
+    const float4* sp = sorted_pos + f * N;
+    for (int c = blockIdx.x; c < m.ncell; c += gridDim.x) {
+        rg_cell_cta<FILL>(c, m, f * N, N, d2_max, pos, cs, sp, s_cand, s_run_beg, s_run_off, deg,
+                          row_ptr, E, edge_index, edge_attr);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Large frames, list variant: pass 1 does ALL the geometry and leaves, per atom, its neighbour
+// list already sorted by atom index (<= kListCap entries, int32) in the workspace; pass 2 is a pure
+// streaming write of the 40 bytes per edge.
+//   rg_cell_list_kernel  one WARP per cell.  The <= 256 atoms of the 27 surrounding cells are read
+//                        once (coalesced float4 loads of the cell-sorted array) into registers,
+//                        8 per lane; each atom of the centre cell is then tested against them
+//                        (fp32 screen, float64 only inside the band), its hits are compacted into
+//                        a per-warp smem buffer and rank-sorted from there.
+//                        Cells whose neighbourhood exceeds 256 atoms and rows longer than kListCap
+//                        only get their degree here and are rebuilt by pass 2 (rg_atom_warp).
+//   rg_list_fill_kernel  one warp per row, rows in atom order so the output is one sequential
+//                        stream; column ids come from the saved list, coordinates of the
+//                        neighbours from `pos` (L2 resident), edge_attr through a 768-byte smem
+//                        staging buffer so that consecutive lanes store consecutive float2.
+// ------------------------------------------------------------------------------------------------
+constexpr int kListCap = 64;
+constexpr int kCellRegs = 8;  // candidates per lane held in registers
+
+constexpr int kHitBuf = 32 * kCellRegs + 4;  // per-warp hit buffer: every candidate + sort padding
+
+__device__ __forceinline__ void sts_u32(uint32_t addr, int v) {
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// One warp per cell, no CTA-level synchronisation: cells are handed out warp by warp.  Cells whose
+// neighbourhood does not fit the registers go to a worklist for rg_crowded_kernel.
+__global__ void __launch_bounds__(kRgThreads, 4)
+rg_cell_list_kernel(int64_t F, int64_t N, int64_t C, D2Bound b, const FrameMeta* __restrict__ meta,
+                    const int32_t* __restrict__ cell_start, const float4* __restrict__ sorted_pos,
+                    int32_t* __restrict__ deg, int32_t* __restrict__ nbr,
+                    int32_t* __restrict__ list_ok, int32_t* __restrict__ crowded_count,
+                    int2* __restrict__ crowded_cells) {
+    __shared__ __align__(16) int s_hit[kRgThreads / 32][kHitBuf];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t f = blockIdx.y;
     const FrameMeta m = meta[f];
     const int32_t* cs = cell_start + f * (C + 1);
     const float4* sp = sorted_pos + f * N;
     const int64_t node0 = f * N;
-    for (int c = blockIdx.x; c < m.ncell; c += gridDim.x) {
+    const unsigned below = (1u << lane) - 1u;
+    const int* hb = s_hit[warp];
+    const uint32_t hb_addr = uint32_t(__cvta_generic_to_shared(s_hit[warp]));
+    constexpr int kWarps = kRgThreads / 32;
+    for (int c = blockIdx.x * kWarps + warp; c < m.ncell; c += gridDim.x * kWarps) {
         const int ib = cs[c], ie = cs[c + 1];
-        if (ib == ie) continue;  // empty centre cell (block-uniform)
+        if (ib == ie) continue;  // warp-uniform
         const int cz = c % m.nz, cy = (c / m.nz) % m.ny, cx = c / (m.nz * m.ny);
-        if (ie - ib < kRgDenseMin) {
-            // sparse centre cell: staging + sorting would cost more than it saves
-            __syncthreads();  // s_cand is about to be reused as per-warp hit buffers
-            for (int i = ib + warp; i < ie; i += kRgThreads / 32) {
-                rg_atom_warp<FILL>(sp[i], node0, cx, cy, cz, m, lane, s_cand + warp * kHitCap, pos,
-                                   d2_max, cs, sp, deg, row_ptr, E, edge_index, edge_attr);
-            }
-            continue;
-        }
-        __syncthreads();  // previous item's smem no longer in use
-        if (threadIdx.x < 9) {
-            const int r = threadIdx.x;
-            const int ax = cx - 1 + r / 3, ay = cy - 1 + r % 3;
-            int jb = 0, je = 0;
+        int jb = 0, je = 0;
+        if (lane < 9) {
+            const int ax = cx - 1 + lane / 3, ay = cy - 1 + lane % 3;
             if (ax >= 0 && ax < m.nx && ay >= 0 && ay < m.ny) {
                 const int z0 = max(cz - 1, 0), z1 = min(cz + 1, m.nz - 1);
                 jb = cs[(ax * m.ny + ay) * m.nz + z0];
                 je = cs[(ax * m.ny + ay) * m.nz + z1 + 1];
             }
-            s_run_beg[r] = jb;
-            s_run_off[r + 1] = je - jb;  // lengths first, prefix-summed below
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int off = 0;
-            for (int r = 0; r < 9; ++r) {
-                const int len = s_run_off[r + 1];
-                s_run_off[r] = off;
-                off += len;
-            }
-            s_run_off[9] = off;
+        const int len = je - jb;
+        int incl = len;
+#pragma unroll
+        for (int off = 1; off < 16; off <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += t;
         }
-        __syncthreads();
-        const int ncand = s_run_off[9];
-        if (ncand > kRgCap) {
-            // oversize neighbourhood: per-atom path straight from global memory
-            __syncthreads();
-            for (int i = ib + warp; i < ie; i += kRgThreads / 32) {
-                rg_atom_warp<FILL>(sp[i], node0, cx, cy, cz, m, lane, s_cand + warp * kHitCap, pos,
-                                   d2_max, cs, sp, deg, row_ptr, E, edge_index, edge_attr);
-            }
+        const int T = __shfl_sync(0xffffffffu, incl, 15);
+        if (T > 32 * kCellRegs) {
+            if (lane == 0) crowded_cells[atomicAdd(crowded_count, 1)] = make_int2(int(f), c);
             continue;
         }
-        for (int r = 0; r < 9; ++r) {
-            const int len = s_run_off[r + 1] - s_run_off[r];
-            for (int t = threadIdx.x; t < len; t += kRgThreads) {
-                s_cand[s_run_off[r] + t] = sp[s_run_beg[r] + t];
+        const int excl = incl - len;
+        float4 cand[kCellRegs];
+        {
+            int rb[9], ro[9];
+#pragma unroll
+            for (int r = 0; r < 9; ++r) {
+                rb[r] = __shfl_sync(0xffffffffu, jb, r);
+                ro[r] = __shfl_sync(0xffffffffu, excl, r);
             }
-        }
-        int P = ncand;
-        if (FILL) {
-            P = 32;
-            while (P < ncand) P <<= 1;
-            for (int t = ncand + threadIdx.x; t < P; t += kRgThreads) {
-                s_cand[t] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7fffffff));
-            }
-            __syncthreads();
-            for (int k = 2; k <= P; k <<= 1) {
-                for (int j = k >> 1; j > 0; j >>= 1) {
-                    for (int t = threadIdx.x; t < P; t += kRgThreads) {
-                        const int u = t ^ j;
-                        if (u > t) {
-                            const float4 a = s_cand[t], b = s_cand[u];
-                            const bool asc = (t & k) == 0;
-                            if ((__float_as_int(a.w) > __float_as_int(b.w)) == asc) {
-                                s_cand[t] = b;
-                                s_cand[u] = a;
-                            }
-                        }
+#pragma unroll
+            for (int q = 0; q < kCellRegs; ++q) {
+                const int t = q * 32 + lane;
+                int bsel = rb[0], osel = ro[0];
+#pragma unroll
+                for (int r = 1; r < 9; ++r) {
+                    if (t >= ro[r]) {
+                        bsel = rb[r];
+                        osel = ro[r];
                     }
-                    __syncthreads();
                 }
+                cand[q] = t < T ? sp[bsel + (t - osel)] : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-        } else {
-            __syncthreads();
         }
-        for (int i = ib + warp; i < ie; i += kRgThreads / 32) {
-            const float4 pi = sp[i];
-            const double xi = pi.x, yi = pi.y, zi = pi.z;
+        for (int a = ib; a < ie; ++a) {
+            const float4 pi = sp[a];  // same address in every lane
             const int64_t g = node0 + __float_as_int(pi.w);
-            const int64_t beg = FILL ? row_ptr[g] : 0;
-            int count = 0;
-            for (int base = 0; base < ncand; base += 32) {
-                const int j = base + lane;
-                bool hit = false;
-                float4 pj = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (j < ncand) {
-                    pj = s_cand[j];
-                    hit = within(xi, yi, zi, pj, d2_max);
+            int total = 0;
+#pragma unroll
+            for (int q = 0; q < kCellRegs; ++q) {
+                if (q * 32 < T) {  // warp-uniform
+                    const bool valid = lane < T - q * 32;
+                    const float fx = cand[q].x - pi.x, fy = cand[q].y - pi.y, fz = cand[q].z - pi.z;
+                    const float d2f = fmaf(fz, fz, fmaf(fy, fy, fx * fx));
+                    bool hit = valid && d2f < b.lo;
+                    unsigned hm = __ballot_sync(0xffffffffu, hit);
+                    const unsigned maybe = __ballot_sync(0xffffffffu, valid && !(d2f > b.hi));
+                    if (hm != maybe) {  // warp-uniform, rare: some pair sits in the fp32 band
+                        hit = valid && within_exact(pi, cand[q], b);
+                        hm = __ballot_sync(0xffffffffu, hit);
+                    }
+                    if (hit) sts_u32(hb_addr + 4u * unsigned(total + __popc(hm & below)),
+                                     __float_as_int(cand[q].w));
+                    total += __popc(hm);
                 }
-                const unsigned mask = __ballot_sync(0xffffffffu, hit);
-                if (FILL && hit) {
-                    const int64_t slot = beg + count + __popc(mask & ((1u << lane) - 1u));
-                    edge_index[slot] = g;
-                    edge_index[E + slot] = node0 + __float_as_int(pj.w);
-                    float2* ea = reinterpret_cast<float2*>(edge_attr + slot * 6);
-                    ea[0] = make_float2(pi.x, pi.y);
-                    ea[1] = make_float2(pi.z, pj.x);
-                    ea[2] = make_float2(pj.y, pj.z);
-                }
-                count += __popc(mask);
             }
-            if (!FILL && lane == 0) deg[g] = count;
+            if (lane == 0) {
+                deg[g] = total;
+                list_ok[g] = total <= kListCap ? 1 : 0;
+            }
+            if (total == 0 || total > kListCap) continue;  // (total == 0: NaN coordinates)
+            if (lane < 3) sts_u32(hb_addr + 4u * unsigned(total + lane), 0x7fffffff);  // padding
+            __syncwarp();
+            // rank sort straight from smem: independent compares, no shuffle dependency chains
+            int32_t* out = nbr + g * kListCap;
+            const int4* hb4 = reinterpret_cast<const int4*>(hb);
+            const int v0 = hb[min(lane, total - 1)];
+            int r0 = 0;
+            if (total <= 32) {
+                for (int k = 0; k < total; k += 4) {
+                    const int4 h = hb4[k >> 2];
+                    r0 += (h.x < v0) + (h.y < v0) + (h.z < v0) + (h.w < v0);
+                }
+                if (lane < total) out[r0] = v0;
+            } else {
+                const int v1 = hb[min(lane + 32, total - 1)];
+                int r1 = 0;
+                for (int k = 0; k < total; k += 4) {
+                    const int4 h = hb4[k >> 2];
+                    r0 += (h.x < v0) + (h.y < v0) + (h.z < v0) + (h.w < v0);
+                    r1 += (h.x < v1) + (h.y < v1) + (h.z < v1) + (h.w < v1);
+                }
+                out[r0] = v0;
+                if (lane + 32 < total) out[r1] = v1;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// Crowded cells parked by rg_cell_list_kernel: the whole CTA works on one cell from shared memory
+// (degrees only - pass 2 rebuilds these rows).
+__global__ void __launch_bounds__(kRgThreads)
+rg_crowded_kernel(const float* __restrict__ pos, int64_t N, int64_t C, D2Bound b,
+                  const FrameMeta* __restrict__ meta, const int32_t* __restrict__ cell_start,
+                  const float4* __restrict__ sorted_pos, int32_t* __restrict__ deg,
+                  int32_t* __restrict__ list_ok, const int32_t* __restrict__ crowded_count,
+                  const int2* __restrict__ crowded_cells) {
+    __shared__ float4 s_cand[kRgCap];
+    __shared__ int s_run_beg[9], s_run_off[10];
+    const int n = *crowded_count;
+    for (int w = blockIdx.x; w < n; w += gridDim.x) {
+        const int2 fc = crowded_cells[w];
+        const int64_t f = fc.x;
+        const FrameMeta m = meta[f];
+        const int32_t* cs = cell_start + f * (C + 1);
+        const float4* sp = sorted_pos + f * N;
+        rg_cell_cta<false>(fc.y, m, f * N, N, b, pos, cs, sp, s_cand, s_run_beg, s_run_off, deg,
+                           nullptr, 0, nullptr, nullptr);
+        for (int a = cs[fc.y] + threadIdx.x; a < cs[fc.y + 1]; a += kRgThreads) {
+            list_ok[f * N + __float_as_int(sp[a].w)] = 0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kRgThreads, 6)
+rg_list_fill_kernel(const float* __restrict__ pos, int64_t F, int64_t N, int64_t C, D2Bound b,
+                    const FrameMeta* __restrict__ meta, const int32_t* __restrict__ cell_start,
+                    const float4* __restrict__ sorted_pos, const int32_t* __restrict__ nbr,
+                    const int32_t* __restrict__ list_ok, const int64_t* __restrict__ row_ptr,
+                    int64_t E, int64_t* __restrict__ edge_index, float* __restrict__ edge_attr) {
+    __shared__ float2 s_stage[kRgThreads / 32][96];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float2* st = s_stage[warp];
+    const int64_t total = F * N;
+    const int64_t wstride = int64_t(gridDim.x) * (kRgThreads / 32);
+    // software pipeline: everything the next row needs from global memory (row pointers, its saved
+    // list, its own coordinates) is requested before the current row is written
+    struct RowIn {
+        int64_t beg, end;
+        int ok, c0, c1;
+        float px, py, pz;
+    };
+    auto fetch = [&](int64_t g) {
+        RowIn r;
+        r.beg = ld_nc_s64_here(row_ptr + g);
+        r.end = ld_nc_s64_here(row_ptr + g + 1);
+        r.ok = int(ld_nc_u32_here(reinterpret_cast<const uint32_t*>(list_ok + g)));
+        r.c0 = int(ld_nc_u32_here(reinterpret_cast<const uint32_t*>(nbr + g * kListCap + lane)));
+        r.c1 = int(ld_nc_u32_here(reinterpret_cast<const uint32_t*>(nbr + g * kListCap + 32 + lane)));
+        r.px = pos[g * 3];
+        r.py = pos[g * 3 + 1];
+        r.pz = pos[g * 3 + 2];
+        return r;
+    };
+    int64_t g = int64_t(blockIdx.x) * (kRgThreads / 32) + warp;
+    RowIn nxt;
+    if (g < total) nxt = fetch(g);
+    for (; g < total; g += wstride) {
+        const RowIn cur = nxt;
+        if (g + wstride < total) nxt = fetch(g + wstride);
+        const int64_t f = g / N;
+        const int64_t node0 = f * N;
+        const int64_t beg = cur.beg;
+        const int d = int(cur.end - beg);
+        const float px = cur.px, py = cur.py, pz = cur.pz;
+        if (!cur.ok) {
+            // rebuild this row from the cell list (crowded cell or more than kListCap neighbours);
+            // the row's own output slots serve as scratch
+            const FrameMeta m = meta[f];
+            int cx, cy, cz;
+            cell_of(m, px, py, pz, cx, cy, cz);
+            rg_atom_warp<true>(make_float4(px, py, pz, __int_as_float(int(g - node0))), node0, cx, cy,
+                               cz, m, lane, nullptr, pos, b, cell_start + f * (C + 1),
+                               sorted_pos + f * N, nullptr, row_ptr, E, edge_index, edge_attr);
+            __syncwarp();
+            continue;
+        }
+        int64_t* er = edge_index + beg;
+        int64_t* ec = edge_index + E + beg;
+        float2* ea = reinterpret_cast<float2*>(edge_attr + beg * 6);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int e0 = 32 * h;
+            if (e0 >= d) break;  // warp-uniform
+            const int e = e0 + lane;
+            if (e < d) {
+                const int64_t col = node0 + (h == 0 ? cur.c0 : cur.c1);
+                const float* pj = pos + col * 3;
+                er[e] = g;
+                ec[e] = col;
+                st[3 * lane] = make_float2(px, py);
+                st[3 * lane + 1] = make_float2(pz, pj[0]);
+                st[3 * lane + 2] = make_float2(pj[1], pj[2]);
+            }
+            __syncwarp();
+            const int n2 = 3 * min(32, d - e0);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int u = 32 * k + lane;
+                if (u < n2) ea[96 * h + u] = st[u];
+            }
+            __syncwarp();
         }
     }
 }
@@ -684,14 +988,6 @@ constexpr int kSmThreads = 256;
 constexpr int kSmWarps = kSmThreads / 32;
 constexpr int kSmMaskWords = 4096;  // smem hit words per CTA in pass 1 (16 KB)
 constexpr int kSmFixCap = 256;      // hit words per CTA that may need the float64 predicate
-
-__device__ __forceinline__ bool within_exact(const float4& pi, const float4& pj, const D2Bound& b) {
-    const double dx = __dsub_rn(double(pj.x), double(pi.x));
-    const double dy = __dsub_rn(double(pj.y), double(pi.y));
-    const double dz = __dsub_rn(double(pj.z), double(pi.z));
-    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-    return d2 <= b.d2_max;
-}
 
 __device__ __forceinline__ void stage_frame_float4(const float* __restrict__ p, int n,
                                                    float4* __restrict__ s_p) {
@@ -838,19 +1134,6 @@ rg_small_rowptr_kernel(const int32_t* __restrict__ deg, const int64_t* __restric
     if (bid == int64_t(gridDim.x) * gridDim.y - 1 && threadIdx.x == 0) {
         row_ptr[int64_t(gridDim.y) * N] = base + total;
     }
-}
-
-// loads that must be ISSUED where they are written (software prefetch of the next row): volatile
-// asm keeps nvcc from sinking them to their first use
-__device__ __forceinline__ unsigned ld_nc_u32_here(const uint32_t* p) {
-    unsigned v;
-    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ int64_t ld_nc_s64_here(const int64_t* p) {
-    long long v;
-    asm volatile("ld.global.nc.s64 %0, [%1];" : "=l"(v) : "l"(p));
-    return int64_t(v);
 }
 
 __global__ void __launch_bounds__(kSmThreads)
@@ -1176,9 +1459,8 @@ extern "C" int gkn_radius_graph_count(const float* pos, int64_t F, int64_t N, do
             return 0;
         }
     } else {
-        cudaError_t err = cudaMemsetAsync(w.cell_count, 0, size_t(F) * (w.C + 1) * 4, st);
-        if (err != cudaSuccess) return set_cuda_error("cudaMemsetAsync(cell_count)", err);
-        rg_frame_setup_kernel<<<unsigned(F), 1024, 0, st>>>(pos, N, threshold, w.C, w.meta);
+        rg_frame_setup_kernel<<<unsigned(F), 1024, 0, st>>>(pos, N, threshold, w.C, w.meta,
+                                                            w.cell_count, w.crowded_count);
         GKN_CHECK_LAUNCH("rg_frame_setup");
         const int ag = grid_for(total, 256, 8);
         rg_assign_kernel<<<ag, 256, 0, st>>>(pos, F, N, w.C, w.meta, w.atom_cell, w.cell_count);
@@ -1186,18 +1468,22 @@ extern "C" int gkn_radius_graph_count(const float* pos, int64_t F, int64_t N, do
         exclusive_scan_kernel<int32_t, int32_t><<<unsigned(F), kScanThreads, 0, st>>>(
             w.cell_count, w.cell_start, w.C, w.C + 1, w.C + 1);
         GKN_CHECK_LAUNCH("rg_scan_cells");
-        err = cudaMemsetAsync(w.cell_count, 0, size_t(F) * (w.C + 1) * 4, st);
-        if (err != cudaSuccess) return set_cuda_error("cudaMemsetAsync(cell cursor)", err);
         rg_place_kernel<<<ag, 256, 0, st>>>(pos, F, N, w.C, w.atom_cell, w.cell_start,
                                             w.cell_count, w.sorted_pos);
         GKN_CHECK_LAUNCH("rg_place");
-        int64_t cgx = (int64_t(sms) * 16 + F - 1) / F;  // CTAs per frame striding over its cells
-        if (cgx > w.C) cgx = w.C;
+        // one warp per cell; cells the registers cannot hold are parked for the CTA-wide kernel
+        int64_t cgx = (int64_t(sms) * 16 + F - 1) / F;
+        if (cgx > (w.C + 7) / 8) cgx = (w.C + 7) / 8;
         const dim3 cg(unsigned(cgx < 1 ? 1 : cgx), unsigned(F));
-        rg_cell_kernel<false><<<cg, kRgThreads, 0, st>>>(pos, F, N, w.C, exact_d2_bound(threshold),
-                                                        w.meta, w.cell_start, w.sorted_pos, deg,
-                                                        nullptr, 0, nullptr, nullptr);
-        GKN_CHECK_LAUNCH("rg_count");
+        const D2Bound bound = exact_d2_bound(threshold);
+        rg_cell_list_kernel<<<cg, kRgThreads, 0, st>>>(F, N, w.C, bound, w.meta, w.cell_start,
+                                                      w.sorted_pos, deg, w.nbr, w.list_ok,
+                                                      w.crowded_count, w.crowded_cells);
+        GKN_CHECK_LAUNCH("rg_cell_list");
+        rg_crowded_kernel<<<unsigned(sms) * 4, kRgThreads, 0, st>>>(
+            pos, N, w.C, bound, w.meta, w.cell_start, w.sorted_pos, deg, w.list_ok,
+            w.crowded_count, w.crowded_cells);
+        GKN_CHECK_LAUNCH("rg_crowded");
     }
     scan_block_sums_kernel<<<unsigned(w.nblk), kScanThreads, 0, st>>>(deg, total, w.block_sums);
     GKN_CHECK_LAUNCH("rg_scan_sums");
@@ -1243,9 +1529,19 @@ extern "C" int gkn_radius_graph_fill(const float* pos, int64_t F, int64_t N, dou
         int64_t cgx = (int64_t(sms) * 16 + F - 1) / F;
         if (cgx > w.C) cgx = w.C;
         const dim3 cg(unsigned(cgx < 1 ? 1 : cgx), unsigned(F));
-        rg_cell_kernel<true><<<cg, kRgThreads, 0, st>>>(pos, F, N, w.C, exact_d2_bound(threshold),
-                                                       w.meta, w.cell_start, w.sorted_pos, nullptr,
-                                                       row_ptr, E, edge_index, edge_attr);
+        if (E > total * 40) {
+            // dense graphs (most rows longer than the saved lists): rebuild per cell from smem
+            rg_cell_kernel<true><<<cg, kRgThreads, 0, st>>>(pos, F, N, w.C,
+                                                           exact_d2_bound(threshold), w.meta,
+                                                           w.cell_start, w.sorted_pos, nullptr,
+                                                           row_ptr, E, edge_index, edge_attr);
+        } else {
+            const int fg = grid_for(total * 32, kRgThreads, 8);
+            rg_list_fill_kernel<<<fg, kRgThreads, 0, st>>>(pos, F, N, w.C, exact_d2_bound(threshold),
+                                                          w.meta, w.cell_start, w.sorted_pos, w.nbr,
+                                                          w.list_ok, row_ptr, E, edge_index,
+                                                          edge_attr);
+        }
     }
     GKN_CHECK_LAUNCH("rg_fill");
     return 0;

@@ -75,6 +75,28 @@ def test_radius_graph_lattice_at_exactly_the_cutoff_spacing(n_side, thr):
     assert np.array_equal(ei.cpu().numpy(), ei_ref) and np.array_equal(ea.cpu().numpy(), ea_ref)
 
 
+def test_radius_graph_mixed_density_large_frames():
+    """Large-frame path with every row flavour in one frame: rows served from the saved neighbour
+    lists, rows longer than the list capacity (rebuilt by pass 2) and cells too crowded for the
+    one-warp-per-cell kernel (CTA-wide worklist kernel)."""
+    from molecular_dynamics_neural_operator_b200 import ops
+    from oracle import gkn_oracle as orc
+
+    rng = np.random.default_rng(7)
+    frames = []
+    for f in range(2):
+        bulk = rng.random((4000, 3)) * 40.0
+        blob_a = 10.0 + rng.random((100, 3)) * 2.5      # 100 neighbours > 64, neighbourhood <= 256
+        blob_b = 30.0 + rng.random((280, 3)) * 3.0      # > 256 atoms around: crowded cells
+        p = np.concatenate([bulk, blob_a, blob_b]).astype(np.float32)
+        frames.append(p[rng.permutation(len(p))])
+    pos = np.stack(frames)
+    ei_ref, ea_ref = orc.radius_graph_batched(pos, 4.2)
+    assert ei_ref.shape[1] < 40 * pos.shape[0] * pos.shape[1]  # stays on the list-driven fill
+    ei, ea = ops.radius_graph(torch.from_numpy(pos).cuda(), 4.2)
+    assert np.array_equal(ei.cpu().numpy(), ei_ref) and np.array_equal(ea.cpu().numpy(), ea_ref)
+
+
 def test_radius_graph_full_size_properties_and_kdtree_oracle():
     """BASELINE config 3 (10k atoms, 4.2 A): equals the kd-tree oracle; symmetric, sorted, self loops."""
     from molecular_dynamics_neural_operator_b200 import ops
