@@ -85,7 +85,7 @@ def test_radius_graph_mixed_density_large_frames():
     rng = np.random.default_rng(7)
     frames = []
     for f in range(2):
-        bulk = rng.random((4000, 3)) * 40.0
+        bulk = rng.random((4000, 3)) * 50.0
         blob_a = 10.0 + rng.random((100, 3)) * 2.5      # 100 neighbours > 64, neighbourhood <= 256
         blob_b = 30.0 + rng.random((280, 3)) * 3.0      # > 256 atoms around: crowded cells
         p = np.concatenate([bulk, blob_a, blob_b]).astype(np.float32)
