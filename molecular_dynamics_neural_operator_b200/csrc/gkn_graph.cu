@@ -1255,9 +1255,10 @@ scan_block_sums_kernel(const int32_t* __restrict__ in, int64_t n, int64_t* __res
     }
 }
 
+template <typename TOut>
 __global__ void __launch_bounds__(kScanThreads)
 scan_apply_kernel(const int32_t* __restrict__ in, int64_t n, const int64_t* __restrict__ offs,
-                  int64_t* __restrict__ out) {
+                  TOut* __restrict__ out) {
     __shared__ int64_t warp_tot[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t base = int64_t(blockIdx.x) * kScanChunk + int64_t(threadIdx.x) * kScanItems;
@@ -1288,10 +1289,10 @@ scan_apply_kernel(const int32_t* __restrict__ in, int64_t n, const int64_t* __re
     int64_t run = offs[blockIdx.x] + (warp == 0 ? 0 : warp_tot[warp - 1]) + incl - tsum;
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) {
-        if (base + k < n) out[base + k] = run;
+        if (base + k < n) out[base + k] = TOut(run);
         run += v[k];
     }
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = offs[gridDim.x];
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = TOut(offs[gridDim.x]);
 }
 
 // Row slices of the small-frame kernels: pass 1 (mask + row pointers) and pass 2 (fill).
@@ -1366,7 +1367,8 @@ int grid_for(int64_t total, int threads, int per_sm) {
 // C ABI
 // ================================================================================================
 extern "C" int64_t gkn_graph_prepare_workspace_bytes(int64_t N, int64_t E) {
-    return (2 * N + 2 * E + 64) * int64_t(sizeof(int32_t));
+    const int64_t nblk = (N + 4095) / 4096;  // row-pointer scans: block sums + their offsets
+    return (2 * N + 2 * E + 64) * int64_t(sizeof(int32_t)) + (2 * nblk + 4) * 8;
 }
 
 extern "C" int gkn_graph_prepare(const int64_t* edge_index, int64_t N, int64_t E, int32_t* perm,
@@ -1386,6 +1388,24 @@ extern "C" int gkn_graph_prepare(const int64_t* edge_index, int64_t N, int64_t E
     int32_t* cnt_src = cnt_dst + N;
     int32_t* tmp = cnt_src + N;
     int32_t* tmp2 = tmp + E;
+    const int64_t nblk = (N + 4095) / 4096;
+    int64_t* blk_sums = reinterpret_cast<int64_t*>(
+        static_cast<uint8_t*>(workspace) + (2 * N + 2 * E + 64) / 2 * 2 * int64_t(sizeof(int32_t)));
+    int64_t* blk_offs = blk_sums + nblk + 1;
+    auto scan_rows = [&](const int32_t* cnt, int32_t* ptr) -> int {
+        if (nblk <= 1) {
+            exclusive_scan_kernel<int32_t, int32_t><<<1, kScanThreads, 0, st>>>(cnt, ptr, N, 0, 0);
+            GKN_CHECK_LAUNCH("prep_scan");
+            return 0;
+        }
+        scan_block_sums_kernel<<<unsigned(nblk), kScanThreads, 0, st>>>(cnt, N, blk_sums);
+        GKN_CHECK_LAUNCH("prep_scan_sums");
+        exclusive_scan_kernel<int64_t, int64_t><<<1, kScanThreads, 0, st>>>(blk_sums, blk_offs, nblk, 0, 0);
+        GKN_CHECK_LAUNCH("prep_scan_offs");
+        scan_apply_kernel<int32_t><<<unsigned(nblk), kScanThreads, 0, st>>>(cnt, N, blk_offs, ptr);
+        GKN_CHECK_LAUNCH("prep_scan_rows");
+        return 0;
+    };
     cudaError_t err = cudaMemsetAsync(cnt_dst, 0, size_t(2 * N) * 4, st);
     if (err != cudaSuccess) return set_cuda_error("cudaMemsetAsync(prepare)", err);
     err = cudaMemsetAsync(status, 0, 4, st);
@@ -1394,10 +1414,8 @@ extern "C" int gkn_graph_prepare(const int64_t* edge_index, int64_t N, int64_t E
     const int ng = grid_for(N * 32, 256, 8);
     prep_count_kernel<<<eg, 256, 0, st>>>(edge_index, N, E, cnt_dst, cnt_src, status);
     GKN_CHECK_LAUNCH("prep_count");
-    exclusive_scan_kernel<int32_t, int32_t><<<1, kScanThreads, 0, st>>>(cnt_dst, dst_ptr, N, 0, 0);
-    GKN_CHECK_LAUNCH("prep_scan_dst");
-    exclusive_scan_kernel<int32_t, int32_t><<<1, kScanThreads, 0, st>>>(cnt_src, src_ptr, N, 0, 0);
-    GKN_CHECK_LAUNCH("prep_scan_src");
+    if (int rc = scan_rows(cnt_dst, dst_ptr)) return rc;
+    if (int rc = scan_rows(cnt_src, src_ptr)) return rc;
     prep_inv_cnt_kernel<<<grid_for(N, 256, 8), 256, 0, st>>>(dst_ptr, inv_cnt, N);
     GKN_CHECK_LAUNCH("prep_inv_cnt");
     err = cudaMemsetAsync(cnt_dst, 0, size_t(2 * N) * 4, st);
@@ -1490,7 +1508,8 @@ extern "C" int gkn_radius_graph_count(const float* pos, int64_t F, int64_t N, do
     exclusive_scan_kernel<int64_t, int64_t>
         <<<1, kScanThreads, 0, st>>>(w.block_sums, w.block_offs, w.nblk, 0, 0);
     GKN_CHECK_LAUNCH("rg_scan_offs");
-    scan_apply_kernel<<<unsigned(w.nblk), kScanThreads, 0, st>>>(deg, total, w.block_offs, row_ptr);
+    scan_apply_kernel<int64_t><<<unsigned(w.nblk), kScanThreads, 0, st>>>(deg, total, w.block_offs,
+                                                                        row_ptr);
     GKN_CHECK_LAUNCH("rg_scan_rows");
     return 0;
 }

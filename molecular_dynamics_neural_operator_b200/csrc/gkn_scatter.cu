@@ -900,7 +900,7 @@ extern "C" int gkn_segment_matvec(const float* rows, const int32_t* perm, const 
         case 16: if (batch_nodes) GKN_SMV(16, 4); else GKN_SMV(16, 1); break;
         case 32: if (batch_nodes) GKN_SMV(32, 4); else GKN_SMV(32, 1); break;
         case 64: if (batch_nodes) GKN_SMV(64, 4); else GKN_SMV(64, 1); break;
-        case 128: if (batch_nodes) GKN_SMV(128, 2); else GKN_SMV(128, 1); break;
+        case 128: if (batch_nodes) GKN_SMV(128, 4); else GKN_SMV(128, 1); break;
         default: return set_error("gkn_segment_matvec: width must be 16, 32, 64 or 128");
     }
 #undef GKN_SMV

@@ -11,8 +11,8 @@ from molecular_dynamics_neural_operator_b200 import synthetic as syn  # noqa: E4
 from molecular_dynamics_neural_operator_b200.graph_kernel import KernelNN  # noqa: E402
 from molecular_dynamics_neural_operator_b200.train import Trainer  # noqa: E402
 
-wl = syn.WORKLOADS["bba_allatom"]
-B = 8
+wl = syn.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "bba_allatom"]
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 model = KernelNN(wl.width, wl.ker_width, wl.depth, 6, in_width=7, out_width=3, window_size=wl.window,
@@ -46,6 +46,13 @@ for e in prof.key_averages():
         rows.append((t / 1e3 / steps, e.count // steps, e.key[:110]))
 rows.sort(reverse=True)
 tot = sum(r[0] for r in rows)
+torch.cuda.synchronize()
+import time
+t0 = time.perf_counter()
+for _ in range(10):
+    step()
+torch.cuda.synchronize()
+print(f"wall per step: {(time.perf_counter() - t0) * 100:.2f} ms")
 print(f"device time per step: {tot:.2f} ms")
 for t, c, k in rows[:45]:
     print(f"{t:9.3f} ms {100 * t / tot:5.1f}%  n={c:4d}  {k}")
