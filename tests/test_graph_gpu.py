@@ -27,7 +27,8 @@ def test_construct_pairdata_bit_exact_vs_reference_golden(name):
                                         (2, 50, 5.0, 0.5), (1, 40, 10.0, 1000.0),
                                         (1, 2300, 5.0, 9.0),   # > 2048 staged candidates: per-atom fallback
                                         (3, 700, 9.0, 3.0), (2, 2048, 30.0, 4.2), (7, 33, 9.0, 4.2),
-                                        (300, 28, 14.0, 8.0), (1, 1999, 12.0, 8.0)])
+                                        (300, 28, 14.0, 8.0), (1, 1999, 12.0, 8.0),
+                                        (5000, 12, 9.0, 4.2)])  # > 4096 pass-1 CTAs: generic row-pointer scan
 def test_radius_graph_bit_exact_vs_scipy_oracle(F, N, L, thr):
     from molecular_dynamics_neural_operator_b200 import ops
     from oracle import gkn_oracle as orc
