@@ -134,6 +134,22 @@ int gkn_edge_outer_sum(const float* xs, const float* gs, const int32_t* src_s,
                        const int32_t* dst_s, void* S, int32_t out_is_bf16, int64_t e0, int64_t e1,
                        int64_t N, int32_t A, int32_t W, void* stream);
 
+/* ---- fused gradient of the edge hidden state (tcgen05) ------------------------------------
+ * dh[e, k] = sum_n S[e, n] * w3[n, k]  with S as above, synthesised tile by tile in shared memory
+ * while the tensor core runs: S never reaches HBM (the autograd of NNConv_old.message,
+ * graph_kernel.py:200-202, through the shared last edge-MLP layer, :271-273).
+ * xs, gs: float32 [A, N, W] (A <= 16); src_s, dst_s: sorted-order endpoints (dst_s non-decreasing);
+ * w3t: bf16 [K, W*W] = net.layers.4.weight transposed; dh: bf16 [E, K] (fp32 accumulation, one
+ * rounding).  W = 64, K % 256 == 0.  workspace: gkn_edge_grad_workspace_bytes(N, W) bytes. */
+int64_t gkn_edge_grad_workspace_bytes(int64_t N, int32_t W);
+/* status[0] = max over 128-edge tiles of the number of distinct destinations in the tile; the fused
+ * kernels below require it to be <= 8 (graphs of lower degree use the staged path). */
+int gkn_edge_grad_max_slots(const int32_t* dst_s, int64_t E, int32_t* status, void* stream);
+int gkn_edge_grad_dh_bf16(const float* xs, const float* gs, const int32_t* src_s,
+                          const int32_t* dst_s, const void* w3t_bf16, void* dh_bf16, int64_t E,
+                          int64_t N, int32_t A, int32_t K, int32_t W, void* workspace,
+                          int64_t workspace_bytes, void* stream);
+
 /* ---- casts ------------------------------------------------------------------------------ */
 /* out_bf16[i] = bf16_rn( relu ? max(in[i] + (bias ? bias[i % cols] : 0), 0) : in[i] + bias ) */
 int gkn_bias_act_cast_bf16(const float* in, const float* bias, void* out_bf16, int64_t rows,

@@ -47,6 +47,12 @@ SIGNATURES = {
         c_int,
         [P, P, P, P, P, c_int32, c_int64, c_int64, c_int64, c_int32, c_int32, P],
     ),
+    "gkn_edge_grad_workspace_bytes": (c_int64, [c_int64, c_int32]),
+    "gkn_edge_grad_max_slots": (c_int, [P, c_int64, P, P]),
+    "gkn_edge_grad_dh_bf16": (
+        c_int,
+        [P, P, P, P, P, P, c_int64, c_int64, c_int32, c_int32, c_int32, P, c_int64, P],
+    ),
     "gkn_bias_act_cast_bf16": (c_int, [P, P, P, c_int64, c_int64, c_int32, P]),
     "gkn_edge_layer0": (c_int, [P, P, P, P, c_int32, c_int64, c_int32, c_int32, P]),
     "gkn_mask_cast_colsum_workspace_bytes": (c_int64, [c_int64, c_int32]),

@@ -71,6 +71,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
+// Same, for waiters that are many (one per warp) or expected to wait long: back off between polls
+// so the spinning does not compete with the tensor core's operand reads for the smem pipe.
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, uint32_t ns) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(ns);
+        if (++spins > (1u << 24)) {
+            __trap();
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // TMA
 // ------------------------------------------------------------------------------------------------

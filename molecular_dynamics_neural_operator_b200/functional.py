@@ -39,6 +39,13 @@ import os
 # GEMM efficiency and dW3 accumulate traffic than they gain in L2 residency.
 _S_CHUNK_EDGES = int(os.environ.get("GKN_S_CHUNK_EDGES", "16384"))
 
+# Experimental: dh_e from the fused tcgen05 kernel (gkn_edge_grad_dh_bf16: S synthesised by the
+# tensor core, never stored) instead of the staged S @ W3 library GEMM.  Bit-for-bit the same
+# operands and accumulation precision, but as measured on B200 it is 2-2.6x SLOWER than the staged
+# GEMM (hand-off latency between its five pipeline roles), so it is off by
+# default; dW3 still needs the staged S either way.
+FUSED_DH = os.environ.get("GKN_FUSED_DH", "0") == "1"
+
 
 def _mm32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """a @ b with an fp32 result (fp32 accumulation for bf16 operands)."""
@@ -87,6 +94,10 @@ def _edge_grads(xs, gns, plan: GraphPlan, ea, h1, h, w1, w2, w3q, need_ea: bool,
     bf16 = precision == "bf16"
     s_dtype = torch.bfloat16 if bf16 else torch.float32
     w2q = w2.to(torch.bfloat16) if bf16 else w2
+    dh_all = None
+    if (FUSED_DH and bf16 and xs.size(2) == 64 and xs.size(0) <= 16 and K % 256 == 0
+            and ops.edge_grad_slots(plan) <= ops.EDGE_GRAD_MAX_SLOTS):
+        dh_all = ops.edge_grad_dh(xs, gns, plan, w3q.t().contiguous())
     for e0 in range(0, E, _S_CHUNK_EDGES):
         e1 = min(E, e0 + _S_CHUNK_EDGES)
         hc, h1c = h[e0:e1], h1[e0:e1]
@@ -95,7 +106,7 @@ def _edge_grads(xs, gns, plan: GraphPlan, ea, h1, h, w1, w2, w3q, need_ea: bool,
         # dh_e for this chunk.  bf16 mode: the GEMM rounds its fp32 accumulators to bf16 itself
         # (rounding before or after the 0/1 ReLU mask is the same), halving the traffic of the
         # mask pass below.
-        dz2 = torch.mm(S, w3q)
+        dz2 = torch.mm(S, w3q) if dh_all is None else dh_all[e0:e1]
         del S
         # backward of "+ b2, ReLU": mask, bias gradient and operand hand-off in one pass
         dz2q = ops.mask_cast_colsum(dz2, hc, db2, s_dtype)

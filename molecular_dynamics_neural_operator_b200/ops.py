@@ -297,6 +297,53 @@ def edge_outer_sum(xs, gs, plan: GraphPlan, e0: int, e1: int, out_dtype=torch.bf
     return S
 
 
+EDGE_GRAD_MAX_SLOTS = 8
+
+
+def edge_grad_slots(plan: GraphPlan) -> int:
+    """Largest number of distinct destinations inside any 128-edge tile of the plan (cached on the
+    plan; one small kernel and a 4-byte read).  The fused edge-gradient kernels need <= 8."""
+    cached = getattr(plan, "_edge_grad_slots", None)
+    if cached is not None:
+        return cached
+    lib = _lib.load()
+    status = torch.zeros(1, dtype=torch.int32, device=plan.dst.device)
+    with torch.cuda.device(plan.dst.device):
+        _lib.check(lib.gkn_edge_grad_max_slots(_p(plan.dst), plan.num_edges, _p(status), _stream()),
+                   "gkn_edge_grad_max_slots")
+    val = int(status.item())
+    object.__setattr__(plan, "_edge_grad_slots", val)
+    return val
+
+
+def edge_grad_dh(xs, gs, plan: GraphPlan, w3t: torch.Tensor) -> torch.Tensor:
+    """dh[e, k] = sum_n S[e, n] * W3[n, k] (bf16 [E, K]) with S = sum_a xs[a, src] (x) gs[a, dst]
+    synthesised inside the tcgen05 kernel - S is never stored.  w3t: bf16 [K, W*W] (W3 transposed)."""
+    lib = _lib.load()
+    A, N, W = (int(s) for s in xs.shape)
+    if gs.shape != xs.shape:
+        raise ValueError("xs and gs must have the same [A, N, W] shape")
+    K = int(w3t.size(0))
+    if w3t.shape != (K, W * W):
+        raise ValueError(f"w3t must be [K, {W * W}], got {tuple(w3t.shape)}")
+    E = plan.num_edges
+    if edge_grad_slots(plan) > EDGE_GRAD_MAX_SLOTS:
+        raise ValueError("edge_grad_dh: a 128-edge tile spans more than 8 destination nodes "
+                         "(use the staged path for graphs of such low degree)")
+    dh = torch.empty((E, K), dtype=torch.bfloat16, device=xs.device)
+    ws_bytes = int(lib.gkn_edge_grad_workspace_bytes(N, W))
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=xs.device)
+    with torch.cuda.device(xs.device):
+        _lib.check(
+            lib.gkn_edge_grad_dh_bf16(
+                _p(xs, torch.float32, "xs"), _p(gs, torch.float32, "gs"), _p(plan.src), _p(plan.dst),
+                _p(w3t, torch.bfloat16, "w3t"), _p(dh), E, N, A, K, W, _p(ws), ws_bytes, _stream(),
+            ),
+            "gkn_edge_grad_dh_bf16",
+        )
+    return dh
+
+
 def bias_act_cast_bf16(x, bias=None, relu=False) -> torch.Tensor:
     lib = _lib.load()
     rows, cols = int(x.size(0)), int(x.size(1))

@@ -222,3 +222,45 @@ def test_mask_cast_colsum_bf16_input_in_place():
     assert out.data_ptr() == d.data_ptr()  # same dtype: masked in place
     assert torch.equal(out.cpu().float(), ref)
     assert torch.allclose(cs.cpu(), ref.sum(0), rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("N,E,A,K", [(40, 3000, 12, 256), (504, 20000, 12, 1024), (100, 5000, 3, 256),
+                                     (300, 12000, 16, 512), (7, 130, 1, 256), (64, 128 * 40, 8, 256),
+                                     (5, 129, 5, 256)])
+def test_fused_edge_hidden_gradient(N, E, A, K):
+    """gkn_edge_grad_dh_bf16 (S synthesised by the tensor core, never stored) against the staged
+    restatement  S = sum_a xs[a, src] (x) gs[a, dst];  dh = S @ W3  in float64 on bf16-rounded
+    operands.  Random graphs: Poisson in-degrees, tiles spanning 2..8 destinations, ragged last tile."""
+    from molecular_dynamics_neural_operator_b200 import ops
+
+    W = 64
+    g = torch.Generator().manual_seed(N + E + A)
+    plan = ops.prepare_graph(rand_graph(N, E, N + E).to(DEV), N)
+    assert ops.edge_grad_slots(plan) <= ops.EDGE_GRAD_MAX_SLOTS
+    xs = torch.randn(A, N, W, generator=g).to(DEV)
+    gs = torch.randn(A, N, W, generator=g).to(DEV)
+    w3 = (torch.randn(W * W, K, generator=g) / W).bfloat16().to(DEV)
+    dh = ops.edge_grad_dh(xs, gs, plan, w3.t().contiguous())
+    assert dh.shape == (E, K) and dh.dtype == torch.bfloat16
+    xq = xs.bfloat16().double()[:, plan.src.long()]  # [A, E, W]
+    gq = gs.bfloat16().double()[:, plan.dst.long()]
+    S = torch.einsum("aei,aeo->eio", xq, gq).reshape(E, W * W)
+    Sq = S.float().bfloat16().double()  # the kernel rounds S to bf16 once (its MMA operand)
+    ref = Sq @ w3.double()
+    err = (dh.double() - ref).norm() / ref.norm()
+    assert err < 2 ** -7, err
+    # and against the existing staged kernel (bf16 S through HBM, library GEMM)
+    S2 = ops.edge_outer_sum(xs, gs, plan, 0, E, torch.bfloat16)
+    ref2 = (S2.double() @ w3.double())
+    assert (dh.double() - ref2).norm() / ref2.norm() < 2 ** -7
+
+
+def test_fused_edge_gradient_rejects_low_degree_graphs():
+    from molecular_dynamics_neural_operator_b200 import ops
+
+    N, E, W, K = 2000, 9000, 64, 256
+    plan = ops.prepare_graph(rand_graph(N, E, 5).to(DEV), N)
+    assert ops.edge_grad_slots(plan) > ops.EDGE_GRAD_MAX_SLOTS
+    xs = torch.zeros(2, N, W, device=DEV)
+    with pytest.raises(ValueError, match="more than 8 destination"):
+        ops.edge_grad_dh(xs, xs, plan, torch.zeros(K, W * W, dtype=torch.bfloat16, device=DEV))

@@ -245,3 +245,38 @@ def test_full_size_properties_bba_allatom():
     lhs = (dxj.double() * x1.double()[plan.src.long()]).sum()
     rhs = (m1.double() * gn.double()[plan.dst.long()]).sum()
     assert abs(float(lhs - rhs)) <= 1e-5 * abs(float(rhs)) + 1e-3
+
+
+def test_experimental_fused_dh_gives_the_same_gradients_as_the_staged_pass():
+    """GKN_FUSED_DH (dh_e from the tcgen05 kernel that synthesises S on the tensor core) against
+    the default staged pass on a BBA all-atom frame: same operands, same precision."""
+    from molecular_dynamics_neural_operator_b200 import functional as GF
+    from molecular_dynamics_neural_operator_b200 import ops
+    from molecular_dynamics_neural_operator_b200 import synthetic as syn
+    from molecular_dynamics_neural_operator_b200.graph_kernel import DenseNet
+
+    wl = syn.WORKLOADS["bba_allatom"]
+    pos = torch.from_numpy(syn.trajectory(wl, 1, seed=3)).cuda()
+    ei, ea, rp = ops.radius_graph(pos, wl.cutoff, return_row_ptr=True)
+    N, W, K = wl.num_atoms, 64, 256
+    plan = ops.plan_from_csr(ei, rp, N)
+    assert ops.edge_grad_slots(plan) <= ops.EDGE_GRAD_MAX_SLOTS
+    torch.manual_seed(0)
+    net = DenseNet([6, K, K, W * W], torch.nn.ReLU).cuda()
+    root = (torch.randn(W, W, device="cuda") / 8).requires_grad_(True)
+    bias = torch.zeros(W, device="cuda", requires_grad=True)
+    x0 = torch.randn(N, W, device="cuda")
+    eas = ea.index_select(0, plan.perm_long)
+    grads = []
+    try:
+        for fused in (False, True):
+            GF.FUSED_DH = fused
+            net.zero_grad()
+            y = GF.gkn_stack(x0, eas, net, root, bias, root, bias, plan, (0, 0, 1), relu=True,
+                             precision="bf16")
+            y.square().sum().backward()
+            grads.append({k: v.grad.clone() for k, v in net.named_parameters()})
+    finally:
+        GF.FUSED_DH = False
+    for k in grads[0]:
+        assert fro_err(grads[1][k], grads[0][k]) <= 2 ** -9, k
