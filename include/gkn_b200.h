@@ -161,6 +161,7 @@ int gkn_bias_act_cast_bf16(const float* in, const float* bias, void* out_bf16, i
  * gkn_mask_cast_colsum: out[r,c] = dz[r,c] * (act[r,c] > 0); dz fp32 or bf16 (bf16 dz needs bf16
  * act/out), out cast to bf16 or kept fp32 (may alias dz when dtypes match); colsum[0,c] (+)= sum_r out[r,c] (bias gradient) and, when side != NULL
  * (nside = 6), colsum[1+j,c] (+)= sum_r out[r,c]*side[r,j] (layer-.0 weight gradient, transposed).
+ * out may be NULL when only the sums are needed.
  * colsum is [(1+nside), cols]; deterministic two-pass reduction, no atomics.  act is the layer's
  * saved post-ReLU activation (bf16 or fp32). */
 int gkn_edge_layer0(const float* ea, const float* w1, const float* b1, void* out,

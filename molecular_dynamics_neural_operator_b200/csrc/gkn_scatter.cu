@@ -566,7 +566,9 @@ mask_cast_colsum_kernel(const DZ* dz, const ACT* __restrict__ act, OUT* out,
                     acc[1 + j].w = fmaf(w.w, sj, acc[1 + j].w);
                 }
                 const int64_t off = r * cols + c;
-                if constexpr (sizeof(OUT) == 2) {
+                if (out == nullptr) {
+                    // sums only (the masked values themselves are not needed downstream)
+                } else if constexpr (sizeof(OUT) == 2) {
                     __nv_bfloat162 lo = __floats2bfloat162_rn(w.x, w.y);
                     __nv_bfloat162 hi = __floats2bfloat162_rn(w.z, w.w);
                     uint2 pk;

@@ -113,7 +113,8 @@ def _edge_grads(xs, gns, plan: GraphPlan, ea, h1, h, w1, w2, w3q, need_ea: bool,
         dw2 = _addmm32(dw2, dz2q.t(), h1c)
         dz1 = _mm32(dz2q, w2q)
         # backward of "+ b1, ReLU" and of layer .0 itself: db1 and dW1 = dz1^T edge_attr
-        dz1 = ops.mask_cast_colsum(dz1, h1c, cs1, torch.float32, side=ea[e0:e1])
+        dz1 = ops.mask_cast_colsum(dz1, h1c, cs1, torch.float32, side=ea[e0:e1],
+                                   sums_only=not need_ea)
         if need_ea:
             torch.mm(dz1, w1, out=dea[e0:e1])
     return dw3, dw2, db2, cs1[1:].t().contiguous(), cs1[0].contiguous(), dea

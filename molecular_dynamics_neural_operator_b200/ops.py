@@ -359,10 +359,12 @@ def bias_act_cast_bf16(x, bias=None, relu=False) -> torch.Tensor:
     return out
 
 
-def mask_cast_colsum(dz, act, colsum, out_dtype, side=None, accumulate: bool = True) -> torch.Tensor:
+def mask_cast_colsum(dz, act, colsum, out_dtype, side=None, accumulate: bool = True,
+                     sums_only: bool = False) -> torch.Tensor:
     """out = dz * (act > 0) in ``out_dtype`` (bf16 / fp32); colsum[0] (+)= out.sum(0) and, with
     ``side`` [rows, 6], colsum[1+j] (+)= (out * side[:, j:j+1]).sum(0).  ``colsum`` is
-    [(1 + nside), cols] (or [cols] without side).  One pass over dz, deterministic reduction."""
+    [(1 + nside), cols] (or [cols] without side).  One pass over dz, deterministic reduction.
+    ``sums_only``: do not write ``out`` (returns None)."""
     lib = _lib.load()
     rows, cols = int(dz.size(0)), int(dz.size(1))
     nside = 0 if side is None else int(side.size(1))
@@ -371,8 +373,11 @@ def mask_cast_colsum(dz, act, colsum, out_dtype, side=None, accumulate: bool = T
     # per-call scratch from the caching allocator (stream-ordered, so safe on any stream)
     ws = torch.empty(int(lib.gkn_mask_cast_colsum_workspace_bytes(cols, nside)), dtype=torch.uint8,
                      device=dz.device)
-    out = dz if out_dtype == dz.dtype else torch.empty((rows, cols), dtype=out_dtype,
-                                                      device=dz.device)
+    if sums_only:
+        out = None  # the kernel skips the stores
+    else:
+        out = dz if out_dtype == dz.dtype else torch.empty((rows, cols), dtype=out_dtype,
+                                                          device=dz.device)
     with torch.cuda.device(dz.device):
         _lib.check(
             lib.gkn_mask_cast_colsum(
