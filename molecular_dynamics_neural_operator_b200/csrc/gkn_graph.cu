@@ -225,7 +225,8 @@ struct RadiusWs {
     float4* sorted_pos;    // [F*N]  xyz + original atom index (bit-cast) in cell order
     int64_t* block_sums;   // [nblk]     row-pointer scan: per-block sums
     int64_t* block_offs;   // [nblk + 1] and their exclusive scan
-    int32_t* nbr;          // large frames: [F*N, kListCap] sorted neighbour lists of pass 1
+    float4* nbr;           // large frames: [F*N, kListCap] sorted neighbour lists of pass 1
+                           // (x, y, z, atom index): pass 2 needs no gather
     int32_t* list_ok;      // large frames: [F*N] 1 = row has its list, 0 = pass 2 rebuilds it
     int32_t* crowded_count;  // large frames: cells left to rg_crowded_kernel
     int2* crowded_cells;     // [F * C] (frame, cell)
@@ -254,7 +255,7 @@ inline RadiusWs carve_radius_ws(void* base, int64_t F, int64_t N) {
     w.block_sums = reinterpret_cast<int64_t*>(take(w.nblk * 8));
     w.block_offs = reinterpret_cast<int64_t*>(take((w.nblk + 1) * 8));
     const bool small = N <= 2048;  // kRgCap
-    w.nbr = reinterpret_cast<int32_t*>(take(small ? 0 : F * N * 64 * 4));  // kListCap
+    w.nbr = reinterpret_cast<float4*>(take(small ? 0 : F * N * 64 * 16));  // kListCap
     w.list_ok = reinterpret_cast<int32_t*>(take(small ? 0 : F * N * 4));
     w.crowded_count = reinterpret_cast<int32_t*>(take(small ? 0 : 4));
     w.crowded_cells = reinterpret_cast<int2*>(take(small ? 0 : F * w.C * 8));
@@ -422,6 +423,13 @@ __device__ __forceinline__ bool within_exact(const float4& pi, const float4& pj,
 __device__ __forceinline__ unsigned ld_nc_u32_here(const uint32_t* p) {
     unsigned v;
     asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ld_nc_f4_here(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
     return v;
 }
 __device__ __forceinline__ int64_t ld_nc_s64_here(const int64_t* p) {
@@ -715,7 +723,7 @@ rg_cell_kernel(const float* __restrict__ pos, int64_t F, int64_t N, int64_t C, D
 
 // ------------------------------------------------------------------------------------------------
 // Large frames, list variant: pass 1 does ALL the geometry and leaves, per atom, its neighbour
-// list already sorted by atom index (<= kListCap entries, int32) in the workspace; pass 2 is a pure
+// list already sorted by atom index (<= kListCap entries of (x, y, z, index)) in the workspace; pass 2 is a pure
 // streaming write of the 40 bytes per edge.
 //   rg_cell_list_kernel  one WARP per cell.  The <= 256 atoms of the 27 surrounding cells are read
 //                        once (coalesced float4 loads of the cell-sorted array) into registers,
@@ -725,9 +733,9 @@ rg_cell_kernel(const float* __restrict__ pos, int64_t F, int64_t N, int64_t C, D
 //                        Cells whose neighbourhood exceeds 256 atoms and rows longer than kListCap
 //                        only get their degree here and are rebuilt by pass 2 (rg_atom_warp).
 //   rg_list_fill_kernel  one warp per row, rows in atom order so the output is one sequential
-//                        stream; column ids come from the saved list, coordinates of the
-//                        neighbours from `pos` (L2 resident), edge_attr through a 768-byte smem
-//                        staging buffer so that consecutive lanes store consecutive float2.
+//                        stream; column ids and neighbour coordinates come from the saved list (no
+//                        gathers), edge_attr through a 768-byte smem staging buffer so that
+//                        consecutive lanes store consecutive float2.
 // ------------------------------------------------------------------------------------------------
 constexpr int kListCap = 64;
 constexpr int kCellRegs = 8;  // candidates per lane held in registers
@@ -743,10 +751,11 @@ __device__ __forceinline__ void sts_u32(uint32_t addr, int v) {
 __global__ void __launch_bounds__(kRgThreads, 4)
 rg_cell_list_kernel(int64_t F, int64_t N, int64_t C, D2Bound b, const FrameMeta* __restrict__ meta,
                     const int32_t* __restrict__ cell_start, const float4* __restrict__ sorted_pos,
-                    int32_t* __restrict__ deg, int32_t* __restrict__ nbr,
+                    int32_t* __restrict__ deg, float4* __restrict__ nbr,
                     int32_t* __restrict__ list_ok, int32_t* __restrict__ crowded_count,
                     int2* __restrict__ crowded_cells) {
     __shared__ __align__(16) int s_hit[kRgThreads / 32][kHitBuf];
+    __shared__ float4 s_hitp[kRgThreads / 32][kListCap];  // coordinates of the first 64 hits
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t f = blockIdx.y;
     const FrameMeta m = meta[f];
@@ -756,6 +765,7 @@ rg_cell_list_kernel(int64_t F, int64_t N, int64_t C, D2Bound b, const FrameMeta*
     const unsigned below = (1u << lane) - 1u;
     const int* hb = s_hit[warp];
     const uint32_t hb_addr = uint32_t(__cvta_generic_to_shared(s_hit[warp]));
+    float4* hp = s_hitp[warp];
     constexpr int kWarps = kRgThreads / 32;
     for (int c = blockIdx.x * kWarps + warp; c < m.ncell; c += gridDim.x * kWarps) {
         const int ib = cs[c], ie = cs[c + 1];
@@ -822,8 +832,11 @@ rg_cell_list_kernel(int64_t F, int64_t N, int64_t C, D2Bound b, const FrameMeta*
                         hit = valid && within_exact(pi, cand[q], b);
                         hm = __ballot_sync(0xffffffffu, hit);
                     }
-                    if (hit) sts_u32(hb_addr + 4u * unsigned(total + __popc(hm & below)),
-                                     __float_as_int(cand[q].w));
+                    if (hit) {
+                        const int at = total + __popc(hm & below);
+                        sts_u32(hb_addr + 4u * unsigned(at), __float_as_int(cand[q].w));
+                        if (at < kListCap) hp[at] = cand[q];
+                    }
                     total += __popc(hm);
                 }
             }
@@ -835,26 +848,28 @@ rg_cell_list_kernel(int64_t F, int64_t N, int64_t C, D2Bound b, const FrameMeta*
             if (lane < 3) sts_u32(hb_addr + 4u * unsigned(total + lane), 0x7fffffff);  // padding
             __syncwarp();
             // rank sort straight from smem: independent compares, no shuffle dependency chains
-            int32_t* out = nbr + g * kListCap;
+            float4* out = nbr + g * kListCap;
             const int4* hb4 = reinterpret_cast<const int4*>(hb);
             const int v0 = hb[min(lane, total - 1)];
+            const float4 p0 = hp[min(lane, total - 1)];
             int r0 = 0;
             if (total <= 32) {
                 for (int k = 0; k < total; k += 4) {
                     const int4 h = hb4[k >> 2];
                     r0 += (h.x < v0) + (h.y < v0) + (h.z < v0) + (h.w < v0);
                 }
-                if (lane < total) out[r0] = v0;
+                if (lane < total) out[r0] = p0;
             } else {
                 const int v1 = hb[min(lane + 32, total - 1)];
+                const float4 p1 = hp[min(lane + 32, total - 1)];
                 int r1 = 0;
                 for (int k = 0; k < total; k += 4) {
                     const int4 h = hb4[k >> 2];
                     r0 += (h.x < v0) + (h.y < v0) + (h.z < v0) + (h.w < v0);
                     r1 += (h.x < v1) + (h.y < v1) + (h.z < v1) + (h.w < v1);
                 }
-                out[r0] = v0;
-                if (lane + 32 < total) out[r1] = v1;
+                out[r0] = p0;
+                if (lane + 32 < total) out[r1] = p1;
             }
             __syncwarp();
         }
@@ -886,10 +901,10 @@ rg_crowded_kernel(const float* __restrict__ pos, int64_t N, int64_t C, D2Bound b
     }
 }
 
-__global__ void __launch_bounds__(kRgThreads, 6)
+__global__ void __launch_bounds__(kRgThreads, 4)
 rg_list_fill_kernel(const float* __restrict__ pos, int64_t F, int64_t N, int64_t C, D2Bound b,
                     const FrameMeta* __restrict__ meta, const int32_t* __restrict__ cell_start,
-                    const float4* __restrict__ sorted_pos, const int32_t* __restrict__ nbr,
+                    const float4* __restrict__ sorted_pos, const float4* __restrict__ nbr,
                     const int32_t* __restrict__ list_ok, const int64_t* __restrict__ row_ptr,
                     int64_t E, int64_t* __restrict__ edge_index, float* __restrict__ edge_attr) {
     __shared__ float2 s_stage[kRgThreads / 32][96];
@@ -901,7 +916,8 @@ rg_list_fill_kernel(const float* __restrict__ pos, int64_t F, int64_t N, int64_t
     // list, its own coordinates) is requested before the current row is written
     struct RowIn {
         int64_t beg, end;
-        int ok, c0, c1;
+        int ok;
+        float4 c0, c1;  // neighbours lane and lane + 32 of the row: (x, y, z, atom index)
         float px, py, pz;
     };
     auto fetch = [&](int64_t g) {
@@ -909,8 +925,8 @@ rg_list_fill_kernel(const float* __restrict__ pos, int64_t F, int64_t N, int64_t
         r.beg = ld_nc_s64_here(row_ptr + g);
         r.end = ld_nc_s64_here(row_ptr + g + 1);
         r.ok = int(ld_nc_u32_here(reinterpret_cast<const uint32_t*>(list_ok + g)));
-        r.c0 = int(ld_nc_u32_here(reinterpret_cast<const uint32_t*>(nbr + g * kListCap + lane)));
-        r.c1 = int(ld_nc_u32_here(reinterpret_cast<const uint32_t*>(nbr + g * kListCap + 32 + lane)));
+        r.c0 = ld_nc_f4_here(nbr + g * kListCap + lane);
+        r.c1 = ld_nc_f4_here(nbr + g * kListCap + 32 + lane);
         r.px = pos[g * 3];
         r.py = pos[g * 3 + 1];
         r.pz = pos[g * 3 + 2];
@@ -948,13 +964,12 @@ rg_list_fill_kernel(const float* __restrict__ pos, int64_t F, int64_t N, int64_t
             if (e0 >= d) break;  // warp-uniform
             const int e = e0 + lane;
             if (e < d) {
-                const int64_t col = node0 + (h == 0 ? cur.c0 : cur.c1);
-                const float* pj = pos + col * 3;
+                const float4 pj = h == 0 ? cur.c0 : cur.c1;
                 er[e] = g;
-                ec[e] = col;
+                ec[e] = node0 + __float_as_int(pj.w);
                 st[3 * lane] = make_float2(px, py);
-                st[3 * lane + 1] = make_float2(pz, pj[0]);
-                st[3 * lane + 2] = make_float2(pj[1], pj[2]);
+                st[3 * lane + 1] = make_float2(pz, pj.x);
+                st[3 * lane + 2] = make_float2(pj.y, pj.z);
             }
             __syncwarp();
             const int n2 = 3 * min(32, d - e0);
