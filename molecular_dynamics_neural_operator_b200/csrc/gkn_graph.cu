@@ -746,9 +746,15 @@ __device__ __forceinline__ void sts_u32(uint32_t addr, int v) {
     asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ void sts_f4(uint32_t addr, const float4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+
 // One warp per cell, no CTA-level synchronisation: cells are handed out warp by warp.  Cells whose
 // neighbourhood does not fit the registers go to a worklist for rg_crowded_kernel.
-__global__ void __launch_bounds__(kRgThreads, 4)
+__global__ void __launch_bounds__(kRgThreads, 3)
 rg_cell_list_kernel(int64_t F, int64_t N, int64_t C, D2Bound b, const FrameMeta* __restrict__ meta,
                     const int32_t* __restrict__ cell_start, const float4* __restrict__ sorted_pos,
                     int32_t* __restrict__ deg, float4* __restrict__ nbr,
@@ -765,7 +771,8 @@ rg_cell_list_kernel(int64_t F, int64_t N, int64_t C, D2Bound b, const FrameMeta*
     const unsigned below = (1u << lane) - 1u;
     const int* hb = s_hit[warp];
     const uint32_t hb_addr = uint32_t(__cvta_generic_to_shared(s_hit[warp]));
-    float4* hp = s_hitp[warp];
+    const float4* hp = s_hitp[warp];
+    const uint32_t hp_addr = uint32_t(__cvta_generic_to_shared(s_hitp[warp]));
     constexpr int kWarps = kRgThreads / 32;
     for (int c = blockIdx.x * kWarps + warp; c < m.ncell; c += gridDim.x * kWarps) {
         const int ib = cs[c], ie = cs[c + 1];
@@ -835,7 +842,7 @@ rg_cell_list_kernel(int64_t F, int64_t N, int64_t C, D2Bound b, const FrameMeta*
                     if (hit) {
                         const int at = total + __popc(hm & below);
                         sts_u32(hb_addr + 4u * unsigned(at), __float_as_int(cand[q].w));
-                        if (at < kListCap) hp[at] = cand[q];
+                        if (at < kListCap) sts_f4(hp_addr + 16u * unsigned(at), cand[q]);
                     }
                     total += __popc(hm);
                 }
