@@ -94,6 +94,37 @@ int gkn_contract_fwd_f32(const float* h, const float* w3, const int32_t* src, co
 int gkn_contract_dx_f32(const float* h, const float* w3, const int32_t* dst, const float* g,
                         float* dxj, int64_t E, int32_t K, int32_t W, void* stream);
 
+/* ---- node-first factorisation of the same contraction (tcgen05 grouped GEMMs) --------------
+ * NNConv_old.message (graph_kernel.py:200-202) is trilinear in (x[src e], h[e], W3); because x is a
+ * node quantity, W3 can be contracted with it once per NODE (a plain dense GEMM done by the
+ * caller: U[n][o,k] = sum_i x[n,i] w3[i*W+o,k]) and the per-edge work drops from 2*K*W*W to 2*K*W
+ * FLOP.  Edge buffers use the "padded source-sorted" layout: the edges of source node n occupy
+ * rows [pptr[n], pptr[n]+deg[n]), groups padded to a multiple of 16 rows (E_pad rows in total).
+ * `units`: int32 [U,4] = (source node, first row, rows to store (<= 128), 0), one per 128-row
+ * tile of a group, ordered by node.  W = 64, K % 256 == 0.  Node-indexed operands may be passed in
+ * chunks of nodes [node_base, node_base + chunk_nodes) covering the units of the launch.
+ *   msg : msg[q,o] = sum_k hs[q,k] * u[src q][o,k]          hs bf16 [E_pad,K], u bf16 [chunk,W,K],
+ *         msg float32 [E_pad,W] (forward message, before the mean)
+ *   du  : dut[n][k,o] = sum_{q in group n} hsT[k,q] * gsT[o,q]      hsT bf16 [K,E_pad] (= hs^T),
+ *         gsT bf16 [W,E_pad] (message gradient per edge, transposed, zero in pad rows),
+ *         dut bf16 [node_end-node_begin, K, W] (gradient w.r.t. U, [k,o] order)
+ *   dh  : dh[q,k] = sum_a sum_o gs[a][q,o] * ut[a][src q][k,o]    gs bf16 [A,E_pad,W],
+ *         ut bf16 [A,chunk,K,W], dh bf16 [E_pad,K] (gradient of the edge hidden state)
+ *   gather: gs[q,:] = bf16(g[idx[q],:]) (zero where idx[q] < 0), gsT its transpose; either output
+ *         may be NULL. */
+int gkn_node_msg_bf16(const void* hs_bf16, const void* u_bf16, const int32_t* units,
+                      int64_t unit_begin, int64_t unit_end, int64_t E_pad, int64_t chunk_nodes,
+                      int32_t node_base, float* msg, int32_t K, int32_t W, void* stream);
+int gkn_node_du_bf16(const void* hsT_bf16, const void* gsT_bf16, const int32_t* pptr,
+                     int64_t node_begin, int64_t node_end, int64_t E_pad, void* dut_bf16,
+                     int32_t K, int32_t W, void* stream);
+int gkn_node_dh_bf16(const void* gs_bf16, const void* ut_bf16, const int32_t* units,
+                     int64_t unit_begin, int64_t unit_end, int64_t E_pad, int64_t chunk_nodes,
+                     int32_t node_base, int32_t A, void* dh_bf16, int32_t K, int32_t W,
+                     void* stream);
+int gkn_node_gather_bf16(const float* g, const int32_t* idx, int64_t E_pad, void* gs_bf16,
+                         void* gsT_bf16, int32_t W, void* stream);
+
 /* ---- segmented mean / sums (replaces PyG aggregate(aggr="mean") + NNConv_old.update,
  *      graph_kernel.py:204-209, and their autograd) --------------------------------------- */
 /* out[n,:] = act( inv_cnt[n] * sum_{p in [dst_ptr[n],dst_ptr[n+1])} (msg[p,:] + xb3[src_s[p],:])

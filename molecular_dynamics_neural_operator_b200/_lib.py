@@ -33,6 +33,16 @@ SIGNATURES = {
     "gkn_contract_dx_bf16": (c_int, [P, P, P, P, P, c_int64, c_int32, c_int32, P]),
     "gkn_contract_fwd_f32": (c_int, [P, P, P, P, P, c_int64, c_int32, c_int32, P]),
     "gkn_contract_dx_f32": (c_int, [P, P, P, P, P, c_int64, c_int32, c_int32, P]),
+    "gkn_node_msg_bf16": (
+        c_int,
+        [P, P, P, c_int64, c_int64, c_int64, c_int64, c_int32, P, c_int32, c_int32, P],
+    ),
+    "gkn_node_du_bf16": (c_int, [P, P, P, c_int64, c_int64, c_int64, P, c_int32, c_int32, P]),
+    "gkn_node_dh_bf16": (
+        c_int,
+        [P, P, P, c_int64, c_int64, c_int64, c_int64, c_int32, c_int32, P, c_int32, c_int32, P],
+    ),
+    "gkn_node_gather_bf16": (c_int, [P, P, c_int64, P, P, c_int32, P]),
     "gkn_scatter_mean_fwd": (
         c_int,
         [P, P, P, P, P, P, P, P, c_int64, c_int64, c_int32, c_int32, P],

@@ -1,0 +1,493 @@
+// Node-first factorisation of the graph-kernel contraction (tcgen05 grouped GEMMs, sm_100a).
+//
+// NNConv_old.message (reference graph_kernel.py:200-202) is the trilinear form
+//     msg[e, o] = sum_{i,k} x[src e, i] * h[e, k] * W3[i*w + o, k]            (+ the b3 term)
+// The edge-first kernels (gkn_contract_tc.cu) contract h with W3 per edge: 2*E*K*w^2 FLOP.  But
+// x[src e] is a NODE quantity, so W3 can be contracted with x once per node instead,
+//     U[n][o, k] = sum_i x[n, i] * W3[i*w + o, k]        (plain dense GEMM [N,w] x [w, w*K])
+//     msg[e, o]  = sum_k h[e, k] * U[src e][o, k]         (GEMM grouped by source node)
+// which is N*2*K*w^2 + E*2*K*w FLOP: w/(1 + w*N/E) times fewer (about 40x for the BBA all-atom
+// graph) and no longer tensor-bound - every kernel here streams the edge hidden state once and
+// is bounded by HBM.  The backward follows from the same two stages:
+//     dU[n][k, o] = sum_{e: src e = n} h[e, k] * gm[e, o]            (gm[e] = gn[dst e])
+//     dx = dU W3^T,  dW3 += x^T dU                                   (plain dense GEMMs)
+//     dh[e, k]    = sum_a sum_o gm_a[e, o] * U_a[src e][o, k]        (all applications at once)
+//
+// Edge layout: "padded source-sorted": the edges of source node n occupy rows
+// [pptr[n], pptr[n] + deg[n]) and every group is padded to a multiple of 16 rows (pad rows carry
+// zero gradients), so a group is a whole number of UMMA K-steps when the edge index is the
+// reduction dimension (MODE_DU) and 128-row M tiles start at a group boundary (MODE_MSG/DH; rows
+// of the tile that belong to the next group are computed and discarded).
+//
+// One persistent kernel template, three modes; all operands K-major bf16 staged by TMA with the
+// 128-byte swizzle, fp32 accumulators in TMEM, warp roles as in gkn_contract_tc.cu:
+//   MODE_MSG  unit = 128-row tile t of group n:  D[128 x w]   = Hs[tile, :] . U[n]^T      (K = kernel width)
+//   MODE_DU   unit = (group n, 128 k-rows c):    D[128 x w]   = HsT[c, grp] . GsT[:, grp]^T (K = padded degree)
+//   MODE_DH   unit = (tile, 256-column chunk c): D[128 x 256] = sum_a Gs_a[tile, :] . Ut_a[n][c, :]^T (K = A*w)
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "gkn_internal.h"
+#include "gkn_ptx.cuh"
+
+#include <cuda_bf16.h>
+
+namespace gkn {
+
+namespace {
+
+constexpr int kM = 128;      // accumulator rows per unit
+constexpr int kKB = 64;      // reduction elements per k-block (one 128-byte swizzle row)
+constexpr int kUmmaK = 16;
+constexpr int kThreads = 192;
+constexpr int kABytes = kM * kKB * 2;  // 16 KB
+constexpr int kW = 64;       // node feature width served by this file
+
+enum { MODE_MSG = 0, MODE_DU = 1, MODE_DH = 2 };
+
+template <int MODE>
+struct NCfg {
+    static constexpr int kBN = MODE == MODE_DH ? 256 : kW;      // accumulator columns
+    static constexpr int kBBytes = kBN * kKB * 2;               // 8 KB / 32 KB
+    static constexpr int kStageBytes = kABytes + kBBytes;       // 24 KB / 48 KB
+    static constexpr int kStages = MODE == MODE_DH ? 4 : 8;     // 192 KB of operands in flight
+    static constexpr int kAcc = MODE == MODE_DH ? 2 : 4;        // TMEM accumulator ring
+    static constexpr int kTmemCols = kAcc * kBN;                // 512 / 256
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+struct NodeParams {
+    const int4* __restrict__ units;     // MSG/DH: (group, first padded row, rows to store, -)
+    const int32_t* __restrict__ pptr;   // DU: padded group pointers [N+1]
+    void* __restrict__ out;
+    int64_t v_begin, v_end;             // unit range of this launch
+    int32_t K;                          // kernel width (columns of h)
+    int32_t A;                          // DH: applications
+    int32_t a_rows_per_app;             // DH: rows of Gs per application (= padded edge count)
+    int32_t b_rows_per_app;             // DH: rows of Ut per application (= chunk nodes * K)
+    int32_t node_base;                  // first node of the U / Ut / dUt chunk
+};
+
+struct Unit {
+    int32_t a_c0, a_c1, b_c0, b_c1;     // TMA coordinates of k-block 0
+    int32_t da_c0, da_c1, db_c0, db_c1; // per-k-block increments
+    int32_t nkb;                        // k-blocks
+    int32_t last_steps;                 // UMMA K-steps in the last k-block (1..4)
+    int32_t row0, rows, group, chunk;   // epilogue
+};
+
+template <int MODE>
+__device__ __forceinline__ Unit decode_unit(const NodeParams& p, int64_t v) {
+    Unit u;
+    if constexpr (MODE == MODE_MSG) {
+        const int4 t = __ldg(p.units + v);
+        u.group = t.x; u.row0 = t.y; u.rows = t.z; u.chunk = 0;
+        u.a_c0 = 0; u.a_c1 = t.y; u.da_c0 = kKB; u.da_c1 = 0;
+        u.b_c0 = 0; u.b_c1 = (t.x - p.node_base) * kW; u.db_c0 = kKB; u.db_c1 = 0;
+        u.nkb = p.K / kKB; u.last_steps = kKB / kUmmaK;
+    } else if constexpr (MODE == MODE_DH) {
+        const int32_t chunks = p.K / 256;
+        const int4 t = __ldg(p.units + v / chunks);
+        u.group = t.x; u.row0 = t.y; u.rows = t.z; u.chunk = int32_t(v % chunks);
+        u.a_c0 = 0; u.a_c1 = t.y; u.da_c0 = 0; u.da_c1 = p.a_rows_per_app;
+        u.b_c0 = 0; u.b_c1 = (t.x - p.node_base) * p.K + u.chunk * 256;
+        u.db_c0 = 0; u.db_c1 = p.b_rows_per_app;
+        u.nkb = p.A; u.last_steps = kKB / kUmmaK;
+    } else {
+        const int32_t chunks = p.K / kM;
+        const int32_t g = p.node_base + int32_t(v / chunks);
+        const int32_t b = __ldg(p.pptr + g), e = __ldg(p.pptr + g + 1);
+        const int32_t len = e - b;  // multiple of 16
+        u.group = g; u.chunk = int32_t(v % chunks); u.row0 = b; u.rows = kM;
+        u.a_c0 = b; u.a_c1 = u.chunk * kM; u.da_c0 = kKB; u.da_c1 = 0;
+        u.b_c0 = b; u.b_c1 = 0; u.db_c0 = kKB; u.db_c1 = 0;
+        u.nkb = (len + kKB - 1) / kKB;
+        u.last_steps = (len - (u.nkb - 1) * kKB) / kUmmaK;
+    }
+    return u;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+node_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                 const __grid_constant__ CUtensorMap tmap_b, const NodeParams p) {
+    using C = NCfg<MODE>;
+    constexpr int kStages = C::kStages;
+    constexpr int kStageBytes = C::kStageBytes;
+    constexpr int kBN = C::kBN;
+    constexpr int kAcc = C::kAcc;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + kStages * kStageBytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + kAcc + s); };
+    const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * kStages + 2 * kAcc);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // contiguous unit range per CTA: consecutive units share the group's B operand (L2 hits)
+    const int64_t total = p.v_end - p.v_begin;
+    const int64_t v0 = p.v_begin + (total * blockIdx.x) / gridDim.x;
+    const int64_t v1 = p.v_begin + (total * (blockIdx.x + 1)) / gridDim.x;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < kAcc; ++s) {
+            mbar_init(tfull_bar(s), 1);
+            mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+        }
+        fence_mbar_init();
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr_smem, C::kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t v = v0; v < v1; ++v) {
+                const Unit u = decode_unit<MODE>(p, v);
+                for (int kb = 0; kb < u.nkb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t sa = smem_base + stage * kStageBytes;
+                    mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
+                    tma_load_2d(sa, &tmap_a, full_bar(stage), u.a_c0 + kb * u.da_c0,
+                                u.a_c1 + kb * u.da_c1);
+                    tma_load_2d(sa + kABytes, &tmap_b, full_bar(stage), u.b_c0 + kb * u.db_c0,
+                                u.b_c1 + kb * u.db_c1);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(kM, kBN, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t it = 0;
+            for (int64_t v = v0; v < v1; ++v) {
+                const Unit u = decode_unit<MODE>(p, v);
+                if (u.nkb == 0) continue;  // empty group: the epilogue writes zeros on its own
+                const uint32_t as = it % kAcc;
+                const uint32_t aphase = (it / kAcc) & 1u;
+                ++it;
+                mbar_wait(tempty_bar(as), aphase ^ 1u);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * kBN;
+                for (int kb = 0; kb < u.nkb; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * kStageBytes;
+                    const uint64_t adesc = umma_smem_desc(sa, 16, 1024, kSwizzle128B);
+                    const uint64_t bdesc = umma_smem_desc(sa + kABytes, 16, 1024, kSwizzle128B);
+                    const int steps = kb == u.nkb - 1 ? u.last_steps : kKB / kUmmaK;
+                    for (int k = 0; k < steps; ++k) {
+                        umma_bf16_ss(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc,
+                                     (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(stage));
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                umma_commit(tfull_bar(as));
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5): thread = accumulator row =====================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t lane_addr = uint32_t(q * 32) << 16;
+        uint32_t it = 0;
+        for (int64_t v = v0; v < v1; ++v) {
+            const Unit u = decode_unit<MODE>(p, v);
+            if (u.nkb == 0) {
+                if constexpr (MODE == MODE_DU) {
+                    uint4* dst = reinterpret_cast<uint4*>(
+                        static_cast<__nv_bfloat16*>(p.out) +
+                        (int64_t(u.group - p.node_base) * p.K + u.chunk * kM + row) * kW);
+#pragma unroll
+                    for (int j = 0; j < kW / 8; ++j) dst[j] = make_uint4(0u, 0u, 0u, 0u);
+                }
+                continue;
+            }
+            const uint32_t as = it % kAcc;
+            const uint32_t aphase = (it / kAcc) & 1u;
+            ++it;
+            if (lane == 0) mbar_wait(tfull_bar(as), aphase);
+            __syncwarp();
+            tc_fence_after();
+            const uint32_t tcol = tmem_base + lane_addr + as * kBN;
+            const bool store = row < u.rows;
+            if constexpr (MODE == MODE_MSG) {
+                float* dst = static_cast<float*>(p.out) + int64_t(u.row0 + row) * kW;
+#pragma unroll
+                for (int piece = 0; piece < kBN / 32; ++piece) {
+                    float f[32];
+                    tmem_ld32(tcol + piece * 32, f);
+                    tmem_ld_wait();
+                    if (store) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            *reinterpret_cast<float4*>(dst + piece * 32 + j) =
+                                make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                        }
+                    }
+                }
+            } else {
+                __nv_bfloat16* dst;
+                if constexpr (MODE == MODE_DH) {
+                    dst = static_cast<__nv_bfloat16*>(p.out) + int64_t(u.row0 + row) * p.K +
+                          u.chunk * 256;
+                } else {
+                    dst = static_cast<__nv_bfloat16*>(p.out) +
+                          (int64_t(u.group - p.node_base) * p.K + u.chunk * kM + row) * kW;
+                }
+#pragma unroll
+                for (int piece = 0; piece < kBN / 32; ++piece) {
+                    float f[32];
+                    tmem_ld32(tcol + piece * 32, f);
+                    tmem_ld_wait();
+                    if (store) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            *reinterpret_cast<uint4*>(dst + piece * 32 + j) =
+                                make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
+                                           pack_bf16(f[j + 4], f[j + 5]), pack_bf16(f[j + 6], f[j + 7]));
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(as));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, C::kTmemCols);
+    }
+}
+
+template <int MODE>
+int launch_node_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const NodeParams& p,
+                     cudaStream_t stream) {
+    auto kern = node_gemm_kernel<MODE>;
+    constexpr int smem = NCfg<MODE>::kSmemBytes;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (err != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(node_gemm)", err);
+    int sms = 0;
+    int rc = device_sm_count(&sms);
+    if (rc) return rc;
+    int64_t grid = p.v_end - p.v_begin;
+    if (grid > sms) grid = sms;
+    if (grid < 1) return 0;
+    kern<<<dim3(unsigned(grid)), dim3(kThreads), smem, stream>>>(ta, tb, p);
+    GKN_CHECK_LAUNCH("node_gemm launch");
+    return 0;
+}
+
+int check_common(const char* name, int32_t K, int32_t W, int64_t E_pad) {
+    static thread_local char buf[160];
+    if (W != kW) {
+        snprintf(buf, sizeof(buf), "%s: width must be %d", name, kW);
+        return set_error(buf);
+    }
+    if (K <= 0 || K % 256 != 0) {
+        snprintf(buf, sizeof(buf), "%s: kernel width K must be a positive multiple of 256", name);
+        return set_error(buf);
+    }
+    if (E_pad < 0 || E_pad % 16 != 0 || E_pad >= (int64_t(1) << 31) - 256) {
+        snprintf(buf, sizeof(buf), "%s: padded edge count must be a multiple of 16 below 2^31", name);
+        return set_error(buf);
+    }
+    return 0;
+}
+
+// Gs[q, :] = bf16(g[idx[q], :]) (zero row where idx[q] < 0) and its transpose GsT[:, q]
+__global__ void __launch_bounds__(256)
+node_gather_kernel(const float* __restrict__ g, const int32_t* __restrict__ idx, int64_t E_pad,
+                   __nv_bfloat16* __restrict__ gs, __nv_bfloat16* __restrict__ gsT) {
+    __shared__ __nv_bfloat16 tile[64][kW + 8];
+    const int t = threadIdx.x;
+    for (int64_t q0 = int64_t(blockIdx.x) * 64; q0 < E_pad; q0 += int64_t(gridDim.x) * 64) {
+        __syncthreads();
+#pragma unroll
+        for (int pass = 0; pass < 4; ++pass) {
+            const int r = pass * 16 + (t >> 4);
+            const int c = (t & 15) * 4;
+            const int64_t qq = q0 + r;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (qq < E_pad) {
+                const int32_t n = __ldg(idx + qq);
+                if (n >= 0) v = __ldg(reinterpret_cast<const float4*>(g + int64_t(n) * kW + c));
+            }
+            const uint2 pk = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+            *reinterpret_cast<uint2*>(&tile[r][c]) = pk;
+            if (gs != nullptr && qq < E_pad) *reinterpret_cast<uint2*>(gs + qq * kW + c) = pk;
+        }
+        __syncthreads();
+        if (gsT != nullptr) {
+            // thread -> channel o = t / 4, 16 consecutive positions (E_pad is a multiple of 16)
+            const int o = t >> 2;
+            const int qb = (t & 3) * 16;
+            if (q0 + qb < E_pad) {
+                uint32_t w[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint16_t lo = *reinterpret_cast<const uint16_t*>(&tile[qb + 2 * j][o]);
+                    const uint16_t hi = *reinterpret_cast<const uint16_t*>(&tile[qb + 2 * j + 1][o]);
+                    w[j] = uint32_t(lo) | (uint32_t(hi) << 16);
+                }
+                uint4* dst = reinterpret_cast<uint4*>(gsT + int64_t(o) * E_pad + q0 + qb);
+                dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            }
+        }
+    }
+}
+
+}  // namespace
+
+}  // namespace gkn
+
+extern "C" int gkn_node_msg_bf16(const void* hs_bf16, const void* u_bf16, const int32_t* units,
+                                 int64_t unit_begin, int64_t unit_end, int64_t E_pad,
+                                 int64_t chunk_nodes, int32_t node_base, float* msg, int32_t K,
+                                 int32_t W, void* stream) {
+    using namespace gkn;
+    if (unit_end <= unit_begin) return 0;
+    if (hs_bf16 == nullptr || u_bf16 == nullptr || units == nullptr || msg == nullptr) {
+        return set_error("gkn_node_msg_bf16: NULL pointer argument");
+    }
+    int rc = check_common("gkn_node_msg_bf16", K, W, E_pad);
+    if (rc) return rc;
+    if (chunk_nodes <= 0 || chunk_nodes * kW >= (int64_t(1) << 31)) {
+        return set_error("gkn_node_msg_bf16: bad node chunk");
+    }
+    CUtensorMap ta, tb;
+    rc = make_tensor_map_bf16_2d(&ta, hs_bf16, uint64_t(K), uint64_t(E_pad), kKB, kM);
+    if (rc) return rc;
+    rc = make_tensor_map_bf16_2d(&tb, u_bf16, uint64_t(K), uint64_t(chunk_nodes) * kW, kKB, kW);
+    if (rc) return rc;
+    NodeParams p{};
+    p.units = reinterpret_cast<const int4*>(units);
+    p.out = msg;
+    p.v_begin = unit_begin;
+    p.v_end = unit_end;
+    p.K = K;
+    p.node_base = node_base;
+    return launch_node_gemm<MODE_MSG>(ta, tb, p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gkn_node_du_bf16(const void* hsT_bf16, const void* gsT_bf16, const int32_t* pptr,
+                                int64_t node_begin, int64_t node_end, int64_t E_pad,
+                                void* dut_bf16, int32_t K, int32_t W, void* stream) {
+    using namespace gkn;
+    if (node_end <= node_begin) return 0;
+    if (hsT_bf16 == nullptr || gsT_bf16 == nullptr || pptr == nullptr || dut_bf16 == nullptr) {
+        return set_error("gkn_node_du_bf16: NULL pointer argument");
+    }
+    int rc = check_common("gkn_node_du_bf16", K, W, E_pad);
+    if (rc) return rc;
+    if (E_pad == 0) return set_error("gkn_node_du_bf16: empty edge set");
+    CUtensorMap ta, tb;
+    rc = make_tensor_map_bf16_2d(&ta, hsT_bf16, uint64_t(E_pad), uint64_t(K), kKB, kM);
+    if (rc) return rc;
+    rc = make_tensor_map_bf16_2d(&tb, gsT_bf16, uint64_t(E_pad), uint64_t(kW), kKB, kW);
+    if (rc) return rc;
+    NodeParams p{};
+    p.pptr = pptr;
+    p.out = dut_bf16;
+    p.v_begin = 0;
+    p.v_end = (node_end - node_begin) * (K / kM);
+    p.K = K;
+    p.node_base = int32_t(node_begin);
+    return launch_node_gemm<MODE_DU>(ta, tb, p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gkn_node_dh_bf16(const void* gs_bf16, const void* ut_bf16, const int32_t* units,
+                                int64_t unit_begin, int64_t unit_end, int64_t E_pad,
+                                int64_t chunk_nodes, int32_t node_base, int32_t A, void* dh_bf16,
+                                int32_t K, int32_t W, void* stream) {
+    using namespace gkn;
+    if (unit_end <= unit_begin) return 0;
+    if (gs_bf16 == nullptr || ut_bf16 == nullptr || units == nullptr || dh_bf16 == nullptr) {
+        return set_error("gkn_node_dh_bf16: NULL pointer argument");
+    }
+    int rc = check_common("gkn_node_dh_bf16", K, W, E_pad);
+    if (rc) return rc;
+    if (A <= 0) return set_error("gkn_node_dh_bf16: A must be positive");
+    const int64_t a_rows = int64_t(A) * E_pad, b_rows = int64_t(A) * chunk_nodes * K;
+    if (chunk_nodes <= 0 || a_rows >= (int64_t(1) << 31) || b_rows >= (int64_t(1) << 31)) {
+        return set_error("gkn_node_dh_bf16: operand too large for one launch (use smaller node chunks)");
+    }
+    CUtensorMap ta, tb;
+    rc = make_tensor_map_bf16_2d(&ta, gs_bf16, uint64_t(kW), uint64_t(a_rows), kKB, kM);
+    if (rc) return rc;
+    rc = make_tensor_map_bf16_2d(&tb, ut_bf16, uint64_t(kW), uint64_t(b_rows), kKB, 256);
+    if (rc) return rc;
+    NodeParams p{};
+    p.units = reinterpret_cast<const int4*>(units);
+    p.out = dh_bf16;
+    p.v_begin = unit_begin * (K / 256);
+    p.v_end = unit_end * (K / 256);
+    p.K = K;
+    p.A = A;
+    p.a_rows_per_app = int32_t(E_pad);
+    p.b_rows_per_app = int32_t(chunk_nodes * K);
+    p.node_base = node_base;
+    return launch_node_gemm<MODE_DH>(ta, tb, p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gkn_node_gather_bf16(const float* g, const int32_t* idx, int64_t E_pad,
+                                    void* gs_bf16, void* gsT_bf16, int32_t W, void* stream) {
+    using namespace gkn;
+    if (E_pad == 0) return 0;
+    if (g == nullptr || idx == nullptr || (gs_bf16 == nullptr && gsT_bf16 == nullptr)) {
+        return set_error("gkn_node_gather_bf16: NULL pointer argument");
+    }
+    int rc = check_common("gkn_node_gather_bf16", 256, W, E_pad);
+    if (rc) return rc;
+    int sms = 0;
+    rc = device_sm_count(&sms);
+    if (rc) return rc;
+    int64_t blocks = (E_pad + 63) / 64;
+    if (blocks > int64_t(sms) * 8) blocks = int64_t(sms) * 8;
+    node_gather_kernel<<<dim3(unsigned(blocks)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        g, idx, E_pad, static_cast<__nv_bfloat16*>(gs_bf16), static_cast<__nv_bfloat16*>(gsT_bf16));
+    GKN_CHECK_LAUNCH("node_gather launch");
+    return 0;
+}

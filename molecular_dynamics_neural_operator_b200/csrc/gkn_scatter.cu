@@ -201,7 +201,8 @@ segment_matvec_kernel(const float* __restrict__ rows, const int32_t* __restrict_
                 float4 rr[4], gg[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    rr[u] = ldg4_stream(rows + int64_t(pp[u]) * W + col);
+                    rr[u] = rows ? ldg4_stream(rows + int64_t(pp[u]) * W + col)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
                     gg[u] = ldg4(gnode + int64_t(ii[u]) * W + col);
                 }
                 ar0 = f4add(ar0, f4add(rr[0], rr[2]));
@@ -211,7 +212,7 @@ segment_matvec_kernel(const float* __restrict__ rows, const int32_t* __restrict_
             }
             for (; q < end; q += RPW) {
                 const int p0 = perm ? perm[q] : q;
-                ar0 = f4add(ar0, ldg4_stream(rows + int64_t(p0) * W + col));
+                if (rows) ar0 = f4add(ar0, ldg4_stream(rows + int64_t(p0) * W + col));
                 ag0 = f4add(ag0, ldg4(gnode + int64_t(gidx[p0]) * W + col));
             }
             float4 ar = f4add(ar0, ar1), ag = f4add(ag0, ag1);
@@ -883,7 +884,8 @@ extern "C" int gkn_segment_matvec(const float* rows, const int32_t* perm, const 
                                   int32_t W, int32_t relu, void* stream) {
     using namespace gkn;
     if (N == 0) return 0;
-    // rows / gidx may be NULL for a graph without edges (never dereferenced: all segments empty)
+    // rows may be NULL: r[n] = 0 (the node-first backward has no per-edge rows to sum);
+    // gidx may be NULL for a graph without edges (never dereferenced: all segments empty)
     if (N < 0 || seg_ptr == nullptr || gnode == nullptr || M1 == nullptr || nin == nullptr ||
         M2 == nullptr || out == nullptr) {
         return set_error("gkn_segment_matvec: bad size or NULL pointer argument");

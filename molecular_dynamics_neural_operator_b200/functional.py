@@ -202,6 +202,183 @@ class _GKNStack(torch.autograd.Function):
                 None, None, None, None)
 
 
+# ------------------------------------------------------------------------------------------------
+# Node-first factorisation (default in bf16 mode at w = 64): the same trilinear form, with W3
+# contracted against the NODE features first (csrc/gkn_node_gemm.cu).  Every application is then
+#   U = x W3r (dense GEMM, [N, w] x [w, w*K])  ->  msg = grouped GEMM(h, U[src])  ->  node update
+# and its backward is  dU = grouped GEMM(h^T, gm)  ->  dx = dU W3^T,  dW3 += x^T dU  (dense GEMMs);
+# dh_e is one grouped GEMM over all applications.  About w/(1 + w N/E) times fewer FLOPs than the
+# edge-first contraction; all kernels stream h once and are HBM-bound.
+# ------------------------------------------------------------------------------------------------
+FACTORIZATION = os.environ.get("GKN_FACTORIZATION", "node")
+# node-indexed temporaries (U, dU: w*K bf16 values per node) are produced for node ranges of at
+# most this many bytes
+_NODE_CHUNK_BYTES = int(os.environ.get("GKN_NODE_CHUNK_MB", "1024")) << 20
+_MLP_BWD_CHUNK_ROWS = int(os.environ.get("GKN_MLP_BWD_CHUNK_ROWS", "65536"))
+
+
+def node_path_supported(W: int, K: int, E: int, precision: str) -> bool:
+    return precision == "bf16" and W == 64 and K % 256 == 0 and E > 0
+
+
+def _node_chunks(N: int, per_node_bytes: int):
+    nc = max(1, min(N, _NODE_CHUNK_BYTES // per_node_bytes))
+    return [(n0, min(N, n0 + nc)) for n0 in range(0, N, nc)]
+
+
+class _GKNStackNode(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x0, ea, w1, b1, w2, b2, w3, b3, root1, bias1, root2, bias2, plan, schedule,
+                relu, precision):
+        W = x0.size(1)
+        det = lambda t: None if t is None else t.detach()  # noqa: E731
+        x0, ea, w1, b1, w2, b2, w3, b3 = map(det, (x0, ea, w1, b1, w2, b2, w3, b3))
+        lay = ops.node_layout(plan)
+        N, K = plan.num_nodes, w3.size(1)
+        bf = torch.bfloat16
+        # edge attributes and the edge MLP in the padded source-sorted layout (pad rows: zeros)
+        ea_s = torch.zeros((lay.e_pad, ea.size(1)), dtype=torch.float32, device=ea.device)
+        ea_s.index_copy_(0, lay.qpos_long, ea.contiguous())
+        h1, hs = _edge_hidden(ea_s, w1, b1.contiguous(), w2, b2.contiguous(), "bf16")
+        w3q = w3.to(bf).contiguous()           # [w*w, K] = [i, o, k]
+        w3r = w3q.view(W, W * K)               # [i, (o, k)]
+        B3c = b3.view(W, W).contiguous()
+        roots = (det(root1), det(root2))
+        biases = (det(bias1), det(bias2))
+        x = x0.contiguous()
+        xs, aggs = [x], []
+        want_agg = any(ctx.needs_input_grad)
+        msg = torch.empty((lay.e_pad, W), dtype=torch.float32, device=x.device)
+        chunks = _node_chunks(N, W * K * 2)
+        for c in schedule:
+            xb = x.to(bf)
+            for n0, n1 in chunks:
+                U = torch.mm(xb[n0:n1], w3r)   # [nc, (o, k)]
+                ops.node_msg(hs, U.view(n1 - n0, W, K), lay, lay.unit_first[n0],
+                             lay.unit_first[n1], n0, msg)
+                del U
+            x_new, agg = ops.segment_matvec(msg, lay.qpos, plan.dst_ptr, lay.src_pad, x,
+                                            plan.inv_cnt, B3c, x, roots[c].contiguous(),
+                                            biases[c].contiguous(), relu, want_agg=want_agg)
+            if want_agg:
+                aggs.append(agg)
+            x = x_new
+            xs.append(x)
+        ctx.plan, ctx.schedule, ctx.relu = plan, schedule, relu
+        ctx.has2 = root2 is not None
+        ctx.n_apps = len(schedule)
+        ctx.save_for_backward(ea_s, h1, hs, w1, w2, w3q, B3c, roots[0],
+                              roots[1] if ctx.has2 else roots[0], *xs, *aggs)
+        return x
+
+    @staticmethod
+    def backward(ctx, gout):
+        ea_s, h1, hs, w1, w2, w3q, B3, r1, r2, *rest = ctx.saved_tensors
+        plan, schedule, relu = ctx.plan, ctx.schedule, ctx.relu
+        lay = ops.node_layout(plan)
+        A = ctx.n_apps
+        xs, aggs = rest[:A + 1], rest[A + 1:]
+        roots = (r1, r2)
+        rootsT = (r1.t().contiguous(), r2.t().contiguous())
+        B3T = B3.t().contiguous()
+        N, W = xs[0].shape
+        K = hs.size(1)
+        bf = torch.bfloat16
+        dev = hs.device
+        need = ctx.needs_input_grad
+        need_x0, need_ea, need_edge = need[0], need[1], any(need[1:8])
+        # W3 as [i, (k, o)]: the operand of dx = dU W3^T, dW3 = x^T dU and of U^T for dh
+        w3kq = w3q.view(W, W, K).permute(0, 2, 1).contiguous().view(W, K * W)
+        hsT = hs.t().contiguous()  # [K, E_pad]: edges become the reduction dimension of dU
+        gsT = torch.empty((W, lay.e_pad), dtype=bf, device=dev)
+        gs_all = torch.empty((A, lay.e_pad, W), dtype=bf, device=dev) if need_edge else None
+        dw3k = torch.zeros((W, K * W), dtype=torch.float32, device=dev) if need_edge else None
+        chunks = _node_chunks(N, W * K * 2)
+        gs = [None] * A
+        xbs = [None] * A
+        gx = gout.contiguous().float()
+        for a in range(A - 1, -1, -1):
+            c = schedule[a]
+            g, gn = ops.relu_grad_scale(gx, xs[a + 1], plan.inv_cnt, relu)
+            gs[a] = g
+            need_dx = a > 0 or need_x0
+            if not (need_dx or need_edge):
+                gx = None
+                continue
+            ops.node_gather(gn, lay, gs_all[a] if need_edge else None, gsT)
+            xbs[a] = xs[a].to(bf)
+            dxc = torch.empty((N, W), dtype=torch.float32, device=dev) if need_dx else None
+            for n0, n1 in chunks:
+                dut = torch.empty((n1 - n0, K * W), dtype=bf, device=dev)
+                ops.node_du(hsT, gsT, lay, n0, n1, dut)
+                if need_dx:
+                    dxc[n0:n1] = _mm32(dut, w3kq.t())
+                if need_edge:
+                    dw3k = _addmm32(dw3k, xbs[a][n0:n1].t(), dut)
+                del dut
+            if need_dx:
+                # (sum over outgoing edges of gn[dst]) @ B3^T + g @ root^T, then + dU W3^T
+                rest_g, _ = ops.segment_matvec(None, plan.src_perm, plan.src_ptr, plan.dst, gn, None,
+                                               B3T, g, rootsT[c], None, False)
+                gx = rest_g.add_(dxc)
+            else:
+                gx = None
+        del hsT, gsT
+        G = torch.stack(gs)
+        X = torch.stack(xs[:A])
+        droot, dbias = [None, None], [None, None]
+        for c in (0, 1):
+            idx = [a for a in range(A) if schedule[a] == c]
+            if idx:
+                droot[c] = torch.bmm(X[idx].transpose(1, 2), G[idx]).sum(0)
+                dbias[c] = G[idx].sum((0, 1))
+            else:
+                droot[c] = torch.zeros_like(roots[c])
+                dbias[c] = torch.zeros(W, dtype=torch.float32, device=dev)
+        dw3 = db3 = dw2 = db2 = dw1 = db1 = dea = None
+        if need_edge:
+            db3 = torch.bmm(torch.stack(list(aggs)).transpose(1, 2), G).sum(0).reshape(-1)
+            dw3 = dw3k.view(W, K, W).permute(0, 2, 1).reshape(W * W, K)
+            # dh_e for all applications at once, node range by node range (U^T recomputed)
+            dh = torch.empty((lay.e_pad, K), dtype=bf, device=dev)
+            for n0, n1 in _node_chunks(N, A * W * K * 2):
+                ut = torch.empty((A, n1 - n0, K * W), dtype=bf, device=dev)
+                for a in range(A):
+                    torch.mm(xbs[a][n0:n1], w3kq, out=ut[a])
+                ops.node_dh(gs_all, ut.view(A, n1 - n0, K, W), lay, lay.unit_first[n0],
+                            lay.unit_first[n1], n0, dh)
+                del ut
+            del gs_all
+            dw2, db2, dw1, db1, dea_s = _mlp_grads(dh, ea_s, h1, hs, w1, w2, need_ea)
+            if need_ea:
+                dea = dea_s.index_select(0, lay.qpos_long)
+        return (gx if need_x0 else None, dea, dw1, db1, dw2, db2, dw3, db3, droot[0], dbias[0],
+                droot[1] if ctx.has2 else None, dbias[1] if ctx.has2 else None,
+                None, None, None, None)
+
+
+def _mlp_grads(dh, ea, h1, h, w1, w2, need_ea: bool):
+    """Backward of edge-MLP layers .0-.3 from dh_e (bf16 [rows, K]); rows in bounded chunks."""
+    E, K = h.shape
+    kin = ea.size(1)
+    f32 = dict(dtype=torch.float32, device=h.device)
+    dw2 = torch.zeros((K, K), **f32)
+    db2 = torch.zeros(K, **f32)
+    cs1 = torch.zeros((1 + kin, K), **f32)
+    dea = torch.empty_like(ea) if need_ea else None
+    w2q = w2.to(torch.bfloat16)
+    for e0 in range(0, E, _MLP_BWD_CHUNK_ROWS):
+        e1 = min(E, e0 + _MLP_BWD_CHUNK_ROWS)
+        dz2q = ops.mask_cast_colsum(dh[e0:e1], h[e0:e1], db2, torch.bfloat16)
+        dw2 = _addmm32(dw2, dz2q.t(), h1[e0:e1])
+        dz1 = _mm32(dz2q, w2q)
+        dz1 = ops.mask_cast_colsum(dz1, h1[e0:e1], cs1, torch.float32, side=ea[e0:e1],
+                                   sums_only=not need_ea)
+        if need_ea:
+            torch.mm(dz1, w1, out=dea[e0:e1])
+    return dw2, db2, cs1[1:].t().contiguous(), cs1[0].contiguous(), dea
+
+
 def gkn_stack(x0, edge_attr_sorted, net, root1, bias1, root2, bias2, plan: GraphPlan, schedule,
               relu: bool, precision: str = "bf16") -> torch.Tensor:
     """Edge MLP + ``len(schedule)`` NNConv applications sharing it.
@@ -212,6 +389,10 @@ def gkn_stack(x0, edge_attr_sorted, net, root1, bias1, root2, bias2, plan: Graph
     if x0.dtype != torch.float32 or edge_attr_sorted.dtype != torch.float32:
         raise TypeError("node features and edge attributes must be float32")
     l0, l2, l4 = net.layers[0], net.layers[2], net.layers[4]
-    return _GKNStack.apply(x0, edge_attr_sorted, l0.weight, l0.bias, l2.weight, l2.bias, l4.weight,
+    fn = _GKNStack
+    if FACTORIZATION == "node" and node_path_supported(x0.size(1), l4.weight.size(1),
+                                                       plan.num_edges, precision):
+        fn = _GKNStackNode
+    return fn.apply(x0, edge_attr_sorted, l0.weight, l0.bias, l2.weight, l2.bias, l4.weight,
                            l4.bias, root1, bias1, root2, bias2, plan, tuple(schedule), bool(relu),
                            precision)

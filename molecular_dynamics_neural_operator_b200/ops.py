@@ -21,10 +21,12 @@ class _KernelTimer:
     def __init__(self):
         self.enabled = False
         self.events: list = []
+        self.tagged: dict = {}
 
     def enable(self, tag: str = "contract"):
         self.enabled = True
         self.events = []
+        self.tagged = {}
 
     def disable(self):
         self.enabled = False
@@ -32,7 +34,10 @@ class _KernelTimer:
     def collect(self) -> dict:
         torch.cuda.synchronize()
         ms = sum(a.elapsed_time(b) for a, b in self.events)
-        return {"count": len(self.events), "ms": ms}
+        out = {"count": len(self.events), "ms": ms}
+        for tag, evs in self.tagged.items():
+            out[tag] = {"count": len(evs), "ms": sum(a.elapsed_time(b) for a, b in evs)}
+        return out
 
 
 KERNEL_TIMER = _KernelTimer()
@@ -428,3 +433,148 @@ def segment_matvec(rows, perm, seg_ptr, gidx, gnode, scale, M1, nin, M2, bias, r
             "gkn_segment_matvec",
         )
     return out, agg
+
+
+# ------------------------------------------------------------------------------------------------
+# Node-first factorisation (csrc/gkn_node_gemm.cu): padded source-sorted edge layout + grouped GEMMs
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class NodeLayout:
+    """Padded source-sorted edge layout of a GraphPlan (see gkn_node_msg_bf16 in gkn_b200.h):
+    the edges of source node n occupy rows [pptr[n], pptr[n] + deg[n]); every group is padded to a
+    multiple of 16 rows."""
+
+    num_nodes: int
+    e_pad: int
+    num_units: int
+    pptr: torch.Tensor  # int32 [N+1]
+    units: torch.Tensor  # int32 [U, 4]  (source node, first row, rows to store, 0)
+    qpos: torch.Tensor  # int32 [E]   destination-sorted position -> padded row
+    src_pad: torch.Tensor  # int32 [E_pad]  source node of every padded row
+    dst_pad: torch.Tensor  # int32 [E_pad]  destination node, -1 in pad rows
+    unit_first: list  # host list [N+1]: first unit of every node (for node-range chunking)
+
+    @property
+    def qpos_long(self) -> torch.Tensor:
+        if not hasattr(self, "_qpos_long"):
+            self._qpos_long = self.qpos.long()
+        return self._qpos_long
+
+    def tensors(self):
+        return [self.pptr, self.units, self.qpos, self.src_pad, self.dst_pad]
+
+
+def node_layout(plan: GraphPlan) -> NodeLayout:
+    """Build (once per plan, cached on it) the padded source-sorted layout.  Index bookkeeping
+    only (torch ops on the device, two small host reads for the data-dependent sizes)."""
+    cached = getattr(plan, "_node_layout", None)
+    if cached is not None:
+        return cached
+    dev = plan.src.device
+    N, E = plan.num_nodes, plan.num_edges
+    sp = plan.src_ptr.long()
+    deg = sp[1:] - sp[:-1]
+    degp = (deg + 15) // 16 * 16
+    tiles = (degp + 127) // 128
+    zero = torch.zeros(1, dtype=torch.long, device=dev)
+    pptr = torch.cat([zero, torch.cumsum(degp, 0)])
+    ufirst = torch.cat([zero, torch.cumsum(tiles, 0)])
+    unit_first = ufirst.tolist()  # host read (also gives the sizes below)
+    e_pad = int(pptr[-1].item())
+    U = unit_first[-1]
+    nodes = torch.arange(N, device=dev)
+    grp = torch.repeat_interleave(nodes, deg, output_size=E)
+    q_of_j = torch.arange(E, device=dev) + (pptr[:-1] - sp[:-1])[grp]
+    p_of_j = plan.src_perm.long()
+    qpos = torch.empty(E, dtype=torch.long, device=dev)
+    qpos[p_of_j] = q_of_j
+    src_pad = torch.repeat_interleave(nodes, degp, output_size=e_pad).int()
+    dst_pad = torch.full((e_pad,), -1, dtype=torch.int32, device=dev)
+    dst_pad[q_of_j] = plan.dst[p_of_j]
+    ug = torch.repeat_interleave(nodes, tiles, output_size=U)
+    t = torch.arange(U, device=dev) - ufirst[:-1][ug]
+    row0 = pptr[:-1][ug] + 128 * t
+    rows = torch.clamp(degp[ug] - 128 * t, max=128)
+    units = torch.stack([ug, row0, rows, torch.zeros_like(ug)], 1).int().contiguous()
+    lay = NodeLayout(N, e_pad, U, pptr.int(), units, qpos.int(), src_pad, dst_pad, unit_first)
+    object.__setattr__(plan, "_node_layout", lay)
+    return lay
+
+
+def _timed(tag: str):
+    """Context manager recording CUDA events around a launch when KERNEL_TIMER is enabled."""
+    class _T:
+        def __enter__(self_inner):
+            if KERNEL_TIMER.enabled:
+                self_inner.ev0 = torch.cuda.Event(enable_timing=True)
+                self_inner.ev0.record()
+
+        def __exit__(self_inner, *exc):
+            if KERNEL_TIMER.enabled:
+                ev1 = torch.cuda.Event(enable_timing=True)
+                ev1.record()
+                KERNEL_TIMER.tagged.setdefault(tag, []).append((self_inner.ev0, ev1))
+            return False
+
+    return _T()
+
+
+def node_msg(hs, u, lay: NodeLayout, unit_begin: int, unit_end: int, node_base: int,
+             msg: torch.Tensor) -> None:
+    """msg[q, :] = hs[q, :] @ u[src q]^T for the units [unit_begin, unit_end) (gkn_node_msg_bf16).
+    hs bf16 [E_pad, K]; u bf16 [chunk_nodes, W, K] for nodes [node_base, ...); msg fp32 [E_pad, W]."""
+    lib = _lib.load()
+    K = int(hs.size(1))
+    W = int(msg.size(1))
+    with torch.cuda.device(hs.device), _timed("node_msg"):
+        _lib.check(
+            lib.gkn_node_msg_bf16(_p(hs, torch.bfloat16, "hs"), _p(u, torch.bfloat16, "u"),
+                                  _p(lay.units, torch.int32, "units"), unit_begin, unit_end,
+                                  lay.e_pad, int(u.size(0)), node_base,
+                                  _p(msg, torch.float32, "msg"), K, W, _stream()),
+            "gkn_node_msg_bf16",
+        )
+
+
+def node_du(hsT, gsT, lay: NodeLayout, node_begin: int, node_end: int, dut: torch.Tensor) -> None:
+    """dut[n - node_begin][k, o] = sum_{q in group n} hsT[k, q] * gsT[o, q]  (gkn_node_du_bf16)."""
+    lib = _lib.load()
+    K = int(hsT.size(0))
+    W = int(gsT.size(0))
+    with torch.cuda.device(hsT.device), _timed("node_du"):
+        _lib.check(
+            lib.gkn_node_du_bf16(_p(hsT, torch.bfloat16, "hsT"), _p(gsT, torch.bfloat16, "gsT"),
+                                 _p(lay.pptr, torch.int32, "pptr"), node_begin, node_end, lay.e_pad,
+                                 _p(dut, torch.bfloat16, "dut"), K, W, _stream()),
+            "gkn_node_du_bf16",
+        )
+
+
+def node_dh(gs, ut, lay: NodeLayout, unit_begin: int, unit_end: int, node_base: int,
+            dh: torch.Tensor) -> None:
+    """dh[q, k] = sum_a gs[a][q, :] . ut[a][src q][k, :]  (gkn_node_dh_bf16).
+    gs bf16 [A, E_pad, W]; ut bf16 [A, chunk_nodes, K, W]; dh bf16 [E_pad, K]."""
+    lib = _lib.load()
+    A, W = int(gs.size(0)), int(gs.size(2))
+    K = int(dh.size(1))
+    with torch.cuda.device(gs.device), _timed("node_dh"):
+        _lib.check(
+            lib.gkn_node_dh_bf16(_p(gs, torch.bfloat16, "gs"), _p(ut, torch.bfloat16, "ut"),
+                                 _p(lay.units, torch.int32, "units"), unit_begin, unit_end,
+                                 lay.e_pad, int(ut.size(1)), node_base, A,
+                                 _p(dh, torch.bfloat16, "dh"), K, W, _stream()),
+            "gkn_node_dh_bf16",
+        )
+
+
+def node_gather(g, lay: NodeLayout, gs: torch.Tensor | None, gsT: torch.Tensor | None) -> None:
+    """gs[q, :] = bf16(g[dst_pad[q], :]) (zero in pad rows) and/or its transpose gsT [W, E_pad]."""
+    lib = _lib.load()
+    W = int(g.size(1))
+    with torch.cuda.device(g.device):
+        _lib.check(
+            lib.gkn_node_gather_bf16(_p(g, torch.float32, "g"), _p(lay.dst_pad, torch.int32, "idx"),
+                                     lay.e_pad, _p(gs, torch.bfloat16, "gs"),
+                                     _p(gsT, torch.bfloat16, "gsT"), W, _stream()),
+            "gkn_node_gather_bf16",
+        )

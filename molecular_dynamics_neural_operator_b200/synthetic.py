@@ -104,6 +104,12 @@ def make_batch(x_window: torch.Tensor, aminoacid: torch.Tensor, y: torch.Tensor 
     if prepare:
         # radius graphs are symmetric and (row, col)-sorted: no sorting needed for the CSR plan
         data._gkn_plan = ops.plan_from_csr(edge_index, row_ptr, B * N, validate=False)
+        from . import functional as GF
+
+        if GF.FACTORIZATION == "node" and edge_index.size(1) > 0:
+            # padded source-sorted layout of the node-first kernels (two small host reads): built
+            # here so that it, too, happens off the training stream when prefetched
+            ops.node_layout(data._gkn_plan)
     return data
 
 
@@ -133,6 +139,9 @@ class BatchPrefetcher:
         if plan is not None:
             tensors += [plan.perm, plan.src, plan.dst, plan.dst_ptr, plan.inv_cnt, plan.src_ptr,
                         plan.src_perm]
+            lay = getattr(plan, "_node_layout", None)
+            if lay is not None:
+                tensors += lay.tensors() + [lay.qpos_long]
         for t in tensors:
             if t is not None and t.is_cuda:
                 t.record_stream(main)

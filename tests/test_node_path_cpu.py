@@ -1,0 +1,252 @@
+"""CPU: the node-first factorisation's host logic (padded source-sorted layout, unit table, the
+autograd algebra of ``functional._GKNStackNode``) checked against the oracle.
+
+The CUDA entry points are replaced here by short torch restatements of what each kernel is
+documented to compute in include/gkn_b200.h (same arguments, same layouts), so everything
+ABOVE the C ABI runs unchanged on the CPU; the kernels themselves are checked on the GPU
+(tests/test_node_path_gpu.py).  The emulation is test infrastructure only.
+"""
+import numpy as np
+import pytest
+import torch
+
+from molecular_dynamics_neural_operator_b200 import functional as GF
+from molecular_dynamics_neural_operator_b200 import ops
+from oracle import gkn_oracle as orc
+
+
+def cpu_plan(edge_index: torch.Tensor, N: int) -> ops.GraphPlan:
+    """What gkn_graph_prepare produces (destination-sorted positions, ties in edge order)."""
+    src, dst = edge_index[0], edge_index[1]
+    E = src.numel()
+    perm = torch.sort(dst * E + torch.arange(E), stable=True).indices
+    src_s, dst_s = src[perm], dst[perm]
+    cnt = torch.bincount(dst_s, minlength=N)
+    dst_ptr = torch.cat([torch.zeros(1, dtype=torch.long), cnt.cumsum(0)])
+    src_perm = torch.sort(src_s * E + torch.arange(E), stable=True).indices
+    scnt = torch.bincount(src_s, minlength=N)
+    src_ptr = torch.cat([torch.zeros(1, dtype=torch.long), scnt.cumsum(0)])
+    inv = 1.0 / cnt.clamp(min=1).float()
+    return ops.GraphPlan(N, E, perm.int(), src_s.int(), dst_s.int(), dst_ptr.int(), inv,
+                         src_ptr.int(), src_perm.int())
+
+
+def random_graph(N, E, seed, isolated=()):
+    g = torch.Generator().manual_seed(seed)
+    ei = torch.randint(0, N, (2, E), generator=g)
+    for n in isolated:  # nodes with no outgoing and no incoming edges
+        ei[ei == n] = (n + 1) % N
+    return ei
+
+
+# ---- torch restatements of the C entry points ----------------------------------------------
+def emu_edge_layer0(ea, w1, b1, out_dtype):
+    return torch.relu(ea @ w1.t() + b1).to(out_dtype)
+
+
+def emu_segment_matvec(rows, perm, seg_ptr, gidx, gnode, scale, M1, nin, M2, bias, relu,
+                       want_agg=False):
+    N, W = nin.shape
+    r = torch.zeros(N, W)
+    agg = torch.zeros(N, W)
+    for n in range(N):
+        q = torch.arange(int(seg_ptr[n]), int(seg_ptr[n + 1]))
+        p = perm[q].long() if perm is not None else q
+        if rows is not None:
+            r[n] = rows[p].sum(0)
+        agg[n] = gnode[gidx[p].long()].sum(0)
+    if scale is not None:
+        r, agg = r * scale[:, None], agg * scale[:, None]
+    out = r + agg @ M1 + nin @ M2
+    if bias is not None:
+        out = out + bias
+    if relu:
+        out = torch.relu(out)
+    return out, (agg if want_agg else None)
+
+
+def emu_relu_grad_scale(gy, y, inv_cnt, relu):
+    g = gy * (y > 0) if relu else gy.clone()
+    return g, g * inv_cnt[:, None]
+
+
+def emu_mask_cast_colsum(dz, act, colsum, out_dtype, side=None, accumulate=True, sums_only=False):
+    out = (dz.float() * (act.float() > 0)).to(out_dtype)
+    o = out.float()
+    cs = colsum.view(-1, dz.size(1))
+    cs[0] += o.sum(0)
+    if side is not None:
+        cs[1:] += side.t() @ o
+    return None if sums_only else out
+
+
+def emu_node_msg(hs, u, lay, u0, u1, node_base, msg):
+    for g, row0, rows, _ in lay.units[u0:u1].tolist():
+        msg[row0:row0 + rows] = hs[row0:row0 + rows].float() @ u[g - node_base].float().t()
+
+
+def emu_node_du(hsT, gsT, lay, n0, n1, dut):
+    K, W = hsT.size(0), gsT.size(0)
+    pp = lay.pptr.tolist()
+    d = dut.view(n1 - n0, K, W)
+    for n in range(n0, n1):
+        sl = slice(pp[n], pp[n + 1])
+        d[n - n0] = (hsT[:, sl].float() @ gsT[:, sl].float().t()).to(dut.dtype)
+
+
+def emu_node_dh(gs, ut, lay, u0, u1, node_base, dh):
+    A = gs.size(0)
+    for g, row0, rows, _ in lay.units[u0:u1].tolist():
+        acc = torch.zeros(rows, dh.size(1))
+        for a in range(A):
+            acc += gs[a, row0:row0 + rows].float() @ ut[a, g - node_base].float().t()
+        dh[row0:row0 + rows] = acc.to(dh.dtype)
+
+
+def emu_node_gather(g, lay, gs, gsT):
+    idx = lay.dst_pad.long()
+    rows = torch.where((idx >= 0)[:, None], g[idx.clamp(min=0)], torch.zeros(1)).to(torch.bfloat16)
+    if gs is not None:
+        gs.copy_(rows)
+    if gsT is not None:
+        gsT.copy_(rows.t())
+
+
+@pytest.fixture
+def emulated(monkeypatch):
+    for name, fn in [("edge_layer0", emu_edge_layer0), ("segment_matvec", emu_segment_matvec),
+                     ("relu_grad_scale", emu_relu_grad_scale),
+                     ("mask_cast_colsum", emu_mask_cast_colsum), ("node_msg", emu_node_msg),
+                     ("node_du", emu_node_du), ("node_dh", emu_node_dh),
+                     ("node_gather", emu_node_gather)]:
+        monkeypatch.setattr(ops, name, fn)
+    monkeypatch.setattr(GF, "_mm32", lambda a, b: a.float() @ b.float())
+    monkeypatch.setattr(GF, "_addmm32", lambda acc, a, b: acc + a.float() @ b.float())
+    monkeypatch.setattr(
+        torch, "_addmm_activation",
+        lambda b, a, w, **kw: torch.relu(a.float() @ w.float() + b.float()).to(a.dtype))
+
+
+# ---- layout ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,E,isolated", [(7, 40, ()), (5, 700, ()), (9, 60, (3, 8)), (4, 1, ())])
+def test_padded_source_sorted_layout_invariants(N, E, isolated):
+    ei = random_graph(N, E, seed=N + E, isolated=isolated)
+    plan = cpu_plan(ei, N)
+    lay = ops.node_layout(plan)
+    pp = lay.pptr.long()
+    deg = torch.bincount(ei[0], minlength=N)
+    assert lay.e_pad % 16 == 0 and int(pp[-1]) == lay.e_pad
+    assert torch.equal((pp[1:] - pp[:-1]), (deg + 15) // 16 * 16)
+    # every edge sits in the group of its source, at a distinct row; pad rows are marked -1
+    q = lay.qpos.long()
+    assert q.unique().numel() == E
+    assert torch.equal(lay.src_pad.long()[q], plan.src.long())
+    assert torch.equal(lay.dst_pad.long()[q], plan.dst.long())
+    assert int((lay.dst_pad >= 0).sum()) == E
+    grp_rows = q - pp[plan.src.long()]
+    assert bool((grp_rows >= 0).all()) and bool((grp_rows < deg[plan.src.long()]).all())
+    # the unit table tiles every group exactly once, in node order
+    covered = torch.zeros(lay.e_pad, dtype=torch.int32)
+    for g, row0, rows, _ in lay.units.tolist():
+        assert 0 < rows <= 128 and pp[g] <= row0 and row0 + rows <= pp[g + 1]
+        covered[row0:row0 + rows] += 1
+    assert bool((covered == 1).all())
+    assert lay.unit_first[0] == 0 and lay.unit_first[-1] == lay.num_units
+    assert torch.equal(lay.units[:, 0].long(), lay.units[:, 0].long().sort().values)
+    assert ops.node_layout(plan) is lay  # cached on the plan
+
+
+# ---- autograd algebra -------------------------------------------------------------------------
+def _stack_case(N, E, K, depth, seed, isolated=()):
+    W = 64
+    ei = random_graph(N, E, seed, isolated)
+    g = torch.Generator().manual_seed(seed + 1)
+    net = orc.make_net_params(6, K, W, seed=seed, dtype=torch.float32)
+    p = {
+        "x": torch.randn(N, W, generator=g), "ea": torch.randn(E, 6, generator=g),
+        "root1": torch.randn(W, W, generator=g) / 8, "bias1": torch.randn(W, generator=g) / 8,
+        "root2": torch.randn(W, W, generator=g) / 8, "bias2": torch.randn(W, generator=g) / 8,
+    }
+    for k, v in net.items():
+        p["net." + k] = v
+    return ei, p, depth
+
+
+def _run_node_stack(ei, p, depth, N, relu=True):
+    plan = cpu_plan(ei, N)
+    t = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    ea_sorted = t["ea"].index_select(0, plan.perm.long())
+    out = GF._GKNStackNode.apply(
+        t["x"], ea_sorted, t["net.layers.0.weight"], t["net.layers.0.bias"],
+        t["net.layers.2.weight"], t["net.layers.2.bias"], t["net.layers.4.weight"],
+        t["net.layers.4.bias"], t["root1"], t["bias1"], t["root2"], t["bias2"], plan,
+        (0,) * depth + (1,) * depth, relu, "bf16")
+    return out, t
+
+
+def _run_oracle_stack(ei, p, depth, relu=True):
+    t = {k: v.double().clone().requires_grad_(True) for k, v in p.items()}
+    net = {k[4:]: v for k, v in t.items() if k.startswith("net.")}
+    if relu:
+        out = orc.conv_stack(t["x"], ei, t["ea"], net, t["root1"], t["bias1"], t["root2"],
+                             t["bias2"], depth)
+    else:  # the same stack without the activation (smooth in the operands: tight tolerances)
+        out = t["x"]
+        for c in (1,) * depth + (2,) * depth:
+            out = orc.nnconv_forward(out, ei, t["ea"], net, t[f"root{c}"], t[f"bias{c}"])
+    return out, t
+
+
+def fro(a, b):
+    a, b = a.detach().double(), b.detach().double()
+    return float((a - b).norm() / b.norm().clamp(min=1e-30))
+
+
+@pytest.mark.parametrize("N,E,K,depth,isolated,chunk_mb", [
+    (6, 90, 256, 1, (), 1024),      # one application, single node chunk
+    (5, 700, 256, 2, (), 1024),     # groups longer than one 128-row tile
+    (9, 120, 256, 2, (2, 7), 0),    # isolated nodes, node-range chunking of U / dU / U^T (1 node)
+])
+def test_node_first_stack_matches_oracle(emulated, monkeypatch, N, E, K, depth, isolated, chunk_mb):
+    """Without the activation between applications the stack is smooth in its operands, so bf16
+    rounding is the only difference from the fp64 oracle: every gradient within 2^-5 except those
+    upstream of the edge MLP's own ReLUs (mask flips, see tests/test_layer_gpu.py)."""
+    monkeypatch.setattr(GF, "_NODE_CHUNK_BYTES", chunk_mb << 20)
+    monkeypatch.setattr(GF, "_MLP_BWD_CHUNK_ROWS", 64)
+    ei, p, depth = _stack_case(N, E, K, depth, seed=11 * N + depth, isolated=isolated)
+    out, t = _run_node_stack(ei, p, depth, N, relu=False)
+    ref, tr = _run_oracle_stack(ei, p, depth, relu=False)
+    assert fro(out, ref) < 2.0 ** -5
+    gen = torch.Generator().manual_seed(5)
+    gout = torch.randn(out.shape, generator=gen)
+    out.backward(gout)
+    ref.backward(gout.double())
+    for k in p:
+        tol = 2.0 ** -2 if k.startswith(("net.layers.0", "net.layers.2", "ea")) else 2.0 ** -5
+        assert t[k].grad is not None, k
+        assert fro(t[k].grad, tr[k].grad) < tol, k
+
+
+def test_node_first_stack_with_relu_matches_oracle(emulated):
+    """With F.relu after every application (graph_kernel.py:299-302): outputs within the stack
+    bound; gradients are compared where the bf16 and fp64 activation masks agree."""
+    N, E, K, depth = 8, 300, 256, 2
+    ei, p, depth = _stack_case(N, E, K, depth, seed=3)
+    out, t = _run_node_stack(ei, p, depth, N, relu=True)
+    ref, tr = _run_oracle_stack(ei, p, depth, relu=True)
+    assert fro(out, ref) < 2.0 ** -5
+    gen = torch.Generator().manual_seed(5)
+    gout = torch.randn(out.shape, generator=gen)
+    out.backward(gout)
+    ref.backward(gout.double())
+    for k in ("x", "root1", "bias2", "net.layers.4.weight", "net.layers.4.bias"):
+        a, b = t[k].grad.double().flatten(), tr[k].grad.flatten()
+        assert float(a.dot(b) / (a.norm() * b.norm())) > 0.98, k
+
+
+def test_node_path_selection():
+    assert GF.node_path_supported(64, 1024, 10, "bf16")
+    assert not GF.node_path_supported(32, 1024, 10, "bf16")
+    assert not GF.node_path_supported(64, 1024, 10, "fp32")
+    assert not GF.node_path_supported(64, 1000, 10, "bf16")
+    assert not GF.node_path_supported(64, 1024, 0, "bf16")

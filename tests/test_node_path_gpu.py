@@ -1,0 +1,183 @@
+"""GPU parity of the node-first factorisation (csrc/gkn_node_gemm.cu) through the C ABI:
+each grouped-GEMM kernel against a torch fp32 restatement on identical bf16 operands, the whole
+stack against the edge-first tensor-core path and the fp64 oracle.
+
+Tolerances: the kernels accumulate bf16 products in fp32, so against an fp32 matmul of the SAME
+bf16 operands only the summation order differs: 1e-5 relative (max-norm) for fp32 outputs, one
+bf16 rounding (one ulp = 2^-7 relative at most, on the max-norm scale) for bf16 outputs.
+Stack level: bounds of tests/test_layer_gpu.py.
+"""
+import pytest
+import torch
+
+from tests.helpers import rel_err
+from tests.test_node_path_cpu import (_run_oracle_stack, _stack_case, cpu_plan, emu_node_dh,
+                                      emu_node_du, emu_node_gather, emu_node_msg, fro,
+                                      random_graph)
+
+pytestmark = pytest.mark.gpu
+
+BF16_OUT_TOL = 2.0 ** -7
+W = 64
+
+
+def _plan_on_gpu(ei, N):
+    from molecular_dynamics_neural_operator_b200 import ops
+
+    return ops.prepare_graph(ei.cuda(), N)
+
+
+def _graphs():
+    # (name, edge_index, N): ragged degrees, groups longer than one and two tiles, isolated nodes
+    g = torch.Generator().manual_seed(0)
+    yield "ragged", random_graph(40, 3000, 1), 40
+    yield "long_groups", random_graph(6, 2000, 2), 6
+    yield "isolated", random_graph(50, 700, 3, isolated=(0, 17, 49)), 50
+    src = torch.randint(0, 300, (20000,), generator=g)
+    dst = torch.randint(0, 300, (20000,), generator=g)
+    yield "mid", torch.stack([src, dst]), 300
+
+
+@pytest.mark.parametrize("case", list(_graphs()), ids=lambda c: c[0])
+@pytest.mark.parametrize("K", [256, 1024])
+def test_grouped_gemm_kernels_match_fp32_restatement(case, K):
+    from molecular_dynamics_neural_operator_b200 import ops
+
+    _, ei, N = case
+    plan = _plan_on_gpu(ei, N)
+    lay = ops.node_layout(plan)
+    cl = ops.node_layout(cpu_plan(ei, N))  # the same layout from the CPU restatement of the plan
+    assert lay.e_pad == cl.e_pad and torch.equal(lay.units.cpu(), cl.units)
+    assert torch.equal(lay.pptr.cpu(), cl.pptr)
+    gen = torch.Generator().manual_seed(K + N)
+    bf = torch.bfloat16
+    E_pad = lay.e_pad
+    hs = torch.randn(E_pad, K, generator=gen).to(bf)
+    u = (torch.randn(N, W, K, generator=gen) / 8).to(bf)
+    gn = torch.randn(N, W, generator=gen)
+    A = 3
+    gs_in = torch.randn(A, N, W, generator=gen)
+    ut = (torch.randn(A, N, K, W, generator=gen) / 8).to(bf)
+
+    # ---- msg ----
+    msg = torch.full((E_pad, W), float("nan"), device="cuda")
+    ops.node_msg(hs.cuda(), u.cuda(), lay, 0, lay.num_units, 0, msg)
+    ref = torch.zeros(E_pad, W)
+    emu_node_msg(hs, u, cl, 0, cl.num_units, 0, ref)
+    assert rel_err(msg, ref) <= 1e-5
+
+    # ---- gather (+ transpose) ----
+    gs = torch.empty(E_pad, W, dtype=bf, device="cuda")
+    gsT = torch.empty(W, E_pad, dtype=bf, device="cuda")
+    ops.node_gather(gn.cuda(), lay, gs, gsT)
+    rgs, rgsT = torch.empty(E_pad, W, dtype=bf), torch.empty(W, E_pad, dtype=bf)
+    # the CPU layout's dst_pad follows the CPU plan's tie order; use the GPU layout's indices
+    import copy
+    cl2 = copy.copy(cl)
+    cl2.dst_pad = lay.dst_pad.cpu()
+    emu_node_gather(gn, cl2, rgs, rgsT)
+    assert torch.equal(gs.cpu(), rgs) and torch.equal(gsT.cpu(), rgsT)
+
+    # ---- dU ----
+    hsT = hs.t().contiguous()
+    dut = torch.full((N, K * W), float("nan"), dtype=bf, device="cuda")
+    ops.node_du(hsT.cuda(), gsT, lay, 0, N, dut)
+    rdut = torch.zeros(N, K * W, dtype=bf)
+    emu_node_du(hsT, rgsT, cl, 0, N, rdut)
+    assert rel_err(dut.float(), rdut.float()) <= BF16_OUT_TOL
+
+    # ---- dh (all applications at once) ----
+    gs_all = torch.empty(A, E_pad, W, dtype=bf, device="cuda")
+    rgs_all = torch.empty(A, E_pad, W, dtype=bf)
+    for a in range(A):
+        ops.node_gather(gs_in[a].cuda(), lay, gs_all[a], None)
+        emu_node_gather(gs_in[a], cl2, rgs_all[a], None)
+    dh = torch.full((E_pad, K), float("nan"), dtype=bf, device="cuda")
+    ops.node_dh(gs_all, ut.cuda(), lay, 0, lay.num_units, 0, dh)
+    rdh = torch.zeros(E_pad, K, dtype=bf)
+    emu_node_dh(rgs_all, ut, cl, 0, cl.num_units, 0, rdh)
+    assert rel_err(dh.float(), rdh.float()) <= BF16_OUT_TOL
+    pad = (lay.dst_pad < 0).cpu()
+    assert float(dh.float().cpu()[pad].abs().max() if pad.any() else 0.0) == 0.0
+
+
+def test_grouped_gemm_node_range_chunks_cover_the_same_result():
+    from molecular_dynamics_neural_operator_b200 import ops
+
+    ei, N, K = random_graph(64, 6000, 9), 64, 256
+    plan = _plan_on_gpu(ei, N)
+    lay = ops.node_layout(plan)
+    gen = torch.Generator().manual_seed(1)
+    bf = torch.bfloat16
+    hs = torch.randn(lay.e_pad, K, generator=gen).to(bf).cuda()
+    u = (torch.randn(N, W, K, generator=gen) / 8).to(bf).cuda()
+    whole = torch.zeros(lay.e_pad, W, device="cuda")
+    ops.node_msg(hs, u, lay, 0, lay.num_units, 0, whole)
+    parts = torch.zeros(lay.e_pad, W, device="cuda")
+    for n0 in range(0, N, 24):
+        n1 = min(N, n0 + 24)
+        ops.node_msg(hs, u[n0:n1].contiguous(), lay, lay.unit_first[n0], lay.unit_first[n1], n0,
+                     parts)
+    assert torch.equal(whole, parts)
+    gsT = torch.randn(W, lay.e_pad, generator=gen).to(bf).cuda()
+    gsT[:, lay.dst_pad < 0] = 0
+    hsT = hs.t().contiguous()
+    d_whole = torch.empty(N, K * W, dtype=bf, device="cuda")
+    ops.node_du(hsT, gsT, lay, 0, N, d_whole)
+    d_parts = torch.empty(N, K * W, dtype=bf, device="cuda")
+    for n0 in range(0, N, 24):
+        n1 = min(N, n0 + 24)
+        ops.node_du(hsT, gsT, lay, n0, n1, d_parts[n0:n1])
+    assert torch.equal(d_whole, d_parts)
+
+
+def _gpu_stack(fn, ei, p, depth, N, relu):
+    from molecular_dynamics_neural_operator_b200 import ops
+
+    plan = ops.prepare_graph(ei.cuda(), N)
+    t = {k: v.clone().cuda().requires_grad_(True) for k, v in p.items()}
+    ea_sorted = t["ea"].index_select(0, plan.perm_long)
+    out = fn.apply(t["x"], ea_sorted, t["net.layers.0.weight"], t["net.layers.0.bias"],
+                   t["net.layers.2.weight"], t["net.layers.2.bias"], t["net.layers.4.weight"],
+                   t["net.layers.4.bias"], t["root1"], t["bias1"], t["root2"], t["bias2"], plan,
+                   (0,) * depth + (1,) * depth, relu, "bf16")
+    return out, t
+
+
+@pytest.mark.parametrize("N,E,K,depth", [(20, 3000, 256, 1), (120, 8000, 1024, 2)])
+def test_node_first_stack_matches_edge_first_stack_and_oracle(N, E, K, depth):
+    """No activation between applications (smooth: only bf16 rounding differs)."""
+    from molecular_dynamics_neural_operator_b200 import functional as GF
+
+    ei, p, depth = _stack_case(N, E, K, depth, seed=N)
+    out_n, tn = _gpu_stack(GF._GKNStackNode, ei, p, depth, N, relu=False)
+    out_e, te = _gpu_stack(GF._GKNStack, ei, p, depth, N, relu=False)
+    ref, tr = _run_oracle_stack(ei, p, depth, relu=False)
+    assert fro(out_n.cpu(), ref) < 2.0 ** -5
+    assert fro(out_n.cpu(), out_e.cpu()) < 2.0 ** -5
+    gout = torch.randn(out_n.shape, generator=torch.Generator().manual_seed(5))
+    out_n.backward(gout.cuda())
+    out_e.backward(gout.cuda())
+    ref.backward(gout.double())
+    for k in p:
+        tol = 2.0 ** -2 if k.startswith(("net.layers.0", "net.layers.2", "ea")) else 2.0 ** -5
+        assert fro(tn[k].grad.cpu(), tr[k].grad) < tol, k
+        assert fro(tn[k].grad.cpu(), te[k].grad.cpu()) < tol, k
+
+
+def test_node_first_is_the_default_for_the_bench_shape():
+    """KernelNN at w = 64 / K = 1024 in bf16 runs the grouped-GEMM kernels (launch accounting)."""
+    from molecular_dynamics_neural_operator_b200 import functional as GF
+    from molecular_dynamics_neural_operator_b200 import ops
+
+    assert GF.FACTORIZATION == "node"
+    ei, p, depth = _stack_case(30, 2000, 1024, 1, seed=2)
+    ops.KERNEL_TIMER.enable()
+    try:
+        out, t = _gpu_stack(GF._GKNStackNode, ei, p, depth, 30, relu=True)
+        out.sum().backward()
+        got = ops.KERNEL_TIMER.collect()
+    finally:
+        ops.KERNEL_TIMER.disable()
+    assert got["node_msg"]["count"] == 2 and got["node_du"]["count"] == 2
+    assert got["node_dh"]["count"] == 1
