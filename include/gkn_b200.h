@@ -122,6 +122,16 @@ int gkn_node_dh_bf16(const void* gs_bf16, const void* ut_bf16, const int32_t* un
                      int64_t unit_begin, int64_t unit_end, int64_t E_pad, int64_t chunk_nodes,
                      int32_t node_base, int32_t A, void* dh_bf16, int32_t K, int32_t W,
                      void* stream);
+/* The same two products with operands read in place as MN-major tensor-core operands: du from
+ * hs [E_pad,K] and gs [E_pad,W] (no transposed copies), dh from u [A,chunk,W,K] (the forward's
+ * [o,k]-ordered U, so it can be saved instead of recomputed in [k,o] order). */
+int gkn_node_du_mn_bf16(const void* hs_bf16, const void* gs_bf16, const int32_t* pptr,
+                        int64_t node_begin, int64_t node_end, int64_t E_pad, void* dut_bf16,
+                        int32_t K, int32_t W, void* stream);
+int gkn_node_dh_mn_bf16(const void* gs_bf16, const void* u_bf16, const int32_t* units,
+                        int64_t unit_begin, int64_t unit_end, int64_t E_pad, int64_t chunk_nodes,
+                        int32_t node_base, int32_t A, void* dh_bf16, int32_t K, int32_t W,
+                        void* stream);
 int gkn_node_gather_bf16(const float* g, const int32_t* idx, int64_t E_pad, void* gs_bf16,
                          void* gsT_bf16, int32_t W, void* stream);
 

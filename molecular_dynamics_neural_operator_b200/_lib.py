@@ -42,6 +42,11 @@ SIGNATURES = {
         c_int,
         [P, P, P, c_int64, c_int64, c_int64, c_int64, c_int32, c_int32, P, c_int32, c_int32, P],
     ),
+    "gkn_node_du_mn_bf16": (c_int, [P, P, P, c_int64, c_int64, c_int64, P, c_int32, c_int32, P]),
+    "gkn_node_dh_mn_bf16": (
+        c_int,
+        [P, P, P, c_int64, c_int64, c_int64, c_int64, c_int32, c_int32, P, c_int32, c_int32, P],
+    ),
     "gkn_node_gather_bf16": (c_int, [P, P, c_int64, P, P, c_int32, P]),
     "gkn_scatter_mean_fwd": (
         c_int,

@@ -43,15 +43,27 @@ constexpr int kThreads = 192;
 constexpr int kABytes = kM * kKB * 2;  // 16 KB
 constexpr int kW = 64;       // node feature width served by this file
 
-enum { MODE_MSG = 0, MODE_DU = 1, MODE_DH = 2 };
+// *_MN: the same products with operands read straight from their natural row-major buffers as
+// MN-major UMMA operands (no transposed copies of h / gm, no [k,o]-ordered copy of U):
+//   MODE_DU_MN  A = hs[grp, c] (M = k contiguous), B = gs[grp, :] (N = o contiguous), K = edges
+//   MODE_DH_MN  A = Gs_a[tile, :] (K-major),        B = U_a[n][:, c] (N = k contiguous), K = o
+enum { MODE_MSG = 0, MODE_DU = 1, MODE_DH = 2, MODE_DU_MN = 3, MODE_DH_MN = 4 };
+
+__host__ __device__ constexpr bool mode_is_dh(int m) { return m == MODE_DH || m == MODE_DH_MN; }
+__host__ __device__ constexpr bool mode_is_du(int m) { return m == MODE_DU || m == MODE_DU_MN; }
+constexpr int kMnBlockBytes = 64 * kKB * 2;  // one MN-major TMA box: 64 K-rows x 64 MN elements
 
 template <int MODE>
 struct NCfg {
-    static constexpr int kBN = MODE == MODE_DH ? 256 : kW;      // accumulator columns
+    static constexpr int kBN = mode_is_dh(MODE) ? 256 : kW;     // accumulator columns
     static constexpr int kBBytes = kBN * kKB * 2;               // 8 KB / 32 KB
     static constexpr int kStageBytes = kABytes + kBBytes;       // 24 KB / 48 KB
-    static constexpr int kStages = MODE == MODE_DH ? 4 : 8;     // 192 KB of operands in flight
-    static constexpr int kAcc = MODE == MODE_DH ? 2 : 4;        // TMEM accumulator ring
+    static constexpr int kStages = mode_is_dh(MODE) ? 4 : 8;    // 192 KB of operands in flight
+    static constexpr int kAcc = mode_is_dh(MODE) ? 2 : 4;       // TMEM accumulator ring
+    static constexpr bool kAMn = MODE == MODE_DU_MN;            // A operand MN-major
+    static constexpr bool kBMn = MODE == MODE_DU_MN || MODE == MODE_DH_MN;
+    static constexpr int kABoxes = kAMn ? kM / 64 : 1;          // TMA boxes per k-block
+    static constexpr int kBBoxes = kBMn ? kBN / 64 : 1;
     static constexpr int kTmemCols = kAcc * kBN;                // 512 / 256
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
@@ -85,6 +97,24 @@ __device__ __forceinline__ Unit decode_unit(const NodeParams& p, int64_t v) {
         u.a_c0 = 0; u.a_c1 = t.y; u.da_c0 = kKB; u.da_c1 = 0;
         u.b_c0 = 0; u.b_c1 = (t.x - p.node_base) * kW; u.db_c0 = kKB; u.db_c1 = 0;
         u.nkb = p.K / kKB; u.last_steps = kKB / kUmmaK;
+    } else if constexpr (MODE == MODE_DH_MN) {
+        const int32_t chunks = p.K / 256;
+        const int4 t = __ldg(p.units + v / chunks);
+        u.group = t.x; u.row0 = t.y; u.rows = t.z; u.chunk = int32_t(v % chunks);
+        u.a_c0 = 0; u.a_c1 = t.y; u.da_c0 = 0; u.da_c1 = p.a_rows_per_app;
+        u.b_c0 = u.chunk * 256; u.b_c1 = (t.x - p.node_base) * kW;
+        u.db_c0 = 0; u.db_c1 = p.b_rows_per_app;
+        u.nkb = p.A; u.last_steps = kKB / kUmmaK;
+    } else if constexpr (MODE == MODE_DU_MN) {
+        const int32_t chunks = p.K / kM;
+        const int32_t g = p.node_base + int32_t(v / chunks);
+        const int32_t b = __ldg(p.pptr + g), e = __ldg(p.pptr + g + 1);
+        const int32_t len = e - b;  // multiple of 16
+        u.group = g; u.chunk = int32_t(v % chunks); u.row0 = b; u.rows = kM;
+        u.a_c0 = u.chunk * kM; u.a_c1 = b; u.da_c0 = 0; u.da_c1 = kKB;
+        u.b_c0 = 0; u.b_c1 = b; u.db_c0 = 0; u.db_c1 = kKB;
+        u.nkb = (len + kKB - 1) / kKB;
+        u.last_steps = (len - (u.nkb - 1) * kKB) / kUmmaK;
     } else if constexpr (MODE == MODE_DH) {
         const int32_t chunks = p.K / 256;
         const int4 t = __ldg(p.units + v / chunks);
@@ -175,10 +205,16 @@ node_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sa = smem_base + stage * kStageBytes;
                     mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
-                    tma_load_2d(sa, &tmap_a, full_bar(stage), u.a_c0 + kb * u.da_c0,
-                                u.a_c1 + kb * u.da_c1);
-                    tma_load_2d(sa + kABytes, &tmap_b, full_bar(stage), u.b_c0 + kb * u.db_c0,
-                                u.b_c1 + kb * u.db_c1);
+#pragma unroll
+                    for (int j = 0; j < C::kABoxes; ++j) {
+                        tma_load_2d(sa + j * kMnBlockBytes, &tmap_a, full_bar(stage),
+                                    u.a_c0 + kb * u.da_c0 + j * 64, u.a_c1 + kb * u.da_c1);
+                    }
+#pragma unroll
+                    for (int j = 0; j < C::kBBoxes; ++j) {
+                        tma_load_2d(sa + kABytes + j * kMnBlockBytes, &tmap_b, full_bar(stage),
+                                    u.b_c0 + kb * u.db_c0 + j * 64, u.b_c1 + kb * u.db_c1);
+                    }
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1u;
@@ -189,7 +225,12 @@ node_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(kM, kBN, 0, 0);
+            constexpr uint32_t idesc = umma_idesc_bf16(kM, kBN, C::kAMn ? 1 : 0, C::kBMn ? 1 : 0);
+            // K-major: 16 K elements = 32 B inside the swizzle row.  MN-major: a K element is a
+            // 128-byte smem row, 64-element MN blocks are kMnBlockBytes apart (LBO), 8-row groups
+            // 1024 B apart (SBO); a K-step of 16 rows advances the start address by 2048 B.
+            constexpr uint32_t a_lbo = C::kAMn ? kMnBlockBytes : 16, b_lbo = C::kBMn ? kMnBlockBytes : 16;
+            constexpr uint64_t a_step = C::kAMn ? (16 * 128) >> 4 : 2, b_step = C::kBMn ? (16 * 128) >> 4 : 2;
             int stage = 0;
             uint32_t phase = 0;
             uint32_t it = 0;
@@ -206,12 +247,12 @@ node_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t sa = smem_base + stage * kStageBytes;
-                    const uint64_t adesc = umma_smem_desc(sa, 16, 1024, kSwizzle128B);
-                    const uint64_t bdesc = umma_smem_desc(sa + kABytes, 16, 1024, kSwizzle128B);
+                    const uint64_t adesc = umma_smem_desc(sa, a_lbo, 1024, kSwizzle128B);
+                    const uint64_t bdesc = umma_smem_desc(sa + kABytes, b_lbo, 1024, kSwizzle128B);
                     const int steps = kb == u.nkb - 1 ? u.last_steps : kKB / kUmmaK;
                     for (int k = 0; k < steps; ++k) {
-                        umma_bf16_ss(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc,
-                                     (kb | k) != 0 ? 1u : 0u);
+                        umma_bf16_ss(tmem_d, adesc + a_step * uint64_t(k), bdesc + b_step * uint64_t(k),
+                                     idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     umma_commit(empty_bar(stage));
                     if (++stage == kStages) {
@@ -231,7 +272,7 @@ node_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int64_t v = v0; v < v1; ++v) {
             const Unit u = decode_unit<MODE>(p, v);
             if (u.nkb == 0) {
-                if constexpr (MODE == MODE_DU) {
+                if constexpr (mode_is_du(MODE)) {
                     uint4* dst = reinterpret_cast<uint4*>(
                         static_cast<__nv_bfloat16*>(p.out) +
                         (int64_t(u.group - p.node_base) * p.K + u.chunk * kM + row) * kW);
@@ -265,7 +306,7 @@ node_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 }
             } else {
                 __nv_bfloat16* dst;
-                if constexpr (MODE == MODE_DH) {
+                if constexpr (mode_is_dh(MODE)) {
                     dst = static_cast<__nv_bfloat16*>(p.out) + int64_t(u.row0 + row) * p.K +
                           u.chunk * 256;
                 } else {
@@ -470,6 +511,66 @@ extern "C" int gkn_node_dh_bf16(const void* gs_bf16, const void* ut_bf16, const 
     p.b_rows_per_app = int32_t(chunk_nodes * K);
     p.node_base = node_base;
     return launch_node_gemm<MODE_DH>(ta, tb, p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gkn_node_du_mn_bf16(const void* hs_bf16, const void* gs_bf16, const int32_t* pptr,
+                                   int64_t node_begin, int64_t node_end, int64_t E_pad,
+                                   void* dut_bf16, int32_t K, int32_t W, void* stream) {
+    using namespace gkn;
+    if (node_end <= node_begin) return 0;
+    if (hs_bf16 == nullptr || gs_bf16 == nullptr || pptr == nullptr || dut_bf16 == nullptr) {
+        return set_error("gkn_node_du_mn_bf16: NULL pointer argument");
+    }
+    int rc = check_common("gkn_node_du_mn_bf16", K, W, E_pad);
+    if (rc) return rc;
+    if (E_pad == 0) return set_error("gkn_node_du_mn_bf16: empty edge set");
+    CUtensorMap ta, tb;
+    rc = make_tensor_map_bf16_2d(&ta, hs_bf16, uint64_t(K), uint64_t(E_pad), 64, kKB);
+    if (rc) return rc;
+    rc = make_tensor_map_bf16_2d(&tb, gs_bf16, uint64_t(kW), uint64_t(E_pad), 64, kKB);
+    if (rc) return rc;
+    NodeParams p{};
+    p.pptr = pptr;
+    p.out = dut_bf16;
+    p.v_begin = 0;
+    p.v_end = (node_end - node_begin) * (K / kM);
+    p.K = K;
+    p.node_base = int32_t(node_begin);
+    return launch_node_gemm<MODE_DU_MN>(ta, tb, p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gkn_node_dh_mn_bf16(const void* gs_bf16, const void* u_bf16, const int32_t* units,
+                                   int64_t unit_begin, int64_t unit_end, int64_t E_pad,
+                                   int64_t chunk_nodes, int32_t node_base, int32_t A,
+                                   void* dh_bf16, int32_t K, int32_t W, void* stream) {
+    using namespace gkn;
+    if (unit_end <= unit_begin) return 0;
+    if (gs_bf16 == nullptr || u_bf16 == nullptr || units == nullptr || dh_bf16 == nullptr) {
+        return set_error("gkn_node_dh_mn_bf16: NULL pointer argument");
+    }
+    int rc = check_common("gkn_node_dh_mn_bf16", K, W, E_pad);
+    if (rc) return rc;
+    if (A <= 0) return set_error("gkn_node_dh_mn_bf16: A must be positive");
+    const int64_t a_rows = int64_t(A) * E_pad, b_rows = int64_t(A) * chunk_nodes * kW;
+    if (chunk_nodes <= 0 || a_rows >= (int64_t(1) << 31) || b_rows >= (int64_t(1) << 31)) {
+        return set_error("gkn_node_dh_mn_bf16: operand too large for one launch (use smaller node chunks)");
+    }
+    CUtensorMap ta, tb;
+    rc = make_tensor_map_bf16_2d(&ta, gs_bf16, uint64_t(kW), uint64_t(a_rows), kKB, kM);
+    if (rc) return rc;
+    rc = make_tensor_map_bf16_2d(&tb, u_bf16, uint64_t(K), uint64_t(b_rows), 64, kKB);
+    if (rc) return rc;
+    NodeParams p{};
+    p.units = reinterpret_cast<const int4*>(units);
+    p.out = dh_bf16;
+    p.v_begin = unit_begin * (K / 256);
+    p.v_end = unit_end * (K / 256);
+    p.K = K;
+    p.A = A;
+    p.a_rows_per_app = int32_t(E_pad);
+    p.b_rows_per_app = int32_t(chunk_nodes * kW);
+    p.node_base = node_base;
+    return launch_node_gemm<MODE_DH_MN>(ta, tb, p, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int gkn_node_gather_bf16(const float* g, const int32_t* idx, int64_t E_pad,

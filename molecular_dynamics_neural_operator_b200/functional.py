@@ -215,6 +215,12 @@ FACTORIZATION = os.environ.get("GKN_FACTORIZATION", "node")
 # most this many bytes
 _NODE_CHUNK_BYTES = int(os.environ.get("GKN_NODE_CHUNK_MB", "1024")) << 20
 _MLP_BWD_CHUNK_ROWS = int(os.environ.get("GKN_MLP_BWD_CHUNK_ROWS", "65536"))
+# MN-major operand variants of the dU / dh kernels: h, gm and U are read in place (no transposed
+# copy of h, no [k,o]-ordered recomputation of U).  GKN_NODE_MN=0 selects the K-major kernels.
+NODE_MN = os.environ.get("GKN_NODE_MN", "1") == "1"
+# U of every application ([A, N, w*K] bf16) is kept for the dh pass when it fits this budget
+# (6.3 GB for 8 BBA frames); otherwise it is recomputed node range by node range in backward
+_SAVE_U_BYTES = int(os.environ.get("GKN_NODE_SAVE_U_MB", "24576")) << 20
 
 
 def node_path_supported(W: int, K: int, E: int, precision: str) -> bool:
@@ -250,13 +256,21 @@ class _GKNStackNode(torch.autograd.Function):
         want_agg = any(ctx.needs_input_grad)
         msg = torch.empty((lay.e_pad, W), dtype=torch.float32, device=x.device)
         chunks = _node_chunks(N, W * K * 2)
-        for c in schedule:
+        A = len(schedule)
+        u_all = None
+        if NODE_MN and want_agg and A * N * W * K * 2 <= _SAVE_U_BYTES:
+            u_all = torch.empty((A, N, W * K), dtype=bf, device=x.device)
+        for a, c in enumerate(schedule):
             xb = x.to(bf)
-            for n0, n1 in chunks:
-                U = torch.mm(xb[n0:n1], w3r)   # [nc, (o, k)]
-                ops.node_msg(hs, U.view(n1 - n0, W, K), lay, lay.unit_first[n0],
-                             lay.unit_first[n1], n0, msg)
-                del U
+            if u_all is not None:
+                torch.mm(xb, w3r, out=u_all[a])   # [N, (o, k)], kept for the dh pass
+                ops.node_msg(hs, u_all[a].view(N, W, K), lay, 0, lay.num_units, 0, msg)
+            else:
+                for n0, n1 in chunks:
+                    U = torch.mm(xb[n0:n1], w3r)   # [nc, (o, k)]
+                    ops.node_msg(hs, U.view(n1 - n0, W, K), lay, lay.unit_first[n0],
+                                 lay.unit_first[n1], n0, msg)
+                    del U
             x_new, agg = ops.segment_matvec(msg, lay.qpos, plan.dst_ptr, lay.src_pad, x,
                                             plan.inv_cnt, B3c, x, roots[c].contiguous(),
                                             biases[c].contiguous(), relu, want_agg=want_agg)
@@ -267,8 +281,10 @@ class _GKNStackNode(torch.autograd.Function):
         ctx.plan, ctx.schedule, ctx.relu = plan, schedule, relu
         ctx.has2 = root2 is not None
         ctx.n_apps = len(schedule)
+        ctx.has_u = u_all is not None
         ctx.save_for_backward(ea_s, h1, hs, w1, w2, w3q, B3c, roots[0],
-                              roots[1] if ctx.has2 else roots[0], *xs, *aggs)
+                              roots[1] if ctx.has2 else roots[0], *xs, *aggs,
+                              *([u_all] if u_all is not None else []))
         return x
 
     @staticmethod
@@ -277,6 +293,7 @@ class _GKNStackNode(torch.autograd.Function):
         plan, schedule, relu = ctx.plan, ctx.schedule, ctx.relu
         lay = ops.node_layout(plan)
         A = ctx.n_apps
+        u_all = rest.pop() if ctx.has_u else None
         xs, aggs = rest[:A + 1], rest[A + 1:]
         roots = (r1, r2)
         rootsT = (r1.t().contiguous(), r2.t().contiguous())
@@ -289,8 +306,13 @@ class _GKNStackNode(torch.autograd.Function):
         need_x0, need_ea, need_edge = need[0], need[1], any(need[1:8])
         # W3 as [i, (k, o)]: the operand of dx = dU W3^T, dW3 = x^T dU and of U^T for dh
         w3kq = w3q.view(W, W, K).permute(0, 2, 1).contiguous().view(W, K * W)
-        hsT = hs.t().contiguous()  # [K, E_pad]: edges become the reduction dimension of dU
-        gsT = torch.empty((W, lay.e_pad), dtype=bf, device=dev)
+        w3r = w3q.view(W, W * K)
+        hsT = gsT = gs_one = None
+        if not NODE_MN:
+            hsT = hs.t().contiguous()  # [K, E_pad]: edges become the reduction dimension of dU
+            gsT = torch.empty((W, lay.e_pad), dtype=bf, device=dev)
+        elif not need_edge:
+            gs_one = torch.empty((lay.e_pad, W), dtype=bf, device=dev)
         gs_all = torch.empty((A, lay.e_pad, W), dtype=bf, device=dev) if need_edge else None
         dw3k = torch.zeros((W, K * W), dtype=torch.float32, device=dev) if need_edge else None
         chunks = _node_chunks(N, W * K * 2)
@@ -305,12 +327,16 @@ class _GKNStackNode(torch.autograd.Function):
             if not (need_dx or need_edge):
                 gx = None
                 continue
-            ops.node_gather(gn, lay, gs_all[a] if need_edge else None, gsT)
+            gs_a = gs_all[a] if need_edge else gs_one
+            ops.node_gather(gn, lay, gs_a, gsT)
             xbs[a] = xs[a].to(bf)
             dxc = torch.empty((N, W), dtype=torch.float32, device=dev) if need_dx else None
             for n0, n1 in chunks:
                 dut = torch.empty((n1 - n0, K * W), dtype=bf, device=dev)
-                ops.node_du(hsT, gsT, lay, n0, n1, dut)
+                if NODE_MN:
+                    ops.node_du_mn(hs, gs_a, lay, n0, n1, dut)
+                else:
+                    ops.node_du(hsT, gsT, lay, n0, n1, dut)
                 if need_dx:
                     dxc[n0:n1] = _mm32(dut, w3kq.t())
                 if need_edge:
@@ -323,7 +349,7 @@ class _GKNStackNode(torch.autograd.Function):
                 gx = rest_g.add_(dxc)
             else:
                 gx = None
-        del hsT, gsT
+        del hsT, gsT, gs_one
         G = torch.stack(gs)
         X = torch.stack(xs[:A])
         droot, dbias = [None, None], [None, None]
@@ -341,14 +367,21 @@ class _GKNStackNode(torch.autograd.Function):
             dw3 = dw3k.view(W, K, W).permute(0, 2, 1).reshape(W * W, K)
             # dh_e for all applications at once, node range by node range (U^T recomputed)
             dh = torch.empty((lay.e_pad, K), dtype=bf, device=dev)
-            for n0, n1 in _node_chunks(N, A * W * K * 2):
-                ut = torch.empty((A, n1 - n0, K * W), dtype=bf, device=dev)
-                for a in range(A):
-                    torch.mm(xbs[a][n0:n1], w3kq, out=ut[a])
-                ops.node_dh(gs_all, ut.view(A, n1 - n0, K, W), lay, lay.unit_first[n0],
-                            lay.unit_first[n1], n0, dh)
-                del ut
-            del gs_all
+            if u_all is not None:
+                ops.node_dh_mn(gs_all, u_all.view(A, N, W, K), lay, 0, lay.num_units, 0, dh)
+            else:
+                for n0, n1 in _node_chunks(N, A * W * K * 2):
+                    ut = torch.empty((A, n1 - n0, K * W), dtype=bf, device=dev)
+                    for a in range(A):
+                        torch.mm(xbs[a][n0:n1], w3r if NODE_MN else w3kq, out=ut[a])
+                    if NODE_MN:
+                        ops.node_dh_mn(gs_all, ut.view(A, n1 - n0, W, K), lay, lay.unit_first[n0],
+                                       lay.unit_first[n1], n0, dh)
+                    else:
+                        ops.node_dh(gs_all, ut.view(A, n1 - n0, K, W), lay, lay.unit_first[n0],
+                                    lay.unit_first[n1], n0, dh)
+                    del ut
+            del gs_all, u_all
             dw2, db2, dw1, db1, dea_s = _mlp_grads(dh, ea_s, h1, hs, w1, w2, need_ea)
             if need_ea:
                 dea = dea_s.index_select(0, lay.qpos_long)
@@ -371,11 +404,16 @@ def _mlp_grads(dh, ea, h1, h, w1, w2, need_ea: bool):
         e1 = min(E, e0 + _MLP_BWD_CHUNK_ROWS)
         dz2q = ops.mask_cast_colsum(dh[e0:e1], h[e0:e1], db2, torch.bfloat16)
         dw2 = _addmm32(dw2, dz2q.t(), h1[e0:e1])
-        dz1 = _mm32(dz2q, w2q)
-        dz1 = ops.mask_cast_colsum(dz1, h1[e0:e1], cs1, torch.float32, side=ea[e0:e1],
-                                   sums_only=not need_ea)
         if need_ea:
+            dz1 = _mm32(dz2q, w2q)
+            dz1 = ops.mask_cast_colsum(dz1, h1[e0:e1], cs1, torch.float32, side=ea[e0:e1])
             torch.mm(dz1, w1, out=dea[e0:e1])
+        else:
+            # only the column sums (db1, dW1) are needed: the GEMM rounds its fp32 accumulators
+            # to bf16 itself, halving the bytes of this pass
+            dz1 = torch.mm(dz2q, w2q)
+            ops.mask_cast_colsum(dz1, h1[e0:e1], cs1, torch.bfloat16, side=ea[e0:e1],
+                                 sums_only=True)
     return dw2, db2, cs1[1:].t().contiguous(), cs1[0].contiguous(), dea
 
 

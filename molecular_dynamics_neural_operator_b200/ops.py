@@ -567,6 +567,36 @@ def node_dh(gs, ut, lay: NodeLayout, unit_begin: int, unit_end: int, node_base: 
         )
 
 
+def node_du_mn(hs, gs, lay: NodeLayout, node_begin: int, node_end: int, dut: torch.Tensor) -> None:
+    """node_du from the row-major hs [E_pad, K] and gs [E_pad, W] (gkn_node_du_mn_bf16)."""
+    lib = _lib.load()
+    K = int(hs.size(1))
+    W = int(gs.size(1))
+    with torch.cuda.device(hs.device), _timed("node_du"):
+        _lib.check(
+            lib.gkn_node_du_mn_bf16(_p(hs, torch.bfloat16, "hs"), _p(gs, torch.bfloat16, "gs"),
+                                    _p(lay.pptr, torch.int32, "pptr"), node_begin, node_end,
+                                    lay.e_pad, _p(dut, torch.bfloat16, "dut"), K, W, _stream()),
+            "gkn_node_du_mn_bf16",
+        )
+
+
+def node_dh_mn(gs, u, lay: NodeLayout, unit_begin: int, unit_end: int, node_base: int,
+               dh: torch.Tensor) -> None:
+    """node_dh from u bf16 [A, chunk_nodes, W, K] (the forward's U) (gkn_node_dh_mn_bf16)."""
+    lib = _lib.load()
+    A, W = int(gs.size(0)), int(gs.size(2))
+    K = int(dh.size(1))
+    with torch.cuda.device(gs.device), _timed("node_dh"):
+        _lib.check(
+            lib.gkn_node_dh_mn_bf16(_p(gs, torch.bfloat16, "gs"), _p(u, torch.bfloat16, "u"),
+                                    _p(lay.units, torch.int32, "units"), unit_begin, unit_end,
+                                    lay.e_pad, int(u.size(1)), node_base, A,
+                                    _p(dh, torch.bfloat16, "dh"), K, W, _stream()),
+            "gkn_node_dh_mn_bf16",
+        )
+
+
 def node_gather(g, lay: NodeLayout, gs: torch.Tensor | None, gsT: torch.Tensor | None) -> None:
     """gs[q, :] = bf16(g[dst_pad[q], :]) (zero in pad rows) and/or its transpose gsT [W, E_pad]."""
     lib = _lib.load()

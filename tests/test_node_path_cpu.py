@@ -103,6 +103,14 @@ def emu_node_dh(gs, ut, lay, u0, u1, node_base, dh):
         dh[row0:row0 + rows] = acc.to(dh.dtype)
 
 
+def emu_node_du_mn(hs, gs, lay, n0, n1, dut):
+    emu_node_du(hs.t(), gs.t(), lay, n0, n1, dut)
+
+
+def emu_node_dh_mn(gs, u, lay, u0, u1, node_base, dh):
+    emu_node_dh(gs, u.transpose(2, 3), lay, u0, u1, node_base, dh)
+
+
 def emu_node_gather(g, lay, gs, gsT):
     idx = lay.dst_pad.long()
     rows = torch.where((idx >= 0)[:, None], g[idx.clamp(min=0)], torch.zeros(1)).to(torch.bfloat16)
@@ -118,6 +126,7 @@ def emulated(monkeypatch):
                      ("relu_grad_scale", emu_relu_grad_scale),
                      ("mask_cast_colsum", emu_mask_cast_colsum), ("node_msg", emu_node_msg),
                      ("node_du", emu_node_du), ("node_dh", emu_node_dh),
+                     ("node_du_mn", emu_node_du_mn), ("node_dh_mn", emu_node_dh_mn),
                      ("node_gather", emu_node_gather)]:
         monkeypatch.setattr(ops, name, fn)
     monkeypatch.setattr(GF, "_mm32", lambda a, b: a.float() @ b.float())
@@ -202,17 +211,22 @@ def fro(a, b):
     return float((a - b).norm() / b.norm().clamp(min=1e-30))
 
 
+@pytest.mark.parametrize("mn,save_u", [(True, True), (True, False), (False, False)],
+                         ids=["mn_saved_u", "mn_recomputed_u", "kmajor"])
 @pytest.mark.parametrize("N,E,K,depth,isolated,chunk_mb", [
     (6, 90, 256, 1, (), 1024),      # one application, single node chunk
     (5, 700, 256, 2, (), 1024),     # groups longer than one 128-row tile
     (9, 120, 256, 2, (2, 7), 0),    # isolated nodes, node-range chunking of U / dU / U^T (1 node)
 ])
-def test_node_first_stack_matches_oracle(emulated, monkeypatch, N, E, K, depth, isolated, chunk_mb):
+def test_node_first_stack_matches_oracle(emulated, monkeypatch, N, E, K, depth, isolated, chunk_mb,
+                                         mn, save_u):
     """Without the activation between applications the stack is smooth in its operands, so bf16
     rounding is the only difference from the fp64 oracle: every gradient within 2^-5 except those
     upstream of the edge MLP's own ReLUs (mask flips, see tests/test_layer_gpu.py)."""
     monkeypatch.setattr(GF, "_NODE_CHUNK_BYTES", chunk_mb << 20)
     monkeypatch.setattr(GF, "_MLP_BWD_CHUNK_ROWS", 64)
+    monkeypatch.setattr(GF, "NODE_MN", mn)
+    monkeypatch.setattr(GF, "_SAVE_U_BYTES", (1 << 40) if save_u else 0)
     ei, p, depth = _stack_case(N, E, K, depth, seed=11 * N + depth, isolated=isolated)
     out, t = _run_node_stack(ei, p, depth, N, relu=False)
     ref, tr = _run_oracle_stack(ei, p, depth, relu=False)

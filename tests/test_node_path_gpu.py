@@ -100,6 +100,14 @@ def test_grouped_gemm_kernels_match_fp32_restatement(case, K):
     pad = (lay.dst_pad < 0).cpu()
     assert float(dh.float().cpu()[pad].abs().max() if pad.any() else 0.0) == 0.0
 
+    # ---- the MN-major operand variants give the same numbers from the untransposed buffers ----
+    dut2 = torch.full((N, K * W), float("nan"), dtype=bf, device="cuda")
+    ops.node_du_mn(hs.cuda(), gs, lay, 0, N, dut2)
+    assert rel_err(dut2.float(), dut.float()) <= BF16_OUT_TOL
+    dh2 = torch.full((E_pad, K), float("nan"), dtype=bf, device="cuda")
+    ops.node_dh_mn(gs_all, ut.transpose(2, 3).contiguous().cuda(), lay, 0, lay.num_units, 0, dh2)
+    assert rel_err(dh2.float(), dh.float()) <= BF16_OUT_TOL
+
 
 def test_grouped_gemm_node_range_chunks_cover_the_same_result():
     from molecular_dynamics_neural_operator_b200 import ops
@@ -144,10 +152,16 @@ def _gpu_stack(fn, ei, p, depth, N, relu):
     return out, t
 
 
+@pytest.mark.parametrize("mn,save_u", [(True, True), (True, False), (False, False)],
+                         ids=["mn_saved_u", "mn_recomputed_u", "kmajor"])
 @pytest.mark.parametrize("N,E,K,depth", [(20, 3000, 256, 1), (120, 8000, 1024, 2)])
-def test_node_first_stack_matches_edge_first_stack_and_oracle(N, E, K, depth):
+def test_node_first_stack_matches_edge_first_stack_and_oracle(monkeypatch, N, E, K, depth, mn, save_u):
     """No activation between applications (smooth: only bf16 rounding differs)."""
     from molecular_dynamics_neural_operator_b200 import functional as GF
+
+    monkeypatch.setattr(GF, "NODE_MN", mn)
+    monkeypatch.setattr(GF, "_SAVE_U_BYTES", (1 << 40) if save_u else 0)
+    monkeypatch.setattr(GF, "_NODE_CHUNK_BYTES", 64 * K * 2 * 7)  # node ranges of 7 nodes
 
     ei, p, depth = _stack_case(N, E, K, depth, seed=N)
     out_n, tn = _gpu_stack(GF._GKNStackNode, ei, p, depth, N, relu=False)
