@@ -65,7 +65,7 @@ struct NCfg {
     static constexpr int kABoxes = kAMn ? kM / 64 : 1;          // TMA boxes per k-block
     static constexpr int kBBoxes = kBMn ? kBN / 64 : 1;
     static constexpr int kTmemCols = kAcc * kBN;                // 512 / 256
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + 4 * 4096 /*output staging*/;
 };
 
 struct NodeParams {
@@ -135,6 +135,21 @@ __device__ __forceinline__ Unit decode_unit(const NodeParams& p, int64_t v) {
         u.last_steps = (len - (u.nkb - 1) * kKB) / kUmmaK;
     }
     return u;
+}
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y),
+                 "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(addr)
+                 : "memory");
+    return v;
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -268,6 +283,7 @@ node_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const uint32_t lane_addr = uint32_t(q * 32) << 16;
+        const uint32_t stage_smem = bar_base + 256 + q * 4096;  // per-warp output staging tile
         uint32_t it = 0;
         for (int64_t v = v0; v < v1; ++v) {
             const Unit u = decode_unit<MODE>(p, v);
@@ -288,45 +304,63 @@ node_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             __syncwarp();
             tc_fence_after();
             const uint32_t tcol = tmem_base + lane_addr + as * kBN;
-            const bool store = row < u.rows;
+            // Output rows leave in 128-byte pieces through a per-warp staging tile (32 rows x 128 B,
+            // 16-byte chunks XOR-swizzled by the row): the accumulator is read row-per-lane, the
+            // global stores go out with 8 consecutive lanes on one row's 128 bytes (whole lines,
+            // and for MODE_DU* 512 contiguous bytes per instruction).
+            const int rows_here = u.rows - q * 32;  // valid rows among this warp's 32
+            uint8_t* gbase;                         // piece 0 of this warp's row 0
+            int64_t pitch;                          // bytes between consecutive output rows
             if constexpr (MODE == MODE_MSG) {
-                float* dst = static_cast<float*>(p.out) + int64_t(u.row0 + row) * kW;
-#pragma unroll
-                for (int piece = 0; piece < kBN / 32; ++piece) {
-                    float f[32];
-                    tmem_ld32(tcol + piece * 32, f);
-                    tmem_ld_wait();
-                    if (store) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            *reinterpret_cast<float4*>(dst + piece * 32 + j) =
-                                make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                        }
-                    }
-                }
+                gbase = reinterpret_cast<uint8_t*>(static_cast<float*>(p.out) +
+                                                   int64_t(u.row0 + q * 32) * kW);
+                pitch = kW * 4;
+            } else if constexpr (mode_is_dh(MODE)) {
+                gbase = reinterpret_cast<uint8_t*>(static_cast<__nv_bfloat16*>(p.out) +
+                                                   int64_t(u.row0 + q * 32) * p.K + u.chunk * 256);
+                pitch = int64_t(p.K) * 2;
             } else {
-                __nv_bfloat16* dst;
-                if constexpr (mode_is_dh(MODE)) {
-                    dst = static_cast<__nv_bfloat16*>(p.out) + int64_t(u.row0 + row) * p.K +
-                          u.chunk * 256;
-                } else {
-                    dst = static_cast<__nv_bfloat16*>(p.out) +
-                          (int64_t(u.group - p.node_base) * p.K + u.chunk * kM + row) * kW;
-                }
+                gbase = reinterpret_cast<uint8_t*>(
+                    static_cast<__nv_bfloat16*>(p.out) +
+                    (int64_t(u.group - p.node_base) * p.K + u.chunk * kM + q * 32) * kW);
+                pitch = kW * 2;
+            }
+            constexpr int kColsPerPiece = MODE == MODE_MSG ? 32 : 64;  // 128 bytes of output
 #pragma unroll
-                for (int piece = 0; piece < kBN / 32; ++piece) {
+            for (int piece = 0; piece < kBN / kColsPerPiece; ++piece) {
+                uint32_t w[32];
+                if constexpr (MODE == MODE_MSG) {
                     float f[32];
                     tmem_ld32(tcol + piece * 32, f);
                     tmem_ld_wait();
-                    if (store) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            *reinterpret_cast<uint4*>(dst + piece * 32 + j) =
-                                make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
-                                           pack_bf16(f[j + 4], f[j + 5]), pack_bf16(f[j + 6], f[j + 7]));
-                        }
+                    for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(f[j]);
+                } else {
+                    float f0[32], f1[32];
+                    tmem_ld32(tcol + piece * 64, f0);
+                    tmem_ld32(tcol + piece * 64 + 32, f1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        w[j] = pack_bf16(f0[2 * j], f0[2 * j + 1]);
+                        w[16 + j] = pack_bf16(f1[2 * j], f1[2 * j + 1]);
                     }
                 }
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    sts128(stage_smem + lane * 128 + ((c ^ (lane & 7)) << 4),
+                           make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
+                }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int r = j * 4 + (lane >> 3), c = lane & 7;
+                    const uint4 t = lds128(stage_smem + r * 128 + ((c ^ (r & 7)) << 4));
+                    if (r < rows_here) {
+                        *reinterpret_cast<uint4*>(gbase + r * pitch + piece * 128 + c * 16) = t;
+                    }
+                }
+                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();
