@@ -307,13 +307,14 @@ def run_b200_arm(args, wl):
     loss_events: list = []
 
     def build_resident(i):
-        return syn.make_batch(dev_x[i % pool], aa, dev_y[i % pool], wl.cutoff, prepare=True)
+        return syn.make_batch(dev_x[i % pool], aa, dev_y[i % pool], wl.cutoff, prepare=True,
+                              ker_width=wl.ker_width)
 
     def build_e2e(i):
         # H2D copy of this step's coordinates from pinned host memory, then the graph build
         x = host_x[i % pool].to(dev, non_blocking=True)
         y = host_y[i % pool].to(dev, non_blocking=True)
-        return syn.make_batch(x, aa, y, wl.cutoff, prepare=True)
+        return syn.make_batch(x, aa, y, wl.cutoff, prepare=True, ker_width=wl.ker_width)
 
     def run_loop(build, steps, read_loss):
         """`steps` training steps; the next batch is built on a side stream while the current

@@ -109,7 +109,10 @@ int gkn_contract_dx_f32(const float* h, const float* w3, const int32_t* dst, con
  *         gsT bf16 [W,E_pad] (message gradient per edge, transposed, zero in pad rows),
  *         dut bf16 [node_end-node_begin, K, W] (gradient w.r.t. U, [k,o] order)
  *   dh  : dh[q,k] = sum_a sum_o gs[a][q,o] * ut[a][src q][k,o]    gs bf16 [A,E_pad,W],
- *         ut bf16 [A,chunk,K,W], dh bf16 [E_pad,K] (gradient of the edge hidden state)
+ *         ut bf16 [A,chunk,K,W], dh bf16 [E_pad,K] (gradient of the edge hidden state).  Its
+ *         `units` table is int32 [U*(K/256),4] = (source node, first row, rows, 256-column chunk)
+ *         in (node, chunk, tile) order, so the tiles of a group that share a chunk of the node's U
+ *         are adjacent (L2 reuse); unit_begin/unit_end count tiles as in msg.
  *   gather: gs[q,:] = bf16(g[idx[q],:]) (zero where idx[q] < 0), gsT its transpose; either output
  *         may be NULL. */
 int gkn_node_msg_bf16(const void* hs_bf16, const void* u_bf16, const int32_t* units,

@@ -191,24 +191,31 @@ segment_matvec_kernel(const float* __restrict__ rows, const int32_t* __restrict_
             const int beg = seg_ptr[n], end = seg_ptr[n + 1];
             float4 ar0 = make_float4(0.f, 0.f, 0.f, 0.f), ar1 = ar0, ag0 = ar0, ag1 = ar0;
             int q = beg + sub;
-            // 4 rows in flight per lane: indices first, then the 8 dependent row loads
-            for (; q + 3 * RPW < end; q += 4 * RPW) {
-                int pp[4], ii[4];
+            // IF rows in flight per lane: indices first, then the 2*IF dependent row loads (the
+            // walk is a chain of three dependent loads per round, so at w <= 64 - two rows per
+            // warp step - eight in flight halve the number of rounds of a ~120-edge segment)
+            constexpr int IF = W <= 64 ? 8 : 4;
+            for (; q + (IF - 1) * RPW < end; q += IF * RPW) {
+                int pp[IF], ii[IF];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) pp[u] = perm ? perm[q + u * RPW] : q + u * RPW;
+                for (int u = 0; u < IF; ++u) pp[u] = perm ? perm[q + u * RPW] : q + u * RPW;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) ii[u] = gidx[pp[u]];
-                float4 rr[4], gg[4];
+                for (int u = 0; u < IF; ++u) ii[u] = gidx[pp[u]];
+                float4 rr[IF], gg[IF];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < IF; ++u) {
                     rr[u] = rows ? ldg4_stream(rows + int64_t(pp[u]) * W + col)
                                  : make_float4(0.f, 0.f, 0.f, 0.f);
                     gg[u] = ldg4(gnode + int64_t(ii[u]) * W + col);
                 }
-                ar0 = f4add(ar0, f4add(rr[0], rr[2]));
-                ar1 = f4add(ar1, f4add(rr[1], rr[3]));
-                ag0 = f4add(ag0, f4add(gg[0], gg[2]));
-                ag1 = f4add(ag1, f4add(gg[1], gg[3]));
+                // fixed pairwise order: even slots into the *0 accumulators, odd into the *1
+#pragma unroll
+                for (int u = 0; u < IF; u += 4) {
+                    ar0 = f4add(ar0, f4add(rr[u], rr[u + 2]));
+                    ar1 = f4add(ar1, f4add(rr[u + 1], rr[u + 3]));
+                    ag0 = f4add(ag0, f4add(gg[u], gg[u + 2]));
+                    ag1 = f4add(ag1, f4add(gg[u + 1], gg[u + 3]));
+                }
             }
             for (; q < end; q += RPW) {
                 const int p0 = perm ? perm[q] : q;

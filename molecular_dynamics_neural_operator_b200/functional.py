@@ -218,6 +218,7 @@ _MLP_BWD_CHUNK_ROWS = int(os.environ.get("GKN_MLP_BWD_CHUNK_ROWS", "65536"))
 # MN-major operand variants of the dU / dh kernels: h, gm and U are read in place (no transposed
 # copy of h, no [k,o]-ordered recomputation of U).  GKN_NODE_MN=0 selects the K-major kernels.
 NODE_MN = os.environ.get("GKN_NODE_MN", "1") == "1"
+_MLP_SIDE_GEMM = os.environ.get("GKN_MLP_SIDE_GEMM", "1") == "1"
 # U of every application ([A, N, w*K] bf16) is kept for the dh pass when it fits this budget
 # (6.3 GB for 8 BBA frames); otherwise it is recomputed node range by node range in backward
 _SAVE_U_BYTES = int(os.environ.get("GKN_NODE_SAVE_U_MB", "24576")) << 20
@@ -400,6 +401,15 @@ def _mlp_grads(dh, ea, h1, h, w1, w2, need_ea: bool):
     cs1 = torch.zeros((1 + kin, K), **f32)
     dea = torch.empty_like(ea) if need_ea else None
     w2q = w2.to(torch.bfloat16)
+    side_gemm = _MLP_SIDE_GEMM and not need_ea
+    if side_gemm:
+        # dW1 = dz1^T edge_attr as a tensor-core GEMM: edge_attr split into bf16 hi + lo parts
+        # (16 columns: hi, lo, zero pad) keeps it exact to 2^-17
+        hi = ea.to(torch.bfloat16)
+        lo = (ea - hi.float()).to(torch.bfloat16)
+        ea_ext = torch.cat([hi, lo, torch.zeros((E, 16 - 2 * kin), dtype=torch.bfloat16,
+                                                device=h.device)], 1)
+        side_acc = torch.zeros((K, 16), **f32)
     for e0 in range(0, E, _MLP_BWD_CHUNK_ROWS):
         e1 = min(E, e0 + _MLP_BWD_CHUNK_ROWS)
         dz2q = ops.mask_cast_colsum(dh[e0:e1], h[e0:e1], db2, torch.bfloat16)
@@ -408,12 +418,17 @@ def _mlp_grads(dh, ea, h1, h, w1, w2, need_ea: bool):
             dz1 = _mm32(dz2q, w2q)
             dz1 = ops.mask_cast_colsum(dz1, h1[e0:e1], cs1, torch.float32, side=ea[e0:e1])
             torch.mm(dz1, w1, out=dea[e0:e1])
+        elif side_gemm:
+            dz1 = torch.mm(dz2q, w2q)  # bf16: the GEMM rounds its fp32 accumulators itself
+            dz1 = ops.mask_cast_colsum(dz1, h1[e0:e1], cs1[0], torch.bfloat16)  # in place, + db1
+            side_acc = _addmm32(side_acc, dz1.t(), ea_ext[e0:e1])
         else:
-            # only the column sums (db1, dW1) are needed: the GEMM rounds its fp32 accumulators
-            # to bf16 itself, halving the bytes of this pass
+            # only the column sums (db1, dW1) are needed
             dz1 = torch.mm(dz2q, w2q)
             ops.mask_cast_colsum(dz1, h1[e0:e1], cs1, torch.bfloat16, side=ea[e0:e1],
                                  sums_only=True)
+    if side_gemm:
+        cs1[1:] = (side_acc[:, :kin] + side_acc[:, kin:2 * kin]).t()
     return dw2, db2, cs1[1:].t().contiguous(), cs1[0].contiguous(), dea
 
 

@@ -453,6 +453,7 @@ class NodeLayout:
     src_pad: torch.Tensor  # int32 [E_pad]  source node of every padded row
     dst_pad: torch.Tensor  # int32 [E_pad]  destination node, -1 in pad rows
     unit_first: list  # host list [N+1]: first unit of every node (for node-range chunking)
+    unit_first_dev: torch.Tensor = None  # the same on the device (int64 [N+1])
 
     @property
     def qpos_long(self) -> torch.Tensor:
@@ -461,14 +462,40 @@ class NodeLayout:
         return self._qpos_long
 
     def tensors(self):
-        return [self.pptr, self.units, self.qpos, self.src_pad, self.dst_pad]
+        return [self.pptr, self.units, self.qpos, self.src_pad, self.dst_pad] + \
+            list(getattr(self, "_dh_units", {}).values())
+
+    def dh_units(self, chunks: int) -> torch.Tensor:
+        """int32 [U*chunks, 4] = (source node, first row, rows, column chunk) in (node, chunk,
+        tile) order: the tiles of a group that share one chunk of the node's U are adjacent, so the
+        second tile finds it in L2.  Node-major, so node ranges are contiguous unit ranges."""
+        cache = self.__dict__.setdefault("_dh_units", {})
+        if chunks not in cache:
+            u = self.units.long()
+            U = u.size(0)
+            uf = self.unit_first_dev
+            first = uf[u[:, 0]]  # first tile of the group
+            t = torch.arange(U, device=u.device) - first
+            c = torch.arange(chunks, device=u.device)
+            tiles = uf.diff()[u[:, 0]]
+            # destination slot of (tile u, chunk c): group's first slot + c * tiles(group) + t
+            slot = (first * chunks)[:, None] + c[None, :] * tiles[:, None] + t[:, None]
+            rec = torch.stack([u[:, 0:1].expand(U, chunks), u[:, 1:2].expand(U, chunks),
+                               u[:, 2:3].expand(U, chunks), c[None, :].expand(U, chunks)], 2)
+            out = torch.empty((U * chunks, 4), dtype=torch.int32, device=u.device)
+            out[slot.reshape(-1)] = rec.reshape(-1, 4).int()
+            cache[chunks] = out
+        return cache[chunks]
 
 
-def node_layout(plan: GraphPlan) -> NodeLayout:
+def node_layout(plan: GraphPlan, dh_chunks: int | None = None) -> NodeLayout:
     """Build (once per plan, cached on it) the padded source-sorted layout.  Index bookkeeping
-    only (torch ops on the device, two small host reads for the data-dependent sizes)."""
+    only (torch ops on the device, two small host reads for the data-dependent sizes).
+    ``dh_chunks`` (= kernel_width // 256) also prebuilds the unit table of the dh pass."""
     cached = getattr(plan, "_node_layout", None)
     if cached is not None:
+        if dh_chunks:
+            cached.dh_units(dh_chunks)
         return cached
     dev = plan.src.device
     N, E = plan.num_nodes, plan.num_edges
@@ -496,8 +523,11 @@ def node_layout(plan: GraphPlan) -> NodeLayout:
     row0 = pptr[:-1][ug] + 128 * t
     rows = torch.clamp(degp[ug] - 128 * t, max=128)
     units = torch.stack([ug, row0, rows, torch.zeros_like(ug)], 1).int().contiguous()
-    lay = NodeLayout(N, e_pad, U, pptr.int(), units, qpos.int(), src_pad, dst_pad, unit_first)
+    lay = NodeLayout(N, e_pad, U, pptr.int(), units, qpos.int(), src_pad, dst_pad, unit_first,
+                     ufirst)
     object.__setattr__(plan, "_node_layout", lay)
+    if dh_chunks:
+        lay.dh_units(dh_chunks)
     return lay
 
 
@@ -560,7 +590,7 @@ def node_dh(gs, ut, lay: NodeLayout, unit_begin: int, unit_end: int, node_base: 
     with torch.cuda.device(gs.device), _timed("node_dh"):
         _lib.check(
             lib.gkn_node_dh_bf16(_p(gs, torch.bfloat16, "gs"), _p(ut, torch.bfloat16, "ut"),
-                                 _p(lay.units, torch.int32, "units"), unit_begin, unit_end,
+                                 _p(lay.dh_units(K // 256), torch.int32, "units"), unit_begin, unit_end,
                                  lay.e_pad, int(ut.size(1)), node_base, A,
                                  _p(dh, torch.bfloat16, "dh"), K, W, _stream()),
             "gkn_node_dh_bf16",
@@ -590,7 +620,7 @@ def node_dh_mn(gs, u, lay: NodeLayout, unit_begin: int, unit_end: int, node_base
     with torch.cuda.device(gs.device), _timed("node_dh"):
         _lib.check(
             lib.gkn_node_dh_mn_bf16(_p(gs, torch.bfloat16, "gs"), _p(u, torch.bfloat16, "u"),
-                                    _p(lay.units, torch.int32, "units"), unit_begin, unit_end,
+                                    _p(lay.dh_units(K // 256), torch.int32, "units"), unit_begin, unit_end,
                                     lay.e_pad, int(u.size(1)), node_base, A,
                                     _p(dh, torch.bfloat16, "dh"), K, W, _stream()),
             "gkn_node_dh_mn_bf16",

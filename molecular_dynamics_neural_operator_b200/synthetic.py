@@ -83,14 +83,16 @@ def window_batch(traj: np.ndarray, starts, window: int, horizon: int = 1):
 
 
 def make_batch(x_window: torch.Tensor, aminoacid: torch.Tensor, y: torch.Tensor | None,
-               cutoff: float, graph_frame: int = 0, prepare: bool = False) -> PairData:
+               cutoff: float, graph_frame: int = 0, prepare: bool = False,
+               ker_width: int | None = None) -> PairData:
     """Device-side feeder.  x_window [B, W, N, 3] (device), aminoacid [N] int64, y [B, N, 3].
 
     Graph and edge attributes come from window frame ``graph_frame`` of every sample: 0 (the
     first frame) at training time as in dataset.py:189-201, -1 (the last) in rollout as in
     graph_kernel.py:363-379.  Equivalent to collate([PairData(...) for each sample]).
     ``prepare=True`` also builds the destination-sorted CSR plan and attaches it to the batch
-    (``KernelNN.forward`` picks it up), so both happen off the training stream when prefetched."""
+    (``KernelNN.forward`` picks it up), so both happen off the training stream when prefetched;
+    ``ker_width`` (the model's kernel width) lets the unit table of the dh pass be prebuilt too."""
     B, W, N, _ = x_window.shape
     frames = x_window[:, graph_frame].contiguous()
     edge_index, edge_attr, row_ptr = ops.radius_graph(frames, cutoff, return_row_ptr=True)
@@ -109,7 +111,7 @@ def make_batch(x_window: torch.Tensor, aminoacid: torch.Tensor, y: torch.Tensor 
         if GF.FACTORIZATION == "node" and edge_index.size(1) > 0:
             # padded source-sorted layout of the node-first kernels (two small host reads): built
             # here so that it, too, happens off the training stream when prefetched
-            ops.node_layout(data._gkn_plan)
+            ops.node_layout(data._gkn_plan, dh_chunks=ker_width // 256 if ker_width else None)
     return data
 
 

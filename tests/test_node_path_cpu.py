@@ -163,6 +163,14 @@ def test_padded_source_sorted_layout_invariants(N, E, isolated):
     assert lay.unit_first[0] == 0 and lay.unit_first[-1] == lay.num_units
     assert torch.equal(lay.units[:, 0].long(), lay.units[:, 0].long().sort().values)
     assert ops.node_layout(plan) is lay  # cached on the plan
+    # unit table of the dh pass: every (tile, chunk) once, node-major, chunk-major inside a node
+    d = lay.dh_units(4)
+    assert d.shape == (lay.num_units * 4, 4)
+    assert len(set(map(tuple, d.tolist()))) == lay.num_units * 4
+    for n in range(N):
+        seg = d[lay.unit_first[n] * 4:lay.unit_first[n + 1] * 4]
+        assert bool((seg[:, 0] == n).all())
+        assert seg[:, 3].tolist() == sorted(seg[:, 3].tolist())
 
 
 # ---- autograd algebra -------------------------------------------------------------------------
@@ -181,9 +189,9 @@ def _stack_case(N, E, K, depth, seed, isolated=()):
     return ei, p, depth
 
 
-def _run_node_stack(ei, p, depth, N, relu=True):
+def _run_node_stack(ei, p, depth, N, relu=True, ea_grad=True):
     plan = cpu_plan(ei, N)
-    t = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    t = {k: v.clone().requires_grad_(ea_grad or k != "ea") for k, v in p.items()}
     ea_sorted = t["ea"].index_select(0, plan.perm.long())
     out = GF._GKNStackNode.apply(
         t["x"], ea_sorted, t["net.layers.0.weight"], t["net.layers.0.bias"],
@@ -256,6 +264,21 @@ def test_node_first_stack_with_relu_matches_oracle(emulated):
     for k in ("x", "root1", "bias2", "net.layers.4.weight", "net.layers.4.bias"):
         a, b = t[k].grad.double().flatten(), tr[k].grad.flatten()
         assert float(a.dot(b) / (a.norm() * b.norm())) > 0.98, k
+
+
+def test_layer0_gradients_agree_with_and_without_edge_attr_gradient(emulated):
+    """Without an edge_attr gradient, dW1 comes from the hi/lo-split bf16 GEMM and db1 from the
+    in-place mask pass; with it, from the fp32 side sums.  Same numbers up to bf16 rounding of dz1."""
+    N, E, K, depth = 7, 200, 256, 1
+    ei, p, depth = _stack_case(N, E, K, depth, seed=4)
+    grads = []
+    for ea_grad in (True, False):
+        out, t = _run_node_stack(ei, p, depth, N, relu=False, ea_grad=ea_grad)
+        out.backward(torch.ones_like(out))
+        grads.append(t)
+    for k in ("net.layers.0.weight", "net.layers.0.bias", "net.layers.2.weight"):
+        assert fro(grads[1][k].grad, grads[0][k].grad) < 2.0 ** -7, k
+    assert grads[1]["ea"].grad is None
 
 
 def test_node_path_selection():
