@@ -6,17 +6,21 @@
 
 Workload (BASELINE.json configs[1]): BBA all-atom-sized frames (504 atoms, 8 A radius graph,
 ~57k directed edges/frame), KernelNN width 64, kernel_width 1024, depth 6 (12 NNConv
-applications), window 10, bf16 tensor-core contraction with fp32 accumulation.  One step = one
-pass of the hot path over one batch of synthetic frames per GPU: radius-graph build from
-coordinates -> forward -> LpLoss -> backward -> (gradient all-reduce) -> Adam.
+applications), window 10, bf16 tensor-core operands with fp32 accumulation, 16 frames per GPU per
+step (the reference's default batch of 128 over 8 GPUs).  One step = one pass of the hot path over
+one batch of synthetic frames per GPU: radius-graph build from coordinates -> forward -> LpLoss
+-> backward -> (gradient all-reduce) -> Adam.
 
 One JSON line is printed by rank 0:
   value     frames/s over all GPUs with the step's coordinates already resident in HBM
   e2e       same metric through the public API with HOST (pinned) coordinates: H2D copy of the
             step's window, graph build, train step and a D2H read of the loss inside the timing
-  roofline  the dominant kernel (fused tcgen05 edge contraction): executed FLOP per launch
-            (= algorithmic 2*E*K*w^2) / CUDA-event duration, measured live in the timed region,
-            against the measured sustained bf16 peak (MEASURED_PEAKS.json)
+  roofline  the dominant kernel.  Default (node-first factorisation): the tcgen05 grouped-GEMM
+            kernel with the largest share of the step (HBM-bound: algorithmic bytes per launch /
+            CUDA-event duration against the measured copy bandwidth in MEASURED_PEAKS.json;
+            all three grouped-GEMM kernels are listed under roofline.kernels).  With
+            GKN_FACTORIZATION=edge: the fused edge-first contraction (tensor-bound: 2*E*K*w^2
+            FLOP per launch against the measured sustained bf16 peak)
   cpu_baseline  the CPU restatement of the reference (oracle/) timed on this box's host cores
 `--impl reference` times that CPU restatement alone (all host threads) with the same metric/config.
 """
@@ -246,9 +250,12 @@ def bench_config(wl, frames_per_gpu, edges_per_frame):
                      f"({2 * wl.depth} NNConv applications), window {wl.window}; step = graph "
                      f"build + fwd + LpLoss + bwd + Adam"),
         "frames_per_gpu_per_step": frames_per_gpu,
-        "untimed_steps_before_timing": "max(8, warmup) resident + warmup//2 host-fed",
+        "batch_note": "reference default batch_size is 128 (graph_kernel.py:318) = 16 frames per GPU "
+                      "on 8 GPUs; per-GPU work is fixed as N grows (weak scaling)",
+        "factorization": os.environ.get("GKN_FACTORIZATION", "node"),
+        "untimed_steps_before_timing": "max(8, warmup) resident + max(3, warmup) host-fed",
         "parallelism": "frames sharded over GPUs, bucketed NCCL gradient all-reduce",
-        "l2_policy": "per-step working set (h_e alone ~0.9 GB at 8 frames) exceeds the 126 MB L2; "
+        "l2_policy": "per-step working set (h_e alone ~0.12 GB per frame) exceeds the 126 MB L2; "
                      "each step uses a different batch of frames",
     }
 
@@ -322,16 +329,23 @@ def run_b200_arm(args, wl):
         host never drains the training stream).  Both timed loops read the loss: it also paces the
         host to one step ahead of the device, which measured steadier than a free-running host
         (intermittent +10 % step times when the host queues two steps ahead)."""
+        trace = os.environ.get("GKN_BENCH_TRACE") == "1"
         prefetch.submit(lambda: build(0))
         done: list = []
         for i in range(steps):
+            t0 = time.perf_counter()
             if len(done) >= 2:
                 done.pop(0).synchronize()  # at most two steps in flight (bounded run-ahead)
             batch = prefetch.get()
+            t1 = time.perf_counter()
             if i + 1 < steps:
                 prefetch.submit(lambda: build(i + 1))
+            t2 = time.perf_counter()
             edge_counts.append(batch.edge_index.size(1))
             loss = trainer.step(batch, B)
+            if trace:  # (diagnostic) host time: wait for step i-2, batch build, step enqueue
+                print(f"trace step {i}: wait {1e3 * (t1 - t0):.1f} build {1e3 * (t2 - t1):.1f} "
+                      f"enqueue {1e3 * (time.perf_counter() - t2):.1f} ms", file=sys.stderr)
             ev_done = torch.cuda.Event()
             ev_done.record()
             done.append(ev_done)
@@ -377,7 +391,10 @@ def run_b200_arm(args, wl):
     # added in front of the W warm-up steps so that at least 8 steps precede the timed region.
     settle = max(0, 8 - args.warmup)
     run_loop(build_resident, settle + args.warmup, True)
-    run_loop(build_e2e, max(1, args.warmup // 2), True)
+    # the host-fed loop allocates its H2D staging tensors on the prefetch stream: it needs its own
+    # warm-up for the caching allocator to reach a steady state (one step was not enough: +-15 %
+    # between otherwise identical runs)
+    run_loop(build_e2e, max(3, args.warmup), True)
     if sampler:
         sampler.lines.clear()  # keep only samples taken during the timed loops
     edge_counts.clear()
@@ -540,7 +557,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames-per-gpu", type=int, default=8)
+    ap.add_argument("--frames-per-gpu", type=int, default=16,
+                    help="frames per GPU per step; 16 = the reference's default batch_size 128 "
+                         "(graph_kernel.py:318) spread over the 8 GPUs of one box")
     ap.add_argument("--pool", type=int, default=4, help="distinct batches cycled through")
     ap.add_argument("--cpu-seconds-per-step", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -41,7 +41,7 @@ constexpr int kKB = 64;      // reduction elements per k-block (one 128-byte swi
 constexpr int kUmmaK = 16;
 constexpr int kThreads = 192;
 constexpr int kABytes = kM * kKB * 2;  // 16 KB
-constexpr int kW = 64;       // node feature width served by this file
+constexpr int kW = 64;       // node feature width of the backward kernels (MODE_MSG: 32/64/128)
 
 // *_MN: the same products with operands read straight from their natural row-major buffers as
 // MN-major UMMA operands (no transposed copies of h / gm, no [k,o]-ordered copy of U):
@@ -53,12 +53,12 @@ __host__ __device__ constexpr bool mode_is_dh(int m) { return m == MODE_DH || m 
 __host__ __device__ constexpr bool mode_is_du(int m) { return m == MODE_DU || m == MODE_DU_MN; }
 constexpr int kMnBlockBytes = 64 * kKB * 2;  // one MN-major TMA box: 64 K-rows x 64 MN elements
 
-template <int MODE>
+template <int MODE, int W>
 struct NCfg {
-    static constexpr int kBN = mode_is_dh(MODE) ? 256 : kW;     // accumulator columns
-    static constexpr int kBBytes = kBN * kKB * 2;               // 8 KB / 32 KB
-    static constexpr int kStageBytes = kABytes + kBBytes;       // 24 KB / 48 KB
-    static constexpr int kStages = mode_is_dh(MODE) ? 4 : 8;    // 192 KB of operands in flight
+    static constexpr int kBN = mode_is_dh(MODE) ? 256 : W;      // accumulator columns
+    static constexpr int kBBytes = kBN * kKB * 2;               // 4 .. 32 KB
+    static constexpr int kStageBytes = kABytes + kBBytes;       // 20 .. 48 KB
+    static constexpr int kStages = 192 * 1024 / kStageBytes > 8 ? 8 : 192 * 1024 / kStageBytes;
     static constexpr int kAcc = mode_is_dh(MODE) ? 2 : 4;       // TMEM accumulator ring
     static constexpr bool kAMn = MODE == MODE_DU_MN;            // A operand MN-major
     static constexpr bool kBMn = MODE == MODE_DU_MN || MODE == MODE_DH_MN;
@@ -90,14 +90,14 @@ struct Unit {
     int32_t row0, rows, group, chunk;   // epilogue
 };
 
-template <int MODE>
+template <int MODE, int W>
 __device__ __forceinline__ Unit decode_unit(const NodeParams& p, int64_t v) {
     Unit u;
     if constexpr (MODE == MODE_MSG) {
         const int4 t = __ldg(p.units + v);
         u.group = t.x; u.row0 = t.y; u.rows = t.z; u.chunk = 0;
         u.a_c0 = 0; u.a_c1 = t.y; u.da_c0 = kKB; u.da_c1 = 0;
-        u.b_c0 = 0; u.b_c1 = (t.x - p.node_base) * kW; u.db_c0 = kKB; u.db_c1 = 0;
+        u.b_c0 = 0; u.b_c1 = (t.x - p.node_base) * W; u.db_c0 = kKB; u.db_c1 = 0;
         u.nkb = p.K / kKB; u.last_steps = kKB / kUmmaK;
     } else if constexpr (MODE == MODE_DH_MN) {
         const int4 t = __ldg(p.units + v);  // (group, first row, rows, column chunk)
@@ -157,11 +157,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&t);
 }
 
-template <int MODE>
+template <int MODE, int W>
 __global__ void __launch_bounds__(kThreads, 1)
 node_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                  const __grid_constant__ CUtensorMap tmap_b, const NodeParams p) {
-    using C = NCfg<MODE>;
+    static_assert(MODE == MODE_MSG || W == kW, "the backward kernels serve w = 64");
+    using C = NCfg<MODE, W>;
     constexpr int kStages = C::kStages;
     constexpr int kStageBytes = C::kStageBytes;
     constexpr int kBN = C::kBN;
@@ -218,8 +219,12 @@ node_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            // the next unit's table entry / row pointers are fetched one unit ahead so that their
+            // load latency never sits between two units (MODE_DU* units are only ~2 k-blocks long)
+            Unit un = v0 < v1 ? decode_unit<MODE, W>(p, v0) : Unit{};
             for (int64_t v = v0; v < v1; v += vstep) {
-                const Unit u = decode_unit<MODE>(p, v);
+                const Unit u = un;
+                if (v + vstep < v1) un = decode_unit<MODE, W>(p, v + vstep);
                 for (int kb = 0; kb < u.nkb; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sa = smem_base + stage * kStageBytes;
@@ -253,8 +258,10 @@ node_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             int stage = 0;
             uint32_t phase = 0;
             uint32_t it = 0;
+            Unit un = v0 < v1 ? decode_unit<MODE, W>(p, v0) : Unit{};
             for (int64_t v = v0; v < v1; v += vstep) {
-                const Unit u = decode_unit<MODE>(p, v);
+                const Unit u = un;
+                if (v + vstep < v1) un = decode_unit<MODE, W>(p, v + vstep);
                 if (u.nkb == 0) continue;  // empty group: the epilogue writes zeros on its own
                 const uint32_t as = it % kAcc;
                 const uint32_t aphase = (it / kAcc) & 1u;
@@ -289,8 +296,10 @@ node_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const uint32_t lane_addr = uint32_t(q * 32) << 16;
         const uint32_t stage_smem = bar_base + 256 + q * 4096;  // per-warp output staging tile
         uint32_t it = 0;
+        Unit un = v0 < v1 ? decode_unit<MODE, W>(p, v0) : Unit{};
         for (int64_t v = v0; v < v1; v += vstep) {
-            const Unit u = decode_unit<MODE>(p, v);
+            const Unit u = un;
+            if (v + vstep < v1) un = decode_unit<MODE, W>(p, v + vstep);
             if (u.nkb == 0) {
                 if constexpr (mode_is_du(MODE)) {
                     uint4* dst = reinterpret_cast<uint4*>(
@@ -317,8 +326,8 @@ node_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             int64_t pitch;                          // bytes between consecutive output rows
             if constexpr (MODE == MODE_MSG) {
                 gbase = reinterpret_cast<uint8_t*>(static_cast<float*>(p.out) +
-                                                   int64_t(u.row0 + q * 32) * kW);
-                pitch = kW * 4;
+                                                   int64_t(u.row0 + q * 32) * W);
+                pitch = W * 4;
             } else if constexpr (mode_is_dh(MODE)) {
                 gbase = reinterpret_cast<uint8_t*>(static_cast<__nv_bfloat16*>(p.out) +
                                                    int64_t(u.row0 + q * 32) * p.K + u.chunk * 256);
@@ -380,11 +389,11 @@ node_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
 }
 
-template <int MODE>
+template <int MODE, int W = kW>
 int launch_node_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const NodeParams& p,
                      cudaStream_t stream) {
-    auto kern = node_gemm_kernel<MODE>;
-    constexpr int smem = NCfg<MODE>::kSmemBytes;
+    auto kern = node_gemm_kernel<MODE, W>;
+    constexpr int smem = NCfg<MODE, W>::kSmemBytes;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (err != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(node_gemm)", err);
     int sms = 0;
@@ -398,10 +407,10 @@ int launch_node_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const NodePar
     return 0;
 }
 
-int check_common(const char* name, int32_t K, int32_t W, int64_t E_pad) {
+int check_common(const char* name, int32_t K, int32_t W, int64_t E_pad, bool any_width = false) {
     static thread_local char buf[160];
-    if (W != kW) {
-        snprintf(buf, sizeof(buf), "%s: width must be %d", name, kW);
+    if (any_width ? (W != 32 && W != 64 && W != 128) : W != kW) {
+        snprintf(buf, sizeof(buf), "%s: width must be %s", name, any_width ? "32, 64 or 128" : "64");
         return set_error(buf);
     }
     if (K <= 0 || K % 256 != 0) {
@@ -471,15 +480,15 @@ extern "C" int gkn_node_msg_bf16(const void* hs_bf16, const void* u_bf16, const 
     if (hs_bf16 == nullptr || u_bf16 == nullptr || units == nullptr || msg == nullptr) {
         return set_error("gkn_node_msg_bf16: NULL pointer argument");
     }
-    int rc = check_common("gkn_node_msg_bf16", K, W, E_pad);
+    int rc = check_common("gkn_node_msg_bf16", K, W, E_pad, true);
     if (rc) return rc;
-    if (chunk_nodes <= 0 || chunk_nodes * kW >= (int64_t(1) << 31)) {
+    if (chunk_nodes <= 0 || chunk_nodes * W >= (int64_t(1) << 31)) {
         return set_error("gkn_node_msg_bf16: bad node chunk");
     }
     CUtensorMap ta, tb;
     rc = make_tensor_map_bf16_2d(&ta, hs_bf16, uint64_t(K), uint64_t(E_pad), kKB, kM);
     if (rc) return rc;
-    rc = make_tensor_map_bf16_2d(&tb, u_bf16, uint64_t(K), uint64_t(chunk_nodes) * kW, kKB, kW);
+    rc = make_tensor_map_bf16_2d(&tb, u_bf16, uint64_t(K), uint64_t(chunk_nodes) * W, kKB, W);
     if (rc) return rc;
     NodeParams p{};
     p.units = reinterpret_cast<const int4*>(units);
@@ -488,7 +497,12 @@ extern "C" int gkn_node_msg_bf16(const void* hs_bf16, const void* u_bf16, const 
     p.v_end = unit_end;
     p.K = K;
     p.node_base = node_base;
-    return launch_node_gemm<MODE_MSG>(ta, tb, p, static_cast<cudaStream_t>(stream));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (W) {
+        case 32: return launch_node_gemm<MODE_MSG, 32>(ta, tb, p, st);
+        case 64: return launch_node_gemm<MODE_MSG, 64>(ta, tb, p, st);
+        default: return launch_node_gemm<MODE_MSG, 128>(ta, tb, p, st);
+    }
 }
 
 extern "C" int gkn_node_du_bf16(const void* hsT_bf16, const void* gsT_bf16, const int32_t* pptr,

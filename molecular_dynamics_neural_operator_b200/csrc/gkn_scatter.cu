@@ -191,22 +191,27 @@ segment_matvec_kernel(const float* __restrict__ rows, const int32_t* __restrict_
             const int beg = seg_ptr[n], end = seg_ptr[n + 1];
             float4 ar0 = make_float4(0.f, 0.f, 0.f, 0.f), ar1 = ar0, ag0 = ar0, ag1 = ar0;
             int q = beg + sub;
-            // IF rows in flight per lane: indices first, then the 2*IF dependent row loads (the
-            // walk is a chain of three dependent loads per round, so at w <= 64 - two rows per
-            // warp step - eight in flight halve the number of rounds of a ~120-edge segment)
+            // IF rows in flight per lane: indices first, then the 2*IF dependent row loads.  The
+            // walk is a chain of three dependent loads per round and one warp per node is latency-
+            // bound, so every round - the last, partial one included - issues all its loads at
+            // once (slots past the end are predicated off and add zeros).
             constexpr int IF = W <= 64 ? 8 : 4;
-            for (; q + (IF - 1) * RPW < end; q += IF * RPW) {
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (; q < end; q += IF * RPW) {
                 int pp[IF], ii[IF];
 #pragma unroll
-                for (int u = 0; u < IF; ++u) pp[u] = perm ? perm[q + u * RPW] : q + u * RPW;
+                for (int u = 0; u < IF; ++u) {
+                    const int qq = q + u * RPW;
+                    pp[u] = qq < end ? (perm ? perm[qq] : qq) : -1;
+                }
 #pragma unroll
-                for (int u = 0; u < IF; ++u) ii[u] = gidx[pp[u]];
+                for (int u = 0; u < IF; ++u) ii[u] = pp[u] >= 0 ? gidx[pp[u]] : 0;
                 float4 rr[IF], gg[IF];
 #pragma unroll
                 for (int u = 0; u < IF; ++u) {
-                    rr[u] = rows ? ldg4_stream(rows + int64_t(pp[u]) * W + col)
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-                    gg[u] = ldg4(gnode + int64_t(ii[u]) * W + col);
+                    const bool ok = pp[u] >= 0;
+                    rr[u] = ok && rows ? ldg4_stream(rows + int64_t(pp[u]) * W + col) : zero4;
+                    gg[u] = ok ? ldg4(gnode + int64_t(ii[u]) * W + col) : zero4;
                 }
                 // fixed pairwise order: even slots into the *0 accumulators, odd into the *1
 #pragma unroll
@@ -216,11 +221,6 @@ segment_matvec_kernel(const float* __restrict__ rows, const int32_t* __restrict_
                     ag0 = f4add(ag0, f4add(gg[u], gg[u + 2]));
                     ag1 = f4add(ag1, f4add(gg[u + 1], gg[u + 3]));
                 }
-            }
-            for (; q < end; q += RPW) {
-                const int p0 = perm ? perm[q] : q;
-                if (rows) ar0 = f4add(ar0, ldg4_stream(rows + int64_t(p0) * W + col));
-                ag0 = f4add(ag0, ldg4(gnode + int64_t(gidx[p0]) * W + col));
             }
             float4 ar = f4add(ar0, ar1), ag = f4add(ag0, ag1);
 #pragma unroll

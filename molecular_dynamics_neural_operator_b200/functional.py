@@ -224,8 +224,11 @@ _MLP_SIDE_GEMM = os.environ.get("GKN_MLP_SIDE_GEMM", "1") == "1"
 _SAVE_U_BYTES = int(os.environ.get("GKN_NODE_SAVE_U_MB", "24576")) << 20
 
 
-def node_path_supported(W: int, K: int, E: int, precision: str) -> bool:
-    return precision == "bf16" and W == 64 and K % 256 == 0 and E > 0
+def node_path_supported(W: int, K: int, E: int, precision: str, needs_grad: bool = True) -> bool:
+    """Training: w = 64 (the dU / dh kernels); forward only (rollout): w in {32, 64, 128}."""
+    if precision != "bf16" or K % 256 != 0 or E <= 0:
+        return False
+    return W == 64 or (not needs_grad and W in (32, 128))
 
 
 def _node_chunks(N: int, per_node_bytes: int):
@@ -443,8 +446,11 @@ def gkn_stack(x0, edge_attr_sorted, net, root1, bias1, root2, bias2, plan: Graph
         raise TypeError("node features and edge attributes must be float32")
     l0, l2, l4 = net.layers[0], net.layers[2], net.layers[4]
     fn = _GKNStack
+    tensors = (x0, edge_attr_sorted, l0.weight, l0.bias, l2.weight, l2.bias, l4.weight, l4.bias,
+               root1, bias1, root2, bias2)
+    needs_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
     if FACTORIZATION == "node" and node_path_supported(x0.size(1), l4.weight.size(1),
-                                                       plan.num_edges, precision):
+                                                       plan.num_edges, precision, needs_grad):
         fn = _GKNStackNode
     return fn.apply(x0, edge_attr_sorted, l0.weight, l0.bias, l2.weight, l2.bias, l4.weight,
                            l4.bias, root1, bias1, root2, bias2, plan, tuple(schedule), bool(relu),

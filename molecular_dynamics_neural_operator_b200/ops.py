@@ -506,8 +506,9 @@ def node_layout(plan: GraphPlan, dh_chunks: int | None = None) -> NodeLayout:
     zero = torch.zeros(1, dtype=torch.long, device=dev)
     pptr = torch.cat([zero, torch.cumsum(degp, 0)])
     ufirst = torch.cat([zero, torch.cumsum(tiles, 0)])
-    unit_first = ufirst.tolist()  # host read (also gives the sizes below)
-    e_pad = int(pptr[-1].item())
+    # one host read for everything data dependent: the unit offsets and the padded edge count
+    host = torch.cat([ufirst, pptr[-1:]]).tolist()
+    unit_first, e_pad = host[:-1], host[-1]
     U = unit_first[-1]
     nodes = torch.arange(N, device=dev)
     grp = torch.repeat_interleave(nodes, deg, output_size=E)

@@ -125,7 +125,9 @@ class BatchPrefetcher:
 
     def __init__(self, device):
         self.device = device
-        self.stream = torch.cuda.Stream(device=device)
+        # high priority: the build is a chain of small kernels with host reads in between (edge
+        # count, layout sizes); they must not queue behind the training stream's long kernels
+        self.stream = torch.cuda.Stream(device=device, priority=-1)
         self._pending = None
         self._event = None
 

@@ -284,6 +284,9 @@ def test_layer0_gradients_agree_with_and_without_edge_attr_gradient(emulated):
 def test_node_path_selection():
     assert GF.node_path_supported(64, 1024, 10, "bf16")
     assert not GF.node_path_supported(32, 1024, 10, "bf16")
+    assert GF.node_path_supported(32, 1024, 10, "bf16", needs_grad=False)
+    assert GF.node_path_supported(128, 1024, 10, "bf16", needs_grad=False)
+    assert not GF.node_path_supported(16, 1024, 10, "bf16", needs_grad=False)
     assert not GF.node_path_supported(64, 1024, 10, "fp32")
     assert not GF.node_path_supported(64, 1000, 10, "bf16")
     assert not GF.node_path_supported(64, 1024, 0, "bf16")

@@ -179,6 +179,37 @@ def test_node_first_stack_matches_edge_first_stack_and_oracle(monkeypatch, N, E,
         assert fro(tn[k].grad.cpu(), te[k].grad.cpu()) < tol, k
 
 
+@pytest.mark.parametrize("width", [32, 128])
+def test_forward_only_node_first_at_other_widths(width):
+    """Rollout (no gradients) takes the node-first message kernel at w = 32 and 128 as well."""
+    from molecular_dynamics_neural_operator_b200 import functional as GF
+    from molecular_dynamics_neural_operator_b200 import ops
+    from oracle import gkn_oracle as orc
+
+    N, E, K = 90, 5000, 256
+    ei = random_graph(N, E, seed=width)
+    gen = torch.Generator().manual_seed(width)
+    net = orc.make_net_params(6, K, width, seed=1, dtype=torch.float32)
+    x = torch.randn(N, width, generator=gen)
+    ea = torch.randn(E, 6, generator=gen)
+    root = torch.randn(width, width, generator=gen) / 8
+    bias = torch.randn(width, generator=gen) / 8
+    ref = orc.nnconv_forward(x.double(), ei, ea.double(), {k: v.double() for k, v in net.items()},
+                             root.double(), bias.double())
+    plan = ops.prepare_graph(ei.cuda(), N)
+    c = lambda t: t.cuda()  # noqa: E731
+    args = (c(x), c(ea).index_select(0, plan.perm_long), c(net["layers.0.weight"]),
+            c(net["layers.0.bias"]), c(net["layers.2.weight"]), c(net["layers.2.bias"]),
+            c(net["layers.4.weight"]), c(net["layers.4.bias"]), c(root), c(bias), None, None, plan,
+            (0,), False, "bf16")
+    assert GF.node_path_supported(width, K, E, "bf16", needs_grad=False)
+    with torch.no_grad():
+        out_n = GF._GKNStackNode.apply(*args)
+        out_e = GF._GKNStack.apply(*args)
+    assert fro(out_n.cpu(), ref) < 2.0 ** -7
+    assert fro(out_n.cpu(), out_e.cpu()) < 2.0 ** -7
+
+
 def test_node_first_is_the_default_for_the_bench_shape():
     """KernelNN at w = 64 / K = 1024 in bf16 runs the grouped-GEMM kernels (launch accounting)."""
     from molecular_dynamics_neural_operator_b200 import functional as GF
