@@ -213,7 +213,9 @@ class _GKNStack(torch.autograd.Function):
 FACTORIZATION = os.environ.get("GKN_FACTORIZATION", "node")
 # node-indexed temporaries (U, dU: w*K bf16 values per node) are produced for node ranges of at
 # most this many bytes
-_NODE_CHUNK_BYTES = int(os.environ.get("GKN_NODE_CHUNK_MB", "1024")) << 20
+_NODE_CHUNK_BYTES = int(os.environ.get("GKN_NODE_CHUNK_MB", "4096")) << 20
+# ... and, when U is recomputed for the dh pass (A * w*K values per node), of this many
+_NODE_DH_CHUNK_BYTES = int(os.environ.get("GKN_NODE_DH_CHUNK_MB", "8192")) << 20
 _MLP_BWD_CHUNK_ROWS = int(os.environ.get("GKN_MLP_BWD_CHUNK_ROWS", "65536"))
 # MN-major operand variants of the dU / dh kernels: h, gm and U are read in place (no transposed
 # copy of h, no [k,o]-ordered recomputation of U).  GKN_NODE_MN=0 selects the K-major kernels.
@@ -231,8 +233,8 @@ def node_path_supported(W: int, K: int, E: int, precision: str, needs_grad: bool
     return W == 64 or (not needs_grad and W in (32, 128))
 
 
-def _node_chunks(N: int, per_node_bytes: int):
-    nc = max(1, min(N, _NODE_CHUNK_BYTES // per_node_bytes))
+def _node_chunks(N: int, per_node_bytes: int, budget: int | None = None):
+    nc = max(1, min(N, (_NODE_CHUNK_BYTES if budget is None else budget) // per_node_bytes))
     return [(n0, min(N, n0 + nc)) for n0 in range(0, N, nc)]
 
 
@@ -374,7 +376,7 @@ class _GKNStackNode(torch.autograd.Function):
             if u_all is not None:
                 ops.node_dh_mn(gs_all, u_all.view(A, N, W, K), lay, 0, lay.num_units, 0, dh)
             else:
-                for n0, n1 in _node_chunks(N, A * W * K * 2):
+                for n0, n1 in _node_chunks(N, A * W * K * 2, _NODE_DH_CHUNK_BYTES):
                     ut = torch.empty((A, n1 - n0, K * W), dtype=bf, device=dev)
                     for a in range(A):
                         torch.mm(xbs[a][n0:n1], w3r if NODE_MN else w3kq, out=ut[a])

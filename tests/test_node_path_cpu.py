@@ -232,6 +232,7 @@ def test_node_first_stack_matches_oracle(emulated, monkeypatch, N, E, K, depth, 
     rounding is the only difference from the fp64 oracle: every gradient within 2^-5 except those
     upstream of the edge MLP's own ReLUs (mask flips, see tests/test_layer_gpu.py)."""
     monkeypatch.setattr(GF, "_NODE_CHUNK_BYTES", chunk_mb << 20)
+    monkeypatch.setattr(GF, "_NODE_DH_CHUNK_BYTES", chunk_mb << 20)
     monkeypatch.setattr(GF, "_MLP_BWD_CHUNK_ROWS", 64)
     monkeypatch.setattr(GF, "NODE_MN", mn)
     monkeypatch.setattr(GF, "_SAVE_U_BYTES", (1 << 40) if save_u else 0)

@@ -162,6 +162,7 @@ def test_node_first_stack_matches_edge_first_stack_and_oracle(monkeypatch, N, E,
     monkeypatch.setattr(GF, "NODE_MN", mn)
     monkeypatch.setattr(GF, "_SAVE_U_BYTES", (1 << 40) if save_u else 0)
     monkeypatch.setattr(GF, "_NODE_CHUNK_BYTES", 64 * K * 2 * 7)  # node ranges of 7 nodes
+    monkeypatch.setattr(GF, "_NODE_DH_CHUNK_BYTES", 2 * depth * 64 * K * 2 * 5)  # and of 5
 
     ei, p, depth = _stack_case(N, E, K, depth, seed=N)
     out_n, tn = _gpu_stack(GF._GKNStackNode, ei, p, depth, N, relu=False)
