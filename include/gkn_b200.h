@@ -156,6 +156,8 @@ int gkn_scatter_src_sum(const float* dxj, const int32_t* src_ptr, const int32_t*
  *   r[n]   = scale[n] * sum_{q in [seg_ptr[n],seg_ptr[n+1])} rows[p,:]      p = perm ? perm[q] : q
  *   agg[n] = scale[n] * sum_q gnode[gidx[p],:]                  (written to agg_out if not NULL)
  *   out[n] = act( r[n] + agg[n] @ M1 + nin[n] @ M2 + bias )     M1, M2: [W,W] row-major
+ *   rows may be NULL (r = 0).  M1 = M2 = NULL (nin unused): plain segment sums, out = act(r + bias)
+ *   - the partial sums of a source-range shard before its all-reduce (sharded.py).
  * forward : rows=msg, perm=NULL, seg_ptr=dst_ptr, gidx=src_s, gnode=x, scale=inv_cnt,
  *           M1 = layers.4.bias viewed [W,W], nin=x, M2=root, bias, relu
  * backward: rows=dxj, perm=src_perm, seg_ptr=src_ptr, gidx=dst_s, gnode=gn, scale=NULL,

@@ -234,7 +234,7 @@ segment_matvec_kernel(const float* __restrict__ rows, const int32_t* __restrict_
                 ag = make_float4(ag.x * sc, ag.y * sc, ag.z * sc, ag.w * sc);
                 *reinterpret_cast<float4*>(&s_r[wib][nb][col]) = ar;
                 *reinterpret_cast<float4*>(&s_g[wib][nb][col]) = ag;
-                *reinterpret_cast<float4*>(&s_n[wib][nb][col]) = ldg4(nin + n * W + col);
+                if (nin) *reinterpret_cast<float4*>(&s_n[wib][nb][col]) = ldg4(nin + n * W + col);
                 if (agg_out) *reinterpret_cast<float4*>(agg_out + n * W + col) = ag;
             }
         }
@@ -250,8 +250,9 @@ segment_matvec_kernel(const float* __restrict__ rows, const int32_t* __restrict_
             for (int nb = 0; nb < NB; ++nb)
 #pragma unroll
                 for (int k = 0; k < CPL; ++k) o[nb][k] = nb < nvalid ? s_r[wib][nb][c0 + k] + bv[k] : 0.f;
+            // M1 == NULL (then M2 is NULL too): plain segment sums, out = r (+ bias), agg_out = agg
 #pragma unroll 4
-            for (int i = 0; i < W; ++i) {
+            for (int i = 0; M1 != nullptr && i < W; ++i) {
                 float m1[CPL], m2[CPL];
                 ldg_vec<CPL>(M1 + i * W + c0, m1);
                 ldg_vec<CPL>(M2 + i * W + c0, m2);
@@ -893,8 +894,9 @@ extern "C" int gkn_segment_matvec(const float* rows, const int32_t* perm, const 
     if (N == 0) return 0;
     // rows may be NULL: r[n] = 0 (the node-first backward has no per-edge rows to sum);
     // gidx may be NULL for a graph without edges (never dereferenced: all segments empty)
-    if (N < 0 || seg_ptr == nullptr || gnode == nullptr || M1 == nullptr || nin == nullptr ||
-        M2 == nullptr || out == nullptr) {
+    // M1 and M2 may both be NULL: no matrix products (plain segment sums; nin is then unused)
+    if (N < 0 || seg_ptr == nullptr || gnode == nullptr || out == nullptr ||
+        (M1 == nullptr) != (M2 == nullptr) || (M1 != nullptr && nin == nullptr)) {
         return set_error("gkn_segment_matvec: bad size or NULL pointer argument");
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);

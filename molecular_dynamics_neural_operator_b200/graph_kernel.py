@@ -267,6 +267,7 @@ def construct_pairdata(x_position, x_aminoacid, threshold: float = 8.0,
                     x_position=x_position, edge_attr=edge_attr, edge_index=edge_index)
     # the radius graph is symmetric and (row, col)-sorted: its CSR plan needs no sorting
     data._gkn_plan = ops.plan_from_csr(edge_index, row_ptr, x_position.size(1), validate=False)
+    data._gkn_row_ptr = row_ptr  # edges are sorted by source: source-range shards are slices
     return data
 
 

@@ -418,11 +418,12 @@ def segment_matvec(rows, perm, seg_ptr, gidx, gnode, scale, M1, nin, M2, bias, r
     """out[n] = act(scale*sum rows[p] + (scale*sum gnode[gidx[p]]) @ M1 + nin[n] @ M2 + bias).
     See gkn_segment_matvec in gkn_b200.h.  Returns (out, agg or None)."""
     lib = _lib.load()
-    N, W = int(nin.size(0)), int(nin.size(1))
+    ref = nin if nin is not None else gnode  # M1 = M2 = nin = None: plain segment sums
+    N, W = int(ref.size(0)), int(ref.size(1))
     f32, i32 = torch.float32, torch.int32
-    out = torch.empty((N, W), dtype=f32, device=nin.device)
-    agg = torch.empty((N, W), dtype=f32, device=nin.device) if want_agg else None
-    with torch.cuda.device(nin.device):
+    out = torch.empty((N, W), dtype=f32, device=ref.device)
+    agg = torch.empty((N, W), dtype=f32, device=ref.device) if want_agg else None
+    with torch.cuda.device(ref.device):
         _lib.check(
             lib.gkn_segment_matvec(
                 _p(rows, f32, "rows"), _p(perm, i32, "perm"), _p(seg_ptr, i32, "seg_ptr"),

@@ -10,6 +10,14 @@ local, and after every application the ranks all-gather the new node features ``
 
 ``emulate_world`` runs all ranks of the exchange in one process on one GPU (the all-gather becomes
 a concatenation): that is how the sharding arithmetic is tested without a multi-GPU box.
+
+Node-first factorisation (functional._GKNStackNode, the default where it applies): the per-edge
+work is grouped by SOURCE node, so a rank owns a contiguous range of source nodes and their
+outgoing edges.  ``U = x W3r`` is then needed only for the owned nodes (no exchange before the
+message kernel), every rank produces PARTIAL sums of messages at all destinations, and the one
+exchange per application is an all-reduce (sum) of those partial node sums (2 x N x w fp32) after
+which every rank applies the (tiny, replicated) node update.  ``SourceShard`` /
+``sharded_stack_forward_node`` / ``emulate_world_node``.
 """
 from __future__ import annotations
 
@@ -114,18 +122,150 @@ def emulate_world(x0, plan: GraphPlan, edge_attr_sorted, net, root1, bias1, root
     return x
 
 
+# ------------------------------------------------------------------------------------------------
+# Source-range sharding of the node-first path
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class SourceShard:
+    """Rank-local slice for the node-first kernels: source nodes [n0, n1) and their outgoing edges
+    (as a plan over all N nodes that holds only those edges, with its padded layout)."""
+
+    n0: int
+    n1: int
+    plan: GraphPlan
+    lay: ops.NodeLayout
+    edge_attr: torch.Tensor  # float32 [E_loc, 6] in the local plan's destination-sorted order
+    inv_cnt: torch.Tensor  # float32 [N]  1 / max(GLOBAL in-degree, 1)
+
+
+def shard_frame_by_source(edge_index: torch.Tensor, edge_attr: torch.Tensor, num_nodes: int,
+                          rank: int, world: int, row_ptr: torch.Tensor | None = None) -> SourceShard:
+    """Equal source-node ranges.  With ``row_ptr`` (edge_index sorted by source, as the radius graph
+    emits it) the local edges are one contiguous slice; otherwise they are selected by a mask."""
+    N = int(num_nodes)
+    rows = (N + world - 1) // world
+    n0, n1 = min(N, rank * rows), min(N, (rank + 1) * rows)
+    if row_ptr is not None:
+        e0, e1 = (int(v) for v in row_ptr[[n0, n1]].tolist())
+        ei, ea = edge_index[:, e0:e1], edge_attr[e0:e1]
+    else:
+        sel = ((edge_index[0] >= n0) & (edge_index[0] < n1)).nonzero().squeeze(1)
+        ei, ea = edge_index.index_select(1, sel), edge_attr.index_select(0, sel)
+    cnt = torch.bincount(edge_index[1], minlength=N)
+    inv_cnt = 1.0 / cnt.clamp(min=1).float()
+    if ei.size(1) == 0:  # this rank owns no edges: it only takes part in the all-reduce
+        return SourceShard(n0, n1, None, None, ea, inv_cnt)
+    plan = ops.prepare_graph(ei.contiguous(), N, validate=False)
+    return SourceShard(n0, n1, plan, ops.node_layout(plan), ea.index_select(0, plan.perm_long),
+                       inv_cnt)
+
+
+def _node_partial_sums(x, shard: SourceShard, hs, w3r, msg):
+    """One application's local work: U for the owned nodes, messages of their outgoing edges, and
+    the partial sums of those messages (and of x_j, for the b3 term) at every destination.
+    Returns [2, N, w] fp32."""
+    N, W = x.shape
+    K = hs.size(1)
+    lay, plan = shard.lay, shard.plan
+    xb = x[shard.n0:shard.n1].to(torch.bfloat16)
+    for c0, c1 in GF._node_chunks(shard.n1 - shard.n0, W * K * 2):
+        U = torch.mm(xb[c0:c1], w3r)
+        ops.node_msg(hs, U.view(c1 - c0, W, K), lay, lay.unit_first[shard.n0 + c0],
+                     lay.unit_first[shard.n0 + c1], shard.n0 + c0, msg)
+        del U
+    r, agg = ops.segment_matvec(msg, lay.qpos, plan.dst_ptr, lay.src_pad, x, None, None, None, None,
+                                None, False, want_agg=True)
+    return torch.stack([r, agg])
+
+
+def _node_update(x, sums, inv_cnt, B3, root, bias, relu: bool):
+    """x' = act(mean msg + (mean x_j) @ B3 + x @ root + bias) from the all-reduced sums."""
+    out = torch.addmm(bias, x, root)
+    out.addmm_(sums[1] * inv_cnt[:, None], B3)
+    out.add_(sums[0] * inv_cnt[:, None])
+    return torch.relu_(out) if relu else out
+
+
+def _node_shard_setup(shard: SourceShard, net, W: int):
+    l0, l2, l4 = net.layers[0], net.layers[2], net.layers[4]
+    K = l4.weight.size(1)
+    if not GF.node_path_supported(W, K, 1, "bf16", needs_grad=False):
+        raise ValueError(f"node-first sharding needs bf16, w in (32, 64, 128), K % 256 == 0 "
+                         f"(got w = {W}, K = {K})")
+    w3r = l4.weight.to(torch.bfloat16).contiguous().view(W, W * K)
+    B3 = l4.bias.view(W, W).contiguous()
+    if shard.lay is None:  # this rank owns no edges
+        return None, w3r, B3, None
+    lay = shard.lay
+    ea_s = torch.zeros((lay.e_pad, shard.edge_attr.size(1)), dtype=torch.float32,
+                       device=shard.edge_attr.device)
+    ea_s.index_copy_(0, lay.qpos_long, shard.edge_attr.contiguous())
+    _, hs = GF._edge_hidden(ea_s, l0.weight, l0.bias.contiguous(), l2.weight, l2.bias.contiguous(),
+                            "bf16")
+    msg = torch.empty((lay.e_pad, W), dtype=torch.float32, device=hs.device)
+    return hs, w3r, B3, msg
+
+
+@torch.no_grad()
+def sharded_stack_forward_node(x0, shard: SourceShard, net, root1, bias1, root2, bias2, schedule,
+                               relu: bool, group=None) -> torch.Tensor:
+    """Forward of the conv stack, node-first kernels, source-range sharding.  Every rank passes the
+    same full ``x0`` [N, w] and gets the full result back."""
+    N, W = x0.shape
+    hs, w3r, B3, msg = _node_shard_setup(shard, net, W)
+    roots, biases = (root1, root2), (bias1, bias2)
+    x = x0.contiguous()
+    for c in schedule:
+        if hs is not None:
+            sums = _node_partial_sums(x, shard, hs, w3r, msg)
+        else:
+            sums = torch.zeros((2, N, W), dtype=torch.float32, device=x.device)
+        dist.all_reduce(sums, group=group)
+        x = _node_update(x, sums, shard.inv_cnt, B3, roots[c], biases[c], relu)
+    return x
+
+
+@torch.no_grad()
+def emulate_world_node(x0, edge_index, edge_attr, net, root1, bias1, root2, bias2, schedule,
+                       relu: bool, world: int, row_ptr=None) -> torch.Tensor:
+    """All ranks of sharded_stack_forward_node in turn on one GPU; the all-reduce is a sum."""
+    N, W = x0.shape
+    shards = [shard_frame_by_source(edge_index, edge_attr, N, r, world, row_ptr)
+              for r in range(world)]
+    setups = [_node_shard_setup(s, net, W) for s in shards]
+    roots, biases = (root1, root2), (bias1, bias2)
+    x = x0.contiguous()
+    for c in schedule:
+        sums = torch.zeros((2, N, W), dtype=torch.float32, device=x.device)
+        for s, (hs, w3r, B3, msg) in zip(shards, setups):
+            if hs is not None:
+                sums += _node_partial_sums(x, s, hs, w3r, msg)
+        x = _node_update(x, sums, shards[0].inv_cnt, setups[0][2], roots[c], biases[c], relu)
+    return x
+
+
 @torch.no_grad()
 def kernelnn_forward_sharded(model, data, group=None) -> torch.Tensor:
     """``KernelNN.forward`` for one large frame with the conv stack sharded over the ranks of
     ``group`` (node encoder and fc2 are tiny and replicated).  Every rank returns the full output."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     x = model.node_encoder(data)
+    schedule = (0,) * model.depth + (1,) * model.depth
+    K = model.conv1.net.layers[4].weight.size(1)
+    if (GF.FACTORIZATION == "node" and data.edge_index.size(1) > 0
+            and GF.node_path_supported(x.size(1), K, 1, model.precision, needs_grad=False)):
+        # node-first kernels: source ranges, one all-reduce of the partial node sums per application
+        shard = shard_frame_by_source(data.edge_index, data.edge_attr, x.size(0), rank, world,
+                                      getattr(data, "_gkn_row_ptr", None))
+        x = sharded_stack_forward_node(x.contiguous(), shard, model.conv1.net, model.conv1.root,
+                                       model.conv1.bias, model.conv2.root, model.conv2.bias,
+                                       schedule, relu=True, group=group)
+        return model.fc2(x)
     plan = getattr(data, "_gkn_plan", None)
     if plan is None:
         plan = ops.prepare_graph(data.edge_index, x.size(0))
     ea = data.edge_attr.index_select(0, plan.perm_long)
     shard = shard_frame(plan, ea, rank, world)
-    schedule = (0,) * model.depth + (1,) * model.depth
     x = sharded_stack_forward(x.contiguous(), shard, model.conv1.net, model.conv1.root,
                               model.conv1.bias, model.conv2.root, model.conv2.bias, schedule,
                               relu=True, precision=model.precision, group=group)
