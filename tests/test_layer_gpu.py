@@ -247,6 +247,52 @@ def test_full_size_properties_bba_allatom():
     assert abs(float(lhs - rhs)) <= 1e-5 * abs(float(rhs)) + 1e-3
 
 
+def test_full_size_node_first_and_edge_first_agree_bba_allatom():
+    """BASELINE config 2 sizes, two frames batched (N = 1008, E ~ 120k, w = 64, K = 1024), two
+    applications without activation: the node-first grouped GEMMs and the edge-first fused
+    contraction compute the same trilinear form - outputs and every gradient agree within the bf16
+    stack bound (each path rounds different intermediates: U and dU vs nothing)."""
+    from molecular_dynamics_neural_operator_b200 import functional as GF
+    from molecular_dynamics_neural_operator_b200 import ops
+    from molecular_dynamics_neural_operator_b200 import synthetic as syn
+    from molecular_dynamics_neural_operator_b200.graph_kernel import DenseNet
+
+    wl = syn.WORKLOADS["bba_allatom"]
+    pos = torch.from_numpy(syn.trajectory(wl, 2, seed=1)).cuda()
+    ei, ea, rp = ops.radius_graph(pos, wl.cutoff, return_row_ptr=True)
+    N, W, K = 2 * wl.num_atoms, wl.width, wl.ker_width
+    plan = ops.plan_from_csr(ei, rp, N)
+    eas = ea.index_select(0, plan.perm_long)
+    torch.manual_seed(0)
+    net = DenseNet([6, K, K, W * W], torch.nn.ReLU).cuda()
+    root = (torch.randn(W, W, device="cuda") / 8).requires_grad_(True)
+    bias = (torch.randn(W, device="cuda") / 8).requires_grad_(True)
+    x0 = torch.randn(N, W, device="cuda", requires_grad=True)
+    gout = torch.randn(N, W, device="cuda")
+    res = {}
+    saved = GF.FACTORIZATION
+    try:
+        for mode in ("node", "edge"):
+            GF.FACTORIZATION = mode
+            for t in (x0, root, bias, *net.parameters()):
+                t.grad = None
+            y = GF.gkn_stack(x0, eas, net, root, bias, root, bias, plan, (0, 1), relu=False,
+                             precision="bf16")
+            y.backward(gout)
+            res[mode] = (y.detach().clone(), x0.grad.clone(), root.grad.clone(), bias.grad.clone(),
+                         {k: v.grad.clone() for k, v in net.named_parameters()})
+    finally:
+        GF.FACTORIZATION = saved
+    yn, dxn, drn, dbn, gn = res["node"]
+    ye, dxe, dre, dbe, ge = res["edge"]
+    assert fro_err(yn, ye) <= BF16_LAYER_TOL
+    assert fro_err(dxn, dxe) <= BF16_STACK_TOL
+    assert fro_err(drn, dre) <= BF16_STACK_TOL and fro_err(dbn, dbe) <= BF16_STACK_TOL
+    for k in gn:
+        assert fro_err(gn[k], ge[k]) <= bf16_grad_tol("net." + k), k
+        assert cosine(gn[k], ge[k]) >= 0.98, k
+
+
 def test_experimental_fused_dh_gives_the_same_gradients_as_the_staged_pass():
     """GKN_FUSED_DH (dh_e from the tcgen05 kernel that synthesises S on the tensor core) against
     the default staged pass on a BBA all-atom frame: same operands, same precision."""
@@ -268,6 +314,8 @@ def test_experimental_fused_dh_gives_the_same_gradients_as_the_staged_pass():
     x0 = torch.randn(N, W, device="cuda")
     eas = ea.index_select(0, plan.perm_long)
     grads = []
+    saved = GF.FACTORIZATION
+    GF.FACTORIZATION = "edge"  # the staged / fused dh passes belong to the edge-first path
     try:
         for fused in (False, True):
             GF.FUSED_DH = fused
@@ -278,5 +326,6 @@ def test_experimental_fused_dh_gives_the_same_gradients_as_the_staged_pass():
             grads.append({k: v.grad.clone() for k, v in net.named_parameters()})
     finally:
         GF.FUSED_DH = False
+        GF.FACTORIZATION = saved
     for k in grads[0]:
         assert fro_err(grads[1][k], grads[0][k]) <= 2 ** -9, k

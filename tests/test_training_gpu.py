@@ -6,12 +6,12 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def make_step(seed=0, frames=4):
+def make_step(seed=0, frames=4, width=32, ker_width=64):
     from molecular_dynamics_neural_operator_b200 import synthetic as syn
     from molecular_dynamics_neural_operator_b200.graph_kernel import KernelNN
     from molecular_dynamics_neural_operator_b200.train import Trainer
 
-    wl = syn.Workload("t", 120, 32, 64, 2, 5.0, 4, 14.0)
+    wl = syn.Workload("t", 120, width, ker_width, 2, 5.0, 4, 14.0)
     traj = syn.trajectory(wl, wl.window + frames + 1, seed=seed)
     xw, y = syn.window_batch(traj, list(range(frames)), wl.window)
     torch.manual_seed(seed)
@@ -28,11 +28,17 @@ def make_step(seed=0, frames=4):
     return model, step
 
 
-def test_training_reduces_the_loss_and_is_deterministic():
-    _, step = make_step()
+@pytest.mark.parametrize("width,ker_width", [(32, 64), (64, 256)], ids=["edge_first", "node_first"])
+def test_training_reduces_the_loss_and_is_deterministic(width, ker_width):
+    """w = 32 / K = 64 trains through the edge-first kernels, w = 64 / K = 256 through the
+    node-first grouped GEMMs (the default wherever it applies)."""
+    from molecular_dynamics_neural_operator_b200 import functional as GF
+
+    assert GF.node_path_supported(width, ker_width, 1, "bf16") == (width == 64)
+    _, step = make_step(width=width, ker_width=ker_width)
     losses = [step() for _ in range(12)]
     assert losses[-1] < 0.9 * losses[0]
-    _, step2 = make_step()
+    _, step2 = make_step(width=width, ker_width=ker_width)
     losses2 = [step2() for _ in range(12)]
     assert losses == losses2  # no atomics on the hot loop => bitwise reproducible
 
