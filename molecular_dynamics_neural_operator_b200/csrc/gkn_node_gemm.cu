@@ -39,7 +39,11 @@ namespace {
 constexpr int kM = 128;      // accumulator rows per unit
 constexpr int kKB = 64;      // reduction elements per k-block (one 128-byte swizzle row)
 constexpr int kUmmaK = 16;
-constexpr int kThreads = 192;
+// epilogue warp groups (4 warps each) taking units alternately.  Measured with 2: node_du 0.582 ->
+// 0.569 ms, node_msg and node_dh 1-2 % slower, step time unchanged - the epilogue is not what
+// paces these kernels, so one group (and 16 KB less shared memory) it is.
+constexpr int kEpiGroups = 1;
+constexpr int kThreads = (2 + 4 * kEpiGroups) * 32;
 constexpr int kABytes = kM * kKB * 2;  // 16 KB
 constexpr int kW = 64;       // node feature width of the backward kernels (MODE_MSG: 32/64/128)
 
@@ -65,7 +69,10 @@ struct NCfg {
     static constexpr int kABoxes = kAMn ? kM / 64 : 1;          // TMA boxes per k-block
     static constexpr int kBBoxes = kBMn ? kBN / 64 : 1;
     static constexpr int kTmemCols = kAcc * kBN;                // 512 / 256
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + 4 * 4096 /*output staging*/;
+    static constexpr int kSmemBytes =
+        kStages * kStageBytes + 1024 + 256 + kEpiGroups * 4 * 4096 /*output staging*/;
+    static_assert(kAcc % kEpiGroups == 0, "accumulator stages are owned by epilogue groups");
+    static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory per CTA");
 };
 
 struct NodeParams {
@@ -80,6 +87,8 @@ struct NodeParams {
     int32_t a_rows_per_app;             // DH: rows of Gs per application (= padded edge count)
     int32_t b_rows_per_app;             // DH: rows of Ut per application (= chunk nodes * K)
     int32_t node_base;                  // first node of the U / Ut / dUt chunk
+    int32_t hints;                      // bit 0: A operand loaded with L2 evict_first; bit 1:
+                                        // streaming (.cs) output stores  (GKN_NODE_HINTS)
 };
 
 struct Unit {
@@ -219,6 +228,7 @@ node_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            const uint64_t pol_stream = l2_policy_evict_first();
             // the next unit's table entry / row pointers are fetched one unit ahead so that their
             // load latency never sits between two units (MODE_DU* units are only ~2 k-blocks long)
             Unit un = v0 < v1 ? decode_unit<MODE, W>(p, v0) : Unit{};
@@ -231,8 +241,14 @@ node_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
 #pragma unroll
                     for (int j = 0; j < C::kABoxes; ++j) {
-                        tma_load_2d(sa + j * kMnBlockBytes, &tmap_a, full_bar(stage),
-                                    u.a_c0 + kb * u.da_c0 + j * 64, u.a_c1 + kb * u.da_c1);
+                        if (p.hints & 1) {
+                            tma_load_2d_hint(sa + j * kMnBlockBytes, &tmap_a, full_bar(stage),
+                                             u.a_c0 + kb * u.da_c0 + j * 64, u.a_c1 + kb * u.da_c1,
+                                             pol_stream);
+                        } else {
+                            tma_load_2d(sa + j * kMnBlockBytes, &tmap_a, full_bar(stage),
+                                        u.a_c0 + kb * u.da_c0 + j * 64, u.a_c1 + kb * u.da_c1);
+                        }
                     }
 #pragma unroll
                     for (int j = 0; j < C::kBBoxes; ++j) {
@@ -290,18 +306,20 @@ node_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5): thread = accumulator row =====================
-        const int q = warp & 3;
+        // ===================== epilogue (warps 2..): thread = accumulator row =====================
+        // kEpiGroups groups of four warps take the units alternately (accumulator stage parity).
+        const int q = warp & 3;               // TMEM lane quarter this warp may access
+        const int grp = (warp - 2) >> 2;      // epilogue group
         const int row = q * 32 + lane;
         const uint32_t lane_addr = uint32_t(q * 32) << 16;
-        const uint32_t stage_smem = bar_base + 256 + q * 4096;  // per-warp output staging tile
+        const uint32_t stage_smem = bar_base + 256 + (grp * 4 + q) * 4096;  // per-warp staging tile
         uint32_t it = 0;
         Unit un = v0 < v1 ? decode_unit<MODE, W>(p, v0) : Unit{};
         for (int64_t v = v0; v < v1; v += vstep) {
             const Unit u = un;
             if (v + vstep < v1) un = decode_unit<MODE, W>(p, v + vstep);
             if (u.nkb == 0) {
-                if constexpr (mode_is_du(MODE)) {
+                if (mode_is_du(MODE) && grp == 0) {
                     uint4* dst = reinterpret_cast<uint4*>(
                         static_cast<__nv_bfloat16*>(p.out) +
                         (int64_t(u.group - p.node_base) * p.K + u.chunk * kM + row) * kW);
@@ -313,6 +331,7 @@ node_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             const uint32_t as = it % kAcc;
             const uint32_t aphase = (it / kAcc) & 1u;
             ++it;
+            if (int(as % kEpiGroups) != grp) continue;  // the other group's unit (kAcc is even)
             if (lane == 0) mbar_wait(tfull_bar(as), aphase);
             __syncwarp();
             tc_fence_after();
@@ -370,7 +389,12 @@ node_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const int r = j * 4 + (lane >> 3), c = lane & 7;
                     const uint4 t = lds128(stage_smem + r * 128 + ((c ^ (r & 7)) << 4));
                     if (r < rows_here) {
-                        *reinterpret_cast<uint4*>(gbase + r * pitch + piece * 128 + c * 16) = t;
+                        uint4* gp = reinterpret_cast<uint4*>(gbase + r * pitch + piece * 128 + c * 16);
+                        if (p.hints & 2) {
+                            __stcs(gp, t);
+                        } else {
+                            *gp = t;
+                        }
                     }
                 }
                 __syncwarp();
@@ -389,6 +413,21 @@ node_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
 }
 
+// cache hints per mode: GKN_NODE_HINTS = "msg,du,dh" (three integers, bit 0 = evict_first loads of
+// the A operand, bit 1 = streaming output stores); defaults chosen by measurement
+int node_hints(int mode) {
+    static int cached[3] = {-1, -1, -1};
+    if (cached[0] < 0) {
+        int v[3] = {0, 0, 0};
+        const char* e = getenv("GKN_NODE_HINTS");
+        if (e != nullptr) sscanf(e, "%d,%d,%d", &v[0], &v[1], &v[2]);
+        cached[1] = v[1];
+        cached[2] = v[2];
+        cached[0] = v[0];
+    }
+    return mode == MODE_MSG ? cached[0] : (mode_is_du(mode) ? cached[1] : cached[2]);
+}
+
 template <int MODE, int W = kW>
 int launch_node_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const NodeParams& p,
                      cudaStream_t stream) {
@@ -402,7 +441,9 @@ int launch_node_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const NodePar
     int64_t grid = p.v_end - p.v_begin;
     if (grid > sms) grid = sms;
     if (grid < 1) return 0;
-    kern<<<dim3(unsigned(grid)), dim3(kThreads), smem, stream>>>(ta, tb, p);
+    NodeParams q = p;
+    q.hints = node_hints(MODE);
+    kern<<<dim3(unsigned(grid)), dim3(kThreads), smem, stream>>>(ta, tb, q);
     GKN_CHECK_LAUNCH("node_gemm launch");
     return 0;
 }
