@@ -264,6 +264,9 @@ def main():
     gen_nnconv(ref, "nnconv_w16_k64", w=16, K=64, n=28, thr=8.0, seed=1)
     gen_nnconv(ref, "nnconv_w32_k64", w=32, K=64, n=40, thr=8.0, seed=2)
     gen_nnconv(ref, "nnconv_w64_k64_isolated", w=64, K=64, n=20, thr=3.0, seed=3, grad_row_stride=16)
+    # w = 64, K = 256: the smallest shape the node-first grouped-GEMM kernels (the default path)
+    # accept; every 16th row of dW3 keeps the fixture at ~5 MB (layers.4.weight alone is 4 MB)
+    gen_nnconv(ref, "nnconv_w64_k256", w=64, K=256, n=48, thr=8.0, seed=9, grad_row_stride=16)
     gen_kernelnn(ref, "kernelnn_w16_k64_d2", w=16, K=64, depth=2, B=2, W=3, R=12, thr=8.0, seed=4)
     gen_kernelnn(ref, "kernelnn_w32_k64_d1", w=32, K=64, depth=1, B=3, W=2, R=10, thr=6.0, seed=5)
     gen_pairdata(ref, "pairdata_n28", n=28, W=3, L=20.0, thr=8.0, seed=6)

@@ -60,7 +60,8 @@ def build_conv(g, precision):
     return conv.cuda()
 
 
-@pytest.mark.parametrize("name", ["nnconv_w16_k64", "nnconv_w32_k64", "nnconv_w64_k64_isolated"])
+@pytest.mark.parametrize("name", ["nnconv_w16_k64", "nnconv_w32_k64", "nnconv_w64_k64_isolated",
+                                  "nnconv_w64_k256"])
 def test_nnconv_fp32_matches_reference_golden(name):
     g = load_golden(name)
     conv = build_conv(g, "fp32")
@@ -78,10 +79,16 @@ def test_nnconv_fp32_matches_reference_golden(name):
         assert rel_err(got, ref) <= 2 * FP32_TOL, k
 
 
-@pytest.mark.parametrize("name", ["nnconv_w32_k64", "nnconv_w64_k64_isolated"])
+@pytest.mark.parametrize("name", ["nnconv_w32_k64", "nnconv_w64_k64_isolated", "nnconv_w64_k256"])
 def test_nnconv_bf16_within_documented_bound(name):
+    """nnconv_w64_k256 (w = 64, K = 256) runs the node-first grouped-GEMM kernels, the others the
+    edge-first contraction: both against vectors produced by the reference's own source."""
+    from molecular_dynamics_neural_operator_b200 import functional as GF
+
     g = load_golden(name)
     conv = build_conv(g, "bf16")
+    w, K = g["sd.root"].shape[0], g["sd.net.layers.0.weight"].shape[0]
+    assert GF.node_path_supported(w, K, 1, "bf16") == (name == "nnconv_w64_k256")
     x = torch.from_numpy(g["x"]).cuda().requires_grad_(True)
     out = conv(x, torch.from_numpy(g["edge_index"]).cuda(), torch.from_numpy(g["edge_attr"]).cuda())
     assert fro_err(out, torch.from_numpy(g["out"])) <= BF16_LAYER_TOL

@@ -7,7 +7,7 @@ import torch
 from oracle import gkn_oracle as orc
 from tests.helpers import grads_of, kernelnn_batch, load_golden, state_dict_of
 
-NNCONV_CASES = ["nnconv_w16_k64", "nnconv_w32_k64", "nnconv_w64_k64_isolated"]
+NNCONV_CASES = ["nnconv_w16_k64", "nnconv_w32_k64", "nnconv_w64_k64_isolated", "nnconv_w64_k256"]
 
 
 @pytest.mark.parametrize("name", NNCONV_CASES)
