@@ -1,6 +1,12 @@
 """Autograd glue for the graph-kernel layer: ONE ``torch.autograd.Function`` for the edge MLP plus
 the whole stack of NNConv applications that share it (reference graph_kernel.py:271-273, :299-302).
 
+Two implementations of the same function sit behind ``gkn_stack``:
+``_GKNStackNode`` (default in bf16 mode at w = 64, and for forward-only calls at w = 32/128) contracts
+W3 with the NODE features first and does the per-edge work as tcgen05 grouped GEMMs - see the
+section "Node-first factorisation" below and DESIGN.md section 1b; ``_GKNStack`` is the edge-first
+fused contraction described next (``GKN_FACTORIZATION=edge``, fp32 mode, other shapes).
+
 Why one Function and not one per layer: the edge hidden state ``h_e`` (output of net.layers.0-.3),
 the last-layer weight W3/b3 and the graph are identical for all 2*depth applications, so
 

@@ -139,9 +139,11 @@ class SourceShard:
 
 
 def shard_frame_by_source(edge_index: torch.Tensor, edge_attr: torch.Tensor, num_nodes: int,
-                          rank: int, world: int, row_ptr: torch.Tensor | None = None) -> SourceShard:
+                          rank: int, world: int, row_ptr: torch.Tensor | None = None,
+                          inv_cnt: torch.Tensor | None = None) -> SourceShard:
     """Equal source-node ranges.  With ``row_ptr`` (edge_index sorted by source, as the radius graph
-    emits it) the local edges are one contiguous slice; otherwise they are selected by a mask."""
+    emits it) the local edges are one contiguous slice; otherwise they are selected by a mask.
+    ``inv_cnt``: 1 / max(global in-degree, 1) if the caller already has it (a full-graph plan)."""
     N = int(num_nodes)
     rows = (N + world - 1) // world
     n0, n1 = min(N, rank * rows), min(N, (rank + 1) * rows)
@@ -151,8 +153,9 @@ def shard_frame_by_source(edge_index: torch.Tensor, edge_attr: torch.Tensor, num
     else:
         sel = ((edge_index[0] >= n0) & (edge_index[0] < n1)).nonzero().squeeze(1)
         ei, ea = edge_index.index_select(1, sel), edge_attr.index_select(0, sel)
-    cnt = torch.bincount(edge_index[1], minlength=N)
-    inv_cnt = 1.0 / cnt.clamp(min=1).float()
+    if inv_cnt is None:
+        cnt = torch.bincount(edge_index[1], minlength=N)
+        inv_cnt = 1.0 / cnt.clamp(min=1).float()
     if ei.size(1) == 0:  # this rank owns no edges: it only takes part in the all-reduce
         return SourceShard(n0, n1, None, None, ea, inv_cnt)
     plan = ops.prepare_graph(ei.contiguous(), N, validate=False)
@@ -179,11 +182,26 @@ def _node_partial_sums(x, shard: SourceShard, hs, w3r, msg):
 
 
 def _node_update(x, sums, inv_cnt, B3, root, bias, relu: bool):
-    """x' = act(mean msg + (mean x_j) @ B3 + x @ root + bias) from the all-reduced sums."""
-    out = torch.addmm(bias, x, root)
-    out.addmm_(sums[1] * inv_cnt[:, None], B3)
-    out.add_(sums[0] * inv_cnt[:, None])
-    return torch.relu_(out) if relu else out
+    """x' = act(mean msg + (mean x_j) @ B3 + x @ root + bias) from the all-reduced sums: the fused
+    node-update kernel with one-element segments (node n "reduces" row n of the summed messages
+    and of the summed x_j), i.e. one pass over the four [N, w] tensors instead of six."""
+    N = x.size(0)
+    ident = _identity_segments(N, x.device)
+    out, _ = ops.segment_matvec(sums[0], None, ident[0], ident[1], sums[1], inv_cnt, B3, x,
+                                root.contiguous(), bias.contiguous(), relu)
+    return out
+
+
+_IDENT_CACHE: dict = {}
+
+
+def _identity_segments(N: int, device):
+    key = (N, str(device))
+    if key not in _IDENT_CACHE:
+        _IDENT_CACHE.clear()  # one graph size at a time
+        _IDENT_CACHE[key] = (torch.arange(N + 1, dtype=torch.int32, device=device),
+                             torch.arange(N, dtype=torch.int32, device=device))
+    return _IDENT_CACHE[key]
 
 
 def _node_shard_setup(shard: SourceShard, net, W: int):
@@ -255,8 +273,10 @@ def kernelnn_forward_sharded(model, data, group=None) -> torch.Tensor:
     if (GF.FACTORIZATION == "node" and data.edge_index.size(1) > 0
             and GF.node_path_supported(x.size(1), K, 1, model.precision, needs_grad=False)):
         # node-first kernels: source ranges, one all-reduce of the partial node sums per application
+        full = getattr(data, "_gkn_plan", None)
         shard = shard_frame_by_source(data.edge_index, data.edge_attr, x.size(0), rank, world,
-                                      getattr(data, "_gkn_row_ptr", None))
+                                      getattr(data, "_gkn_row_ptr", None),
+                                      None if full is None else full.inv_cnt)
         x = sharded_stack_forward_node(x.contiguous(), shard, model.conv1.net, model.conv1.root,
                                        model.conv1.bias, model.conv2.root, model.conv2.bias,
                                        schedule, relu=True, group=group)
