@@ -1,5 +1,7 @@
-"""CPU, world_size 2, gloo: the frame-sharded data-parallel path (GradReducer / Trainer) produces
-the single-process gradient and parameter update.  The GKN kernels themselves need a GPU, so a
+"""CPU, world_size 2, gloo: (1) the frame-sharded data-parallel path (GradReducer / Trainer)
+produces the single-process gradient and parameter update; (2) the source-range sharded rollout of
+the node-first path (sharded.py: partial node sums + all-reduce) gives the unsharded result, with
+the CUDA entry points replaced by their torch restatements (tests/test_node_path_cpu.py).  The GKN kernels themselves need a GPU, so a
 small CPU module with the same structural quirk (one sub-network shared by two layers, reference
 graph_kernel.py:271-273) stands in for the model; the reducer never looks inside the model."""
 import os
@@ -112,3 +114,65 @@ def test_reducer_is_a_noop_without_process_group():
         hi = lo + red.flat[b].numel() * 4
         assert lo <= p.grad.data_ptr() < hi
     red.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# source-range sharding of the node-first rollout (sharded.sharded_stack_forward_node)
+# ------------------------------------------------------------------------------------------------
+def _rollout_case():
+    from oracle import gkn_oracle as orc
+    from tests.test_node_path_cpu import random_graph
+
+    N, E, W, K = 11, 400, 64, 256
+    ei = random_graph(N, E, seed=5, isolated=(4,))
+    g = torch.Generator().manual_seed(6)
+    net_p = orc.make_net_params(6, K, W, seed=7, dtype=torch.float32)
+    net = torch.nn.Module()
+    net.layers = torch.nn.ModuleList([torch.nn.Linear(6, K), torch.nn.ReLU(), torch.nn.Linear(K, K),
+                                      torch.nn.ReLU(), torch.nn.Linear(K, W * W)])
+    with torch.no_grad():
+        for i in (0, 2, 4):
+            net.layers[i].weight.copy_(net_p[f"layers.{i}.weight"])
+            net.layers[i].bias.copy_(net_p[f"layers.{i}.bias"])
+    x0 = torch.randn(N, W, generator=g)
+    ea = torch.randn(E, 6, generator=g)
+    roots = [torch.randn(W, W, generator=g) / 8 for _ in range(2)]
+    biases = [torch.randn(W, generator=g) / 8 for _ in range(2)]
+    return ei, ea, x0, net, roots, biases
+
+
+def rollout_worker(rank, world, port, out):
+    from molecular_dynamics_neural_operator_b200 import sharded
+    from tests.test_node_path_cpu import install_emulation
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        install_emulation(setattr)
+        ei, ea, x0, net, roots, biases = _rollout_case()
+        shard = sharded.shard_frame_by_source(ei, ea, x0.size(0), rank, world)
+        y = sharded.sharded_stack_forward_node(x0, shard, net, roots[0], biases[0], roots[1],
+                                               biases[1], (0, 1, 1), relu=True)
+        out[rank] = y
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_two_rank_source_sharded_rollout_matches_unsharded_stack(monkeypatch):
+    from molecular_dynamics_neural_operator_b200 import functional as GF
+    from tests.test_node_path_cpu import cpu_plan, install_emulation
+
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(rollout_worker, args=(world, free_port(), out), nprocs=world, join=True)
+    install_emulation(monkeypatch.setattr)
+    ei, ea, x0, net, roots, biases = _rollout_case()
+    plan = cpu_plan(ei, x0.size(0))
+    with torch.no_grad():
+        ref = GF.gkn_stack(x0, ea.index_select(0, plan.perm.long()), net, roots[0], biases[0],
+                           roots[1], biases[1], plan, (0, 1, 1), relu=True, precision="bf16")
+    assert torch.equal(out[0], out[1])  # every rank returns the full, identical result
+    err = float((out[0] - ref).abs().max() / ref.abs().max())
+    assert err <= 2.0 ** -9  # fp32 re-association, amplified at most to a few bf16 ulps

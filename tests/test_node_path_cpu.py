@@ -46,7 +46,7 @@ def emu_edge_layer0(ea, w1, b1, out_dtype):
 
 def emu_segment_matvec(rows, perm, seg_ptr, gidx, gnode, scale, M1, nin, M2, bias, relu,
                        want_agg=False):
-    N, W = nin.shape
+    N, W = (nin if nin is not None else gnode).shape
     r = torch.zeros(N, W)
     agg = torch.zeros(N, W)
     for n in range(N):
@@ -57,7 +57,7 @@ def emu_segment_matvec(rows, perm, seg_ptr, gidx, gnode, scale, M1, nin, M2, bia
         agg[n] = gnode[gidx[p].long()].sum(0)
     if scale is not None:
         r, agg = r * scale[:, None], agg * scale[:, None]
-    out = r + agg @ M1 + nin @ M2
+    out = r if M1 is None else r + agg @ M1 + nin @ M2  # M1 = M2 = None: plain segment sums
     if bias is not None:
         out = out + bias
     if relu:
@@ -120,20 +120,26 @@ def emu_node_gather(g, lay, gs, gsT):
         gsT.copy_(rows.t())
 
 
-@pytest.fixture
-def emulated(monkeypatch):
+def install_emulation(setattr_fn):
+    """Replace every CUDA entry point the node-first host code calls by its torch restatement
+    (``setattr_fn(obj, name, value)``: monkeypatch.setattr, or plain setattr in a spawned worker)."""
     for name, fn in [("edge_layer0", emu_edge_layer0), ("segment_matvec", emu_segment_matvec),
                      ("relu_grad_scale", emu_relu_grad_scale),
                      ("mask_cast_colsum", emu_mask_cast_colsum), ("node_msg", emu_node_msg),
                      ("node_du", emu_node_du), ("node_dh", emu_node_dh),
                      ("node_du_mn", emu_node_du_mn), ("node_dh_mn", emu_node_dh_mn),
                      ("node_gather", emu_node_gather)]:
-        monkeypatch.setattr(ops, name, fn)
-    monkeypatch.setattr(GF, "_mm32", lambda a, b: a.float() @ b.float())
-    monkeypatch.setattr(GF, "_addmm32", lambda acc, a, b: acc + a.float() @ b.float())
-    monkeypatch.setattr(
-        torch, "_addmm_activation",
-        lambda b, a, w, **kw: torch.relu(a.float() @ w.float() + b.float()).to(a.dtype))
+        setattr_fn(ops, name, fn)
+    setattr_fn(ops, "prepare_graph", lambda ei, N, validate=True: cpu_plan(ei, N))
+    setattr_fn(GF, "_mm32", lambda a, b: a.float() @ b.float())
+    setattr_fn(GF, "_addmm32", lambda acc, a, b: acc + a.float() @ b.float())
+    setattr_fn(torch, "_addmm_activation",
+               lambda b, a, w, **kw: torch.relu(a.float() @ w.float() + b.float()).to(a.dtype))
+
+
+@pytest.fixture
+def emulated(monkeypatch):
+    install_emulation(monkeypatch.setattr)
 
 
 # ---- layout ----------------------------------------------------------------------------------
