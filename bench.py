@@ -253,7 +253,8 @@ def bench_config(wl, frames_per_gpu, edges_per_frame):
         "batch_note": "reference default batch_size is 128 (graph_kernel.py:318) = 16 frames per GPU "
                       "on 8 GPUs; per-GPU work is fixed as N grows (weak scaling)",
         "factorization": os.environ.get("GKN_FACTORIZATION", "node"),
-        "untimed_steps_before_timing": "max(8, warmup) resident + max(3, warmup) host-fed",
+        "untimed_steps_before_timing": "max(8, warmup) resident + max(3, warmup) host-fed + 2 resident; "
+                                       "Python cyclic GC disabled inside the timed loops",
         "parallelism": "frames sharded over GPUs, bucketed NCCL gradient all-reduce",
         "l2_policy": "per-step working set (h_e alone ~0.12 GB per frame) exceeds the 126 MB L2; "
                      "each step uses a different batch of frames",
@@ -392,11 +393,19 @@ def run_b200_arm(args, wl):
     # warm-up steps vs 124 with 10 in the FIRST process on a box.  Extra untimed settle steps are
     # added in front of the W warm-up steps so that at least 8 steps precede the timed region.
     settle = max(0, 8 - args.warmup)
+    # Host pauses are the remaining source of run-to-run jitter (the device queue holds less than
+    # one step of work, so a 30 ms pause of the enqueueing thread shows up as idle GPU time):
+    # Python's cyclic collector is therefore switched off for the timed loops (nothing here creates
+    # reference cycles per step; a full collection runs first).
+    import gc
     run_loop(build_resident, settle + args.warmup, True)
     # the host-fed loop allocates its H2D staging tensors on the prefetch stream: it needs its own
     # warm-up for the caching allocator to reach a steady state (one step was not enough: +-15 %
     # between otherwise identical runs)
     run_loop(build_e2e, max(3, args.warmup), True)
+    run_loop(build_resident, 2, True)  # back to the resident pattern before it is timed
+    gc.collect()
+    gc.disable()
     if sampler:
         sampler.lines.clear()  # keep only samples taken during the timed loops
     edge_counts.clear()
@@ -415,6 +424,7 @@ def run_b200_arm(args, wl):
         timer = ops.KERNEL_TIMER.collect()
         ops.KERNEL_TIMER.disable()
     clocks = sampler.stop() if sampler else None
+    gc.enable()
     # The literal north-star kernel (edge-first fused tcgen05 contraction, the path that carries the
     # tensor-core-utilisation target) measured in the same process on the same batches: a few
     # steps with GKN_FACTORIZATION=edge semantics, its launches timed like the ones above.
@@ -599,7 +609,7 @@ def run_b200_arm(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames-per-gpu", type=int, default=16,
