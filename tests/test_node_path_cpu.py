@@ -288,6 +288,26 @@ def test_layer0_gradients_agree_with_and_without_edge_attr_gradient(emulated):
     assert grads[1]["ea"].grad is None
 
 
+def test_only_the_node_features_need_a_gradient(emulated):
+    """Frozen edge MLP / roots (e.g. a rollout differentiated w.r.t. its input): no dh pass, no
+    message-gradient stack, dx still through dU."""
+    N, E, K, depth = 6, 150, 256, 1
+    ei, p, depth = _stack_case(N, E, K, depth, seed=8)
+    plan = cpu_plan(ei, N)
+    t = {k: v.clone() for k, v in p.items()}
+    t["x"].requires_grad_(True)
+    out = GF._GKNStackNode.apply(
+        t["x"], t["ea"].index_select(0, plan.perm.long()), t["net.layers.0.weight"],
+        t["net.layers.0.bias"], t["net.layers.2.weight"], t["net.layers.2.bias"],
+        t["net.layers.4.weight"], t["net.layers.4.bias"], t["root1"], t["bias1"], t["root2"],
+        t["bias2"], plan, (0, 1), False, "bf16")
+    ref, tr = _run_oracle_stack(ei, p, depth, relu=False)
+    gout = torch.randn(out.shape, generator=torch.Generator().manual_seed(1))
+    out.backward(gout)
+    ref.backward(gout.double())
+    assert fro(t["x"].grad, tr["x"].grad) < 2.0 ** -5
+
+
 def test_node_path_selection():
     assert GF.node_path_supported(64, 1024, 10, "bf16")
     assert not GF.node_path_supported(32, 1024, 10, "bf16")
