@@ -64,18 +64,31 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     nvcc = find_nvcc()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libgkn_b200.so (set NVCC=/path/to/nvcc)")
-    tmp = LIB_PATH.with_suffix(".so.tmp")
-    cmd = [nvcc, *NVCC_FLAGS, f"-I{INCLUDE}", "-o", str(tmp), *map(str, _sources())]
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if proc.returncode != 0:
-        raise RuntimeError(f"nvcc failed ({proc.returncode}):\n{proc.stdout}\n{proc.stderr}")
-    if verbose:
-        print(proc.stderr)
-    os.replace(tmp, LIB_PATH)
-    HASH_PATH.write_text(_digest() + "\n")
+    # Several ranks of one torchrun job may get here at once with a stale library: serialise the
+    # build with an exclusive file lock, re-check under the lock (the first rank builds, the others
+    # find it current) and give every process its own temporary output name.
+    import fcntl
+
+    with open(LIB_PATH.with_suffix(".so.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and is_current():
+                return LIB_PATH
+            tmp = LIB_PATH.with_suffix(f".so.{os.getpid()}.tmp")
+            cmd = [nvcc, *NVCC_FLAGS, f"-I{INCLUDE}", "-o", str(tmp), *map(str, _sources())]
+            if verbose:
+                cmd.insert(1, "-Xptxas")
+                cmd.insert(2, "-v")
+            proc = subprocess.run(cmd, capture_output=True, text=True)
+            if proc.returncode != 0:
+                tmp.unlink(missing_ok=True)
+                raise RuntimeError(f"nvcc failed ({proc.returncode}):\n{proc.stdout}\n{proc.stderr}")
+            if verbose:
+                print(proc.stderr)
+            os.replace(tmp, LIB_PATH)
+            HASH_PATH.write_text(_digest() + "\n")
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 

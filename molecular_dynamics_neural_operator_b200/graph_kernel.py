@@ -25,37 +25,26 @@ EPS = 1e-15
 
 
 # ------------------------------------------------------------------------------------------------
-# LpLoss — reference graph_kernel.py:75-122 (only .rel is used, :121-122, :547)
+# LpLoss — the relative L2 loss the reference trains with (graph_kernel.py:105-119, used :462, :547)
 # ------------------------------------------------------------------------------------------------
-class LpLoss(object):
-    def __init__(self, d=2, p=2, size_average=True, reduction=True):
-        assert d > 0 and p > 0
-        self.d = d
-        self.p = p
-        self.reduction = reduction
-        self.size_average = size_average
+class LpLoss:
+    """``loss_fn(out, y)`` = per-example ||out_b - y_b||_p / ||y_b||_p, summed
+    (``size_average=False``, the reference's setting), averaged, or un-reduced.  Only the relative
+    form exists here: it is the only one the reference ever calls."""
 
-    def abs(self, x, y):
-        num_examples = x.size()[0]
-        h = 1.0 / (x.size()[1] - 1.0)
-        all_norms = (h ** (self.d / self.p)) * torch.norm(
-            x.reshape(num_examples, -1) - y.reshape(num_examples, -1), self.p, 1)
-        if self.reduction:
-            return torch.mean(all_norms) if self.size_average else torch.sum(all_norms)
-        return all_norms
+    def __init__(self, d: int = 2, p: int = 2, size_average: bool = True, reduction: bool = True):
+        if d <= 0 or p <= 0:
+            raise ValueError("LpLoss: d and p must be positive")
+        self.d, self.p, self.size_average, self.reduction = d, p, size_average, reduction
 
-    def rel(self, x, y):
-        num_examples = x.size()[0]
-        diff_norms = torch.norm(x.reshape(num_examples, -1) - y.reshape(num_examples, -1), self.p, 1)
-        y_norms = torch.norm(y.reshape(num_examples, -1), self.p, 1)
-        if self.reduction:
-            if self.size_average:
-                return torch.mean(diff_norms / y_norms)
-            return torch.sum(diff_norms / y_norms)
-        return diff_norms / y_norms
+    def rel(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        b = x.size(0)
+        ratio = (x.reshape(b, -1) - y.reshape(b, -1)).norm(self.p, 1) / y.reshape(b, -1).norm(self.p, 1)
+        if not self.reduction:
+            return ratio
+        return ratio.mean() if self.size_average else ratio.sum()
 
-    def __call__(self, x, y):
-        return self.rel(x, y)
+    __call__ = rel
 
 
 # ------------------------------------------------------------------------------------------------
@@ -271,11 +260,24 @@ def construct_pairdata(x_position, x_aminoacid, threshold: float = 8.0,
     return data
 
 
+def _forecast_copy(data: PairData, to_cpu: bool) -> PairData:
+    """What the rollout hands back per step: the PairData fields only (no cached CSR plan, padded
+    layout or row pointers - those stay with the step that used them and are freed with it)."""
+    fields = {k: getattr(data, k) for k in PairData._FIELDS}
+    if to_cpu:
+        fields = {k: (v.to("cpu", non_blocking=True) if torch.is_tensor(v) else v)
+                  for k, v in fields.items()}
+    return PairData(**fields)
+
+
 def recursive_propagation(model, dataset, device, num_steps: int, starting_points: list,
-                          threshold: float = 8.0):
+                          threshold: float = 8.0, forecasts_to_cpu: bool = True):
     """Autoregressive rollout (reference graph_kernel.py:396-413) kept on the device: the model
     output becomes the newest window frame and the graph is rebuilt by the radius-graph kernel;
-    no per-step GPU->CPU->GPU round trip."""
+    no per-step GPU->CPU->GPU round trip inside the loop.  As in the reference (:411) the returned
+    forecasts live on the CPU (asynchronous copies, one synchronisation at the end), so a long
+    rollout does not accumulate graphs in HBM; ``forecasts_to_cpu=False`` keeps them on the device
+    (fields only, without the cached plan / layout)."""
     forecasts = []
     net = model.module if hasattr(model, "module") else model
     net.eval()
@@ -287,5 +289,7 @@ def recursive_propagation(model, dataset, device, num_steps: int, starting_point
                 new_x_position = torch.cat([input_.x_position[1:], output.detach()[None]], dim=0)
                 input_ = construct_pairdata(new_x_position, input_.x_aminoacid, threshold=threshold,
                                             device=device)
-                forecasts.append(input_)
+                forecasts.append(_forecast_copy(input_, forecasts_to_cpu))
+    if forecasts_to_cpu and torch.cuda.is_available():
+        torch.cuda.synchronize(device)
     return forecasts

@@ -463,7 +463,8 @@ class NodeLayout:
         return self._qpos_long
 
     def tensors(self):
-        return [self.pptr, self.units, self.qpos, self.src_pad, self.dst_pad] + \
+        extra = [self.unit_first_dev] if self.unit_first_dev is not None else []
+        return [self.pptr, self.units, self.qpos, self.src_pad, self.dst_pad] + extra + \
             list(getattr(self, "_dh_units", {}).values())
 
     def dh_units(self, chunks: int) -> torch.Tensor:

@@ -133,6 +133,9 @@ class BatchPrefetcher:
 
     def submit(self, build_fn) -> None:
         main = torch.cuda.current_stream(self.device)
+        # inputs of build_fn may have been produced on the training stream (a rollout output fed
+        # back in, a trajectory tensor just created): order the side stream after it
+        self.stream.wait_stream(main)
         with torch.cuda.stream(self.stream):
             batch = build_fn()
             ev = torch.cuda.Event()

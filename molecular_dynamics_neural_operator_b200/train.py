@@ -45,6 +45,7 @@ class GradReducer:
             self.buckets.append(cur)
         self.flat: list[torch.Tensor] = []
         self.bucket_of: dict[int, int] = {}
+        self.offset_of: dict[int, int] = {}
         for b, ps in enumerate(self.buckets):
             n = sum(p.numel() for p in ps)
             flat = torch.zeros(n, dtype=ps[0].dtype, device=ps[0].device)
@@ -52,6 +53,7 @@ class GradReducer:
             for p in ps:
                 # gradients live inside the bucket buffer (no pack/unpack copies)
                 p.grad = flat[off:off + p.numel()].view_as(p)
+                self.offset_of[id(p)] = off
                 off += p.numel()
                 self.bucket_of[id(p)] = b
             self.flat.append(flat)
@@ -68,8 +70,15 @@ class GradReducer:
         self.works = []
 
     def zero_grad(self):
+        """Zero the bucket buffers (use this, not optimizer.zero_grad(): the default
+        set_to_none=True would detach the gradients from the buffers that are reduced; the hook
+        re-attaches them if that happens anyway)."""
         for flat in self.flat:
             flat.zero_()
+        for p in self.params:
+            slot = self._slot(p)
+            if p.grad is None or p.grad.data_ptr() != slot.data_ptr():
+                p.grad = slot.view_as(p)
         self.reset()
 
     def _launch(self, b: int):
@@ -84,8 +93,22 @@ class GradReducer:
             w = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         self.works.append(w)
 
+    def _slot(self, p: torch.nn.Parameter) -> torch.Tensor:
+        b, off = self.bucket_of[id(p)], self.offset_of[id(p)]
+        return self.flat[b][off:off + p.numel()]
+
     def _hook(self, p: torch.nn.Parameter):
         b = self.bucket_of[id(p)]
+        slot = self._slot(p)
+        if p.grad is None or p.grad.data_ptr() != slot.data_ptr():
+            # someone (optimizer.zero_grad(set_to_none=True), model.zero_grad()) replaced the view
+            # into the bucket: move the gradient back so that what is reduced is what Adam reads
+            if p.grad is not None:
+                slot.copy_(p.grad.reshape(-1))
+            p.grad = slot.view_as(p)
+        if self.pending[b] <= 0:
+            raise RuntimeError("GradReducer: a second backward() ran before finish(); call "
+                               "Trainer.step / reducer.finish() once per backward")
         self.pending[b] -= 1
         if self.pending[b] == 0:
             self._launch(b)
@@ -96,21 +119,15 @@ class GradReducer:
         for b, left in enumerate(self.pending):
             if left > 0:
                 self._launch(b)
-                self.pending[b] = 0
         for w in self.works:
             w.wait()
         if self.cuda:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
-        self.works = []
+        self.reset()
 
     def close(self):
         for h in self.handles:
             h.remove()
-
-
-def unique_parameters(model: torch.nn.Module) -> list[torch.nn.Parameter]:
-    """Parameters once each (conv2.net aliases conv1.net, reference graph_kernel.py:271-273)."""
-    return list(model.parameters())  # nn.Module.parameters() already de-duplicates shared tensors
 
 
 class Trainer:
@@ -122,7 +139,8 @@ class Trainer:
                  scheduler_step: int = 50, scheduler_gamma: float = 0.8,
                  bucket_bytes: int = 8 << 20, process_group=None):
         self.model = model
-        params = unique_parameters(model)
+        # nn.Module.parameters() de-duplicates the shared edge MLP (conv2.net is conv1.net, :271-273)
+        params = list(model.parameters())
         self.reducer = GradReducer(params, bucket_bytes, process_group)
         # reference: Adam(lr, weight_decay) + StepLR (graph_kernel.py:541-546)
         self.optimizer = torch.optim.Adam(params, lr=lr, weight_decay=weight_decay,
@@ -130,15 +148,23 @@ class Trainer:
         self.scheduler = torch.optim.lr_scheduler.StepLR(self.optimizer, step_size=scheduler_step,
                                                          gamma=scheduler_gamma)
         self.loss_fn = LpLoss(size_average=False)
+        self.last_mse: Optional[torch.Tensor] = None
 
-    def step(self, batch, num_frames: int) -> torch.Tensor:
+    def step(self, batch, num_frames: int, with_mse: bool = False) -> torch.Tensor:
         self.reducer.zero_grad()
         out = self.model(batch)
         loss = self.loss_fn(out.view(num_frames, -1), batch.y.view(num_frames, -1))
         loss.backward()
         self.reducer.finish()
         self.optimizer.step()
+        if with_mse:  # the reference logs it beside the loss (graph_kernel.py:465)
+            self.last_mse = torch.nn.functional.mse_loss(out.detach(), batch.y)
         return loss.detach()
+
+    def end_epoch(self) -> float:
+        """`scheduler.step()` once per epoch (reference graph_kernel.py:622); returns the new lr."""
+        self.scheduler.step()
+        return float(self.scheduler.get_last_lr()[0])
 
 
 def shard_frames(num_frames: int, rank: int, world: int) -> range:
@@ -148,7 +174,7 @@ def shard_frames(num_frames: int, rank: int, world: int) -> range:
 
 def broadcast_parameters(model: torch.nn.Module, src: int = 0, process_group=None) -> None:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1:
-        for p in unique_parameters(model):
+        for p in model.parameters():
             dist.broadcast(p.data, src=src, group=process_group)
         for b in model.buffers():
             dist.broadcast(b.data, src=src, group=process_group)
@@ -157,14 +183,21 @@ def broadcast_parameters(model: torch.nn.Module, src: int = 0, process_group=Non
 # --------------------------------------------------------------------------------------------
 # Epoch loops and checkpoints with the reference's layout (graph_kernel.py:445-493, :631-639)
 # --------------------------------------------------------------------------------------------
-def train_epoch(trainer: Trainer, batches, frames_per_batch: int):
-    """`train` of the reference (graph_kernel.py:445-474) over an iterable of batched PairData."""
+def train_epoch(trainer: Trainer, batches, frames_per_batch: int, with_mse: bool = False):
+    """`train` of the reference (graph_kernel.py:445-474) over an iterable of batched PairData:
+    mean loss per batch (and mean MSE with ``with_mse``).  The losses stay on the device until the
+    epoch ends, so the loop never waits for the GPU."""
     trainer.model.train()
-    total, n = 0.0, 0
+    losses, mses = [], []
     for batch in batches:
-        total += float(trainer.step(batch, frames_per_batch))
-        n += 1
-    return total / max(n, 1)
+        losses.append(trainer.step(batch, frames_per_batch, with_mse=with_mse))
+        if with_mse:
+            mses.append(trainer.last_mse)
+    n = max(len(losses), 1)
+    loss = float(torch.stack(losses).sum()) / n if losses else 0.0
+    if with_mse:
+        return loss, (float(torch.stack(mses).sum()) / n if mses else 0.0)
+    return loss
 
 
 @torch.no_grad()
@@ -173,13 +206,15 @@ def validate(model: torch.nn.Module, batches, frames_per_batch: int):
     model.eval()
     loss_fn = LpLoss(size_average=False)
     mse_fn = torch.nn.MSELoss()
-    tot_loss, tot_mse, n = 0.0, 0.0, 0
+    losses, mses = [], []
     for batch in batches:
         out = model(batch)
-        tot_loss += float(loss_fn(out.view(frames_per_batch, -1), batch.y.view(frames_per_batch, -1)))
-        tot_mse += float(mse_fn(out, batch.y))
-        n += 1
-    return tot_loss / max(n, 1), tot_mse / max(n, 1)
+        losses.append(loss_fn(out.view(frames_per_batch, -1), batch.y.view(frames_per_batch, -1)))
+        mses.append(mse_fn(out, batch.y))
+    n = max(len(losses), 1)
+    if not losses:
+        return 0.0, 0.0
+    return float(torch.stack(losses).sum()) / n, float(torch.stack(mses).sum()) / n
 
 
 def save_checkpoint(path, epoch: int, trainer: Trainer, dataparallel_prefix: bool = True) -> None:
@@ -208,3 +243,44 @@ def load_checkpoint(path, model: torch.nn.Module, trainer: Optional[Trainer] = N
         if "scheduler_state_dict" in ckpt:
             trainer.scheduler.load_state_dict(ckpt["scheduler_state_dict"])
     return int(ckpt.get("epoch", 0))
+
+
+def fit(trainer: Trainer, train_batches, valid_batches, frames_per_batch: int, epochs: int,
+        run_path=None, metrics_file: str = "metrics.jsonl", start_epoch: int = 0,
+        best_loss: float = float("inf"), log=None) -> list[dict]:
+    """The epoch loop of the reference's ``main`` (graph_kernel.py:583-639) without W&B, movies
+    and plots: train, validate, one JSON line of metrics per epoch (in place of ``wandb.log``,
+    :618-621), ``scheduler.step()`` (:622) and ``best.pt`` whenever the validation loss improves
+    (:631-639, same dictionary, ``module.``-prefixed keys).  ``train_batches`` / ``valid_batches``
+    are callables returning a fresh iterable per epoch, or re-iterable containers.  Under
+    torch.distributed only rank 0 writes files.  Returns the list of per-epoch records."""
+    import json
+    import os
+    from timeit import default_timer
+
+    rank0 = not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
+    if run_path is not None and rank0:
+        os.makedirs(run_path, exist_ok=True)
+    history = []
+    for epoch in range(start_epoch, start_epoch + epochs):
+        t0 = default_timer()
+        tb = train_batches() if callable(train_batches) else train_batches
+        vb = valid_batches() if callable(valid_batches) else valid_batches
+        train_loss, train_mse = train_epoch(trainer, tb, frames_per_batch, with_mse=True)
+        valid_loss, valid_mse = validate(trainer.model, vb, frames_per_batch)
+        lr_used = float(trainer.optimizer.param_groups[0]["lr"])
+        trainer.end_epoch()
+        rec = {"epoch": epoch, "avg_train_loss": train_loss, "avg_valid_loss": valid_loss,
+               "avg_train_mse": train_mse, "avg_valid_mse": valid_mse, "lr": lr_used,
+               "time_s": default_timer() - t0, "best": valid_loss < best_loss}
+        history.append(rec)
+        if log is not None:
+            log(rec)
+        if run_path is not None and rank0:
+            with open(os.path.join(run_path, metrics_file), "a") as f:
+                f.write(json.dumps(rec) + "\n")
+        if valid_loss < best_loss:
+            best_loss = valid_loss
+            if run_path is not None and rank0:
+                save_checkpoint(os.path.join(run_path, "best.pt"), epoch, trainer)
+    return history
