@@ -138,6 +138,57 @@ int gkn_node_dh_mn_bf16(const void* gs_bf16, const void* u_bf16, const int32_t* 
 int gkn_node_gather_bf16(const float* g, const int32_t* idx, int64_t E_pad, void* gs_bf16,
                          void* gsT_bf16, int32_t W, void* stream);
 
+/* ---- node-first factorisation, fused producer/consumer (tcgen05) ------------------------------
+ * One persistent kernel per NNConv application that BOTH produces U = x @ W3r with the tensor
+ * core and consumes it in the grouped message GEMM (NNConv_old.message, graph_kernel.py:200-202)
+ * while it is still in the L2 - U never takes the HBM round trip of the two-kernel form above.
+ * The kernel executes a host-ordered list of work items, dealt round-robin over one CTA per SM;
+ * an item is 8 int32:
+ *     (kind, r0, r1, r2,  wait_idx, wait_target, signal_idx, r3)
+ *   kind 0 "P": U[r2 + i, r1 .. r1+256) = x[r0 + i, :] @ W3r[:, r1 .. r1+256) for i < r3 (<= 128)
+ *   kind 1 "C": msg[r0 + i, :] = hs[r0 + i, :] @ U[r2]^T for i < r1 (<= 128)   (U[r2]: [W, K])
+ *   kind 2    : no-op
+ *   wait_idx >= 0: the item waits until flags[wait_idx] >= wait_target (C: before it reads U;
+ *   P: before it overwrites its rows of U - the "ring" use, where U holds a few node blocks only);
+ *   signal_idx >= 0: each of the 4 epilogue warps adds 1 to flags[signal_idx] when the item's
+ *   output is in memory.  Every wait must refer to items that precede the waiter in list order
+ *   (the list is executed in order by every CTA; all CTAs are co-resident).
+ * x bf16 [N, max(W,64)] (zero padded), w3r bf16 [max(W,64), W*K] = layers.4.weight viewed
+ * [i, (o,k)] (zero rows beyond W), hs bf16 [E_pad, K], u bf16 [u_rows, W*K], msg fp32 [E_pad, W],
+ * flags int32 (zeroed by the caller before the launch).  hs and msg may be NULL when E_pad = 0
+ * (P items only: a plain dense GEMM).  W in {32, 64, 128}, K % 256 == 0. */
+int gkn_node_fused_fwd_bf16(const void* x_bf16, const void* w3r_bf16, const void* hs_bf16,
+                            void* u_bf16, const int32_t* items, int64_t num_items, int32_t* flags,
+                            float* msg, int64_t N, int64_t E_pad, int64_t u_rows, int32_t K,
+                            int32_t W, void* stream);
+
+/* Fused backward of one application (w = 64): the gradient w.r.t. U is produced by "D" items
+ * (dU[n][k,o] = sum_{e: src e = n} hs[e,k] * gs[e,o], as gkn_node_du_mn_bf16) into a ring of node
+ * blocks and consumed from the L2 by "X" items that feed BOTH
+ *     dwT[(k,o), i] (+)= sum_n dU[n][(k,o)] * x[n, i]           (gradient of layers.4.weight,
+ *                                                                 accumulated in TMEM for the launch)
+ *     dx_part[c][n, i] = sum_{(k,o) in slice(c)} dU[n][(k,o)] * w3k[i, (k,o)]
+ * from one read of dU; CTA c owns a fixed slice of the w*K columns, gkn_sum_partials adds the
+ * `parts` partial dx tensors in a fixed order.  Items (8 int32, as above):
+ *   kind 0 "D": (0, node, chunk of 128 k-rows, row of the dU buffer, wait_idx, target, signal_idx, 0)
+ *   kind 1 "X": (1, first node of the block, first dU row of the block, valid rows <= 128, ...)
+ *               must sit at list positions == CTA index (mod grid), one per CTA and block
+ * gkn_node_fused_bwd_grid returns the grid size the X items must be laid out for (one CTA per SM)
+ * and the number of dx partials.  hs bf16 [E_pad,K]; gs bf16 [E_pad,64] (zero pad rows); pptr int32
+ * [N+1]; x bf16 [N,64]; w3k bf16 [64, K*64] = layers.4.weight as [i, (k,o)]; du bf16
+ * [du_rows, K*64] (zero-initialised once by the caller); dx_part fp32 [parts,N,64] or NULL (dx not
+ * needed); dwT fp32 [K*64, 64] or NULL; accumulate_dw: add to dwT instead of overwriting it. */
+int gkn_node_fused_bwd_grid(int32_t K, int32_t W, int32_t* grid, int32_t* parts);
+int gkn_node_fused_bwd_bf16(const void* hs_bf16, const void* gs_bf16, const int32_t* pptr,
+                            const void* x_bf16, const void* w3k_bf16, void* du_bf16,
+                            const int32_t* items, int64_t num_items, int32_t* flags,
+                            float* dx_part, float* dwT, int32_t accumulate_dw, int64_t N,
+                            int64_t E_pad, int64_t du_rows, int32_t K, int32_t W, void* stream);
+/* out[j] = (addend ? addend[j] : 0) + sum_{c < parts} part[c*n + j], summed in order of c
+ * (n % 4 == 0; out may alias addend). */
+int gkn_sum_partials(const float* part, int32_t parts, int64_t n, const float* addend, float* out,
+                     void* stream);
+
 /* ---- segmented mean / sums (replaces PyG aggregate(aggr="mean") + NNConv_old.update,
  *      graph_kernel.py:204-209, and their autograd) --------------------------------------- */
 /* out[n,:] = act( inv_cnt[n] * sum_{p in [dst_ptr[n],dst_ptr[n+1])} (msg[p,:] + xb3[src_s[p],:])

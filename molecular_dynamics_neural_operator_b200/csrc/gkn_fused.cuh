@@ -1,0 +1,69 @@
+// Shared device helpers of the fused producer/consumer kernels (gkn_node_fused.cu,
+// gkn_node_fused_bwd.cu): the work-item record, cross-CTA counters, epilogue staging primitives.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace gkn {
+namespace fused {
+
+// One work item = two int4 words; the meaning of r0..r3 depends on the kind (see the kernels).
+//   a = (kind, r0, r1, r2)      b = (wait_idx, wait_target, signal_idx, r3)
+// wait_idx >= 0: the item waits until flags[wait_idx] >= wait_target; signal_idx >= 0: each of the
+// four epilogue warps adds 1 to flags[signal_idx] when the item's output is in memory.
+struct Item {
+    int4 a, b;
+};
+
+__device__ __forceinline__ Item load_item(const Item* items, int64_t v) {
+    Item it;
+    const int4* p = reinterpret_cast<const int4*>(items + v);
+    it.a = __ldg(p);
+    it.b = __ldg(p + 1);
+    return it;
+}
+
+__device__ __forceinline__ int32_t ld_acquire(const int32_t* p) {
+    int32_t v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// orders this thread's later async-proxy (TMA) accesses to global memory after the generic-proxy
+// writes it has just observed through an acquire load
+__device__ __forceinline__ void fence_proxy_async_global() {
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+
+// Spin until a counter written by other CTAs reaches `target` (watchdog: trap instead of hanging).
+__device__ __forceinline__ void wait_counter(const int32_t* flag, int32_t target) {
+    uint32_t spins = 0;
+    while (ld_acquire(flag) < target) {
+        __nanosleep(64);
+        if (++spins > (1u << 25)) __trap();
+    }
+}
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y),
+                 "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(addr)
+                 : "memory");
+    return v;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+
+}  // namespace fused
+}  // namespace gkn

@@ -230,6 +230,17 @@ _MLP_SIDE_GEMM = os.environ.get("GKN_MLP_SIDE_GEMM", "1") == "1"
 # U of every application ([A, N, w*K] bf16) is kept for the dh pass when it fits this budget
 # (6.3 GB for 8 BBA frames); otherwise it is recomputed node range by node range in backward
 _SAVE_U_BYTES = int(os.environ.get("GKN_NODE_SAVE_U_MB", "24576")) << 20
+# Fused producer/consumer forward (csrc/gkn_node_fused.cu): U = x W3r is produced by the same
+# kernel that consumes it and crosses the L2 instead of HBM.  GKN_NODE_FUSED=0 selects the
+# two-kernel form (library GEMM + grouped message kernel).
+NODE_FUSED = os.environ.get("GKN_NODE_FUSED", "1") == "1"
+# node blocks of the U ring when U is not kept for the backward (forward-only calls)
+_FUSED_RING = int(os.environ.get("GKN_NODE_FUSED_RING", "4"))
+_FUSED_SLACK = float(os.environ.get("GKN_NODE_FUSED_SLACK", "0.5"))
+# Fused backward (csrc/gkn_node_fused_bwd.cu): dU is produced into a ring of node blocks and
+# consumed from the L2 by the weight-gradient / dx products of the same launch.
+NODE_FUSED_BWD = os.environ.get("GKN_NODE_FUSED_BWD", "1") == "1"
+_FUSED_BWD_RING = int(os.environ.get("GKN_NODE_FUSED_BWD_RING", "3"))
 
 
 def node_path_supported(W: int, K: int, E: int, precision: str, needs_grad: bool = True) -> bool:
@@ -272,9 +283,23 @@ class _GKNStackNode(torch.autograd.Function):
         u_all = None
         if NODE_MN and want_agg and A * N * W * K * 2 <= _SAVE_U_BYTES:
             u_all = torch.empty((A, N, W * K), dtype=bf, device=x.device)
+        fused = None
+        if NODE_FUSED and (u_all is not None or not want_agg):
+            # one launch per application: U tiles are produced and consumed inside it.  With a
+            # backward to come U is written to the kept buffer; forward-only calls use a small ring
+            ring = 0 if u_all is not None else _FUSED_RING
+            fused = ops.fused_fwd_schedule(lay, W, K, ring=ring, slack=_FUSED_SLACK)
+            flags = torch.zeros((A, fused.num_flags), dtype=torch.int32, device=x.device)
+            u_ring = None if u_all is not None else torch.empty((fused.u_rows, W * K), dtype=bf,
+                                                                device=x.device)
+            w3p = w3r if W >= 64 else torch.cat([w3r, torch.zeros_like(w3r)], 0)
         for a, c in enumerate(schedule):
             xb = x.to(bf)
-            if u_all is not None:
+            if fused is not None:
+                xp = xb if W >= 64 else torch.cat([xb, torch.zeros_like(xb)], 1)
+                ops.node_fused_fwd(xp, w3p, hs, u_all[a] if u_all is not None else u_ring, fused,
+                                   flags[a], msg, N, lay.e_pad, K, W)
+            elif u_all is not None:
                 torch.mm(xb, w3r, out=u_all[a])   # [N, (o, k)], kept for the dh pass
                 ops.node_msg(hs, u_all[a].view(N, W, K), lay, 0, lay.num_units, 0, msg)
             else:
@@ -326,7 +351,22 @@ class _GKNStackNode(torch.autograd.Function):
         elif not need_edge:
             gs_one = torch.empty((lay.e_pad, W), dtype=bf, device=dev)
         gs_all = torch.empty((A, lay.e_pad, W), dtype=bf, device=dev) if need_edge else None
-        dw3k = torch.zeros((W, K * W), dtype=torch.float32, device=dev) if need_edge else None
+        fused_bwd = NODE_FUSED_BWD and NODE_MN and W == 64
+        if fused_bwd:
+            try:
+                bsched = ops.fused_bwd_schedule(N, K, W, dev, ring=_FUSED_BWD_RING)
+            except RuntimeError:  # fewer SMs than the column slicing of this kernel width needs
+                fused_bwd = False
+        dw3k = dwT = None
+        if need_edge and not fused_bwd:
+            dw3k = torch.zeros((W, K * W), dtype=torch.float32, device=dev)
+        if fused_bwd:
+            _, parts = ops.fused_bwd_grid(K, W)
+            du_ring = torch.zeros((bsched.u_rows, K * W), dtype=bf, device=dev)
+            bflags = torch.zeros((A, bsched.num_flags), dtype=torch.int32, device=dev)
+            dx_part = torch.empty((parts, N, W), dtype=torch.float32, device=dev)
+            dwT = torch.empty((K * W, W), dtype=torch.float32, device=dev) if need_edge else None
+            first_dw = True
         chunks = _node_chunks(N, W * K * 2)
         gs = [None] * A
         xbs = [None] * A
@@ -342,6 +382,17 @@ class _GKNStackNode(torch.autograd.Function):
             gs_a = gs_all[a] if need_edge else gs_one
             ops.node_gather(gn, lay, gs_a, gsT)
             xbs[a] = xs[a].to(bf)
+            if fused_bwd:
+                ops.node_fused_bwd(hs, gs_a, lay, xbs[a], w3kq, du_ring, bsched, bflags[a],
+                                   dx_part if need_dx else None, dwT, not first_dw)
+                first_dw = False
+                if need_dx:
+                    rest_g, _ = ops.segment_matvec(None, plan.src_perm, plan.src_ptr, plan.dst, gn,
+                                                   None, B3T, g, rootsT[c], None, False)
+                    gx = ops.sum_partials(dx_part, rest_g, rest_g)
+                else:
+                    gx = None
+                continue
             dxc = torch.empty((N, W), dtype=torch.float32, device=dev) if need_dx else None
             for n0, n1 in chunks:
                 dut = torch.empty((n1 - n0, K * W), dtype=bf, device=dev)
@@ -361,6 +412,10 @@ class _GKNStackNode(torch.autograd.Function):
                 gx = rest_g.add_(dxc)
             else:
                 gx = None
+        if fused_bwd:
+            del du_ring, dx_part
+            if need_edge:
+                dw3k = dwT.t()  # [i, (k, o)]
         del hsT, gsT, gs_one
         G = torch.stack(gs)
         X = torch.stack(xs[:A])
@@ -376,7 +431,7 @@ class _GKNStackNode(torch.autograd.Function):
         dw3 = db3 = dw2 = db2 = dw1 = db1 = dea = None
         if need_edge:
             db3 = torch.bmm(torch.stack(list(aggs)).transpose(1, 2), G).sum(0).reshape(-1)
-            dw3 = dw3k.view(W, K, W).permute(0, 2, 1).reshape(W * W, K)
+            dw3 = dw3k.reshape(W, K, W).permute(0, 2, 1).reshape(W * W, K)
             # dh_e for all applications at once, node range by node range (U^T recomputed)
             dh = torch.empty((lay.e_pad, K), dtype=bf, device=dev)
             if u_all is not None:

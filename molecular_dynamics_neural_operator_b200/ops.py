@@ -465,7 +465,8 @@ class NodeLayout:
     def tensors(self):
         extra = [self.unit_first_dev] if self.unit_first_dev is not None else []
         return [self.pptr, self.units, self.qpos, self.src_pad, self.dst_pad] + extra + \
-            list(getattr(self, "_dh_units", {}).values())
+            list(getattr(self, "_dh_units", {}).values()) + \
+            [s.items for s in getattr(self, "_fused_sched", {}).values()]
 
     def dh_units(self, chunks: int) -> torch.Tensor:
         """int32 [U*chunks, 4] = (source node, first row, rows, column chunk) in (node, chunk,
@@ -641,3 +642,216 @@ def node_gather(g, lay: NodeLayout, gs: torch.Tensor | None, gsT: torch.Tensor |
                                      _p(gsT, torch.bfloat16, "gsT"), W, _stream()),
             "gkn_node_gather_bf16",
         )
+
+
+# ------------------------------------------------------------------------------------------------
+# Fused producer/consumer forward of the node-first path (csrc/gkn_node_fused.cu)
+# ------------------------------------------------------------------------------------------------
+FUSED_BLOCK = 128     # nodes per block of U (the M tile of the producer GEMM)
+FUSED_TILE_COLS = 256  # columns of U per producer tile
+IT_P, IT_C, IT_NOP = 0, 1, 2
+
+
+@dataclass
+class FusedSchedule:
+    """Work-item list of gkn_node_fused_fwd_bf16 for one padded layout (see gkn_b200.h).
+
+    Order: the producer tiles of node block b are spread over list positions [b-1, b) (in units of
+    one block's worth of work) and the message units of block b over [b+slack, b+1+slack): the
+    tiles of a block are complete ``slack`` blocks before its first consumer needs them and live
+    for at most ~2.5 blocks (40 MB at w = 64) - inside the L2.  ``ring`` > 0: U is a ring of that
+    many node blocks; a producer tile of block b then waits for the consumers of block b - ring."""
+
+    items: torch.Tensor   # int32 [num_items, 8]
+    num_items: int
+    num_flags: int
+    u_rows: int           # rows ([W, K] slabs) of the U buffer the items address
+    ring: int
+
+
+def fused_fwd_schedule(lay: NodeLayout, W: int, K: int, ring: int = 0,
+                       slack: float = 0.5) -> FusedSchedule:
+    """Build (cached on the layout) the item list.  Device-side index arithmetic only."""
+    cache = lay.__dict__.setdefault("_fused_sched", {})
+    key = (W, K, ring, slack)
+    if key in cache:
+        return cache[key]
+    if ring and ring < 2 + slack:
+        raise ValueError("fused_fwd_schedule: the ring must hold at least 2 + slack node blocks "
+                         "(a tile may only wait for consumers that precede it in the list)")
+    dev = lay.units.device
+    N, U = lay.num_nodes, lay.num_units
+    NB = (N + FUSED_BLOCK - 1) // FUSED_BLOCK
+    J = W * K // FUSED_TILE_COLS
+    i64 = dict(dtype=torch.long, device=dev)
+    # units per node block, from the per-node unit offsets (no host read)
+    edges = torch.arange(0, NB + 1, **i64).mul_(FUSED_BLOCK).clamp_(max=N)
+    ufirst_blk = lay.unit_first_dev[edges]           # [NB+1]
+    T = ufirst_blk.diff()                             # C items per block
+    # ---- producer tiles
+    b = torch.arange(NB, **i64).repeat_interleave(J)
+    j = torch.arange(J, **i64).repeat(NB)
+    p_key = (b - 1).double() + (j.double() + 0.5) / J
+    neg = torch.full_like(b, -1)
+    if ring:
+        slot = b % ring
+        p_wait = torch.where(b >= ring, NB + b - ring, neg)
+        p_target = torch.where(b >= ring, 4 * T[(b - ring).clamp_(min=0)], torch.zeros_like(b))
+    else:
+        slot, p_wait, p_target = b, neg, torch.zeros_like(b)
+    p_items = torch.stack([torch.full_like(b, IT_P), b * FUSED_BLOCK, j * FUSED_TILE_COLS,
+                           slot * FUSED_BLOCK, p_wait, p_target, b,
+                           (N - b * FUSED_BLOCK).clamp_(max=FUSED_BLOCK)], 1)
+    # ---- message units
+    u = lay.units.long()
+    grp, row0, rows = u[:, 0], u[:, 1], u[:, 2]
+    blk = grp // FUSED_BLOCK
+    t = torch.arange(U, **i64) - ufirst_blk[blk]
+    c_key = blk.double() + slack + (t.double() + 0.5) / T[blk].clamp(min=1).double()
+    urow = (blk % ring) * FUSED_BLOCK + grp % FUSED_BLOCK if ring else grp
+    c_items = torch.stack([torch.full_like(grp, IT_C), row0, rows, urow, blk,
+                           torch.full_like(grp, 4 * J), NB + blk if ring else torch.full_like(grp, -1),
+                           torch.zeros_like(grp)], 1)
+    keys = torch.cat([p_key, c_key])
+    order = torch.argsort(keys, stable=True)
+    items = torch.cat([p_items, c_items])[order].int().contiguous()
+    sched = FusedSchedule(items, int(items.size(0)), 2 * NB, ring * FUSED_BLOCK if ring else N, ring)
+    cache[key] = sched
+    return sched
+
+
+def node_fused_fwd(xb, w3r, hs, u, sched: FusedSchedule, flags, msg, N: int, e_pad: int, K: int,
+                   W: int) -> None:
+    """One NNConv application's U production + message GEMM in one launch
+    (gkn_node_fused_fwd_bf16).  xb bf16 [N, max(W,64)]; w3r bf16 [max(W,64), W*K]; hs bf16
+    [e_pad, K]; u bf16 [sched.u_rows, W*K] (written, and read back through the L2); flags int32
+    [sched.num_flags], zero on entry; msg fp32 [e_pad, W]."""
+    lib = _lib.load()
+    Wp = max(W, 64)
+    if xb.shape != (N, Wp) or w3r.shape != (Wp, W * K):
+        raise ValueError(f"node_fused_fwd: xb must be [{N}, {Wp}] and w3r [{Wp}, {W * K}]")
+    if u.numel() != sched.u_rows * W * K:
+        raise ValueError("node_fused_fwd: the U buffer does not match the schedule")
+    if flags.numel() < sched.num_flags:
+        raise ValueError("node_fused_fwd: flags too small")
+    with torch.cuda.device(xb.device), _timed("node_fused_fwd"):
+        _lib.check(
+            lib.gkn_node_fused_fwd_bf16(
+                _p(xb, torch.bfloat16, "xb"), _p(w3r, torch.bfloat16, "w3r"),
+                _p(hs, torch.bfloat16, "hs"), _p(u, torch.bfloat16, "u"),
+                _p(sched.items, torch.int32, "items"), sched.num_items,
+                _p(flags, torch.int32, "flags"), _p(msg, torch.float32, "msg"), N, e_pad,
+                sched.u_rows, K, W, _stream()),
+            "gkn_node_fused_fwd_bf16",
+        )
+
+
+# ------------------------------------------------------------------------------------------------
+# Fused backward of one application (csrc/gkn_node_fused_bwd.cu)
+# ------------------------------------------------------------------------------------------------
+IT_D, IT_X = 0, 1
+_BWD_SCHED_CACHE: dict = {}
+
+
+def fused_bwd_grid(K: int, W: int) -> tuple[int, int]:
+    """(grid size the X items are laid out for, number of dx partials) on the current device."""
+    import ctypes
+
+    lib = _lib.load()
+    g, parts = ctypes.c_int32(0), ctypes.c_int32(0)
+    _lib.check(lib.gkn_node_fused_bwd_grid(K, W, ctypes.byref(g), ctypes.byref(parts)),
+               "gkn_node_fused_bwd_grid")
+    return int(g.value), int(parts.value)
+
+
+def fused_bwd_items(N: int, K: int, W: int, grid: int, ring: int):
+    """Host-side construction of the item list of gkn_node_fused_bwd_bf16 (numpy int32 [n, 8]).
+    It depends only on (N, K, grid, ring) - every node has K/128 "D" items whether or not it has
+    edges - so it is built once and cached.
+
+    Order: all D items of block 0; then for every block b: the first half of D(b+1), no-ops up to
+    a multiple of `grid`, the `grid` X items of block b (one per CTA), the second half of D(b+1).
+    So the gradient tiles of a block are complete half a block before they are consumed and the
+    ring slot of block b is free again (X(b) done) before D(b+2) starts."""
+    import numpy as np
+
+    if ring < 2:
+        raise ValueError("fused_bwd_items: the dU ring must hold at least 2 node blocks")
+    C = K // 128
+    NB = (N + FUSED_BLOCK - 1) // FUSED_BLOCK
+    nodes_of = [min(FUSED_BLOCK, N - FUSED_BLOCK * b) for b in range(NB)]
+
+    def d_items(b):
+        n = np.repeat(np.arange(nodes_of[b], dtype=np.int64), C) + FUSED_BLOCK * b
+        c = np.tile(np.arange(C, dtype=np.int64), nodes_of[b])
+        out = np.zeros((n.size, 8), dtype=np.int64)
+        out[:, 0], out[:, 1], out[:, 2] = IT_D, n, c
+        out[:, 3] = (b % ring) * FUSED_BLOCK + n % FUSED_BLOCK
+        out[:, 4] = NB + b - ring if b >= ring else -1
+        out[:, 5] = 4 * grid if b >= ring else 0
+        out[:, 6] = b
+        return out
+
+    def x_items(b):
+        out = np.zeros((grid, 8), dtype=np.int64)
+        out[:, 0], out[:, 1], out[:, 2] = IT_X, FUSED_BLOCK * b, (b % ring) * FUSED_BLOCK
+        out[:, 3] = nodes_of[b]
+        out[:, 4], out[:, 5], out[:, 6] = b, 4 * nodes_of[b] * C, NB + b
+        return out
+
+    nop = np.zeros((1, 8), dtype=np.int64)
+    nop[0, 0], nop[0, 4], nop[0, 6] = IT_NOP, -1, -1
+    chunks, count = [d_items(0)], nodes_of[0] * C
+    for b in range(NB):
+        nxt = d_items(b + 1) if b + 1 < NB else np.zeros((0, 8), dtype=np.int64)
+        h = nxt.shape[0] // 2
+        pad = (-(count + h)) % grid
+        chunks += [nxt[:h], np.repeat(nop, pad, 0), x_items(b), nxt[h:]]
+        count += nxt.shape[0] + pad + grid
+    return np.concatenate(chunks).astype(np.int32), 2 * NB
+
+
+def fused_bwd_schedule(N: int, K: int, W: int, device, ring: int = 3) -> FusedSchedule:
+    grid, _ = fused_bwd_grid(K, W)
+    key = (N, K, W, grid, ring, str(device))
+    if key not in _BWD_SCHED_CACHE:
+        items, nflags = fused_bwd_items(N, K, W, grid, ring)
+        t = torch.from_numpy(items).to(device)
+        _BWD_SCHED_CACHE[key] = FusedSchedule(t, int(t.size(0)), nflags, ring * FUSED_BLOCK, ring)
+    return _BWD_SCHED_CACHE[key]
+
+
+def node_fused_bwd(hs, gs, lay: NodeLayout, xb, w3k, du, sched: FusedSchedule, flags, dx_part, dwT,
+                   accumulate_dw: bool) -> None:
+    """dU produced and consumed in one launch: dwT (+)= dU^T-by-x products, dx partials per CTA
+    (gkn_node_fused_bwd_bf16).  du: the zero-initialised ring [sched.u_rows, W*K] bf16."""
+    lib = _lib.load()
+    K, W = int(hs.size(1)), int(gs.size(1))
+    N = lay.num_nodes
+    if du.numel() != sched.u_rows * W * K:
+        raise ValueError("node_fused_bwd: the dU ring does not match the schedule")
+    with torch.cuda.device(hs.device), _timed("node_fused_bwd"):
+        _lib.check(
+            lib.gkn_node_fused_bwd_bf16(
+                _p(hs, torch.bfloat16, "hs"), _p(gs, torch.bfloat16, "gs"),
+                _p(lay.pptr, torch.int32, "pptr"), _p(xb, torch.bfloat16, "xb"),
+                _p(w3k, torch.bfloat16, "w3k"), _p(du, torch.bfloat16, "du"),
+                _p(sched.items, torch.int32, "items"), sched.num_items,
+                _p(flags, torch.int32, "flags"), _p(dx_part, torch.float32, "dx_part"),
+                _p(dwT, torch.float32, "dwT"), int(bool(accumulate_dw)), N, lay.e_pad, sched.u_rows,
+                K, W, _stream()),
+            "gkn_node_fused_bwd_bf16",
+        )
+
+
+def sum_partials(part: torch.Tensor, addend: torch.Tensor | None, out: torch.Tensor) -> torch.Tensor:
+    """out = addend + part.sum(0) with a fixed summation order (gkn_sum_partials)."""
+    lib = _lib.load()
+    parts = int(part.size(0))
+    n = part.numel() // max(parts, 1)
+    with torch.cuda.device(part.device):
+        _lib.check(lib.gkn_sum_partials(_p(part, torch.float32, "part"), parts, n,
+                                        _p(addend, torch.float32, "addend"),
+                                        _p(out, torch.float32, "out"), _stream()),
+                   "gkn_sum_partials")
+    return out

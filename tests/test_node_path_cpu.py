@@ -120,6 +120,105 @@ def emu_node_gather(g, lay, gs, gsT):
         gsT.copy_(rows.t())
 
 
+def emu_node_fused_fwd(xb, w3r, hs, u, sched, flags, msg, N, e_pad, K, W, num_ctas=5, seed=0):
+    """Executes the item list the way the kernel does: ``num_ctas`` CTAs, item v belongs to CTA
+    v % num_ctas, every CTA runs its items strictly in order, an item whose counter has not reached
+    its target blocks its CTA.  CTAs are advanced in a random order; a state in which no CTA can
+    advance is a deadlock (AssertionError).  A producer tile additionally refuses to overwrite a
+    U row that a not-yet-executed consumer still needs only through the counters - exactly the
+    kernel's protection - so a wrong schedule shows up as wrong numbers."""
+    items = sched.items.tolist()
+    queues = [items[c::num_ctas] for c in range(num_ctas)]
+    pos = [0] * num_ctas
+    rng = np.random.default_rng(seed)
+    uf = u.view(sched.u_rows, W * K)
+    left = len(items)
+    while left:
+        progressed = False
+        for c in rng.permutation(num_ctas):
+            while pos[c] < len(queues[c]):
+                kind, r0, r1, r2, widx, wtarget, sidx, r3 = queues[c][pos[c]]
+                if widx >= 0 and int(flags[widx]) < wtarget:
+                    break
+                if kind == ops.IT_P:
+                    tile = xb[r0:r0 + r3].float() @ w3r[:, r1:r1 + ops.FUSED_TILE_COLS].float()
+                    uf[r2:r2 + r3, r1:r1 + ops.FUSED_TILE_COLS] = tile.to(u.dtype)
+                elif kind == ops.IT_C:
+                    msg[r0:r0 + r1] = hs[r0:r0 + r1].float() @ uf[r2].view(W, K).float().t()
+                if sidx >= 0 and kind != ops.IT_NOP:
+                    flags[sidx] += 4  # one per epilogue warp
+                pos[c] += 1
+                left -= 1
+                progressed = True
+                if rng.random() < 0.3:
+                    break  # let another CTA run: interleavings differ from run to run
+        assert progressed, "fused schedule deadlocked"
+
+
+EMU_GRID = 7  # CTAs of the emulated fused backward
+
+
+def emu_node_fused_bwd(hs, gs, lay, xb, w3k, du, sched, flags, dx_part, dwT, accumulate_dw, seed=0):
+    """In-order multi-CTA execution of the backward item list (see emu_node_fused_fwd): D items
+    write dU tiles into the ring, X items (one per CTA and node block, at list positions equal to
+    the CTA index modulo the grid) consume the CTA's column slice of the block."""
+    K, W = hs.size(1), gs.size(1)
+    N = lay.num_nodes
+    grid = dx_part.size(0) if dx_part is not None else EMU_GRID
+    items = sched.items.tolist()
+    queues = [items[c::grid] for c in range(grid)]
+    pos = [0] * grid
+    pairs = W * K // 128
+    base, rem = divmod(pairs, grid)
+    sl = []
+    for c in range(grid):
+        np_, p0 = base + (c < rem), c * base + min(c, rem)
+        sl.append(slice(p0 * 128, (p0 + np_) * 128))
+    pp = lay.pptr.tolist()
+    duf = du.view(sched.u_rows, K * W)
+    acc = [torch.zeros(sl[c].stop - sl[c].start, W) for c in range(grid)]
+    rng = np.random.default_rng(seed)
+    left = len(items)
+    while left:
+        progressed = False
+        for c in rng.permutation(grid):
+            while pos[c] < len(queues[c]):
+                kind, r0, r1, r2, widx, wtarget, sidx, r3 = queues[c][pos[c]]
+                if widx >= 0 and int(flags[widx]) < wtarget:
+                    break
+                if kind == ops.IT_D:
+                    rows = slice(pp[r0], pp[r0 + 1])
+                    tile = hs[rows, r1 * 128:(r1 + 1) * 128].float().t() @ gs[rows].float()
+                    duf[r2].view(K, W)[r1 * 128:(r1 + 1) * 128] = tile.to(du.dtype)
+                elif kind == ops.IT_X:
+                    assert (c + pos[c] * grid) % grid == c
+                    blk = duf[r1:r1 + r2][:, sl[c]].float()
+                    xt = xb[r0:r0 + r2].float()
+                    acc[c] += blk.t() @ xt
+                    if dx_part is not None:
+                        dx_part[c, r0:r0 + r2] = blk @ w3k[:, sl[c]].float().t()
+                if sidx >= 0 and kind != ops.IT_NOP:
+                    flags[sidx] += 4
+                pos[c] += 1
+                left -= 1
+                progressed = True
+                if rng.random() < 0.3:
+                    break
+        assert progressed, "fused backward schedule deadlocked"
+    if dwT is not None:
+        for c in range(grid):
+            if accumulate_dw:
+                dwT[sl[c]] += acc[c]
+            else:
+                dwT[sl[c]] = acc[c]
+
+
+def emu_sum_partials(part, addend, out):
+    tot = part.sum(0).reshape(out.shape)
+    out.copy_(tot if addend is None else addend + tot)
+    return out
+
+
 def install_emulation(setattr_fn):
     """Replace every CUDA entry point the node-first host code calls by its torch restatement
     (``setattr_fn(obj, name, value)``: monkeypatch.setattr, or plain setattr in a spawned worker)."""
@@ -128,7 +227,9 @@ def install_emulation(setattr_fn):
                      ("mask_cast_colsum", emu_mask_cast_colsum), ("node_msg", emu_node_msg),
                      ("node_du", emu_node_du), ("node_dh", emu_node_dh),
                      ("node_du_mn", emu_node_du_mn), ("node_dh_mn", emu_node_dh_mn),
-                     ("node_gather", emu_node_gather)]:
+                     ("node_gather", emu_node_gather), ("node_fused_fwd", emu_node_fused_fwd),
+                     ("node_fused_bwd", emu_node_fused_bwd), ("sum_partials", emu_sum_partials),
+                     ("fused_bwd_grid", lambda K, W: (EMU_GRID, EMU_GRID))]:
         setattr_fn(ops, name, fn)
     setattr_fn(ops, "prepare_graph", lambda ei, N, validate=True: cpu_plan(ei, N))
     setattr_fn(GF, "_mm32", lambda a, b: a.float() @ b.float())
@@ -317,3 +418,130 @@ def test_node_path_selection():
     assert not GF.node_path_supported(64, 1024, 10, "fp32")
     assert not GF.node_path_supported(64, 1000, 10, "bf16")
     assert not GF.node_path_supported(64, 1024, 0, "bf16")
+
+
+# ---- fused producer/consumer forward: schedule ------------------------------------------------
+@pytest.mark.parametrize("N,E,W,ring", [(300, 5000, 64, 0), (300, 5000, 64, 3), (700, 3000, 32, 4),
+                                        (130, 400, 128, 3), (40, 90, 64, 0)])
+def test_fused_forward_schedule_is_ordered_and_complete(N, E, W, ring):
+    K = 256
+    plan = cpu_plan(random_graph(N, E, seed=N), N)
+    lay = ops.node_layout(plan)
+    sched = ops.fused_fwd_schedule(lay, W, K, ring=ring)
+    it = sched.items.long()
+    NB, J = -(-N // 128), W * K // 256
+    assert sched.num_items == NB * J + lay.num_units and sched.num_flags == 2 * NB
+    P, C = it[it[:, 0] == ops.IT_P], it[it[:, 0] == ops.IT_C]
+    # every tile of U once, every message unit once
+    assert len({(int(a), int(b)) for a, b in P[:, 1:3]}) == NB * J
+    assert sorted(C[:, 1].tolist()) == sorted(lay.units[:, 1].tolist())
+    # a consumer comes after every tile of its block; in ring mode a tile comes after every
+    # consumer of the block whose slot it overwrites, and targets count 4 warps per item
+    where = {k: [] for k in ("p", "c")}
+    first_c, last_c = {}, {}
+    last_p, first_p = {}, {}
+    for v, row in enumerate(it.tolist()):
+        if row[0] == ops.IT_P:
+            b = row[1] // 128
+            last_p[b] = v
+            first_p.setdefault(b, v)
+        elif row[0] == ops.IT_C:
+            b = row[4]
+            first_c.setdefault(b, v)
+            last_c[b] = v
+            assert row[5] == 4 * J
+    for b, v in first_c.items():
+        assert last_p[b] < v
+    cnt = torch.bincount(C[:, 4], minlength=NB)
+    for row in P.tolist():
+        b = row[1] // 128
+        if ring and b >= ring:
+            assert row[4] == NB + b - ring and row[5] == 4 * int(cnt[b - ring])
+            if (b - ring) in last_c:
+                assert last_c[b - ring] < first_p[b]
+            assert row[3] == (b % ring) * 128
+        else:
+            assert row[4] == -1
+    assert ops.fused_fwd_schedule(lay, W, K, ring=ring) is sched  # cached on the layout
+
+
+@pytest.mark.parametrize("ring", [0, 3])
+@pytest.mark.parametrize("num_ctas", [1, 3, 148])
+def test_fused_forward_emulated_execution_matches_two_kernel_form(ring, num_ctas):
+    N, E, W, K = 400, 6000, 64, 256
+    plan = cpu_plan(random_graph(N, E, seed=1), N)
+    lay = ops.node_layout(plan)
+    g = torch.Generator().manual_seed(0)
+    xb = torch.randn(N, W, generator=g).bfloat16()
+    w3r = (torch.randn(W, W * K, generator=g) / 8).bfloat16()
+    hs = torch.randn(lay.e_pad, K, generator=g).bfloat16()
+    sched = ops.fused_fwd_schedule(lay, W, K, ring=ring)
+    u = torch.zeros(sched.u_rows, W * K, dtype=torch.bfloat16)
+    msg = torch.zeros(lay.e_pad, W)
+    emu_node_fused_fwd(xb, w3r, hs, u, sched, torch.zeros(sched.num_flags, dtype=torch.int32), msg,
+                       N, lay.e_pad, K, W, num_ctas=num_ctas, seed=num_ctas)
+    U = (xb.float() @ w3r.float()).bfloat16()
+    ref = torch.zeros_like(msg)
+    emu_node_msg(hs, U.view(N, W, K), lay, 0, lay.num_units, 0, ref)
+    assert torch.equal(msg, ref)
+    if not ring:
+        assert torch.equal(u, U)
+
+
+def test_fused_forward_ring_must_cover_the_slack():
+    plan = cpu_plan(random_graph(300, 2000, seed=2), 300)
+    with pytest.raises(ValueError, match="ring"):
+        ops.fused_fwd_schedule(ops.node_layout(plan), 64, 256, ring=2, slack=0.5)
+
+
+# ---- fused backward: schedule -------------------------------------------------------------------
+@pytest.mark.parametrize("N,K,grid,ring", [(300, 256, 7, 3), (128, 512, 148, 2), (1000, 1024, 148, 3),
+                                           (5, 256, 4, 3)])
+def test_fused_backward_schedule_layout(N, K, grid, ring):
+    items, nflags = ops.fused_bwd_items(N, K, 64, grid, ring)
+    NB, C = -(-N // 128), K // 128
+    assert nflags == 2 * NB
+    kinds = items[:, 0]
+    D, X = items[kinds == ops.IT_D], items[kinds == ops.IT_X]
+    # every (node, chunk) once; every (block, CTA) once, at a list position == CTA (mod grid)
+    assert len({(int(a), int(b)) for a, b in D[:, 1:3]}) == N * C == len(D)
+    xpos = np.nonzero(kinds == ops.IT_X)[0]
+    assert len(X) == NB * grid
+    for b in range(NB):
+        seg = xpos[b * grid:(b + 1) * grid]
+        assert (seg % grid == np.arange(grid)).all() and (items[seg, 1] == 128 * b).all()
+        nodes = min(128, N - 128 * b)
+        assert (items[seg, 3] == nodes).all() and (items[seg, 5] == 4 * nodes * C).all()
+        # all D items of the block precede its X items; the ring slot is reused only after them
+        dpos = np.nonzero((kinds == ops.IT_D) & (items[:, 1] // 128 == b))[0]
+        assert dpos.max() < seg.min()
+        if b + ring < NB:
+            later = np.nonzero((kinds == ops.IT_D) & (items[:, 1] // 128 == b + ring))[0]
+            assert later.min() > seg.max()
+            assert (items[later, 4] == NB + b).all() and (items[later, 5] == 4 * grid).all()
+            assert (items[later, 3] // 128 == b % ring).all()
+    with pytest.raises(ValueError):
+        ops.fused_bwd_items(N, K, 64, grid, 1)
+
+
+def test_fused_backward_emulated_execution_matches_dense_products():
+    N, E, K, W = 300, 5000, 256, 64
+    plan = cpu_plan(random_graph(N, E, seed=3, isolated=(5, 299)), N)
+    lay = ops.node_layout(plan)
+    g = torch.Generator().manual_seed(0)
+    hs = torch.randn(lay.e_pad, K, generator=g).bfloat16()
+    gs = torch.randn(lay.e_pad, W, generator=g).bfloat16()
+    gs[lay.dst_pad < 0] = 0
+    xb = torch.randn(N, W, generator=g).bfloat16()
+    w3k = (torch.randn(W, K * W, generator=g) / 8).bfloat16()
+    items, nflags = ops.fused_bwd_items(N, K, W, EMU_GRID, 3)
+    sched = ops.FusedSchedule(torch.from_numpy(items), len(items), nflags, 3 * 128, 3)
+    du = torch.zeros(3 * 128, K * W, dtype=torch.bfloat16)
+    dx_part = torch.zeros(EMU_GRID, N, W)
+    dwT = torch.full((K * W, W), 7.0)
+    emu_node_fused_bwd(hs, gs, lay, xb, w3k, du, sched, torch.zeros(nflags, dtype=torch.int32),
+                       dx_part, dwT, False)
+    dut = torch.zeros(N, K * W, dtype=torch.bfloat16)
+    emu_node_du_mn(hs, gs, lay, 0, N, dut)
+    assert fro(dx_part.sum(0), dut.float() @ w3k.float().t()) < 1e-6
+    assert fro(dwT, dut.float().t() @ xb.float()) < 1e-6

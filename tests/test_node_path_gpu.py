@@ -225,5 +225,7 @@ def test_node_first_is_the_default_for_the_bench_shape():
         got = ops.KERNEL_TIMER.collect()
     finally:
         ops.KERNEL_TIMER.disable()
-    assert got["node_msg"]["count"] == 2 and got["node_du"]["count"] == 2
+    fwd = got.get("node_fused_fwd", got.get("node_msg"))
+    bwd = got.get("node_fused_bwd", got.get("node_du"))
+    assert fwd["count"] == 2 and bwd["count"] == 2
     assert got["node_dh"]["count"] == 1
