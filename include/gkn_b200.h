@@ -142,8 +142,8 @@ int gkn_node_gather_bf16(const float* g, const int32_t* idx, int64_t E_pad, void
  * One persistent kernel per NNConv application that BOTH produces U = x @ W3r with the tensor
  * core and consumes it in the grouped message GEMM (NNConv_old.message, graph_kernel.py:200-202)
  * while it is still in the L2 - U never takes the HBM round trip of the two-kernel form above.
- * The kernel executes a host-ordered list of work items, dealt round-robin over one CTA per SM;
- * an item is 8 int32:
+ * The kernel executes a host-ordered list of work items: item v belongs to CTA v % grid (grid <=
+ * the SM count; 0 = one CTA per SM), every CTA runs its items in list order; an item is 8 int32:
  *     (kind, r0, r1, r2,  wait_idx, wait_target, signal_idx, r3)
  *   kind 0 "P": U[r2 + i, r1 .. r1+256) = x[r0 + i, :] @ W3r[:, r1 .. r1+256) for i < r3 (<= 128)
  *   kind 1 "C": msg[r0 + i, :] = hs[r0 + i, :] @ U[r2]^T for i < r1 (<= 128)   (U[r2]: [W, K])
@@ -151,8 +151,9 @@ int gkn_node_gather_bf16(const float* g, const int32_t* idx, int64_t E_pad, void
  *   wait_idx >= 0: the item waits until flags[wait_idx] >= wait_target (C: before it reads U;
  *   P: before it overwrites its rows of U - the "ring" use, where U holds a few node blocks only);
  *   signal_idx >= 0: each of the 4 epilogue warps adds 1 to flags[signal_idx] when the item's
- *   output is in memory.  Every wait must refer to items that precede the waiter in list order
- *   (the list is executed in order by every CTA; all CTAs are co-resident).
+ *   output is in memory.  The waits must be acyclic together with the per-CTA order (e.g. every
+ *   wait refers to items with a smaller time key and every CTA's items are in key order); all
+ *   CTAs are co-resident, so a waiting CTA only ever waits for CTAs that are running.
  * x bf16 [N, max(W,64)] (zero padded), w3r bf16 [max(W,64), W*K] = layers.4.weight viewed
  * [i, (o,k)] (zero rows beyond W), hs bf16 [E_pad, K], u bf16 [u_rows, W*K], msg fp32 [E_pad, W],
  * flags int32 (zeroed by the caller before the launch).  hs and msg may be NULL when E_pad = 0
@@ -160,7 +161,7 @@ int gkn_node_gather_bf16(const float* g, const int32_t* idx, int64_t E_pad, void
 int gkn_node_fused_fwd_bf16(const void* x_bf16, const void* w3r_bf16, const void* hs_bf16,
                             void* u_bf16, const int32_t* items, int64_t num_items, int32_t* flags,
                             float* msg, int64_t N, int64_t E_pad, int64_t u_rows, int32_t K,
-                            int32_t W, void* stream);
+                            int32_t W, int32_t grid, void* stream);
 
 /* Fused backward of one application (w = 64): the gradient w.r.t. U is produced by "D" items
  * (dU[n][k,o] = sum_{e: src e = n} hs[e,k] * gs[e,o], as gkn_node_du_mn_bf16) into a ring of node

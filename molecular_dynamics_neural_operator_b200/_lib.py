@@ -50,7 +50,7 @@ SIGNATURES = {
     "gkn_node_gather_bf16": (c_int, [P, P, c_int64, P, P, c_int32, P]),
     "gkn_node_fused_fwd_bf16": (
         c_int,
-        [P, P, P, P, P, c_int64, P, P, c_int64, c_int64, c_int64, c_int32, c_int32, P],
+        [P, P, P, P, P, c_int64, P, P, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, P],
     ),
     "gkn_node_fused_bwd_grid": (c_int, [c_int32, c_int32, ctypes.POINTER(c_int32),
                                         ctypes.POINTER(c_int32)]),

@@ -30,19 +30,37 @@ __device__ __forceinline__ int32_t ld_acquire(const int32_t* p) {
     return v;
 }
 
+// counter += 1 with release semantics at GPU scope: everything this thread has observed (its own
+// stores, and - after a __syncwarp - those of the other lanes of its warp) is visible to whoever
+// acquires the new value.  One MEMBAR.ALL.GPU in one lane; __threadfence() in all 32 lanes is a
+// sequentially-consistent fence plus an L1 invalidation each (measured: +40 % on producer tiles).
+__device__ __forceinline__ void red_release_add(int32_t* p, int32_t v) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // orders this thread's later async-proxy (TMA) accesses to global memory after the generic-proxy
 // writes it has just observed through an acquire load
 __device__ __forceinline__ void fence_proxy_async_global() {
     asm volatile("fence.proxy.async.global;" ::: "memory");
 }
 
+__device__ __forceinline__ int32_t ld_relaxed(const int32_t* p) {
+    int32_t v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // Spin until a counter written by other CTAs reaches `target` (watchdog: trap instead of hanging).
+// The polls are relaxed loads and ONE acquire fence follows the successful one: an acquire load
+// per poll invalidates the SM's L1 every time (CCTL.IVALL) and with it the item records and row
+// pointers every role of the CTA keeps there.
 __device__ __forceinline__ void wait_counter(const int32_t* flag, int32_t target) {
     uint32_t spins = 0;
-    while (ld_acquire(flag) < target) {
+    while (ld_relaxed(flag) < target) {
         __nanosleep(64);
         if (++spins > (1u << 25)) __trap();
     }
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {

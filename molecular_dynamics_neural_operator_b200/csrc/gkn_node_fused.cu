@@ -36,9 +36,11 @@ namespace {
 constexpr int kM = 128;           // accumulator rows per item
 constexpr int kKB = 64;           // reduction elements per k-block (one 128-byte swizzle row)
 constexpr int kUmmaK = 16;
-constexpr int kThreads = 6 * 32;  // TMA producer, MMA issuer, 4 epilogue warps
-constexpr int kStageBytes = 48 * 1024;
-constexpr int kStages = 4;
+// Two groups of four epilogue warps drain the two accumulator slots alternately: the epilogue of a
+// producer tile is a latency chain (TMEM load, convert, staging, stores, GPU-scope fence before the
+// counter moves) and one group alone paced the kernel (3 us per tile measured).
+constexpr int kEpiGroups = 2;
+constexpr int kThreads = (2 + 4 * kEpiGroups) * 32;  // TMA producer, MMA issuer, epilogue warps
 constexpr int kAcc = 2;           // TMEM accumulator slots
 constexpr int kAccCols = 256;     // columns per slot (P tiles use all, C tiles the first W)
 constexpr int kABytes = kM * kKB * 2;        // 16 KB: one K-major A box (128 rows x 64)
@@ -60,17 +62,26 @@ using fused::fence_proxy_async_global;
 using fused::sts128;
 using fused::lds128;
 using fused::pack_bf16;
+using fused::red_release_add;
 
+// Shared-memory pipeline.  w <= 64: eight 24 KB stages; a message k-block (hs 16 KB + U[n] 4/8 KB)
+// takes one stage, a producer fill (x tile 16 KB + four 8 KB boxes of W3) takes two consecutive
+// ones - every item uses an even number of stages, so a fill always starts on an even stage and
+// never wraps around the ring.  w = 128: four 48 KB stages, one k-block (32 KB) or fill per stage.
+// (Coarser 48 KB stages for everything measured 12 % slower on the message items.)
 template <int W>
 struct FCfg {
     static constexpr int kWp = W < 64 ? 64 : W;             // reduction width of P (x zero-padded)
-    static constexpr int kPFills = kWp / kKB;               // stage fills per P tile
+    static constexpr int kPFills = kWp / kKB;               // fills per P tile
+    static constexpr bool kFine = W <= 64;
+    static constexpr int kStageBytes = kFine ? 24 * 1024 : 48 * 1024;
+    static constexpr int kStages = kFine ? 8 : 4;
+    static constexpr int kPStages = kFine ? 2 : 1;          // stages per P fill
     static constexpr int kCBBytes = W * kKB * 2;            // U[n] k-block: W rows x 64
     static constexpr int kCKbBytes = kABytes + kCBBytes;    // one C k-block
-    static constexpr int kCKbPerFill = kStageBytes / kCKbBytes;  // 2, 2, 1 at W = 32, 64, 128
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + 4 * 4096;
-    static_assert(kCKbPerFill >= 1, "a C k-block must fit one stage");
-    static_assert(kCKbBytes % 1024 == 0, "swizzled tiles start on 1 KB boundaries");
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kEpiGroups * 4 * 4096;
+    static_assert(kCKbBytes <= kStageBytes, "a C k-block must fit one stage");
+    static_assert(kPStages * kStageBytes >= kABytes + 4 * kMnBlockBytes, "a P fill must fit");
     static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory per CTA");
 };
 
@@ -81,6 +92,8 @@ struct FusedParams {
     __nv_bfloat16* __restrict__ u;  // [u_rows, W*K]
     float* __restrict__ msg;        // [E_pad, W]
     int32_t K;
+    int32_t tune;  // GKN_FUSED_TUNE bits (experiments): 1 = plain (unhinted) loads of hs,
+                   // 2 = one epilogue group drains both accumulator slots
 };
 
 // tmap_x : x bf16 [N, Wp]            box 64 x 128   (A of P, K-major)
@@ -94,6 +107,8 @@ node_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
                       const __grid_constant__ CUtensorMap tmap_hs,
                       const __grid_constant__ CUtensorMap tmap_u, const FusedParams p) {
     using C = FCfg<W>;
+    constexpr int kStages = C::kStages;
+    constexpr int kStageBytes = C::kStageBytes;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + kStages * kStageBytes;
@@ -114,8 +129,9 @@ node_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
         }
         for (int s = 0; s < kAcc; ++s) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), 4);
+            mbar_init(tempty_bar(s), 4);  // the four warps of the group that drains the slot
         }
+        static_assert(kAcc % kEpiGroups == 0, "accumulator slots are owned by epilogue groups");
         fence_mbar_init();
     }
     if (warp == 0 && lane == 0) {
@@ -134,14 +150,19 @@ node_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
-    const int nkb = p.K / kKB;  // k-blocks of a C item
-
+    const int nkb = p.K / kKB;  // k-blocks of a C item (a multiple of 4)
     if (warp == 0) {
         // ===================== TMA producer =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        auto advance = [&]() {
+            if (++stage == kStages) {
+                stage = 0;
+                phase ^= 1u;
+            }
+        };
+        const uint64_t pol_stream = l2_policy_evict_first();
         if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            const uint64_t pol_stream = l2_policy_evict_first();
             Item nx = v0 < v1 ? load_item(p.items, v0) : Item{};
             for (int64_t v = v0; v < v1; v += vstep) {
                 const Item it = nx;
@@ -149,59 +170,67 @@ node_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
                 if (it.a.x == IT_P) {
 #pragma unroll
                     for (int f = 0; f < C::kPFills; ++f) {
-                        mbar_wait(empty_bar(stage), phase ^ 1u);
+                        // x tile + first box(es) of W3 in the first stage, the rest in the next
                         const uint32_t sa = smem_base + stage * kStageBytes;
-                        mbar_arrive_expect_tx(full_bar(stage), kABytes + 4 * kMnBlockBytes);
+                        constexpr int kFirst = C::kFine ? 1 : 4;  // W3 boxes in the first stage
+                        mbar_wait(empty_bar(stage), phase ^ 1u);
+                        mbar_arrive_expect_tx(full_bar(stage), kABytes + kFirst * kMnBlockBytes);
                         tma_load_2d(sa, &tmap_x, full_bar(stage), f * kKB, it.a.y);
 #pragma unroll
-                        for (int j = 0; j < kPCols / 64; ++j) {
+                        for (int j = 0; j < kFirst; ++j) {
                             tma_load_2d(sa + kABytes + j * kMnBlockBytes, &tmap_w3, full_bar(stage),
                                         it.a.z + j * 64, f * kKB);
                         }
-                        if (++stage == kStages) {
-                            stage = 0;
-                            phase ^= 1u;
+                        advance();
+                        if constexpr (C::kFine) {
+                            mbar_wait(empty_bar(stage), phase ^ 1u);
+                            mbar_arrive_expect_tx(full_bar(stage), 3 * kMnBlockBytes);
+#pragma unroll
+                            for (int j = 1; j < 4; ++j) {
+                                tma_load_2d(sa + kABytes + j * kMnBlockBytes, &tmap_w3,
+                                            full_bar(stage), it.a.z + j * 64, f * kKB);
+                            }
+                            advance();
                         }
                     }
                 } else if (it.a.x == IT_C) {
                     bool ready = it.b.x < 0;
-                    for (int s = 0; s < nkb / C::kCKbPerFill; ++s) {
+                    for (int kb = 0; kb < nkb; ++kb) {
                         mbar_wait(empty_bar(stage), phase ^ 1u);
                         const uint32_t sa = smem_base + stage * kStageBytes;
-                        mbar_arrive_expect_tx(full_bar(stage), C::kCKbPerFill * C::kCKbBytes);
-                        // the edge hidden state does not depend on this launch: its loads go out
+                        mbar_arrive_expect_tx(full_bar(stage), C::kCKbBytes);
+                        // the edge hidden state does not depend on this launch: its load goes out
                         // before the counter is polled
-#pragma unroll
-                        for (int t = 0; t < C::kCKbPerFill; ++t) {
-                            tma_load_2d_hint(sa + t * C::kCKbBytes, &tmap_hs, full_bar(stage),
-                                             (s * C::kCKbPerFill + t) * kKB, it.a.y, pol_stream);
+                        if (p.tune & 1) {
+                            tma_load_2d(sa, &tmap_hs, full_bar(stage), kb * kKB, it.a.y);
+                        } else {
+                            tma_load_2d_hint(sa, &tmap_hs, full_bar(stage), kb * kKB, it.a.y, pol_stream);
                         }
                         if (!ready) {
                             wait_counter(p.flags + it.b.x, it.b.y);
                             fence_proxy_async_global();
                             ready = true;
                         }
-#pragma unroll
-                        for (int t = 0; t < C::kCKbPerFill; ++t) {
-                            tma_load_2d(sa + t * C::kCKbBytes + kABytes, &tmap_u, full_bar(stage),
-                                        (s * C::kCKbPerFill + t) * kKB, it.a.w * W);
-                        }
-                        if (++stage == kStages) {
-                            stage = 0;
-                            phase ^= 1u;
-                        }
+                        tma_load_2d(sa + kABytes, &tmap_u, full_bar(stage), kb * kKB, it.a.w * W);
+                        advance();
                     }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
+        constexpr uint32_t idesc_p = umma_idesc_bf16(kM, kPCols, 0, 1);
+        constexpr uint32_t idesc_c = umma_idesc_bf16(kM, W, 0, 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        auto advance = [&]() {
+            if (++stage == kStages) {
+                stage = 0;
+                phase ^= 1u;
+            }
+        };
+        uint32_t n_acc = 0;
         if (lane == 0) {
-            constexpr uint32_t idesc_p = umma_idesc_bf16(kM, kPCols, 0, 1);
-            constexpr uint32_t idesc_c = umma_idesc_bf16(kM, W, 0, 0);
-            int stage = 0;
-            uint32_t phase = 0;
-            uint32_t n_acc = 0;
             Item nx = v0 < v1 ? load_item(p.items, v0) : Item{};
             for (int64_t v = v0; v < v1; v += vstep) {
                 const Item it = nx;
@@ -216,9 +245,12 @@ node_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
                 if (it.a.x == IT_P) {
 #pragma unroll
                     for (int f = 0; f < C::kPFills; ++f) {
-                        mbar_wait(full_bar(stage), phase);
-                        tc_fence_after();
                         const uint32_t sa = smem_base + stage * kStageBytes;
+                        const int s0 = stage;
+                        const uint32_t ph0 = phase;
+                        mbar_wait(full_bar(s0), ph0);
+                        if constexpr (C::kFine) mbar_wait(full_bar(s0 + 1), ph0);  // never wraps
+                        tc_fence_after();
                         const uint64_t adesc = umma_smem_desc(sa, 16, 1024, kSwizzle128B);
                         const uint64_t bdesc =
                             umma_smem_desc(sa + kABytes, kMnBlockBytes, 1024, kSwizzle128B);
@@ -229,45 +261,50 @@ node_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
                                          (f | k) != 0 ? 1u : 0u);
                         }
                         umma_commit(empty_bar(stage));
-                        if (++stage == kStages) {
-                            stage = 0;
-                            phase ^= 1u;
+                        advance();
+                        if constexpr (C::kFine) {
+                            umma_commit(empty_bar(stage));
+                            advance();
                         }
                     }
                 } else {
-                    for (int s = 0; s < nkb / C::kCKbPerFill; ++s) {
+                    for (int kb = 0; kb < nkb; ++kb) {
                         mbar_wait(full_bar(stage), phase);
                         tc_fence_after();
                         const uint32_t sa = smem_base + stage * kStageBytes;
+                        const uint64_t adesc = umma_smem_desc(sa, 16, 1024, kSwizzle128B);
+                        const uint64_t bdesc = umma_smem_desc(sa + kABytes, 16, 1024, kSwizzle128B);
 #pragma unroll
-                        for (int t = 0; t < C::kCKbPerFill; ++t) {
-                            const uint64_t adesc =
-                                umma_smem_desc(sa + t * C::kCKbBytes, 16, 1024, kSwizzle128B);
-                            const uint64_t bdesc = umma_smem_desc(sa + t * C::kCKbBytes + kABytes, 16,
-                                                                  1024, kSwizzle128B);
-#pragma unroll
-                            for (int k = 0; k < kKB / kUmmaK; ++k) {
-                                umma_bf16_ss(tmem_d, adesc + 2ull * k, bdesc + 2ull * k, idesc_c,
-                                             (s | t | k) != 0 ? 1u : 0u);
-                            }
+                        for (int k = 0; k < kKB / kUmmaK; ++k) {
+                            umma_bf16_ss(tmem_d, adesc + 2ull * k, bdesc + 2ull * k, idesc_c,
+                                         (kb | k) != 0 ? 1u : 0u);
                         }
                         umma_commit(empty_bar(stage));
-                        if (++stage == kStages) {
-                            stage = 0;
-                            phase ^= 1u;
-                        }
+                        advance();
                     }
                 }
                 umma_commit(tfull_bar(as));
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5): thread = accumulator row =====================
-        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        // ===================== epilogue (warps 2..): thread = accumulator row =====================
+        const int q = warp & 3;           // TMEM lane quarter this warp may access
+        const int grp = (warp - 2) >> 2;  // epilogue group = accumulator slot it drains
         const uint32_t lane_addr = uint32_t(q * 32) << 16;
-        const uint32_t stage_smem = bar_base + 256 + q * 4096;  // per-warp 32 x 128 B staging tile
-        const int64_t u_pitch = int64_t(W) * p.K * 2;           // bytes per row of the U buffer
+        const uint32_t stage_smem = bar_base + 256 + (grp * 4 + q) * 4096;  // per-warp staging tile
+        const int64_t u_pitch = int64_t(W) * p.K * 2;                        // bytes per row of U
         uint32_t n_acc = 0;
+        // The counter of a producer tile moves with release semantics after the tile's stores, and
+        // a release right behind the stores waits for their full round trip.  So the update of
+        // tile t is issued when this warp next has to wait anyway or is about to store item t+1.
+        int32_t pending = -1;
+        auto flush = [&]() {
+            if (pending >= 0) {
+                __syncwarp();
+                if (lane == 0) red_release_add(p.flags + pending, 1);
+                pending = -1;
+            }
+        };
         Item nx = v0 < v1 ? load_item(p.items, v0) : Item{};
         for (int64_t v = v0; v < v1; v += vstep) {
             const Item it = nx;
@@ -276,14 +313,27 @@ node_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
             const uint32_t as = n_acc % kAcc;
             const uint32_t aphase = (n_acc / kAcc) & 1u;
             ++n_acc;
+            if (p.tune & 2) {
+                if (grp != 0) continue;
+            } else if (int(as % kEpiGroups) != grp) {
+                continue;  // the other group's item
+            }
             const bool is_p = it.a.x == IT_P;
+            // never block with a counter update outstanding: somebody may be waiting for it
+            uint32_t ready = 0;
+            if (lane == 0) ready = mbar_try_wait(tfull_bar(as), aphase);
+            ready = __shfl_sync(0xffffffffu, ready, 0);
+            if (!ready || (is_p && it.b.x >= 0)) flush();
             if (lane == 0) {
-                mbar_wait(tfull_bar(as), aphase);
+                if (!ready) mbar_wait(tfull_bar(as), aphase);
                 // ring mode: the slot this tile overwrites must have been consumed
                 if (is_p && it.b.x >= 0) wait_counter(p.flags + it.b.x, it.b.y);
             }
             __syncwarp();
             tc_fence_after();
+            // a consumer's counter only says "U[n] has been read" (every MMA of the item is
+            // complete): no data is published, so it moves at once and without a release
+            if (!is_p && it.b.z >= 0 && lane == 0) atomicAdd(p.flags + it.b.z, 1);
             const uint32_t tcol = tmem_base + lane_addr + as * kAccCols;
             const int rows_here = (is_p ? it.b.w : it.a.z) - q * 32;
             uint8_t* gbase;
@@ -318,6 +368,12 @@ node_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
 #pragma unroll
                     for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(f[j]);
                 }
+                if (piece == pieces - 1) {  // accumulator fully read: hand the slot back now
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar(as));
+                }
+                if (piece == 0) flush();  // the previous item's counter, before this item's stores
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     sts128(stage_smem + lane * 128 + ((c ^ (lane & 7)) << 4),
@@ -334,14 +390,9 @@ node_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
                 }
                 __syncwarp();
             }
-            tc_fence_before();
-            if (it.b.z >= 0) __threadfence();  // this lane's stores are visible GPU-wide ...
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(tempty_bar(as));
-                if (it.b.z >= 0) atomicAdd(p.flags + it.b.z, 1);  // ... before the counter moves
-            }
+            if (is_p) pending = it.b.z;
         }
+        flush();
     }
 
     tc_fence_before();
@@ -354,7 +405,8 @@ node_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
 
 template <int W>
 int launch_fused_fwd(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& th,
-                     const CUtensorMap& tu, const FusedParams& p, cudaStream_t stream) {
+                     const CUtensorMap& tu, const FusedParams& p, int32_t want_grid,
+                     cudaStream_t stream) {
     auto kern = node_fused_fwd_kernel<W>;
     constexpr int smem = FCfg<W>::kSmemBytes;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -363,7 +415,11 @@ int launch_fused_fwd(const CUtensorMap& tx, const CUtensorMap& tw, const CUtenso
     int rc = device_sm_count(&sms);
     if (rc) return rc;
     // co-residency of the whole grid is what makes the in-kernel waits safe: one CTA per SM
-    int64_t grid = p.num_items < sms ? p.num_items : sms;
+    if (want_grid > sms) {
+        return set_error("gkn_node_fused_fwd_bf16: the item list was dealt for more CTAs than "
+                         "this device has SMs");
+    }
+    int64_t grid = want_grid > 0 ? want_grid : (p.num_items < sms ? p.num_items : sms);
     if (grid < 1) return 0;
     kern<<<dim3(unsigned(grid)), dim3(kThreads), smem, stream>>>(tx, tw, th, tu, p);
     GKN_CHECK_LAUNCH("node_fused_fwd launch");
@@ -377,7 +433,8 @@ int launch_fused_fwd(const CUtensorMap& tx, const CUtensorMap& tw, const CUtenso
 extern "C" int gkn_node_fused_fwd_bf16(const void* x_bf16, const void* w3r_bf16, const void* hs_bf16,
                                        void* u_bf16, const int32_t* items, int64_t num_items,
                                        int32_t* flags, float* msg, int64_t N, int64_t E_pad,
-                                       int64_t u_rows, int32_t K, int32_t W, void* stream) {
+                                       int64_t u_rows, int32_t K, int32_t W, int32_t grid,
+                                       void* stream) {
     using namespace gkn;
     if (num_items <= 0) return 0;
     if (x_bf16 == nullptr || w3r_bf16 == nullptr || u_bf16 == nullptr || items == nullptr ||
@@ -417,10 +474,18 @@ extern "C" int gkn_node_fused_fwd_bf16(const void* x_bf16, const void* w3r_bf16,
     p.u = static_cast<__nv_bfloat16*>(u_bf16);
     p.msg = msg;
     p.K = K;
+    {
+        static int tune = -1;
+        if (tune < 0) {
+            const char* e = getenv("GKN_FUSED_TUNE");
+            tune = e != nullptr ? atoi(e) : 0;
+        }
+        p.tune = tune;
+    }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (W) {
-        case 32: return launch_fused_fwd<32>(tx, tw, th, tu, p, st);
-        case 64: return launch_fused_fwd<64>(tx, tw, th, tu, p, st);
-        default: return launch_fused_fwd<128>(tx, tw, th, tu, p, st);
+        case 32: return launch_fused_fwd<32>(tx, tw, th, tu, p, grid, st);
+        case 64: return launch_fused_fwd<64>(tx, tw, th, tu, p, grid, st);
+        default: return launch_fused_fwd<128>(tx, tw, th, tu, p, grid, st);
     }
 }

@@ -37,6 +37,7 @@ using fused::Item;
 using fused::lds128;
 using fused::load_item;
 using fused::pack_bf16;
+using fused::red_release_add;
 using fused::sts128;
 using fused::wait_counter;
 
@@ -45,17 +46,27 @@ constexpr int kKB = 64;
 constexpr int kUmmaK = 16;
 constexpr int kW = 64;             // node feature width served by this kernel
 constexpr int kThreads = 6 * 32;   // TMA producer, MMA issuer, 4 epilogue warps
-constexpr int kStageBytes = 48 * 1024;
-constexpr int kStages = 3;
+// Eight 24 KB stages - all the shared memory there is: the D items stream h from HBM, the kernel is
+// bound by the bytes it keeps in flight (measured: 6 stages 0.75 ms, 8 stages of the stand-alone
+// dU kernel 0.58 ms for the same items), so the epilogue makes do with one group of four warps, one
+// x tile and one dx accumulator.  A D k-block (two 8 KB boxes of hs + one of gs) takes one stage; a 128-column
+// pair of an X item takes two consecutive stages, each holding one 64-column half (dU box 16 KB +
+// W3k box 8 KB).  The pair must not wrap around the ring (the weight-gradient product addresses
+// both dU boxes through one descriptor), so it starts on an even stage: when the ring position is
+// odd, producer and issuer both pass over one stage (an empty hand-shake on its barriers).
+constexpr int kStageBytes = 24 * 1024;
+constexpr int kStages = 8;
 constexpr int kXbBytes = kM * kW * 2;          // 16 KB: x tile of a node block
 constexpr int kDKbBytes = 24 * 1024;           // D k-block: hs 2 x 8 KB + gs 8 KB
+static_assert(kDKbBytes == kStageBytes && kStages % 2 == 0, "see the stage layout above");
 constexpr int kMnBlockBytes = 64 * kKB * 2;    // 8 KB: MN-major box of 64 K-rows x 64 elements
 constexpr int kDuBoxBytes = kM * kKB * 2;      // 16 KB: 128 node rows x 64 columns of dU
 constexpr int kMaxPairs = 4;                   // 128-column pairs of dU per CTA
 constexpr int kPairCols = 128;
-// TMEM columns: [0, 256) dW3k^T accumulators (4 pairs x 64), [256, 384) dx slots, [384, 512) D slots
-constexpr uint32_t kTmemDw = 0, kTmemDx = 256, kTmemD = 384;
-constexpr int kSmemBytes = kStages * kStageBytes + 2 * kXbBytes + 1024 + 256 + 4 * 4096;
+// TMEM columns: [0, 256) dW3k^T accumulators (4 pairs x 64), [256, 320) dx, [320, 512) three D slots
+constexpr uint32_t kTmemDw = 0, kTmemDx = 256, kTmemD = 320;
+constexpr int kDSlots = 3;
+constexpr int kSmemBytes = kStages * kStageBytes + kXbBytes + 1024 + 256 + 4 * 4096;
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory per CTA");
 
 enum { IT_D = 0, IT_X = 1, IT_NOP = 2 };
@@ -63,28 +74,33 @@ enum { IT_D = 0, IT_X = 1, IT_NOP = 2 };
 // Item fields (fused::Item):
 //   D: r0 = node n, r1 = chunk c (128 k-rows of dU[n]), r2 = row of the dU buffer for node n
 //      wait (ring, before the stores): flags[wait_idx] >= wait_target;  signal: flags[signal_idx]
-//   X: r0 = first node of the block (row of x and of the dx partials), r1 = first row of the block
-//      in the dU buffer, r2 = valid rows (<= 128); wait (before the loads of dU); signal
+//      (the host puts the wait on the first and the signal on the last D item a CTA has in a node
+//      block: a release covers every earlier store of the warp that issues it)
+//   X: one 128-column pair of the CTA's slice for one node block.  r0 = first node of the block
+//      (row of x and of the dx partials), r1 = first row of the block in the dU buffer, r2 = valid
+//      rows (<= 128), r3 = pair index q | first << 8 | last << 9.  The first pair of a block waits
+//      (before the loads of dU), the last one signals "block consumed" and hands the dx tile to
+//      the epilogue.  The pairs of a block are spread between the CTA's D items, so that their L2
+//      traffic overlaps the D items' HBM stream.
 struct BwdParams {
     const Item* __restrict__ items;
     int64_t num_items;
     int32_t* flags;
     const int32_t* __restrict__ pptr;   // padded group pointers [N+1]
     __nv_bfloat16* __restrict__ du;     // [du_rows, w*K]   (k, o) order
-    float* __restrict__ dx_part;        // [grid, N, w] or NULL
+    float* __restrict__ dx_part;        // [parts, N, w] or NULL
     float* __restrict__ dwT;            // [w*K, w] fp32 or NULL
     int64_t N;
     int32_t K;
     int32_t accumulate_dw;              // dwT += (1) or = (0)
+    int32_t tune;                       // GKN_FUSED_TUNE bit 0: plain (unhinted) loads of hs
 };
 
 struct DUnit {
     int32_t row0, nkb, last_steps;
 };
 
-__device__ __forceinline__ DUnit decode_d(const BwdParams& p, int32_t n) {
-    const int32_t b = __ldg(p.pptr + n), e = __ldg(p.pptr + n + 1);
-    const int32_t len = e - b;  // multiple of 16
+__device__ __forceinline__ DUnit make_dunit(int32_t b, int32_t len) {  // len: multiple of 16
     DUnit u;
     u.row0 = b;
     u.nkb = (len + kKB - 1) / kKB;
@@ -106,17 +122,17 @@ node_fused_bwd_kernel(const __grid_constant__ CUtensorMap tmap_hs,
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t xb_base = smem_base + kStages * kStageBytes;
-    const uint32_t bar_base = xb_base + 2 * kXbBytes;
+    const uint32_t bar_base = xb_base + kXbBytes;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-    auto xfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
-    auto xempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
-    auto dfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 4 + s); };
-    auto dempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 6 + s); };
-    auto gfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 8 + s); };   // dx slots
-    auto gempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 10 + s); };
-    const uint32_t wdone_bar = bar_base + 8u * (2 * kStages + 12);
-    const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * kStages + 13);
+    auto dfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+    auto dempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + kDSlots + s); };
+    const uint32_t xfull_bar = bar_base + 8u * (2 * kStages + 2 * kDSlots);       // x tile
+    const uint32_t xempty_bar = xfull_bar + 8u;
+    const uint32_t gfull_bar = xfull_bar + 16u;                                   // dx accumulator
+    const uint32_t gempty_bar = xfull_bar + 24u;
+    const uint32_t wdone_bar = xfull_bar + 32u;
+    const uint32_t tmem_ptr_smem = xfull_bar + 40u;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -129,19 +145,26 @@ node_fused_bwd_kernel(const __grid_constant__ CUtensorMap tmap_hs,
     const int np = pbase + (int(blockIdx.x) < prem ? 1 : 0);
     const int p0 = int(blockIdx.x) * pbase + (int(blockIdx.x) < prem ? int(blockIdx.x) : prem);
 
+    // the padded row range of a D item's node: two loads from a table that consecutive items of a
+    // CTA walk almost sequentially (L1 hits after the first touch of a line)
+    auto decode_d = [&](int32_t n) {
+        const int32_t b = __ldg(p.pptr + n);
+        return make_dunit(b, __ldg(p.pptr + n + 1) - b);
+    };
+
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(xfull_bar(s), 1);
-            mbar_init(xempty_bar(s), 1);
+        for (int s = 0; s < kDSlots; ++s) {
             mbar_init(dfull_bar(s), 1);
             mbar_init(dempty_bar(s), 4);
-            mbar_init(gfull_bar(s), 1);
-            mbar_init(gempty_bar(s), 4);
         }
+        mbar_init(xfull_bar, 1);
+        mbar_init(xempty_bar, 1);
+        mbar_init(gfull_bar, 1);
+        mbar_init(gempty_bar, 4);
         mbar_init(wdone_bar, 1);
         fence_mbar_init();
     }
@@ -164,247 +187,283 @@ node_fused_bwd_kernel(const __grid_constant__ CUtensorMap tmap_hs,
 
     if (warp == 0) {
         // ===================== TMA producer =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        auto advance = [&]() {
+            if (++stage == kStages) {
+                stage = 0;
+                phase ^= 1u;
+            }
+        };
+        uint32_t n_x = 0;  // node blocks consumed so far
+        const uint64_t pol_stream = l2_policy_evict_first();
         if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            uint32_t n_x = 0;
-            const uint64_t pol_stream = l2_policy_evict_first();
             Item nx = v0 < v1 ? load_item(p.items, v0) : Item{};
+            DUnit un = (v0 < v1 && nx.a.x == IT_D) ? decode_d(nx.a.y) : DUnit{};
             for (int64_t v = v0; v < v1; v += vstep) {
                 const Item it = nx;
-                if (v + vstep < v1) nx = load_item(p.items, v + vstep);
+                const DUnit u = un;
+                if (v + vstep < v1) {
+                    nx = load_item(p.items, v + vstep);
+                    if (nx.a.x == IT_D) un = decode_d(nx.a.y);
+                }
                 if (it.a.x == IT_D) {
-                    const DUnit u = decode_d(p, it.a.y);
-                    for (int f = 0; f * 2 < u.nkb; ++f) {
-                        const int nk = u.nkb - 2 * f < 2 ? u.nkb - 2 * f : 2;
+                    for (int kb = 0; kb < u.nkb; ++kb) {
                         mbar_wait(empty_bar(stage), phase ^ 1u);
-                        const uint32_t sa = smem_base + stage * kStageBytes;
-                        mbar_arrive_expect_tx(full_bar(stage), nk * kDKbBytes);
-                        for (int t = 0; t < nk; ++t) {
-                            const int32_t r = u.row0 + (2 * f + t) * kKB;
-                            const uint32_t st = sa + t * kDKbBytes;
+                        const uint32_t st = smem_base + stage * kStageBytes;
+                        mbar_arrive_expect_tx(full_bar(stage), kDKbBytes);
+                        const int32_t r = u.row0 + kb * kKB;
+                        if (p.tune & 1) {
+                            tma_load_2d(st, &tmap_hs, full_bar(stage), it.a.z * kM, r);
+                            tma_load_2d(st + kMnBlockBytes, &tmap_hs, full_bar(stage), it.a.z * kM + 64, r);
+                        } else {
                             tma_load_2d_hint(st, &tmap_hs, full_bar(stage), it.a.z * kM, r, pol_stream);
                             tma_load_2d_hint(st + kMnBlockBytes, &tmap_hs, full_bar(stage),
                                              it.a.z * kM + 64, r, pol_stream);
-                            tma_load_2d(st + 2 * kMnBlockBytes, &tmap_gs, full_bar(stage), 0, r);
                         }
-                        if (++stage == kStages) {
-                            stage = 0;
-                            phase ^= 1u;
-                        }
+                        tma_load_2d(st + 2 * kMnBlockBytes, &tmap_gs, full_bar(stage), 0, r);
+                        advance();
                     }
                 } else if (it.a.x == IT_X) {
-                    if (do_dw) {
-                        const uint32_t xs = n_x & 1u, xphase = (n_x >> 1) & 1u;
-                        mbar_wait(xempty_bar(xs), xphase ^ 1u);
-                        mbar_arrive_expect_tx(xfull_bar(xs), kXbBytes);
-                        tma_load_2d(xb_base + xs * kXbBytes, &tmap_x, xfull_bar(xs), 0, it.a.y);
+                    const int q = it.b.w & 0xff;
+                    const bool first = (it.b.w >> 8) & 1, last = (it.b.w >> 9) & 1;
+                    if (first && do_dw) {
+                        mbar_wait(xempty_bar, (n_x & 1u) ^ 1u);
+                        mbar_arrive_expect_tx(xfull_bar, kXbBytes);
+                        tma_load_2d(xb_base, &tmap_x, xfull_bar, 0, it.a.y);
                     }
-                    ++n_x;
-                    if (np > 0 && it.b.x >= 0) {
+                    if (last) ++n_x;
+                    if (it.b.x >= 0) {
                         wait_counter(p.flags + it.b.x, it.b.y);
                         fence_proxy_async_global();
                     }
-                    for (int q = 0; q < np; ++q) {
+                    if (stage & 1) {  // a pair starts on an even stage
                         mbar_wait(empty_bar(stage), phase ^ 1u);
-                        const uint32_t sa = smem_base + stage * kStageBytes;
-                        mbar_arrive_expect_tx(full_bar(stage), 2 * kDuBoxBytes + 2 * kMnBlockBytes);
-                        const int32_t c0 = (p0 + q) * kPairCols;
+                        mbar_arrive(full_bar(stage));
+                        advance();
+                    }
+                    const int32_t c0 = (p0 + q) * kPairCols;
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            tma_load_2d(sa + j * kDuBoxBytes, &tmap_du, full_bar(stage), c0 + j * 64,
-                                        it.a.z);
-                            tma_load_2d(sa + 2 * kDuBoxBytes + j * kMnBlockBytes, &tmap_w3k,
-                                        full_bar(stage), c0 + j * 64, 0);
-                        }
-                        if (++stage == kStages) {
-                            stage = 0;
-                            phase ^= 1u;
-                        }
+                    for (int j = 0; j < 2; ++j) {
+                        mbar_wait(empty_bar(stage), phase ^ 1u);
+                        const uint32_t st = smem_base + stage * kStageBytes;
+                        mbar_arrive_expect_tx(full_bar(stage), kDuBoxBytes + kMnBlockBytes);
+                        tma_load_2d(st, &tmap_du, full_bar(stage), c0 + j * 64, it.a.z);
+                        tma_load_2d(st + kDuBoxBytes, &tmap_w3k, full_bar(stage), c0 + j * 64, 0);
+                        advance();
                     }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
+        constexpr uint32_t idesc_mn = umma_idesc_bf16(kM, kW, 1, 1);  // D and dW3k^T products
+        constexpr uint32_t idesc_k = umma_idesc_bf16(kM, kW, 0, 0);   // dx product
+        int stage = 0;
+        uint32_t phase = 0;
+        auto advance = [&]() {
+            if (++stage == kStages) {
+                stage = 0;
+                phase ^= 1u;
+            }
+        };
+        uint32_t n_d = 0, n_x = 0;
         if (lane == 0) {
-            constexpr uint32_t idesc_mn = umma_idesc_bf16(kM, kW, 1, 1);  // D and dW3k^T products
-            constexpr uint32_t idesc_k = umma_idesc_bf16(kM, kW, 0, 0);   // dx product
-            int stage = 0;
-            uint32_t phase = 0;
-            uint32_t n_d = 0, n_x = 0;
             Item nx = v0 < v1 ? load_item(p.items, v0) : Item{};
+            DUnit un = (v0 < v1 && nx.a.x == IT_D) ? decode_d(nx.a.y) : DUnit{};
             for (int64_t v = v0; v < v1; v += vstep) {
                 const Item it = nx;
-                if (v + vstep < v1) nx = load_item(p.items, v + vstep);
+                const DUnit u = un;
+                if (v + vstep < v1) {
+                    nx = load_item(p.items, v + vstep);
+                    if (nx.a.x == IT_D) un = decode_d(nx.a.y);
+                }
                 if (it.a.x == IT_D) {
-                    const DUnit u = decode_d(p, it.a.y);
-                    if (u.nkb == 0) continue;  // empty group: the epilogue writes zeros on its own
-                    const uint32_t ds = n_d & 1u, dphase = (n_d >> 1) & 1u;
+                    // every D item takes a turn on the accumulator slots - also the one of an empty
+                    // group (no MMAs: the commit fires at once and the epilogue stores zeros)
+                    const uint32_t ds = n_d % kDSlots, dphase = (n_d / kDSlots) & 1u;
                     ++n_d;
                     mbar_wait(dempty_bar(ds), dphase ^ 1u);
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + kTmemD + ds * kW;
-                    for (int f = 0; f * 2 < u.nkb; ++f) {
-                        const int nk = u.nkb - 2 * f < 2 ? u.nkb - 2 * f : 2;
+                    for (int kb = 0; kb < u.nkb; ++kb) {
                         mbar_wait(full_bar(stage), phase);
                         tc_fence_after();
-                        const uint32_t sa = smem_base + stage * kStageBytes;
-                        for (int t = 0; t < nk; ++t) {
-                            const uint32_t st = sa + t * kDKbBytes;
-                            const uint64_t adesc = umma_smem_desc(st, kMnBlockBytes, 1024, kSwizzle128B);
-                            const uint64_t bdesc =
-                                umma_smem_desc(st + 2 * kMnBlockBytes, kMnBlockBytes, 1024, kSwizzle128B);
-                            const int kb = 2 * f + t;
-                            const int steps = kb == u.nkb - 1 ? u.last_steps : kKB / kUmmaK;
-                            for (int k = 0; k < steps; ++k) {
-                                // MN-major operands: a K-step of 16 rows advances the start by 2 KB
-                                umma_bf16_ss(tmem_d, adesc + 128ull * k, bdesc + 128ull * k, idesc_mn,
-                                             (kb | k) != 0 ? 1u : 0u);
-                            }
+                        const uint32_t st = smem_base + stage * kStageBytes;
+                        const uint64_t adesc = umma_smem_desc(st, kMnBlockBytes, 1024, kSwizzle128B);
+                        const uint64_t bdesc =
+                            umma_smem_desc(st + 2 * kMnBlockBytes, kMnBlockBytes, 1024, kSwizzle128B);
+                        const int steps = kb == u.nkb - 1 ? u.last_steps : kKB / kUmmaK;
+                        for (int k = 0; k < steps; ++k) {
+                            // MN-major operands: a K-step of 16 rows advances the start by 2 KB
+                            umma_bf16_ss(tmem_d, adesc + 128ull * k, bdesc + 128ull * k, idesc_mn,
+                                         (kb | k) != 0 ? 1u : 0u);
                         }
                         umma_commit(empty_bar(stage));
-                        if (++stage == kStages) {
-                            stage = 0;
-                            phase ^= 1u;
-                        }
+                        advance();
                     }
                     umma_commit(dfull_bar(ds));
                 } else if (it.a.x == IT_X) {
-                    const uint32_t xs = n_x & 1u, xphase = (n_x >> 1) & 1u;
-                    const bool first_x = n_x == 0;
-                    ++n_x;
-                    mbar_wait(gempty_bar(xs), xphase ^ 1u);  // dx slot (same parity as the x tile)
-                    if (do_dw) mbar_wait(xfull_bar(xs), xphase);
-                    tc_fence_after();
-                    const uint32_t tmem_x = tmem_base + kTmemDx + xs * kW;
-                    const uint64_t xdesc =
-                        umma_smem_desc(xb_base + xs * kXbBytes, kMnBlockBytes, 1024, kSwizzle128B);
-                    for (int q = 0; q < np; ++q) {
-                        mbar_wait(full_bar(stage), phase);
+                    const int q = it.b.w & 0xff;
+                    const bool first = (it.b.w >> 8) & 1, last = (it.b.w >> 9) & 1;
+                    const uint32_t xphase = n_x & 1u;
+                    const bool first_block = n_x == 0;
+                    if (first) {
+                        mbar_wait(gempty_bar, xphase ^ 1u);  // the dx accumulator has been drained
+                        if (do_dw) mbar_wait(xfull_bar, xphase);
                         tc_fence_after();
-                        const uint32_t sa = smem_base + stage * kStageBytes;
-                        if (do_dw) {
-                            // dW3k^T[128 cols x 64 i] += dU_tile^T . x_tile  (reduction: 128 nodes)
-                            const uint64_t adesc = umma_smem_desc(sa, kDuBoxBytes, 1024, kSwizzle128B);
-#pragma unroll
-                            for (int k = 0; k < kM / kUmmaK; ++k) {
-                                umma_bf16_ss(tmem_base + kTmemDw + q * kW, adesc + 128ull * k,
-                                             xdesc + 128ull * k, idesc_mn, (!first_x || k != 0) ? 1u : 0u);
-                            }
-                        }
-                        if (do_dx) {
-                            // dx[128 nodes x 64 i] += dU_tile . W3k_tile^T  (reduction: 128 columns)
-#pragma unroll
-                            for (int j = 0; j < 2; ++j) {
-                                const uint64_t adesc =
-                                    umma_smem_desc(sa + j * kDuBoxBytes, 16, 1024, kSwizzle128B);
-                                const uint64_t bdesc = umma_smem_desc(
-                                    sa + 2 * kDuBoxBytes + j * kMnBlockBytes, 16, 1024, kSwizzle128B);
-#pragma unroll
-                                for (int k = 0; k < kKB / kUmmaK; ++k) {
-                                    umma_bf16_ss(tmem_x, adesc + 2ull * k, bdesc + 2ull * k, idesc_k,
-                                                 (q | j | k) != 0 ? 1u : 0u);
-                                }
-                            }
-                        }
+                    }
+                    const uint32_t tmem_x = tmem_base + kTmemDx;
+                    const uint64_t xdesc = umma_smem_desc(xb_base, kMnBlockBytes, 1024, kSwizzle128B);
+                    if (stage & 1) {  // the producer passed over this stage
+                        mbar_wait(full_bar(stage), phase);
                         umma_commit(empty_bar(stage));
-                        if (++stage == kStages) {
-                            stage = 0;
-                            phase ^= 1u;
+                        advance();
+                    }
+                    const uint32_t st = smem_base + stage * kStageBytes;  // even: st + 24 KB is next
+                    mbar_wait(full_bar(stage), phase);
+                    mbar_wait(full_bar(stage + 1), phase);
+                    tc_fence_after();
+                    if (do_dw) {
+                        // dW3k^T[128 cols x 64 i] += dU_tile^T . x_tile  (reduction: 128 nodes);
+                        // the two 64-column boxes of dU are one stage (24 KB) apart
+                        const uint64_t adesc = umma_smem_desc(st, kStageBytes, 1024, kSwizzle128B);
+#pragma unroll
+                        for (int k = 0; k < kM / kUmmaK; ++k) {
+                            umma_bf16_ss(tmem_base + kTmemDw + q * kW, adesc + 128ull * k,
+                                         xdesc + 128ull * k, idesc_mn, (!first_block || k != 0) ? 1u : 0u);
                         }
                     }
-                    if (do_dw) umma_commit(xempty_bar(xs));
-                    umma_commit(gfull_bar(xs));
+                    if (do_dx) {
+                        // dx[128 nodes x 64 i] += dU_tile . W3k_tile^T  (reduction: 128 columns)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const uint64_t adesc =
+                                umma_smem_desc(st + j * kStageBytes, 16, 1024, kSwizzle128B);
+                            const uint64_t bdesc = umma_smem_desc(st + j * kStageBytes + kDuBoxBytes, 16,
+                                                                  1024, kSwizzle128B);
+#pragma unroll
+                            for (int k = 0; k < kKB / kUmmaK; ++k) {
+                                umma_bf16_ss(tmem_x, adesc + 2ull * k, bdesc + 2ull * k, idesc_k,
+                                             (!first || (j | k) != 0) ? 1u : 0u);
+                            }
+                        }
+                    }
+                    umma_commit(empty_bar(stage));
+                    advance();
+                    umma_commit(empty_bar(stage));
+                    advance();
+                    if (last) {
+                        if (do_dw) umma_commit(xempty_bar);
+                        umma_commit(gfull_bar);
+                        ++n_x;
+                    }
                 }
             }
             umma_commit(wdone_bar);
         }
     } else {
         // ===================== epilogue (warps 2..5): thread = accumulator row =====================
-        const int q4 = warp & 3;  // TMEM lane quarter this warp may access
-        const int row = q4 * 32 + lane;
+        const int q4 = warp & 3;           // TMEM lane quarter this warp may access
         const uint32_t lane_addr = uint32_t(q4 * 32) << 16;
         const uint32_t stage_smem = bar_base + 256 + q4 * 4096;
         const int64_t du_pitch = int64_t(kW) * p.K;  // elements per row of the dU buffer
         uint32_t n_d = 0, n_x = 0;
+        // The counter update of a D item (a release, then the add) is deferred until this warp next
+        // has to wait or is about to store the next item: a release right behind the stores waits
+        // for their whole round trip.  It is never held across a blocking wait.
+        int32_t pending = -1;
+        auto flush = [&]() {
+            if (pending >= 0) {
+                __syncwarp();
+                if (lane == 0) red_release_add(p.flags + pending, 1);
+                pending = -1;
+            }
+        };
+        auto wait_full = [&](uint32_t bar, uint32_t parity) {
+            uint32_t ready = 0;
+            if (lane == 0) ready = mbar_try_wait(bar, parity);
+            ready = __shfl_sync(0xffffffffu, ready, 0);
+            if (!ready) {
+                flush();
+                if (lane == 0) mbar_wait_backoff(bar, parity, 32);
+            }
+            __syncwarp();
+        };
         Item nx = v0 < v1 ? load_item(p.items, v0) : Item{};
+        DUnit un = (v0 < v1 && nx.a.x == IT_D) ? decode_d(nx.a.y) : DUnit{};
         for (int64_t v = v0; v < v1; v += vstep) {
             const Item it = nx;
-            if (v + vstep < v1) nx = load_item(p.items, v + vstep);
+            const DUnit u = un;
+            if (v + vstep < v1) {
+                nx = load_item(p.items, v + vstep);
+                if (nx.a.x == IT_D) un = decode_d(nx.a.y);
+            }
             if (it.a.x == IT_D) {
-                const DUnit u = decode_d(p, it.a.y);
+                const uint32_t ds = n_d % kDSlots, dphase = (n_d / kDSlots) & 1u;
+                ++n_d;
                 __nv_bfloat16* out = p.du + int64_t(it.a.w) * du_pitch + int64_t(it.a.z) * kM * kW;
-                if (lane == 0 && it.b.x >= 0) wait_counter(p.flags + it.b.x, it.b.y);  // ring slot free
-                __syncwarp();
-                if (u.nkb == 0) {
-                    uint4* dst = reinterpret_cast<uint4*>(out + row * kW);
-#pragma unroll
-                    for (int j = 0; j < kW / 8; ++j) dst[j] = make_uint4(0u, 0u, 0u, 0u);
-                } else {
-                    const uint32_t ds = n_d & 1u, dphase = (n_d >> 1) & 1u;
-                    ++n_d;
-                    if (lane == 0) mbar_wait(dfull_bar(ds), dphase);
+                if (it.b.x >= 0) {  // ring slot free?
+                    flush();
+                    if (lane == 0) wait_counter(p.flags + it.b.x, it.b.y);
                     __syncwarp();
-                    tc_fence_after();
+                }
+                wait_full(dfull_bar(ds), dphase);
+                tc_fence_after();
+                uint32_t w[32];
+                if (u.nkb == 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) w[j] = 0u;
+                } else {
                     const uint32_t tcol = tmem_base + lane_addr + kTmemD + ds * kW;
                     float f0[32], f1[32];
                     tmem_ld32(tcol, f0);
                     tmem_ld32(tcol + 32, f1);
                     tmem_ld_wait();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(dempty_bar(ds));
-                    uint32_t w[32];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         w[j] = pack_bf16(f0[2 * j], f0[2 * j + 1]);
                         w[16 + j] = pack_bf16(f1[2 * j], f1[2 * j + 1]);
                     }
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        sts128(stage_smem + lane * 128 + ((c ^ (lane & 7)) << 4),
-                               make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
-                    }
-                    __syncwarp();
-                    // rows of dU[n][chunk] are 128 B and consecutive: 512 contiguous bytes per store
-                    uint8_t* gbase = reinterpret_cast<uint8_t*>(out + q4 * 32 * kW);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int r = j * 4 + (lane >> 3), c = lane & 7;
-                        const uint4 t = lds128(stage_smem + r * 128 + ((c ^ (r & 7)) << 4));
-                        *reinterpret_cast<uint4*>(gbase + r * 128 + c * 16) = t;
-                    }
-                    __syncwarp();
                 }
-                if (it.b.z >= 0) {
-                    __threadfence();
-                    __syncwarp();
-                    if (lane == 0) atomicAdd(p.flags + it.b.z, 1);
-                }
-            } else if (it.a.x == IT_X) {
-                const uint32_t xs = n_x & 1u, xphase = (n_x >> 1) & 1u;
-                ++n_x;
-                if (lane == 0) mbar_wait(gfull_bar(xs), xphase);
+                tc_fence_before();
                 __syncwarp();
+                if (lane == 0) mbar_arrive(dempty_bar(ds));
+                flush();  // the previous item's counter, before this item's stores
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    sts128(stage_smem + lane * 128 + ((c ^ (lane & 7)) << 4),
+                           make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
+                }
+                __syncwarp();
+                // rows of dU[n][chunk] are 128 B and consecutive: 512 contiguous bytes per store
+                uint8_t* gbase = reinterpret_cast<uint8_t*>(out + q4 * 32 * kW);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int r = j * 4 + (lane >> 3), c = lane & 7;
+                    const uint4 t = lds128(stage_smem + r * 128 + ((c ^ (r & 7)) << 4));
+                    *reinterpret_cast<uint4*>(gbase + r * 128 + c * 16) = t;
+                }
+                __syncwarp();
+                pending = it.b.z;
+            } else if (it.a.x == IT_X) {
+                if (!((it.b.w >> 9) & 1)) continue;  // only the last pair of a block ends in an epilogue
+                const uint32_t xphase = n_x & 1u;
+                ++n_x;
+                wait_full(gfull_bar, xphase);
                 tc_fence_after();
-                // every MMA of the item has completed: this CTA is done with the block's dU
+                // every MMA of the block has completed: this CTA is done with the block's dU
                 if (it.b.z >= 0 && lane == 0) atomicAdd(p.flags + it.b.z, 1);
                 if (do_dx) {
-                    const uint32_t tcol = tmem_base + lane_addr + kTmemDx + xs * kW;
+                    const uint32_t tcol = tmem_base + lane_addr + kTmemDx;
                     const int rows_here = it.a.w - q4 * 32;
                     uint8_t* gbase = reinterpret_cast<uint8_t*>(
                         p.dx_part + (int64_t(blockIdx.x) * p.N + it.a.y + q4 * 32) * kW);
 #pragma unroll
                     for (int piece = 0; piece < 2; ++piece) {
                         float f[32];
-                        if (np > 0) {
-                            tmem_ld32(tcol + piece * 32, f);
-                            tmem_ld_wait();
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) f[j] = 0.f;
-                        }
+                        tmem_ld32(tcol + piece * 32, f);
+                        tmem_ld_wait();
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
                             sts128(stage_smem + lane * 128 + ((c ^ (lane & 7)) << 4),
@@ -425,9 +484,10 @@ node_fused_bwd_kernel(const __grid_constant__ CUtensorMap tmap_hs,
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(gempty_bar(xs));
+                if (lane == 0) mbar_arrive(gempty_bar);
             }
         }
+        flush();
         // ---- the weight-gradient accumulators of this CTA's column slice leave TMEM once
         if (do_dw && np > 0) {
             if (lane == 0) mbar_wait(wdone_bar, 0);
@@ -519,7 +579,7 @@ extern "C" int gkn_node_fused_bwd_grid(int32_t K, int32_t W, int32_t* grid, int3
                          "(more than 4 column pairs per CTA)");
     }
     if (grid) *grid = sms;
-    if (parts) *parts = sms;
+    if (parts) *parts = pairs < sms ? pairs : sms;  // CTAs that own at least one column pair
     return 0;
 }
 
@@ -564,6 +624,14 @@ extern "C" int gkn_node_fused_bwd_bf16(const void* hs_bf16, const void* gs_bf16,
     p.N = N;
     p.K = K;
     p.accumulate_dw = accumulate_dw;
+    {
+        static int tune = -1;
+        if (tune < 0) {
+            const char* e = getenv("GKN_FUSED_TUNE");
+            tune = e != nullptr ? atoi(e) : 0;
+        }
+        p.tune = tune;
+    }
     cudaError_t err = cudaFuncSetAttribute(node_fused_bwd_kernel,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (err != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(node_fused_bwd)", err);

@@ -230,16 +230,25 @@ _MLP_SIDE_GEMM = os.environ.get("GKN_MLP_SIDE_GEMM", "1") == "1"
 # U of every application ([A, N, w*K] bf16) is kept for the dh pass when it fits this budget
 # (6.3 GB for 8 BBA frames); otherwise it is recomputed node range by node range in backward
 _SAVE_U_BYTES = int(os.environ.get("GKN_NODE_SAVE_U_MB", "24576")) << 20
-# Fused producer/consumer forward (csrc/gkn_node_fused.cu): U = x W3r is produced by the same
-# kernel that consumes it and crosses the L2 instead of HBM.  GKN_NODE_FUSED=0 selects the
-# two-kernel form (library GEMM + grouped message kernel).
-NODE_FUSED = os.environ.get("GKN_NODE_FUSED", "1") == "1"
+# How U = x W3r reaches the grouped message kernel (csrc/gkn_node_fused.cu), GKN_NODE_FUSED:
+#   "gemm" (default) U is written by the producer half of the fused kernel run on its own (a
+#           hand-written tcgen05 GEMM: 0.205 ms per application at the bench shape, the library GEMM
+#           0.185) and read back by gkn_node_msg_bf16;
+#   "1"     one launch per application produces AND consumes U, which then crosses the L2 only
+#           (-17 % HBM traffic by ncu, but the in-order item pipelines leave it latency-bound:
+#           0.75 ms in the training step against 0.71 for "gemm" - see DESIGN.md section 6);
+#   "0"     library GEMM (torch.mm) + grouped message kernel, as in round 1.
+_NODE_FUSED_MODE = os.environ.get("GKN_NODE_FUSED", "gemm")
+NODE_FUSED = _NODE_FUSED_MODE == "1"
+NODE_U_GEMM = _NODE_FUSED_MODE == "gemm"
 # node blocks of the U ring when U is not kept for the backward (forward-only calls)
 _FUSED_RING = int(os.environ.get("GKN_NODE_FUSED_RING", "4"))
-_FUSED_SLACK = float(os.environ.get("GKN_NODE_FUSED_SLACK", "0.5"))
-# Fused backward (csrc/gkn_node_fused_bwd.cu): dU is produced into a ring of node blocks and
-# consumed from the L2 by the weight-gradient / dx products of the same launch.
-NODE_FUSED_BWD = os.environ.get("GKN_NODE_FUSED_BWD", "1") == "1"
+_FUSED_SLACK = float(os.environ.get("GKN_NODE_FUSED_SLACK", "1.5"))
+# Fused backward (csrc/gkn_node_fused_bwd.cu, GKN_NODE_FUSED_BWD=1): dU is produced into a ring of
+# node blocks and consumed from the L2 by the weight-gradient / dx products of the same launch - no
+# library GEMM and 41 % less HBM traffic per application (ncu), but 1.05 ms against 0.94 ms for
+# the three-kernel form at the bench shape, so it is opt-in.
+NODE_FUSED_BWD = os.environ.get("GKN_NODE_FUSED_BWD", "0") == "1"
 _FUSED_BWD_RING = int(os.environ.get("GKN_NODE_FUSED_BWD_RING", "3"))
 
 
@@ -284,6 +293,8 @@ class _GKNStackNode(torch.autograd.Function):
         if NODE_MN and want_agg and A * N * W * K * 2 <= _SAVE_U_BYTES:
             u_all = torch.empty((A, N, W * K), dtype=bf, device=x.device)
         fused = None
+        if NODE_U_GEMM:
+            w3g = w3r if W >= 64 else torch.cat([w3r, torch.zeros_like(w3r)], 0)
         if NODE_FUSED and (u_all is not None or not want_agg):
             # one launch per application: U tiles are produced and consumed inside it.  With a
             # backward to come U is written to the kept buffer; forward-only calls use a small ring
@@ -300,11 +311,20 @@ class _GKNStackNode(torch.autograd.Function):
                 ops.node_fused_fwd(xp, w3p, hs, u_all[a] if u_all is not None else u_ring, fused,
                                    flags[a], msg, N, lay.e_pad, K, W)
             elif u_all is not None:
-                torch.mm(xb, w3r, out=u_all[a])   # [N, (o, k)], kept for the dh pass
+                if NODE_U_GEMM:
+                    xp = xb if W >= 64 else torch.cat([xb, torch.zeros_like(xb)], 1)
+                    ops.node_u_gemm(xp, w3g, u_all[a], N, K, W)   # [N, (o, k)], kept for the dh pass
+                else:
+                    torch.mm(xb, w3r, out=u_all[a])
                 ops.node_msg(hs, u_all[a].view(N, W, K), lay, 0, lay.num_units, 0, msg)
             else:
                 for n0, n1 in chunks:
-                    U = torch.mm(xb[n0:n1], w3r)   # [nc, (o, k)]
+                    if NODE_U_GEMM:
+                        xp = xb[n0:n1] if W >= 64 else torch.cat([xb[n0:n1], torch.zeros_like(xb[n0:n1])], 1)
+                        U = torch.empty((n1 - n0, W * K), dtype=bf, device=x.device)
+                        ops.node_u_gemm(xp.contiguous(), w3g, U, n1 - n0, K, W)
+                    else:
+                        U = torch.mm(xb[n0:n1], w3r)   # [nc, (o, k)]
                     ops.node_msg(hs, U.view(n1 - n0, W, K), lay, lay.unit_first[n0],
                                  lay.unit_first[n1], n0, msg)
                     del U

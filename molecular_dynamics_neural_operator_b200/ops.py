@@ -654,31 +654,48 @@ IT_P, IT_C, IT_NOP = 0, 1, 2
 
 @dataclass
 class FusedSchedule:
-    """Work-item list of gkn_node_fused_fwd_bf16 for one padded layout (see gkn_b200.h).
-
-    Order: the producer tiles of node block b are spread over list positions [b-1, b) (in units of
-    one block's worth of work) and the message units of block b over [b+slack, b+1+slack): the
-    tiles of a block are complete ``slack`` blocks before its first consumer needs them and live
-    for at most ~2.5 blocks (40 MB at w = 64) - inside the L2.  ``ring`` > 0: U is a ring of that
-    many node blocks; a producer tile of block b then waits for the consumers of block b - ring."""
+    """Work-item list of a fused producer/consumer kernel (see gkn_b200.h).  Item v is executed by
+    CTA ``v % grid``; every CTA runs its items in list order."""
 
     items: torch.Tensor   # int32 [num_items, 8]
     num_items: int
     num_flags: int
-    u_rows: int           # rows ([W, K] slabs) of the U buffer the items address
+    u_rows: int           # rows of the U / dU buffer the items address
     ring: int
+    grid: int = 0         # CTAs the list was dealt for (0: any)
 
 
-def fused_fwd_schedule(lay: NodeLayout, W: int, K: int, ring: int = 0,
-                       slack: float = 0.5) -> FusedSchedule:
-    """Build (cached on the layout) the item list.  Device-side index arithmetic only."""
+def device_sm_count() -> int:
+    import ctypes
+
+    lib = _lib.load()
+    n = ctypes.c_int(0)
+    _lib.check(lib.gkn_device_info(ctypes.byref(n), None, None), "gkn_device_info")
+    return int(n.value)
+
+
+def fused_fwd_schedule(lay: NodeLayout, W: int, K: int, ring: int = 0, slack: float = 1.0,
+                       grid: int | None = None) -> FusedSchedule:
+    """Item list of gkn_node_fused_fwd_bf16 for one padded layout (cached on it).  Device-side
+    index arithmetic only.
+
+    Every item gets a time key in units of "one node block's worth of work": the producer tiles of
+    block b are spread over [b-1, b), the message units of block b over [b+slack, b+1+slack) - a
+    block of U is complete ``slack`` blocks before its first consumer asks for it and lives for
+    about 2 + slack blocks (16 MB each at w = 64), inside the L2.  Tiles and units are dealt
+    round-robin over the ``grid`` CTAs SEPARATELY (every CTA gets the same number of each kind) and
+    each CTA's queue is sorted by key; queue slot t of CTA c is list position t*grid + c, unused
+    slots are no-ops.  Waits only ever refer to items with a smaller key, and every queue is in
+    key order, so the waits cannot form a cycle.  ``ring`` > 0: U is a ring of that many node
+    blocks; a producer tile of block b then waits for the consumers of block b - ring."""
     cache = lay.__dict__.setdefault("_fused_sched", {})
-    key = (W, K, ring, slack)
+    G = int(grid) if grid else device_sm_count()
+    key = (W, K, ring, slack, G)
     if key in cache:
         return cache[key]
     if ring and ring < 2 + slack:
         raise ValueError("fused_fwd_schedule: the ring must hold at least 2 + slack node blocks "
-                         "(a tile may only wait for consumers that precede it in the list)")
+                         "(a tile may only wait for consumers with a smaller time key)")
     dev = lay.units.device
     N, U = lay.num_nodes, lay.num_units
     NB = (N + FUSED_BLOCK - 1) // FUSED_BLOCK
@@ -712,12 +729,61 @@ def fused_fwd_schedule(lay: NodeLayout, W: int, K: int, ring: int = 0,
     c_items = torch.stack([torch.full_like(grp, IT_C), row0, rows, urow, blk,
                            torch.full_like(grp, 4 * J), NB + blk if ring else torch.full_like(grp, -1),
                            torch.zeros_like(grp)], 1)
+    # ---- deal both kinds round-robin, sort every CTA's queue by key, interleave the queues
+    nP = NB * J
+    cta = torch.cat([torch.arange(nP, **i64) % G, torch.arange(U, **i64) % G])
     keys = torch.cat([p_key, c_key])
-    order = torch.argsort(keys, stable=True)
-    items = torch.cat([p_items, c_items])[order].int().contiguous()
-    sched = FusedSchedule(items, int(items.size(0)), 2 * NB, ring * FUSED_BLOCK if ring else N, ring)
+    by_key = torch.argsort(keys, stable=True)
+    order = by_key[torch.argsort(cta[by_key], stable=True)]     # sorted by (cta, key)
+    cta_s = cta[order]
+    cnt = torch.bincount(cta_s, minlength=G)
+    first = torch.cumsum(cnt, 0) - cnt
+    rank = torch.arange(nP + U, **i64) - first[cta_s]
+    qlen = (nP + G - 1) // G + (U + G - 1) // G      # longest queue (host arithmetic, no sync)
+    items = torch.zeros((qlen * G, 8), **i64)
+    items[:, 0], items[:, 4], items[:, 6] = IT_NOP, -1, -1
+    items[rank * G + cta_s] = torch.cat([p_items, c_items])[order]
+    sched = FusedSchedule(items.int().contiguous(), qlen * G, 2 * NB,
+                          ring * FUSED_BLOCK if ring else N, ring, G)
     cache[key] = sched
     return sched
+
+
+_GEMM_SCHED_CACHE: dict = {}
+
+
+def node_u_gemm(xb, w3r, u, N: int, K: int, W: int) -> None:
+    """U = x @ W3r on the producer half of the fused kernel alone (gkn_node_fused_fwd_bf16 with
+    "P" items only, no counters): the dense node-level GEMM of the node-first forward as a
+    hand-written tcgen05 kernel - A = x tile, B = W3 read in place as an MN-major operand, bf16
+    output through the swizzled staging tile.  xb bf16 [N, max(W,64)], w3r bf16 [max(W,64), W*K],
+    u bf16 [N, W*K]."""
+    lib = _lib.load()
+    Wp = max(W, 64)
+    if xb.shape != (N, Wp) or w3r.shape != (Wp, W * K) or u.numel() != N * W * K:
+        raise ValueError("node_u_gemm: shape mismatch")
+    G = device_sm_count()
+    key = (N, W, K, G, str(xb.device))
+    if key not in _GEMM_SCHED_CACHE:
+        import numpy as np
+
+        NB, J = (N + FUSED_BLOCK - 1) // FUSED_BLOCK, W * K // FUSED_TILE_COLS
+        b = np.repeat(np.arange(NB, dtype=np.int64), J)
+        j = np.tile(np.arange(J, dtype=np.int64), NB)
+        it = np.zeros((NB * J, 8), dtype=np.int64)
+        it[:, 0], it[:, 1], it[:, 2], it[:, 3] = IT_P, b * FUSED_BLOCK, j * FUSED_TILE_COLS, b * FUSED_BLOCK
+        it[:, 4], it[:, 6] = -1, -1
+        it[:, 7] = np.minimum(FUSED_BLOCK, N - b * FUSED_BLOCK)
+        _GEMM_SCHED_CACHE[key] = torch.from_numpy(it.astype(np.int32)).to(xb.device)
+    items = _GEMM_SCHED_CACHE[key]
+    with torch.cuda.device(xb.device), _timed("node_u_gemm"):
+        _lib.check(
+            lib.gkn_node_fused_fwd_bf16(
+                _p(xb, torch.bfloat16, "xb"), _p(w3r, torch.bfloat16, "w3r"), c_void_p(0),
+                _p(u, torch.bfloat16, "u"), _p(items, torch.int32, "items"), int(items.size(0)),
+                _p(items, torch.int32, "flags"), c_void_p(0), N, 0, N, K, W, G, _stream()),
+            "gkn_node_fused_fwd_bf16",
+        )
 
 
 def node_fused_fwd(xb, w3r, hs, u, sched: FusedSchedule, flags, msg, N: int, e_pad: int, K: int,
@@ -741,7 +807,7 @@ def node_fused_fwd(xb, w3r, hs, u, sched: FusedSchedule, flags, msg, N: int, e_p
                 _p(hs, torch.bfloat16, "hs"), _p(u, torch.bfloat16, "u"),
                 _p(sched.items, torch.int32, "items"), sched.num_items,
                 _p(flags, torch.int32, "flags"), _p(msg, torch.float32, "msg"), N, e_pad,
-                sched.u_rows, K, W, _stream()),
+                sched.u_rows, K, W, sched.grid, _stream()),
             "gkn_node_fused_fwd_bf16",
         )
 
@@ -764,60 +830,114 @@ def fused_bwd_grid(K: int, W: int) -> tuple[int, int]:
     return int(g.value), int(parts.value)
 
 
-def fused_bwd_items(N: int, K: int, W: int, grid: int, ring: int):
+def fused_bwd_items(N: int, K: int, W: int, grid: int, ring: int, slack: float = 1.0,
+                    groups: int = 1):
     """Host-side construction of the item list of gkn_node_fused_bwd_bf16 (numpy int32 [n, 8]).
-    It depends only on (N, K, grid, ring) - every node has K/128 "D" items whether or not it has
-    edges - so it is built once and cached.
+    It depends only on (N, K, grid, ring, slack) - every node has K/128 "D" items whether or not it
+    has edges - so it is built once and cached.
 
-    Order: all D items of block 0; then for every block b: the first half of D(b+1), no-ops up to
-    a multiple of `grid`, the `grid` X items of block b (one per CTA), the second half of D(b+1).
-    So the gradient tiles of a block are complete half a block before they are consumed and the
-    ring slot of block b is free again (X(b) done) before D(b+2) starts."""
+    Time keys as in the forward: the D items of block b are spread over [b-1, b); CTA c's X items
+    of block b (one per 128-column pair of its slice) over [b+slack, b+slack+0.9), i.e. in between
+    the CTA's D items of later blocks.  D items are dealt round-robin; every CTA's queue is sorted
+    by key and queue slot t of CTA c is list position t*grid + c (unused slots are no-ops).  Inside
+    a queue the D items alternate between the ``groups`` epilogue groups of the kernel (one, as
+    built); the first D item a (CTA, group) has in a block carries the ring wait (block b-ring
+    consumed), the last one the signal - a release covers all earlier stores of its warp.  Waits
+    only refer to items with smaller keys: X(b) >= b+slack > D(b); D(b+ring) >= b+ring-1 >=
+    b+slack+0.9 > X(b)."""
     import numpy as np
 
-    if ring < 2:
-        raise ValueError("fused_bwd_items: the dU ring must hold at least 2 node blocks")
+    if ring < 1.9 + slack:
+        raise ValueError("fused_bwd_items: the dU ring must hold at least 1.9 + slack node blocks")
     C = K // 128
     NB = (N + FUSED_BLOCK - 1) // FUSED_BLOCK
-    nodes_of = [min(FUSED_BLOCK, N - FUSED_BLOCK * b) for b in range(NB)]
+    pairs = W * K // 128
+    base, rem = divmod(pairs, grid)
+    parts = min(grid, pairs)
+    # ---- D items: global order (node, chunk), round-robin over the CTAs
+    nD = N * C
+    d = np.arange(nD, dtype=np.int64)
+    node, chunk = d // C, d % C
+    blk = node // FUSED_BLOCK
+    t_blk = np.minimum(FUSED_BLOCK, N - blk * FUSED_BLOCK) * C
+    idx_in_blk = d - blk * FUSED_BLOCK * C
+    d_key = blk - 1 + (idx_in_blk + 0.5) / t_blk
+    d_cta = d % grid
+    D = np.zeros((nD, 8), dtype=np.int64)
+    D[:, 0], D[:, 1], D[:, 2] = IT_D, node, chunk
+    D[:, 3] = (blk % ring) * FUSED_BLOCK + node % FUSED_BLOCK
+    D[:, 4], D[:, 6] = -1, -1
+    # ---- X items: per CTA with a non-empty slice, per block, per pair
+    npairs = base + (np.arange(grid) < rem)
+    xc = np.repeat(np.arange(grid), npairs)                    # CTA of every (cta, q)
+    xq = np.concatenate([np.arange(n) for n in npairs]) if pairs else np.zeros(0, dtype=np.int64)
+    xn = npairs[xc]
+    nXb = xc.size                                               # X items per block
+    xb = np.repeat(np.arange(NB), nXb)
+    xc, xq, xn = np.tile(xc, NB), np.tile(xq, NB), np.tile(xn, NB)
+    x_key = xb + slack + 0.9 * (xq + 0.5) / xn
+    X = np.zeros((xb.size, 8), dtype=np.int64)
+    X[:, 0], X[:, 1], X[:, 2] = IT_X, FUSED_BLOCK * xb, (xb % ring) * FUSED_BLOCK
+    X[:, 3] = np.minimum(FUSED_BLOCK, N - FUSED_BLOCK * xb)
+    first, last = xq == 0, xq == xn - 1
+    X[:, 4] = np.where(first, xb, -1)
+    X[:, 6] = np.where(last, NB + xb, -1)
+    X[:, 7] = xq | (first.astype(np.int64) << 8) | (last.astype(np.int64) << 9)
+    # ---- per-CTA queues in key order
+    items = np.concatenate([D, X])
+    cta = np.concatenate([d_cta, xc])
+    key = np.concatenate([d_key, x_key])
+    kind_blk = np.concatenate([blk, xb])
+    order = np.lexsort((key, cta))                              # by cta, then key (stable)
+    items, cta, kind_blk = items[order], cta[order], kind_blk[order]
+    cnt = np.bincount(cta, minlength=grid)
+    start = np.cumsum(cnt) - cnt
+    rank = np.arange(items.shape[0]) - start[cta]
+    # D items alternate between the epilogue groups in queue order
+    is_d = items[:, 0] == IT_D
+    d_rank = np.cumsum(is_d) - 1
+    d_first_of_cta = np.zeros(grid, dtype=np.int64)
+    d_cnt = np.bincount(cta[is_d], minlength=grid)
+    d_first_of_cta[1:] = np.cumsum(d_cnt)[:-1]
+    grp = (d_rank - d_first_of_cta[cta]) % groups
+    # first / last D item of every (cta, group, block)
+    di = np.nonzero(is_d)[0]
+    gid = (cta[di] * groups + grp[di]) * NB + kind_blk[di]           # non-decreasing runs per (cta, grp)?
+    o = np.argsort(gid, kind="stable")
+    gs, dis = gid[o], di[o]
+    run_first = np.ones(gs.size, dtype=bool)
+    run_first[1:] = gs[1:] != gs[:-1]
+    run_last = np.ones(gs.size, dtype=bool)
+    run_last[:-1] = gs[1:] != gs[:-1]
+    firsts, lasts = dis[run_first], dis[run_last]
+    bl = kind_blk[lasts]
+    items[lasts, 6] = bl
+    signals = np.bincount(bl, minlength=NB)                     # releases per block
+    bf = kind_blk[firsts]
+    w = bf >= ring
+    items[firsts[w], 4] = NB + bf[w] - ring
+    items[firsts[w], 5] = 4 * parts
+    # X items wait for every release of their block
+    xi = np.nonzero((items[:, 0] == IT_X) & (items[:, 4] >= 0))[0]
+    items[xi, 5] = 4 * signals[items[xi, 4]]
+    qlen = int(cnt.max()) if cnt.size else 0
+    out = np.zeros((qlen * grid, 8), dtype=np.int64)
+    out[:, 0], out[:, 4], out[:, 6] = IT_NOP, -1, -1
+    out[rank * grid + cta] = items
+    return out.astype(np.int32), 2 * NB
 
-    def d_items(b):
-        n = np.repeat(np.arange(nodes_of[b], dtype=np.int64), C) + FUSED_BLOCK * b
-        c = np.tile(np.arange(C, dtype=np.int64), nodes_of[b])
-        out = np.zeros((n.size, 8), dtype=np.int64)
-        out[:, 0], out[:, 1], out[:, 2] = IT_D, n, c
-        out[:, 3] = (b % ring) * FUSED_BLOCK + n % FUSED_BLOCK
-        out[:, 4] = NB + b - ring if b >= ring else -1
-        out[:, 5] = 4 * grid if b >= ring else 0
-        out[:, 6] = b
-        return out
 
-    def x_items(b):
-        out = np.zeros((grid, 8), dtype=np.int64)
-        out[:, 0], out[:, 1], out[:, 2] = IT_X, FUSED_BLOCK * b, (b % ring) * FUSED_BLOCK
-        out[:, 3] = nodes_of[b]
-        out[:, 4], out[:, 5], out[:, 6] = b, 4 * nodes_of[b] * C, NB + b
-        return out
-
-    nop = np.zeros((1, 8), dtype=np.int64)
-    nop[0, 0], nop[0, 4], nop[0, 6] = IT_NOP, -1, -1
-    chunks, count = [d_items(0)], nodes_of[0] * C
-    for b in range(NB):
-        nxt = d_items(b + 1) if b + 1 < NB else np.zeros((0, 8), dtype=np.int64)
-        h = nxt.shape[0] // 2
-        pad = (-(count + h)) % grid
-        chunks += [nxt[:h], np.repeat(nop, pad, 0), x_items(b), nxt[h:]]
-        count += nxt.shape[0] + pad + grid
-    return np.concatenate(chunks).astype(np.int32), 2 * NB
-
-
-def fused_bwd_schedule(N: int, K: int, W: int, device, ring: int = 3) -> FusedSchedule:
+def fused_bwd_schedule(N: int, K: int, W: int, device, ring: int = 3,
+                       slack: float = 1.0) -> FusedSchedule:
     grid, _ = fused_bwd_grid(K, W)
-    key = (N, K, W, grid, ring, str(device))
+    if not 1.9 + slack <= ring:
+        raise ValueError("fused_bwd_schedule: ring must be at least 1.9 + slack")
+    key = (N, K, W, grid, ring, slack, str(device))
     if key not in _BWD_SCHED_CACHE:
-        items, nflags = fused_bwd_items(N, K, W, grid, ring)
+        items, nflags = fused_bwd_items(N, K, W, grid, ring, slack)
         t = torch.from_numpy(items).to(device)
-        _BWD_SCHED_CACHE[key] = FusedSchedule(t, int(t.size(0)), nflags, ring * FUSED_BLOCK, ring)
+        _BWD_SCHED_CACHE[key] = FusedSchedule(t, int(t.size(0)), nflags, ring * FUSED_BLOCK, ring,
+                                              grid)
     return _BWD_SCHED_CACHE[key]
 
 

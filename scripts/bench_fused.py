@@ -86,28 +86,36 @@ def fused_runner(sched, ubuf_of):
     return run
 
 
-for slack in (0.25, 0.5, 1.0):
+for slack in (0.5, 1.0, 1.5):
     name = f"fwd_fused_keep_slack{slack}"
     if want(name):
         s = ops.fused_fwd_schedule(lay, W, K, ring=0, slack=slack)
         emit(name, timed(fused_runner(s, lambda i: u_all[i % A])), items=s.num_items)
-for ring in (3, 4, 6):
+for ring in (3, 4):
     name = f"fwd_fused_ring{ring}"
     if want(name):
-        s = ops.fused_fwd_schedule(lay, W, K, ring=ring, slack=0.5)
+        s = ops.fused_fwd_schedule(lay, W, K, ring=ring, slack=1.0)
         ub = torch.empty(s.u_rows, W * K, dtype=bf, device="cuda")
         emit(name, timed(fused_runner(s, lambda i: ub)), items=s.num_items)
 # ablations: only the producer tiles / only the consumers (U already in memory, no waits)
-base = ops.fused_fwd_schedule(lay, W, K, ring=0, slack=0.5)
+base = ops.fused_fwd_schedule(lay, W, K, ring=0, slack=1.0)
 it = base.items
 if want("fwd_fused_P_only"):
-    p_only = ops.FusedSchedule(it[it[:, 0] == ops.IT_P].contiguous(), int((it[:, 0] == ops.IT_P).sum()),
-                               base.num_flags, base.u_rows, 0)
+    pi = it.clone()
+    pi[pi[:, 0] == ops.IT_C, 0] = ops.IT_NOP   # the consumers become no-ops: same dealing
+    p_only = ops.FusedSchedule(pi, base.num_items, base.num_flags, base.u_rows, 0, base.grid)
     emit("fwd_fused_P_only", timed(fused_runner(p_only, lambda i: u_all[i % A])), items=p_only.num_items)
+if want("fwd_fused_P_only_nosig"):
+    pi = it.clone()
+    pi[pi[:, 0] == ops.IT_C, 0] = ops.IT_NOP
+    pi[:, 6] = -1   # no counter updates: no GPU-scope fences in the epilogue
+    p_only = ops.FusedSchedule(pi, base.num_items, base.num_flags, base.u_rows, 0, base.grid)
+    emit("fwd_fused_P_only_nosig", timed(fused_runner(p_only, lambda i: u_all[i % A])))
 if want("fwd_fused_C_only"):
-    c = it[it[:, 0] == ops.IT_C].clone()
+    c = it.clone()
+    c[c[:, 0] == ops.IT_P, 0] = ops.IT_NOP
     c[:, 4] = -1
-    c_only = ops.FusedSchedule(c.contiguous(), int(c.size(0)), base.num_flags, base.u_rows, 0)
+    c_only = ops.FusedSchedule(c, base.num_items, base.num_flags, base.u_rows, 0, base.grid)
     two_kernel(0)
     emit("fwd_fused_C_only", timed(fused_runner(c_only, lambda i: u_all[0])), items=c_only.num_items)
 
@@ -126,11 +134,19 @@ if hasattr(ops, "node_fused_bwd"):
     if want("bwd_du_only"):
         emit("bwd_du_only", timed(lambda i: ops.node_du_mn(hs, gs_all[i % A], lay, 0, N, dut)))
     grid, parts = ops.fused_bwd_grid(K, W)
-    for ring in (2, 3, 4):
-        name = f"bwd_fused_ring{ring}"
+    for ring, slack, mode in ((3, 0.5, "all"), (3, 1.0, "all"), (4, 1.0, "all"), (4, 2.0, "all"),
+                              (3, 1.0, "D_only"), (3, 1.0, "D_only_nosig"), (3, 1.0, "X_only")):
+        name = f"bwd_fused_ring{ring}_slack{slack}" + ("" if mode == "all" else "_" + mode)
         if not want(name):
             continue
-        s = ops.fused_bwd_schedule(N, K, W, hs.device, ring=ring)
+        s = ops.fused_bwd_schedule(N, K, W, hs.device, ring=ring, slack=slack)
+        if mode != "all":
+            t = s.items.clone()
+            t[t[:, 0] == (ops.IT_D if mode == "X_only" else ops.IT_X), 0] = ops.IT_NOP
+            t[:, 4] = -1
+            if mode.endswith("nosig"):
+                t[:, 6] = -1
+            s = ops.FusedSchedule(t, s.num_items, s.num_flags, s.u_rows, s.ring, s.grid)
         du = torch.zeros(s.u_rows, K * W, dtype=bf, device="cuda")
         dx_part = torch.empty(parts, N, W, device="cuda")
         dwT = torch.zeros(K * W, W, device="cuda")

@@ -20,21 +20,46 @@ peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASU
     "hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
 
 
-def timeit(fn, iters=10, warm=3):
+_FLUSH = None
+
+
+def timeit(fn, iters=10, warm=3, flush_l2=False):
+    """Mean device time of fn (CUDA events on the current stream).  flush_l2: every launch is timed
+    on its own with a 256 MB write in between, for working sets smaller than the 126 MB L2."""
+    global _FLUSH
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    if not flush_l2:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+    if _FLUSH is None:
+        _FLUSH = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    tot = 0.0
     for _ in range(iters):
+        _FLUSH.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         fn()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / iters
+
+
+RESULTS: list = []   # every record is also kept here (bench.py imports this module)
+QUIET = False
 
 
 def emit(**kw):
-    print(json.dumps(kw), flush=True)
+    RESULTS.append(kw)
+    if not QUIET:
+        print(json.dumps(kw), flush=True)
 
 
 def graph_pass_times(pos, thr, iters=10):

@@ -100,8 +100,28 @@ def test_fused_forward_is_deterministic_and_reentrant_on_flags():
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
 
 
-@pytest.mark.parametrize("needs_grad", [True, False], ids=["train_kept_u", "inference_ring"])
-def test_stack_with_fused_forward_matches_two_kernel_form(monkeypatch, needs_grad):
+@pytest.mark.parametrize("N,W,K", [(300, 64, 256), (2000, 64, 1024), (129, 32, 256), (500, 128, 512)])
+def test_own_u_gemm_matches_fp32_restatement(N, W, K):
+    """U = x @ W3r from the producer items alone (the default forward's dense GEMM)."""
+    from molecular_dynamics_neural_operator_b200 import ops
+
+    g = torch.Generator().manual_seed(N + W)
+    Wp = max(W, 64)
+    xb = torch.zeros(N, Wp)
+    xb[:, :W] = torch.randn(N, W, generator=g)
+    w3r = torch.zeros(Wp, W * K)
+    w3r[:W] = torch.randn(W, W * K, generator=g) / 8
+    xb, w3r = xb.bfloat16(), w3r.bfloat16()
+    u = torch.full((N, W * K), float("nan"), dtype=torch.bfloat16, device="cuda")
+    ops.node_u_gemm(xb.cuda(), w3r.cuda(), u, N, K, W)
+    ref = xb.float() @ w3r.float()
+    assert rel_err(u.float(), ref) < 2.0 ** -7
+
+
+@pytest.mark.parametrize("fwd_mode,fused_bwd", [("gemm", False), ("1", False), ("1", True), ("gemm", True)],
+                         ids=["own_gemm", "fused_fwd", "fused_fwd_bwd", "own_gemm_fused_bwd"])
+@pytest.mark.parametrize("needs_grad", [True, False], ids=["train_kept_u", "inference"])
+def test_stack_variants_match_library_gemm_form(monkeypatch, needs_grad, fwd_mode, fused_bwd):
     from molecular_dynamics_neural_operator_b200 import functional as GF
     from molecular_dynamics_neural_operator_b200 import ops
     from oracle import gkn_oracle as orc
@@ -116,8 +136,10 @@ def test_stack_with_fused_forward_matches_two_kernel_form(monkeypatch, needs_gra
             "root2": torch.randn(W, W, generator=g) / 8, "bias2": torch.randn(W, generator=g) / 8}
     base.update({"net." + k: v for k, v in net.items()})
     results = []
-    for fused in (True, False):
-        monkeypatch.setattr(GF, "NODE_FUSED", fused)
+    for variant in (True, False):
+        monkeypatch.setattr(GF, "NODE_FUSED", variant and fwd_mode == "1")
+        monkeypatch.setattr(GF, "NODE_U_GEMM", variant and fwd_mode == "gemm")
+        monkeypatch.setattr(GF, "NODE_FUSED_BWD", variant and fused_bwd)
         t = {k: v.cuda().requires_grad_(needs_grad) for k, v in base.items()}
         with torch.set_grad_enabled(needs_grad):
             out = GF._GKNStackNode.apply(
@@ -128,7 +150,8 @@ def test_stack_with_fused_forward_matches_two_kernel_form(monkeypatch, needs_gra
         if needs_grad:
             out.backward(torch.ones_like(out))
         results.append((out.detach().cpu(), {k: v.grad.cpu() for k, v in t.items()} if needs_grad else {}))
-    # same operands, same roundings except the summation order inside U: well inside one layer's bound
+    # same operands, same roundings except the summation order inside U / dU: well inside one
+    # layer's bound
     assert fro(results[0][0], results[1][0]) < 2.0 ** -7
     for k in results[0][1]:
         assert fro(results[0][1][k], results[1][1][k]) < 2.0 ** -5, k
@@ -138,7 +161,7 @@ def test_stack_with_fused_forward_matches_two_kernel_form(monkeypatch, needs_gra
 @pytest.mark.parametrize("N,E,K,ring,with_dx,with_dw", [
     (300, 9000, 256, 3, True, True),      # 3 node blocks, partial last block
     (2000, 60000, 1024, 3, True, True),   # the model's kernel width: every CTA owns 3-4 column pairs
-    (2000, 60000, 1024, 2, True, True),   # smallest ring
+    (2000, 60000, 1024, 4, True, True),   # larger ring
     (1000, 30000, 512, 3, True, False),   # dx only (frozen edge MLP)
     (1000, 30000, 512, 3, False, True),   # weight gradient only (first application, x0 needs no grad)
     (130, 3000, 256, 4, True, True),      # second block holds two nodes; isolated nodes below
@@ -173,8 +196,11 @@ def test_fused_backward_matches_separate_products(N, E, K, ring, with_dx, with_d
     ops.node_du_mn(hs, gs, lay, 0, N, dut)
     NB = -(-N // 128)
     f = flags.cpu()
-    assert f[:NB].tolist() == [4 * min(128, N - 128 * b) * (K // 128) for b in range(NB)]
-    assert f[NB:].tolist() == [4 * grid] * NB
+    # counters: four warps per release (the last D item a CTA has in a block) and per consumed block
+    it = sched.items.cpu()
+    rel = torch.bincount(it[(it[:, 0] == ops.IT_D) & (it[:, 6] >= 0), 6].long(), minlength=NB)
+    assert f[:NB].tolist() == (4 * rel).tolist()
+    assert f[NB:].tolist() == [4 * parts] * NB
     if with_dx:
         addend = torch.randn(N, W, generator=g).cuda()
         dx = ops.sum_partials(dx_part, addend, torch.empty_like(addend))

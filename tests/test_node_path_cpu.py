@@ -120,14 +120,19 @@ def emu_node_gather(g, lay, gs, gsT):
         gsT.copy_(rows.t())
 
 
-def emu_node_fused_fwd(xb, w3r, hs, u, sched, flags, msg, N, e_pad, K, W, num_ctas=5, seed=0):
-    """Executes the item list the way the kernel does: ``num_ctas`` CTAs, item v belongs to CTA
-    v % num_ctas, every CTA runs its items strictly in order, an item whose counter has not reached
+def emu_node_u_gemm(xb, w3r, u, N, K, W):
+    u.view(N, W * K).copy_((xb.float() @ w3r.float()).to(u.dtype))
+
+
+def emu_node_fused_fwd(xb, w3r, hs, u, sched, flags, msg, N, e_pad, K, W, seed=0):
+    """Executes the item list the way the kernel does: ``sched.grid`` CTAs, item v belongs to CTA
+    v % grid, every CTA runs its items strictly in order, an item whose counter has not reached
     its target blocks its CTA.  CTAs are advanced in a random order; a state in which no CTA can
     advance is a deadlock (AssertionError).  A producer tile additionally refuses to overwrite a
     U row that a not-yet-executed consumer still needs only through the counters - exactly the
     kernel's protection - so a wrong schedule shows up as wrong numbers."""
     items = sched.items.tolist()
+    num_ctas = sched.grid
     queues = [items[c::num_ctas] for c in range(num_ctas)]
     pos = [0] * num_ctas
     rng = np.random.default_rng(seed)
@@ -160,23 +165,25 @@ EMU_GRID = 7  # CTAs of the emulated fused backward
 
 def emu_node_fused_bwd(hs, gs, lay, xb, w3k, du, sched, flags, dx_part, dwT, accumulate_dw, seed=0):
     """In-order multi-CTA execution of the backward item list (see emu_node_fused_fwd): D items
-    write dU tiles into the ring, X items (one per CTA and node block, at list positions equal to
-    the CTA index modulo the grid) consume the CTA's column slice of the block."""
+    write dU tiles into the ring (alternating between the CTA's two epilogue groups; a signal
+    releases every earlier store of its group, which is why only the last D item a group has in a
+    block carries one), X items consume one 128-column pair of the CTA's slice of a block."""
     K, W = hs.size(1), gs.size(1)
-    N = lay.num_nodes
-    grid = dx_part.size(0) if dx_part is not None else EMU_GRID
+    grid = sched.grid
     items = sched.items.tolist()
     queues = [items[c::grid] for c in range(grid)]
     pos = [0] * grid
     pairs = W * K // 128
     base, rem = divmod(pairs, grid)
-    sl = []
-    for c in range(grid):
-        np_, p0 = base + (c < rem), c * base + min(c, rem)
-        sl.append(slice(p0 * 128, (p0 + np_) * 128))
+    p0 = [c * base + min(c, rem) for c in range(grid)]
+    npair = [base + (c < rem) for c in range(grid)]
     pp = lay.pptr.tolist()
     duf = du.view(sched.u_rows, K * W)
-    acc = [torch.zeros(sl[c].stop - sl[c].start, W) for c in range(grid)]
+    acc = [torch.zeros(npair[c] * 128, W) for c in range(grid)]
+    dxa = [None] * grid
+    # stores of a group become visible only when that group signals (models the deferred release)
+    staged = [[[], []] for _ in range(grid)]
+    dcount = [0] * grid
     rng = np.random.default_rng(seed)
     left = len(items)
     while left:
@@ -187,30 +194,41 @@ def emu_node_fused_bwd(hs, gs, lay, xb, w3k, du, sched, flags, dx_part, dwT, acc
                 if widx >= 0 and int(flags[widx]) < wtarget:
                     break
                 if kind == ops.IT_D:
+                    g = 0  # one epilogue group
+                    dcount[c] += 1
                     rows = slice(pp[r0], pp[r0 + 1])
                     tile = hs[rows, r1 * 128:(r1 + 1) * 128].float().t() @ gs[rows].float()
-                    duf[r2].view(K, W)[r1 * 128:(r1 + 1) * 128] = tile.to(du.dtype)
+                    staged[c][g].append((r2, r1, tile.to(du.dtype)))
+                    if sidx >= 0:
+                        for row, ch, t in staged[c][g]:
+                            duf[row].view(K, W)[ch * 128:(ch + 1) * 128] = t
+                        staged[c][g] = []
+                        flags[sidx] += 4
                 elif kind == ops.IT_X:
-                    assert (c + pos[c] * grid) % grid == c
-                    blk = duf[r1:r1 + r2][:, sl[c]].float()
-                    xt = xb[r0:r0 + r2].float()
-                    acc[c] += blk.t() @ xt
-                    if dx_part is not None:
-                        dx_part[c, r0:r0 + r2] = blk @ w3k[:, sl[c]].float().t()
-                if sidx >= 0 and kind != ops.IT_NOP:
-                    flags[sidx] += 4
+                    q, first, last = r3 & 0xff, (r3 >> 8) & 1, (r3 >> 9) & 1
+                    cols = slice((p0[c] + q) * 128, (p0[c] + q + 1) * 128)
+                    blk = duf[r1:r1 + r2][:, cols].float()
+                    acc[c][q * 128:(q + 1) * 128] += blk.t() @ xb[r0:r0 + r2].float()
+                    part = blk @ w3k[:, cols].float().t()
+                    dxa[c] = part if first else dxa[c] + part
+                    if last:
+                        if dx_part is not None:
+                            dx_part[c, r0:r0 + r2] = dxa[c]
+                        flags[sidx] += 4
                 pos[c] += 1
                 left -= 1
                 progressed = True
                 if rng.random() < 0.3:
                     break
         assert progressed, "fused backward schedule deadlocked"
+    assert all(not g for s in staged for g in s), "a D item was never released"
     if dwT is not None:
         for c in range(grid):
+            sl = slice(p0[c] * 128, (p0[c] + npair[c]) * 128)
             if accumulate_dw:
-                dwT[sl[c]] += acc[c]
+                dwT[sl] += acc[c]
             else:
-                dwT[sl[c]] = acc[c]
+                dwT[sl] = acc[c]
 
 
 def emu_sum_partials(part, addend, out):
@@ -228,8 +246,10 @@ def install_emulation(setattr_fn):
                      ("node_du", emu_node_du), ("node_dh", emu_node_dh),
                      ("node_du_mn", emu_node_du_mn), ("node_dh_mn", emu_node_dh_mn),
                      ("node_gather", emu_node_gather), ("node_fused_fwd", emu_node_fused_fwd),
+                     ("node_u_gemm", emu_node_u_gemm),
                      ("node_fused_bwd", emu_node_fused_bwd), ("sum_partials", emu_sum_partials),
-                     ("fused_bwd_grid", lambda K, W: (EMU_GRID, EMU_GRID))]:
+                     ("fused_bwd_grid", lambda K, W: (EMU_GRID, EMU_GRID)),
+                     ("device_sm_count", lambda: EMU_GRID)]:
         setattr_fn(ops, name, fn)
     setattr_fn(ops, "prepare_graph", lambda ei, N, validate=True: cpu_plan(ei, N))
     setattr_fn(GF, "_mm32", lambda a, b: a.float() @ b.float())
@@ -333,8 +353,10 @@ def fro(a, b):
     (5, 700, 256, 2, (), 1024),     # groups longer than one 128-row tile
     (9, 120, 256, 2, (2, 7), 0),    # isolated nodes, node-range chunking of U / dU / U^T (1 node)
 ])
+@pytest.mark.parametrize("fwd_mode,fused_bwd", [("gemm", False), ("1", True), ("0", False)],
+                         ids=["own_gemm", "fused_fwd_bwd", "library_gemm"])
 def test_node_first_stack_matches_oracle(emulated, monkeypatch, N, E, K, depth, isolated, chunk_mb,
-                                         mn, save_u):
+                                         mn, save_u, fwd_mode, fused_bwd):
     """Without the activation between applications the stack is smooth in its operands, so bf16
     rounding is the only difference from the fp64 oracle: every gradient within 2^-5 except those
     upstream of the edge MLP's own ReLUs (mask flips, see tests/test_layer_gpu.py)."""
@@ -343,6 +365,9 @@ def test_node_first_stack_matches_oracle(emulated, monkeypatch, N, E, K, depth, 
     monkeypatch.setattr(GF, "_MLP_BWD_CHUNK_ROWS", 64)
     monkeypatch.setattr(GF, "NODE_MN", mn)
     monkeypatch.setattr(GF, "_SAVE_U_BYTES", (1 << 40) if save_u else 0)
+    monkeypatch.setattr(GF, "NODE_FUSED", fwd_mode == "1")
+    monkeypatch.setattr(GF, "NODE_U_GEMM", fwd_mode == "gemm")
+    monkeypatch.setattr(GF, "NODE_FUSED_BWD", fused_bwd)
     ei, p, depth = _stack_case(N, E, K, depth, seed=11 * N + depth, isolated=isolated)
     out, t = _run_node_stack(ei, p, depth, N, relu=False)
     ref, tr = _run_oracle_stack(ei, p, depth, relu=False)
@@ -421,48 +446,51 @@ def test_node_path_selection():
 
 
 # ---- fused producer/consumer forward: schedule ------------------------------------------------
-@pytest.mark.parametrize("N,E,W,ring", [(300, 5000, 64, 0), (300, 5000, 64, 3), (700, 3000, 32, 4),
-                                        (130, 400, 128, 3), (40, 90, 64, 0)])
-def test_fused_forward_schedule_is_ordered_and_complete(N, E, W, ring):
+@pytest.mark.parametrize("N,E,W,ring,grid", [(300, 5000, 64, 0, 7), (300, 5000, 64, 3, 148),
+                                             (700, 3000, 32, 4, 5), (130, 400, 128, 3, 16),
+                                             (40, 90, 64, 0, 148)])
+def test_fused_forward_schedule_is_balanced_ordered_and_complete(N, E, W, ring, grid):
     K = 256
     plan = cpu_plan(random_graph(N, E, seed=N), N)
     lay = ops.node_layout(plan)
-    sched = ops.fused_fwd_schedule(lay, W, K, ring=ring)
+    sched = ops.fused_fwd_schedule(lay, W, K, ring=ring, grid=grid)
     it = sched.items.long()
     NB, J = -(-N // 128), W * K // 256
-    assert sched.num_items == NB * J + lay.num_units and sched.num_flags == 2 * NB
+    assert sched.grid == grid and sched.num_items % grid == 0 and sched.num_flags == 2 * NB
     P, C = it[it[:, 0] == ops.IT_P], it[it[:, 0] == ops.IT_C]
     # every tile of U once, every message unit once
-    assert len({(int(a), int(b)) for a, b in P[:, 1:3]}) == NB * J
+    assert len(P) == NB * J and len({(int(a), int(b)) for a, b in P[:, 1:3]}) == NB * J
     assert sorted(C[:, 1].tolist()) == sorted(lay.units[:, 1].tolist())
-    # a consumer comes after every tile of its block; in ring mode a tile comes after every
-    # consumer of the block whose slot it overwrites, and targets count 4 warps per item
-    where = {k: [] for k in ("p", "c")}
-    first_c, last_c = {}, {}
-    last_p, first_p = {}, {}
-    for v, row in enumerate(it.tolist()):
-        if row[0] == ops.IT_P:
-            b = row[1] // 128
-            last_p[b] = v
-            first_p.setdefault(b, v)
-        elif row[0] == ops.IT_C:
-            b = row[4]
-            first_c.setdefault(b, v)
-            last_c[b] = v
-            assert row[5] == 4 * J
-    for b, v in first_c.items():
-        assert last_p[b] < v
+    # both kinds are spread evenly: every CTA gets the same number of each, +-1
+    cta = torch.arange(sched.num_items) % grid
+    for kind in (ops.IT_P, ops.IT_C):
+        per = torch.bincount(cta[it[:, 0] == kind], minlength=grid)
+        assert int(per.max() - per.min()) <= 1
+    # time keys: (block of the item, phase) reconstructed from the fields; every CTA's queue is in
+    # key order and a wait only refers to a block whose items all have smaller keys
     cnt = torch.bincount(C[:, 4], minlength=NB)
+    for c in range(grid):
+        q = it[c::grid]
+        last = -10.0
+        for row in q.tolist():
+            if row[0] == ops.IT_P:
+                key = row[1] // 128 - 1 + (row[2] // 256 + 0.5) / J
+            elif row[0] == ops.IT_C:
+                key = row[4] + 1.0  # lower bound of [b + slack, b + 1 + slack), slack = 1
+            else:
+                continue
+            assert key >= last - 1.0 + 1e-9 if row[0] == ops.IT_C else key >= last - 1e-9
+            last = max(last, key)
+    for row in C.tolist():
+        assert row[5] == 4 * J and 0 <= row[4] < NB
     for row in P.tolist():
         b = row[1] // 128
         if ring and b >= ring:
             assert row[4] == NB + b - ring and row[5] == 4 * int(cnt[b - ring])
-            if (b - ring) in last_c:
-                assert last_c[b - ring] < first_p[b]
             assert row[3] == (b % ring) * 128
         else:
             assert row[4] == -1
-    assert ops.fused_fwd_schedule(lay, W, K, ring=ring) is sched  # cached on the layout
+    assert ops.fused_fwd_schedule(lay, W, K, ring=ring, grid=grid) is sched  # cached on the layout
 
 
 @pytest.mark.parametrize("ring", [0, 3])
@@ -475,11 +503,11 @@ def test_fused_forward_emulated_execution_matches_two_kernel_form(ring, num_ctas
     xb = torch.randn(N, W, generator=g).bfloat16()
     w3r = (torch.randn(W, W * K, generator=g) / 8).bfloat16()
     hs = torch.randn(lay.e_pad, K, generator=g).bfloat16()
-    sched = ops.fused_fwd_schedule(lay, W, K, ring=ring)
+    sched = ops.fused_fwd_schedule(lay, W, K, ring=ring, grid=num_ctas)
     u = torch.zeros(sched.u_rows, W * K, dtype=torch.bfloat16)
     msg = torch.zeros(lay.e_pad, W)
     emu_node_fused_fwd(xb, w3r, hs, u, sched, torch.zeros(sched.num_flags, dtype=torch.int32), msg,
-                       N, lay.e_pad, K, W, num_ctas=num_ctas, seed=num_ctas)
+                       N, lay.e_pad, K, W, seed=num_ctas)
     U = (xb.float() @ w3r.float()).bfloat16()
     ref = torch.zeros_like(msg)
     emu_node_msg(hs, U.view(N, W, K), lay, 0, lay.num_units, 0, ref)
@@ -491,37 +519,60 @@ def test_fused_forward_emulated_execution_matches_two_kernel_form(ring, num_ctas
 def test_fused_forward_ring_must_cover_the_slack():
     plan = cpu_plan(random_graph(300, 2000, seed=2), 300)
     with pytest.raises(ValueError, match="ring"):
-        ops.fused_fwd_schedule(ops.node_layout(plan), 64, 256, ring=2, slack=0.5)
+        ops.fused_fwd_schedule(ops.node_layout(plan), 64, 256, ring=2, slack=0.5, grid=8)
 
 
 # ---- fused backward: schedule -------------------------------------------------------------------
-@pytest.mark.parametrize("N,K,grid,ring", [(300, 256, 7, 3), (128, 512, 148, 2), (1000, 1024, 148, 3),
-                                           (5, 256, 4, 3)])
-def test_fused_backward_schedule_layout(N, K, grid, ring):
-    items, nflags = ops.fused_bwd_items(N, K, 64, grid, ring)
+@pytest.mark.parametrize("N,K,grid,ring,slack", [(300, 256, 7, 3, 1.0), (128, 512, 148, 3, 0.5),
+                                                 (1000, 1024, 148, 3, 1.0), (5, 256, 4, 4, 2.0),
+                                                 (700, 256, 160, 3, 1.0)])
+def test_fused_backward_schedule_layout(N, K, grid, ring, slack):
+    items, nflags = ops.fused_bwd_items(N, K, 64, grid, ring, slack)
     NB, C = -(-N // 128), K // 128
-    assert nflags == 2 * NB
+    pairs = 64 * K // 128
+    parts = min(grid, pairs)
+    assert nflags == 2 * NB and items.shape[0] % grid == 0
     kinds = items[:, 0]
     D, X = items[kinds == ops.IT_D], items[kinds == ops.IT_X]
-    # every (node, chunk) once; every (block, CTA) once, at a list position == CTA (mod grid)
+    # every (node, chunk) once; every (block, pair) once
     assert len({(int(a), int(b)) for a, b in D[:, 1:3]}) == N * C == len(D)
-    xpos = np.nonzero(kinds == ops.IT_X)[0]
-    assert len(X) == NB * grid
+    assert len(X) == NB * pairs
+    base, rem = divmod(pairs, grid)
+    for c in range(grid):
+        q = items[c::grid]
+        npair = base + (c < rem)
+        xq = q[q[:, 0] == ops.IT_X]
+        assert len(xq) == NB * npair
+        # pairs of a block in order, first / last flags, the wait on the first, the signal on the last
+        for b in range(NB if npair else 0):
+            rows = xq[b * npair:(b + 1) * npair]
+            assert (rows[:, 1] == 128 * b).all() and (rows[:, 7] & 0xff).tolist() == list(range(npair))
+            assert ((rows[:, 7] >> 8) & 1).tolist() == [1] + [0] * (npair - 1)
+            assert ((rows[:, 7] >> 9) & 1).tolist() == [0] * (npair - 1) + [1]
+            assert rows[0, 4] == b and (rows[1:, 4] == -1).all()
+            assert rows[-1, 6] == NB + b and (rows[:-1, 6] == -1).all()
+        # per block one wait (if the slot is being reused) on the CTA's first D item and one signal
+        # on its last (one epilogue group; with two the D items would alternate between them)
+        dq = q[q[:, 0] == ops.IT_D]
+        for g in (0,):
+            mine = dq
+            blk = mine[:, 1] // 128
+            for b in np.unique(blk):
+                rows = mine[blk == b]
+                assert rows[-1, 6] == b and (rows[:-1, 6] == -1).all()
+                if b >= ring:
+                    assert rows[0, 4] == NB + b - ring and rows[0, 5] == 4 * parts
+                    assert (rows[1:, 4] == -1).all()
+                else:
+                    assert (rows[:, 4] == -1).all()
+                assert (rows[:, 3] // 128 == b % ring).all()
+    # the X items of a block wait for every release of that block
     for b in range(NB):
-        seg = xpos[b * grid:(b + 1) * grid]
-        assert (seg % grid == np.arange(grid)).all() and (items[seg, 1] == 128 * b).all()
-        nodes = min(128, N - 128 * b)
-        assert (items[seg, 3] == nodes).all() and (items[seg, 5] == 4 * nodes * C).all()
-        # all D items of the block precede its X items; the ring slot is reused only after them
-        dpos = np.nonzero((kinds == ops.IT_D) & (items[:, 1] // 128 == b))[0]
-        assert dpos.max() < seg.min()
-        if b + ring < NB:
-            later = np.nonzero((kinds == ops.IT_D) & (items[:, 1] // 128 == b + ring))[0]
-            assert later.min() > seg.max()
-            assert (items[later, 4] == NB + b).all() and (items[later, 5] == 4 * grid).all()
-            assert (items[later, 3] // 128 == b % ring).all()
+        sig = int(((kinds == ops.IT_D) & (items[:, 6] == b)).sum())
+        firsts = X[(X[:, 1] == 128 * b) & (X[:, 4] >= 0)]
+        assert (firsts[:, 5] == 4 * sig).all() and len(firsts) == parts
     with pytest.raises(ValueError):
-        ops.fused_bwd_items(N, K, 64, grid, 1)
+        ops.fused_bwd_items(N, K, 64, grid, 2, 0.5)
 
 
 def test_fused_backward_emulated_execution_matches_dense_products():
@@ -535,10 +586,11 @@ def test_fused_backward_emulated_execution_matches_dense_products():
     xb = torch.randn(N, W, generator=g).bfloat16()
     w3k = (torch.randn(W, K * W, generator=g) / 8).bfloat16()
     items, nflags = ops.fused_bwd_items(N, K, W, EMU_GRID, 3)
-    sched = ops.FusedSchedule(torch.from_numpy(items), len(items), nflags, 3 * 128, 3)
+    sched = ops.FusedSchedule(torch.from_numpy(items), len(items), nflags, 3 * 128, 3, EMU_GRID)
     du = torch.zeros(3 * 128, K * W, dtype=torch.bfloat16)
     dx_part = torch.zeros(EMU_GRID, N, W)
     dwT = torch.full((K * W, W), 7.0)
+    assert min(EMU_GRID, W * K // 128) == EMU_GRID
     emu_node_fused_bwd(hs, gs, lay, xb, w3k, du, sched, torch.zeros(nflags, dtype=torch.int32),
                        dx_part, dwT, False)
     dut = torch.zeros(N, K * W, dtype=torch.bfloat16)
