@@ -276,6 +276,123 @@ def bench_config(wl, frames_per_gpu, edges_per_frame, reference=False):
     }
 
 
+
+# ------------------------------------------------------------------------------------------------
+# extra measurements carried by the N = 1 line: HBM-bound kernels in isolation, the other configs
+# ------------------------------------------------------------------------------------------------
+def micro_rooflines(peaks):
+    """K0 (radius graph) and K2 (segmented node update / mean) on batches of frames, each launch
+    timed alone with CUDA events (scripts/bench_kernels.py): algorithmic bytes of SURVEY.md 8(d)
+    (B_g = 12 N + 40 E per graph build, B_s = 4 E w + 4 E + 4 N w + 4 N per reduction) / time
+    against the measured copy bandwidth."""
+    sys.path.insert(0, str(ROOT / "scripts"))
+    import bench_kernels as bk
+
+    bk.QUIET = True
+    out = {}
+    for name, frames in (("bba_allatom", 64), ("synthetic_10k", 16)):
+        bk.RESULTS.clear()
+        ei, ea, N, E = bk.bench_graph(name, frames)
+        bk.bench_node_update(name, frames, ei, N, E)
+        del ei, ea
+        for r in bk.RESULTS:
+            k = r["kernel"]
+            if k.startswith("radius_graph device time"):
+                key, extra = "radius_graph", {"count_pass_ms": r["count_ms"], "fill_pass_ms": r["fill_ms"]}
+            elif k.startswith("segment_matvec fwd"):
+                key, extra = "segment_matvec_fwd", {}
+            elif k.startswith("segment_matvec bwd"):
+                key, extra = "segment_matvec_bwd", {}
+            elif k.startswith("scatter_mean_fwd"):
+                key, extra = "scatter_mean_fwd", {}
+            else:
+                continue
+            out[f"{key}[{name} x{frames}]"] = {
+                "bound": "hbm", "avg_launch_ms": r["ms"], "bytes_per_launch": r["algorithmic_bytes"],
+                "achieved_gbs": r["gbs"], "frac": r["gbs"] / peaks["hbm_gbs"], "edges": r["edges"],
+                **extra}
+    torch.cuda.empty_cache()
+    return out
+
+
+def quick_train(dev, name, frames, steps, warm=3):
+    """A few training steps of another BASELINE config on one GPU (coordinates resident, graph
+    built every step): frames/s."""
+    from molecular_dynamics_neural_operator_b200 import functional as GF
+    from molecular_dynamics_neural_operator_b200 import synthetic as syn
+    from molecular_dynamics_neural_operator_b200.graph_kernel import KernelNN
+    from molecular_dynamics_neural_operator_b200.train import Trainer
+
+    wl = syn.WORKLOADS[name]
+    torch.manual_seed(0)
+    model = KernelNN(wl.width, wl.ker_width, wl.depth, 6, in_width=7, out_width=3,
+                     window_size=wl.window, num_residues=wl.num_atoms, precision="bf16").to(dev)
+    trainer = Trainer(model, lr=0.01, weight_decay=5e-4)
+    traj = syn.trajectory(wl, wl.window + 1 + frames, seed=0)
+    aa = torch.from_numpy(syn.residue_ids(wl)).to(dev)
+    xw, y = syn.window_batch(traj, list(range(frames)), wl.window)
+    x_d, y_d = torch.from_numpy(xw).to(dev), torch.from_numpy(y).to(dev)
+    edges = 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(warm + steps):
+        if i == warm:
+            torch.cuda.synchronize()
+            ev0.record()
+        batch = syn.make_batch(x_d, aa, y_d, wl.cutoff, prepare=True, ker_width=wl.ker_width)
+        edges = batch.edge_index.size(1)
+        loss = trainer.step(batch, frames)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / steps
+    node = GF.FACTORIZATION == "node" and GF.node_path_supported(wl.width, wl.ker_width, edges, "bf16")
+    res = {"workload": name, "frames_per_step": frames, "steps": steps, "ms_per_step": ms,
+           "frames_per_s": frames / (ms * 1e-3), "edges_per_frame": edges / frames,
+           "edges_per_s": edges / (ms * 1e-3), "width": wl.width, "depth": wl.depth,
+           "factorization": "node" if node else "edge", "loss_finite": bool(torch.isfinite(loss)),
+           "mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9}
+    del trainer, model, batch
+    torch.cuda.empty_cache()
+    return res
+
+
+def quick_rollout(dev, name, steps, window=2):
+    """BASELINE config 5 on ONE GPU: device-resident operator rollout (forward -> new positions ->
+    radius graph rebuilt on the GPU), reference graph_kernel.py:396-413: rollout steps/s."""
+    from molecular_dynamics_neural_operator_b200 import synthetic as syn
+    from molecular_dynamics_neural_operator_b200.graph_kernel import KernelNN, construct_pairdata
+
+    wl = syn.WORKLOADS[name]
+    torch.manual_seed(0)
+    model = KernelNN(wl.width, wl.ker_width, wl.depth, 6, in_width=7, out_width=3, window_size=window,
+                     num_residues=wl.num_atoms, precision="bf16").to(dev).eval()
+    traj = torch.from_numpy(syn.trajectory(wl, window, seed=0)).to(dev)
+    aa = torch.from_numpy(syn.residue_ids(wl)).to(dev)
+    data = construct_pairdata(traj, aa, threshold=wl.cutoff, device=dev)
+    edges = []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.no_grad():
+        for step in range(steps + 1):
+            if step == 1:
+                torch.cuda.synchronize()
+                ev0.record()
+            out = model(data, single_example=True)
+            # random-init weights: bound the predicted displacement so the rollout stays physical
+            pos = data.x_position[-1] + 0.05 * torch.tanh(torch.nan_to_num(out))
+            data = construct_pairdata(torch.cat([data.x_position[1:], pos[None]], 0), aa,
+                                      threshold=wl.cutoff, device=dev)
+            edges.append(int(data.edge_index.size(1)))
+        ev1.record()
+        torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / steps
+    res = {"workload": name, "mode": "rollout (inference), one GPU", "steps": steps,
+           "ms_per_rollout_step": ms, "steps_per_s": 1e3 / ms, "atoms": wl.num_atoms,
+           "edges_per_step": edges[-1], "edges_per_s": edges[-1] / (ms * 1e-3), "width": wl.width,
+           "depth": wl.depth, "mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9}
+    del model, data
+    torch.cuda.empty_cache()
+    return res
+
+
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
@@ -569,6 +686,42 @@ def run_b200_arm(args, wl):
         hw_peak = sms * 8192 * clocks["sm_mhz"] * 1e6 / 1e12  # 4096 bf16 MAC/clk/SM
         roofline["hw_peak_at_sampled_clock"] = hw_peak
         roofline["frac_hw_at_sampled_clock"] = roofline["achieved"] / hw_peak
+    # Strong scaling beside the weak-scaling headline: a fixed GLOBAL batch
+    # of 16 frames split evenly over the ranks (16 / N frames per GPU per step).
+    strong = None
+    if not args.no_strong and 16 % world == 0:
+        Bs = 16 // world
+        dev_xs = [t[:Bs].contiguous() for t in dev_x]
+        dev_ys = [t[:Bs].contiguous() for t in dev_y]
+
+        def build_strong(i):
+            return syn.make_batch(dev_xs[i % pool], aa, dev_ys[i % pool], wl.cutoff, prepare=True,
+                                  ker_width=wl.ker_width)
+
+        def run_strong(steps):
+            prefetch.submit(lambda: build_strong(0))
+            for i in range(steps):
+                batch = prefetch.get()
+                if i + 1 < steps:
+                    prefetch.submit(lambda: build_strong(i + 1))
+                trainer.step(batch, Bs)
+
+        run_strong(max(4, pool))
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_strong = max(5, args.steps // 2)
+        ev0.record()
+        run_strong(n_strong)
+        ev1.record()
+        barrier()
+        ms_s = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms_s], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_s = float(t.item())
+        strong = {"scaling": "strong", "global_batch": 16, "frames_per_gpu_per_step": Bs,
+                  "steps": n_strong, "ms_per_step": ms_s / n_strong, "value": 16 * n_strong / (ms_s * 1e-3),
+                  "unit": UNIT}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -587,6 +740,7 @@ def run_b200_arm(args, wl):
         "clocks": clocks,
         "roofline": roofline,
         "edge_first": edge_first,
+        "strong_scaling": strong,
         "edges_per_s": value * edges_per_frame,
         "flops": {
             "algorithmic_train_flop_per_frame": 4 * A * unit_flop,
@@ -627,6 +781,40 @@ def run_b200_arm(args, wl):
                        f"{int(edges_per_frame)} per full frame, {dt:.1f} s in total; "
                        f"frames/s = edge-fraction / step time"),
         }
+        # the reference's own default is ONE host thread (graph_kernel.py:501): a smaller sample
+        ref1 = CpuReference(wl, 1)
+        n1 = max(32, n_atoms // 3)
+        ref1.step(xw, y, aa_np, max(32, n1 // 2))
+        dt1, e1_, k1 = 0.0, 0, 0
+        while dt1 < 5.0 and k1 < 4:
+            dti, ei_ = ref1.step(xw, y, aa_np, n1)
+            dt1 += dti
+            e1_ += ei_
+            k1 += 1
+        line["cpu_baseline"]["value_1_thread"] = (e1_ / edges_per_frame) / dt1
+        line["cpu_baseline"]["sample_1_thread"] = (f"{k1} steps on {n1}/{wl.num_atoms} atoms, "
+                                                   f"{e1_ // k1} edges per step, {dt1:.1f} s")
+        torch.set_num_threads(threads)
+    if world == 1 and not args.no_extras:
+        # the HBM-bound kernels on their own (K0 graph build, K2 segmented reductions) and the
+        # other BASELINE configs, measured in this same process after the headline
+        del trainer, model
+        dev_x.clear()
+        dev_y.clear()
+        torch.cuda.empty_cache()
+        try:
+            if line["roofline"] is not None:
+                line["roofline"]["kernels"].update(micro_rooflines(peaks))
+            line["configs"] = {
+                "bba_ca (configs[0] shape: 28 residues, w 32, depth 4, batch 128)":
+                    quick_train(dev, "bba_ca", 128, steps=5),
+                "synthetic_10k (configs[2]: 10k atoms, 4.2 A, w 64, depth 6, 4 frames/step)":
+                    quick_train(dev, "synthetic_10k", 4, steps=3),
+                "synthetic_100k (configs[4] on ONE GPU: 100k atoms, w 128, depth 8, rollout)":
+                    quick_rollout(dev, "synthetic_100k", steps=3),
+            }
+        except Exception as exc:  # the headline stands even if an extra fails: say so in the line
+            line["extras_error"] = f"{type(exc).__name__}: {exc}"
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -645,6 +833,9 @@ def main():
     ap.add_argument("--cpu-seconds-per-step", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timer", action="store_true", help="(diagnostic) no per-launch events")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the isolated K0/K2 rooflines and the other configs (N=1 only)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling steps")
     ap.add_argument("--no-edge-first", action="store_true",
                     help="skip the extra steps that time the edge-first contraction (N=1 only)")
     ap.add_argument("--workload", default=WORKLOAD, help="(diagnostic) another BASELINE.json shape")

@@ -230,15 +230,16 @@ _MLP_SIDE_GEMM = os.environ.get("GKN_MLP_SIDE_GEMM", "1") == "1"
 # U of every application ([A, N, w*K] bf16) is kept for the dh pass when it fits this budget
 # (6.3 GB for 8 BBA frames); otherwise it is recomputed node range by node range in backward
 _SAVE_U_BYTES = int(os.environ.get("GKN_NODE_SAVE_U_MB", "24576")) << 20
-# How U = x W3r reaches the grouped message kernel (csrc/gkn_node_fused.cu), GKN_NODE_FUSED:
-#   "gemm" (default) U is written by the producer half of the fused kernel run on its own (a
-#           hand-written tcgen05 GEMM: 0.205 ms per application at the bench shape, the library GEMM
-#           0.185) and read back by gkn_node_msg_bf16;
-#   "1"     one launch per application produces AND consumes U, which then crosses the L2 only
-#           (-17 % HBM traffic by ncu, but the in-order item pipelines leave it latency-bound:
-#           0.75 ms in the training step against 0.71 for "gemm" - see DESIGN.md section 6);
-#   "0"     library GEMM (torch.mm) + grouped message kernel, as in round 1.
-_NODE_FUSED_MODE = os.environ.get("GKN_NODE_FUSED", "gemm")
+# How U = x W3r reaches the grouped message kernel (csrc/gkn_node_fused.cu), GKN_NODE_FUSED.
+# Measured at the bench shape (16 BBA frames, one B200):
+#   "0" (default) library GEMM (torch.mm, 0.185 ms) + gkn_node_msg_bf16 (0.51 ms): 36.4 ms/step;
+#   "gemm"  U written by the producer half of the fused kernel run on its own - a hand-written
+#           tcgen05 GEMM, 0.205 ms isolated - then gkn_node_msg_bf16: 37.3 ms/step;
+#   "1"     one launch per application produces AND consumes U, which crosses the L2 only
+#           (-17 % HBM traffic by ncu), but its in-order item pipelines leave it latency-bound:
+#           0.75 ms per application in the step, 37.7 ms/step.
+# The fastest form is the default; the other two are the same function (tests compare all three).
+_NODE_FUSED_MODE = os.environ.get("GKN_NODE_FUSED", "0")
 NODE_FUSED = _NODE_FUSED_MODE == "1"
 NODE_U_GEMM = _NODE_FUSED_MODE == "gemm"
 # node blocks of the U ring when U is not kept for the backward (forward-only calls)

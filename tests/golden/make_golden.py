@@ -239,6 +239,63 @@ def gen_kernelnn(ref, name, w, K, depth, B, W, R, thr, seed):
     print(name, "N", B * R, "E", batch.edge_index.shape[1], "loss", float(loss))
 
 
+def gen_kernelnn_seeded(ref, name, w, K, depth, B, W, R, thr, seed, grad_row_stride=16):
+    """A model too large to ship its weights (BASELINE configs[0]: w = 32, K = 1024, depth 4,
+    28 residues, window 10): weights come from tests.helpers.seeded_state_dict(seed) on both
+    sides, the file holds inputs, output, loss and every ``grad_row_stride``-th row of the large
+    gradients."""
+    sys.path.insert(0, str(HERE.parents[1]))
+    from tests.helpers import seeded_state_dict  # noqa: PLC0415
+
+    rng = np.random.default_rng(seed)
+    ref.args = argparse.Namespace(window_size=W, num_residues=R, batch_size=B)
+    base = chain(rng, R)
+    traj = (base[None] + 0.3 * rng.normal(size=(B + W + 1, R, 3))).astype(np.float32)
+    aa = torch.from_numpy(rng.integers(0, 20, size=R).astype(np.int64))
+    samples = []
+    for b in range(B):
+        win = traj[b:b + W]
+        g = ref.construct_pairdata(win[:1], aa, threshold=thr)
+        samples.append(dict(x_position=torch.from_numpy(win), edge_index=g.edge_index,
+                            edge_attr=g.edge_attr, y=torch.from_numpy(traj[b + W])))
+    batch = ref.PairData(
+        x_aminoacid=aa.repeat(B),
+        x_position=torch.cat([s["x_position"] for s in samples]).double(),
+        y=torch.cat([s["y"] for s in samples]).double(),
+        edge_attr=torch.cat([s["edge_attr"] for s in samples]).double(),
+        edge_index=torch.cat([s["edge_index"] + i * R for i, s in enumerate(samples)], dim=1),
+    )
+    model = ref.KernelNN(w, K, depth, 6, in_width=7, out_width=3)
+    model.load_state_dict(seeded_state_dict(model.state_dict(), seed))
+    model = model.double()
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.set_default_dtype(torch.float64)
+    try:
+        out = model(batch)
+    finally:
+        torch.Tensor.cuda = orig_cuda
+        torch.set_default_dtype(torch.float32)
+    loss = ref.LpLoss(size_average=False)(out.view(B, -1), batch.y.view(B, -1))
+    loss.backward()
+    arrays = dict(
+        traj=traj, aminoacid=aa.numpy(), threshold=np.float64(thr), depth=np.int64(depth),
+        window=np.int64(W), num_residues=np.int64(R), batch=np.int64(B), width=np.int64(w),
+        ker_width=np.int64(K), weight_seed=np.int64(seed), grad_row_stride=np.int64(grad_row_stride),
+        edge_index=batch.edge_index.numpy(), edge_attr=batch.edge_attr.numpy().astype(np.float32),
+        out=out.detach().numpy(), loss=loss.detach().numpy(),
+    )
+    seen = set()
+    for k, p in model.named_parameters():
+        if id(p) in seen:
+            continue
+        seen.add(id(p))
+        g = p.grad.numpy()
+        arrays[f"grad.{k}"] = g[::grad_row_stride] if g.ndim == 2 and g.shape[0] >= 256 else g
+    np.savez_compressed(HERE / f"{name}.npz", **arrays)
+    print(name, "N", B * R, "E", batch.edge_index.shape[1], "loss", float(loss))
+
+
 def gen_pairdata(ref, name, n, W, L, thr, seed):
     rng = np.random.default_rng(seed)
     xp = (rng.random((W, n, 3)) * L).astype(np.float32)
@@ -269,6 +326,9 @@ def main():
     gen_nnconv(ref, "nnconv_w64_k256", w=64, K=256, n=48, thr=8.0, seed=9, grad_row_stride=16)
     gen_kernelnn(ref, "kernelnn_w16_k64_d2", w=16, K=64, depth=2, B=2, W=3, R=12, thr=8.0, seed=4)
     gen_kernelnn(ref, "kernelnn_w32_k64_d1", w=32, K=64, depth=1, B=3, W=2, R=10, thr=6.0, seed=5)
+    # BASELINE configs[0] shape (reference defaults graph_kernel.py:318-341 at width 32, depth 4)
+    gen_kernelnn_seeded(ref, "kernelnn_cfg1_w32_k1024_d4", w=32, K=1024, depth=4, B=2, W=10, R=28,
+                        thr=8.0, seed=11)
     gen_pairdata(ref, "pairdata_n28", n=28, W=3, L=20.0, thr=8.0, seed=6)
     gen_pairdata(ref, "pairdata_n300", n=300, W=1, L=20.0, thr=4.2, seed=7)
     gen_lploss(ref, "lploss", seed=8)

@@ -41,3 +41,24 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     """max |a-b| / max |b|  (the relative measure the parity tolerances are stated in)."""
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).abs().max() / b.abs().max().clamp(min=1e-30))
+
+
+def seeded_state_dict(template: dict, seed: int) -> dict:
+    """float32 weights drawn from numpy's PCG64 stream (stable across versions and machines) for
+    every tensor of ``template`` (name -> tensor, only the shapes are used), names in sorted
+    order, U(-1/sqrt(fan_in), 1/sqrt(fan_in)).  ``conv2.net.*`` aliases ``conv1.net.*``
+    (reference graph_kernel.py:271-273).  Lets a large model be pinned by a golden file that holds
+    only outputs and gradients: generator and test rebuild the same weights from the seed."""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for k in sorted(template):
+        if k.startswith("conv2.net."):
+            continue
+        shape = tuple(template[k].shape)
+        fan_in = shape[-1] if len(shape) > 1 else shape[0]
+        b = 1.0 / np.sqrt(max(fan_in, 1))
+        out[k] = torch.from_numpy(rng.uniform(-b, b, size=shape).astype(np.float32))
+    for k in template:
+        if k.startswith("conv2.net."):
+            out[k] = out["conv1.net." + k[len("conv2.net."):]]
+    return out

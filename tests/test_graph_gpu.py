@@ -121,6 +121,22 @@ def test_radius_graph_full_size_properties_and_kdtree_oracle():
     assert 250000 < ei_np.shape[1] // 2 < 340000  # ~291k edges / frame
 
 
+def test_radius_graph_100k_atoms_matches_kdtree_oracle():
+    """BASELINE config 5's frame (100k atoms, 100 A box, 4.2 A): bit-exact against the kd-tree
+    oracle (the dense SciPy path would need an 80 GB distance matrix)."""
+    from molecular_dynamics_neural_operator_b200 import ops
+    from molecular_dynamics_neural_operator_b200 import synthetic as syn
+    from oracle import gkn_oracle as orc
+
+    wl = syn.WORKLOADS["synthetic_100k"]
+    pos = syn.trajectory(wl, 1, seed=3)
+    ei, ea = ops.radius_graph(torch.from_numpy(pos).cuda(), wl.cutoff)
+    ei_ref, ea_ref = orc.radius_graph_kdtree(pos[0], wl.cutoff)
+    assert 2_900_000 < ei_ref.shape[1] < 3_200_000  # ~3.06 M edges (SURVEY 8)
+    assert np.array_equal(ei.cpu().numpy(), ei_ref)
+    assert np.array_equal(ea.cpu().numpy(), ea_ref)
+
+
 def test_prepare_graph_against_numpy_stable_sort():
     from molecular_dynamics_neural_operator_b200 import ops
 

@@ -10,14 +10,16 @@ Tolerances (relative = max|a-b| / max|b| unless noted):
               ~sqrt(#applications) through a stack.  Bounds used (relative Frobenius):
                 <= 2^-7 = 7.8e-3  one layer: output, dx
                 <= 2^-5 = 3.1e-2  stacks of up to 12 applications; gradients of W3, b3, root, bias
-                <= 2^-2           gradients of parameters UPSTREAM of a ReLU whose pre-activation
+                <= 2^-4 / 2^-2    gradients of parameters UPSTREAM of a ReLU whose pre-activation
                                   came from bf16 operands (edge-MLP layers .0/.2 and everything
                                   before the conv stack).  There the error is dominated by ReLU
                                   mask flips: a pre-activation within ~1.6e-3 sigma of zero flips
                                   with bf16 operands (~0.13 % of entries), an O(1) change of that
                                   entry of the gradient, i.e. sqrt(0.0013) ~ 3.6 % in Frobenius
-                                  norm on a few-hundred-edge graph (measured 3.5-3.8 %), more on
-                                  the 32-edge fixture (14 %).  Inherent to any bf16 forward.
+                                  norm on a few-hundred-edge graph (measured 3.5-3.8 %: bound
+                                  2^-4 = 6.25 % for fixtures of >= 300 edges), more on the
+                                  32-edge fixture (14 %: bound 2^-2 for < 300 edges).  Inherent to
+                                  any bf16 forward.
               plus cosine similarity >= 0.98 between every bf16 gradient and the reference's.
 """
 import numpy as np
@@ -31,12 +33,17 @@ pytestmark = pytest.mark.gpu
 FP32_TOL = 1e-5
 BF16_LAYER_TOL = 2.0 ** -7
 BF16_STACK_TOL = 2.0 ** -5
-BF16_UPSTREAM_TOL = 2.0 ** -2
+BF16_UPSTREAM_TOL = 2.0 ** -2        # fixtures of < 300 edges
+BF16_UPSTREAM_TOL_LARGE = 2.0 ** -4  # >= 300 edges: mask flips average out (measured ~3.6 %)
 UPSTREAM = ("net.layers.0.", "net.layers.2.", "lstm", "emb.", "fc1.")
 
 
-def bf16_grad_tol(key):
-    return BF16_UPSTREAM_TOL if any(u in key for u in UPSTREAM) else BF16_STACK_TOL
+def upstream_tol(num_edges):
+    return BF16_UPSTREAM_TOL_LARGE if num_edges >= 300 else BF16_UPSTREAM_TOL
+
+
+def bf16_grad_tol(key, num_edges=0):
+    return upstream_tol(num_edges) if any(u in key for u in UPSTREAM) else BF16_STACK_TOL
 
 
 def cosine(a, b):
@@ -100,7 +107,7 @@ def test_nnconv_bf16_within_documented_bound(name):
         got = params[k].grad
         if k == "net.layers.4.weight" and stride > 1:
             got = got[::stride]
-        assert fro_err(got, ref) <= bf16_grad_tol(k), k
+        assert fro_err(got, ref) <= bf16_grad_tol(k, g["edge_index"].shape[1]), k
         assert cosine(got, ref) >= 0.98, k
 
 
@@ -156,6 +163,93 @@ def test_kernelnn_bf16_within_documented_bound():
         assert cosine(params[k].grad, ref) >= 0.98, k
 
 
+def _config1_model(g, precision):
+    from molecular_dynamics_neural_operator_b200.graph_kernel import KernelNN
+    from tests.helpers import seeded_state_dict
+
+    model = KernelNN(int(g["width"]), int(g["ker_width"]), int(g["depth"]), 6, in_width=7, out_width=3,
+                     window_size=int(g["window"]), num_residues=int(g["num_residues"]),
+                     precision=precision)
+    model.load_state_dict(seeded_state_dict(model.state_dict(), int(g["weight_seed"])))
+    return model.cuda()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_kernelnn_config1_shape_matches_reference_golden(precision):
+    """BASELINE configs[0] shape - width 32, kernel_width 1024, depth 4, 28 residues, window 10 -
+    against output, loss and gradients produced by the reference's own source (weights rebuilt
+    from the generator's seed).  782 edges: the >= 300-edge bf16 bounds apply."""
+    from molecular_dynamics_neural_operator_b200.graph_kernel import LpLoss
+
+    g = load_golden("kernelnn_cfg1_w32_k1024_d4")
+    model = _config1_model(g, precision)
+    data = kernelnn_batch(g, torch.float32, "cuda")
+    out = model(data)
+    B, E = int(g["batch"]), g["edge_index"].shape[1]
+    loss = LpLoss(size_average=False)(out.view(B, -1), data.y.view(B, -1))
+    loss.backward()
+    stride = int(g["grad_row_stride"])
+    params = dict(model.named_parameters())
+    if precision == "fp32":
+        assert rel_err(out, torch.from_numpy(g["out"])) <= FP32_TOL
+        assert abs(loss.item() - float(g["loss"])) <= FP32_TOL * abs(float(g["loss"]))
+    else:
+        assert fro_err(out, torch.from_numpy(g["out"])) <= BF16_STACK_TOL
+    for k, ref in grads_of(g).items():
+        got = params[k].grad
+        if got.dim() == 2 and got.size(0) >= 256:
+            got = got[::stride]
+        if precision == "fp32":
+            assert rel_err(got, ref) <= 5 * FP32_TOL, k
+        elif ref.abs().max() > 0:
+            up = any(u in k for u in UPSTREAM) or k.startswith("conv1.")
+            assert fro_err(got, ref) <= (upstream_tol(E) if up else 2 * BF16_STACK_TOL), k
+            assert cosine(got, ref) >= 0.98, k
+
+
+def _chunked_oracle_layer(x, ei, ea, sd, chunk=4096):
+    from oracle import gkn_oracle as orc
+
+    net = {k[len("net."):]: v.double() for k, v in sd.items() if k.startswith("net.")}
+    return orc.nnconv_forward_chunked(x.double(), ei, ea.double(), net, sd["root"].double(),
+                                      sd["bias"].double(), chunk=chunk)
+
+
+@pytest.mark.parametrize("factorization", ["node", "edge"])
+@pytest.mark.parametrize("shape", ["config2_full_frame", "config5_width"])
+def test_one_application_at_full_width_matches_chunked_oracle(monkeypatch, shape, factorization):
+    """ONE NNConv application at BASELINE sizes against the fp64 oracle evaluated in edge chunks
+    (oracle.nnconv_forward_chunked - the [E, w, w] tensor of a whole frame would be 0.9 GB):
+    config 2 in full (504 atoms, ~60k edges, w = 64, K = 1024) and config 5's layer shape
+    (w = 128, K = 1024) on a 1500-atom frame, for both factorisations of the contraction."""
+    from molecular_dynamics_neural_operator_b200 import functional as GF
+    from molecular_dynamics_neural_operator_b200 import ops
+    from molecular_dynamics_neural_operator_b200 import synthetic as syn
+    from molecular_dynamics_neural_operator_b200.graph_kernel import DenseNet, NNConv_old
+
+    monkeypatch.setattr(GF, "FACTORIZATION", factorization)
+    torch.manual_seed(0)
+    if shape == "config2_full_frame":
+        wl = syn.WORKLOADS["bba_allatom"]
+        pos = torch.from_numpy(syn.trajectory(wl, 1, seed=0))
+        w, K, thr = wl.width, wl.ker_width, wl.cutoff
+    else:
+        w, K, thr = 128, 1024, 4.2
+        rng = np.random.default_rng(1)
+        pos = torch.from_numpy((rng.random((1, 1500, 3)) * 24.7).astype(np.float32))
+    N = pos.size(1)
+    ei, ea = ops.radius_graph(pos.cuda(), thr)
+    conv = NNConv_old(w, w, DenseNet([6, K, K, w * w], torch.nn.ReLU), aggr="mean",
+                      precision="bf16").cuda()
+    x = torch.randn(N, w)
+    with torch.no_grad():
+        out = conv(x.cuda(), ei, ea)
+    sd = {k: v.detach().cpu() for k, v in conv.state_dict().items()}
+    ref = _chunked_oracle_layer(x, ei.cpu(), ea.cpu(), sd)
+    assert ei.size(1) > (50000 if shape == "config2_full_frame" else 30000)
+    assert fro_err(out, ref) <= BF16_LAYER_TOL
+
+
 def test_state_dict_layout_is_the_reference_layout():
     g = load_golden("kernelnn_w16_k64_d2")
     model = build_model(g, "fp32")
@@ -208,7 +302,7 @@ def test_conv_stack_matches_oracle_on_seeded_frame(precision, tol):
     for k in ("conv1.root", "conv1.bias", "conv2.root", "conv2.bias", "conv1.net.layers.0.weight",
               "conv1.net.layers.0.bias", "conv1.net.layers.2.weight", "conv1.net.layers.2.bias",
               "conv1.net.layers.4.weight", "conv1.net.layers.4.bias"):
-        ktol = 3 * tol if precision == "fp32" else max(3 * tol, bf16_grad_tol(k))
+        ktol = 3 * tol if precision == "fp32" else max(3 * tol, bf16_grad_tol(k, ei.size(1)))
         assert metric(params[k].grad, sd[k].grad) <= ktol, k
 
 

@@ -175,7 +175,9 @@ def test_node_first_stack_matches_edge_first_stack_and_oracle(monkeypatch, N, E,
     out_e.backward(gout.cuda())
     ref.backward(gout.double())
     for k in p:
-        tol = 2.0 ** -2 if k.startswith(("net.layers.0", "net.layers.2", "ea")) else 2.0 ** -5
+        # upstream of the edge MLP's own ReLUs the error is mask flips: 2^-4 on these graphs of
+        # thousands of edges (tests/test_layer_gpu.py header; 2^-2 is kept for < 300 edges only)
+        tol = 2.0 ** -4 if k.startswith(("net.layers.0", "net.layers.2", "ea")) else 2.0 ** -5
         assert fro(tn[k].grad.cpu(), tr[k].grad) < tol, k
         assert fro(tn[k].grad.cpu(), te[k].grad.cpu()) < tol, k
 

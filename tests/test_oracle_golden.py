@@ -55,6 +55,43 @@ def test_kernelnn_forward_loss_backward_matches_reference(name):
         np.testing.assert_allclose(sd[k].grad.numpy(), ref.numpy(), rtol=1e-8, atol=1e-11, err_msg=k)
 
 
+def test_kernelnn_config1_shape_matches_reference():
+    """BASELINE configs[0] shape (width 32, kernel_width 1024, depth 4, 28 residues, window 10):
+    weights rebuilt from the seed the generator used, output / loss / gradients produced by the
+    reference's own source."""
+    from tests.helpers import seeded_state_dict
+
+    g = load_golden("kernelnn_cfg1_w32_k1024_d4")
+    w, K, R = int(g["width"]), int(g["ker_width"]), int(g["num_residues"])
+    shapes = {"lstm.weight_ih_l0": (12, 3), "lstm.weight_hh_l0": (12, 3), "lstm.bias_ih_l0": (12,),
+              "lstm.bias_hh_l0": (12,), "lstm_fc.weight": (3, 3), "lstm_fc.bias": (3,),
+              "emb.weight": (20, 4), "fc1.weight": (w, 7), "fc1.bias": (w,), "fc2.weight": (3, w),
+              "fc2.bias": (3,)}
+    for c in ("conv1", "conv2"):
+        shapes.update({f"{c}.root": (w, w), f"{c}.bias": (w,),
+                       f"{c}.net.layers.0.weight": (K, 6), f"{c}.net.layers.0.bias": (K,),
+                       f"{c}.net.layers.2.weight": (K, K), f"{c}.net.layers.2.bias": (K,),
+                       f"{c}.net.layers.4.weight": (w * w, K), f"{c}.net.layers.4.bias": (w * w,)})
+    template = {k: torch.empty(v) for k, v in shapes.items()}
+    sd32 = seeded_state_dict(template, int(g["weight_seed"]))
+    sd = {}
+    for k, v in sd32.items():
+        sd[k] = sd["conv1.net." + k[10:]] if k.startswith("conv2.net.") else v.double().requires_grad_(True)
+    data = kernelnn_batch(g)
+    out = orc.kernelnn_forward(sd, data, int(g["depth"]), int(g["window"]), R)
+    np.testing.assert_allclose(out.detach().numpy(), g["out"], rtol=1e-10, atol=1e-12)
+    B = int(g["batch"])
+    loss = orc.lp_loss_rel(out.view(B, -1), data.y.view(B, -1), size_average=False)
+    np.testing.assert_allclose(loss.item(), float(g["loss"]), rtol=1e-12)
+    loss.backward()
+    stride = int(g["grad_row_stride"])
+    for k, ref in grads_of(g).items():
+        got = sd[k].grad
+        if got.dim() == 2 and got.size(0) >= 256:
+            got = got[::stride]
+        np.testing.assert_allclose(got.numpy(), ref.numpy(), rtol=1e-8, atol=1e-11, err_msg=k)
+
+
 @pytest.mark.parametrize("name", ["pairdata_n28", "pairdata_n300"])
 def test_construct_pairdata_matches_reference(name):
     g = load_golden(name)
