@@ -45,6 +45,18 @@ import torch  # noqa: E402
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
+LR_NOTE = {"lr": 1e-4}
+STDOUT_FD = {"fd": None}  # the real stdout while fd 1 is parked on stderr (multi-GPU runs)
+
+
+def emit_line(line: dict) -> None:
+    text = json.dumps(line) + "\n"
+    if STDOUT_FD["fd"] is not None:
+        sys.stdout.flush()
+        os.write(STDOUT_FD["fd"], text.encode())
+    else:
+        sys.stdout.write(text)
+        sys.stdout.flush()
 METRIC = "gkn_train_frames_per_s"
 UNIT = "frames/s"
 WORKLOAD = "bba_allatom"
@@ -137,7 +149,7 @@ class CpuReference:
     (graph_kernel.py:362-393), KernelNN forward with the materialised [E,w,w] kernel
     (:194-209, :277-309), LpLoss.rel (:105-119), backward, Adam (:541)."""
 
-    def __init__(self, wl, threads: int, seed: int = 0):
+    def __init__(self, wl, threads: int, seed: int = 0, lr: float = 1e-4):
         from oracle import gkn_oracle as orc
         from molecular_dynamics_neural_operator_b200.graph_kernel import KernelNN
 
@@ -154,7 +166,7 @@ class CpuReference:
             if k.startswith("conv2.net."):
                 self.sd[k] = self.sd["conv1.net." + k[len("conv2.net."):]]
         uniq = {id(v): v for v in self.sd.values()}
-        self.opt = torch.optim.Adam(list(uniq.values()), lr=0.01, weight_decay=5e-4)
+        self.opt = torch.optim.Adam(list(uniq.values()), lr=lr, weight_decay=5e-4)
 
     def calibrate_gflops(self) -> float:
         a = torch.randn(2048, 1024)
@@ -268,6 +280,12 @@ def bench_config(wl, frames_per_gpu, edges_per_frame, reference=False):
         "batch_note": "reference default batch_size is 128 (graph_kernel.py:318) = 16 frames per GPU "
                       "on 8 GPUs; per-GPU work is fixed as N grows (weak scaling)",
         "factorization": os.environ.get("GKN_FACTORIZATION", "node"),
+        "optimizer": f"Adam(lr={LR_NOTE['lr']}, weight_decay=5e-4) as graph_kernel.py:541-543.  The "
+                     "reference's default lr 0.01 (graph_kernel.py:319) sends THIS random-init model on "
+                     "THESE synthetic coordinates to inf after the first update (loss 1.1e8 -> inf -> "
+                     "NaN: 12 tied applications amplify every weight change), lr 1e-3 kills every ReLU; "
+                     "at 1e-4 the loss falls steadily (1.1e8 -> 29 in 60 steps), so the timed steps "
+                     "carry finite activations and gradients.  Throughput does not depend on lr",
         "untimed_steps_before_timing": "max(8, warmup) resident + max(3, warmup) host-fed + 2 resident; "
                                        "Python cyclic GC disabled inside the timed loops",
         "parallelism": "frames sharded over GPUs, bucketed NCCL gradient all-reduce",
@@ -327,7 +345,7 @@ def quick_train(dev, name, frames, steps, warm=3):
     torch.manual_seed(0)
     model = KernelNN(wl.width, wl.ker_width, wl.depth, 6, in_width=7, out_width=3,
                      window_size=wl.window, num_residues=wl.num_atoms, precision="bf16").to(dev)
-    trainer = Trainer(model, lr=0.01, weight_decay=5e-4)
+    trainer = Trainer(model, lr=LR_NOTE["lr"], weight_decay=5e-4)
     traj = syn.trajectory(wl, wl.window + 1 + frames, seed=0)
     aa = torch.from_numpy(syn.residue_ids(wl)).to(dev)
     xw, y = syn.window_batch(traj, list(range(frames)), wl.window)
@@ -355,6 +373,16 @@ def quick_train(dev, name, frames, steps, warm=3):
     return res
 
 
+def _tame_rollout_model(model):
+    """A random-init KernelNN amplifies its input ~30x per application on raw Angstrom coordinates
+    (16 applications at depth 8: inf).  For the rollout measurements the last edge-MLP layer is
+    scaled by 0.02 so that every application maps O(1) features to O(1) features: same kernels,
+    same work, finite numbers - which the sharded-vs-unsharded agreement check needs."""
+    with torch.no_grad():
+        model.conv1.net.layers[4].weight.mul_(0.02)
+        model.conv1.net.layers[4].bias.mul_(0.02)
+
+
 def quick_rollout(dev, name, steps, window=2):
     """BASELINE config 5 on ONE GPU: device-resident operator rollout (forward -> new positions ->
     radius graph rebuilt on the GPU), reference graph_kernel.py:396-413: rollout steps/s."""
@@ -365,6 +393,7 @@ def quick_rollout(dev, name, steps, window=2):
     torch.manual_seed(0)
     model = KernelNN(wl.width, wl.ker_width, wl.depth, 6, in_width=7, out_width=3, window_size=window,
                      num_residues=wl.num_atoms, precision="bf16").to(dev).eval()
+    _tame_rollout_model(model)
     traj = torch.from_numpy(syn.trajectory(wl, window, seed=0)).to(dev)
     aa = torch.from_numpy(syn.residue_ids(wl)).to(dev)
     data = construct_pairdata(traj, aa, threshold=wl.cutoff, device=dev)
@@ -392,6 +421,59 @@ def quick_rollout(dev, name, steps, window=2):
     torch.cuda.empty_cache()
     return res
 
+def sharded_rollout(dev, world, rank, steps=3, window=2, name="synthetic_100k"):
+    """BASELINE config 5 with ONE 100k-atom frame sharded over the N ranks of this run
+    (sharded.kernelnn_forward_sharded: source-range shards, one NCCL all-reduce of partial node
+    sums per application).  The first step's output is checked against the unsharded forward that
+    every rank also computes (same kernels, whole frame); then `steps` rollout steps are timed."""
+    import torch.distributed as dist
+
+    from molecular_dynamics_neural_operator_b200 import synthetic as syn
+    from molecular_dynamics_neural_operator_b200.graph_kernel import KernelNN, construct_pairdata
+    from molecular_dynamics_neural_operator_b200.sharded import kernelnn_forward_sharded
+
+    wl = syn.WORKLOADS[name]
+    torch.manual_seed(0)
+    model = KernelNN(wl.width, wl.ker_width, wl.depth, 6, in_width=7, out_width=3, window_size=window,
+                     num_residues=wl.num_atoms, precision="bf16").to(dev).eval()
+    _tame_rollout_model(model)
+    for p_ in model.parameters():
+        dist.broadcast(p_.data, src=0)
+    traj = torch.from_numpy(syn.trajectory(wl, window, seed=0)).to(dev)
+    aa = torch.from_numpy(syn.residue_ids(wl)).to(dev)
+    data = construct_pairdata(traj, aa, threshold=wl.cutoff, device=dev)
+    edges = []
+    with torch.no_grad():
+        ref = model(data, single_example=True)
+        out = kernelnn_forward_sharded(model, data)
+        diff = float((out - ref).norm() / ref.norm().clamp(min=1e-30))
+        del ref
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for step in range(steps + 1):
+            if step == 1:
+                dist.barrier()
+                torch.cuda.synchronize()
+                ev0.record()
+            out = kernelnn_forward_sharded(model, data)
+            pos = data.x_position[-1] + 0.05 * torch.tanh(torch.nan_to_num(out))
+            data = construct_pairdata(torch.cat([data.x_position[1:], pos[None]], 0), aa,
+                                      threshold=wl.cutoff, device=dev)
+            edges.append(int(data.edge_index.size(1)))
+        ev1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+    t = torch.tensor([ev0.elapsed_time(ev1) / steps, diff], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, diff = float(t[0]), float(t[1])
+    res = {"workload": name, "mode": f"rollout, one frame sharded over {world} GPUs "
+                                     "(source ranges, all-reduce of partial node sums)",
+           "steps": steps, "ms_per_rollout_step": ms, "steps_per_s": 1e3 / ms, "atoms": wl.num_atoms,
+           "edges_per_step": edges[-1], "rel_fro_vs_unsharded_forward": diff,
+           "agrees_with_unsharded": diff < 2.0 ** -7}
+    del model, data
+    torch.cuda.empty_cache()
+    return res
+
 
 # ------------------------------------------------------------------------------------------------
 # B200 arm
@@ -412,10 +494,16 @@ def run_b200_arm(args, wl):
     dev = torch.device("cuda", local)
     if world > 1:
         # stdout carries the single JSON line; NCCL's own log (communicator ranks, NVLS, rings)
-        # stays ON - at INFO level unless the caller chose one - and goes to stderr
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")
+        # stays ON and goes to stderr.  Level VERSION prints its banner with a bare printf to
+        # stdout, so it is raised to INFO (which goes through NCCL's logger and NCCL_DEBUG_FILE);
+        # and, belt and braces, file descriptor 1 points at stderr until the JSON line is written.
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        sys.stdout.flush()
+        STDOUT_FD["fd"] = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
 
@@ -427,7 +515,7 @@ def run_b200_arm(args, wl):
     model = KernelNN(wl.width, wl.ker_width, wl.depth, 6, in_width=7, out_width=3,
                      window_size=wl.window, num_residues=wl.num_atoms, precision="bf16").to(dev)
     broadcast_parameters(model)
-    trainer = Trainer(model, lr=0.01, weight_decay=5e-4)
+    trainer = Trainer(model, lr=args.lr, weight_decay=5e-4)
 
     # synthetic trajectory; rank r takes frames r, r+world, ... of every global batch
     n_frames = wl.window + 1 + pool * B * world
@@ -447,6 +535,7 @@ def run_b200_arm(args, wl):
     prefetch = syn.BatchPrefetcher(dev)
     loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
     loss_events: list = []
+    loss_log: list = []  # every step's loss as read back by the host (rank-local sum over frames)
 
     def build_resident(i):
         return syn.make_batch(dev_x[i % pool], aa, dev_y[i % pool], wl.cutoff, prepare=True,
@@ -487,14 +576,14 @@ def run_b200_arm(args, wl):
             if read_loss:
                 if loss_events:
                     loss_events.pop().synchronize()
-                    float(loss_host[0])  # D2H read of the previous step's result
+                    loss_log.append(float(loss_host[0]))  # D2H read of the previous step's result
                 loss_host.copy_(loss.reshape(1), non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record()
                 loss_events.append(ev)
         if read_loss and loss_events:
             loss_events.pop().synchronize()
-            float(loss_host[0])
+            loss_log.append(float(loss_host[0]))
 
     def barrier():
         if world > 1:
@@ -542,8 +631,11 @@ def run_b200_arm(args, wl):
         sampler.lines.clear()  # keep only samples taken during the timed loops
     edge_counts.clear()
     launches0 = _lib.launch_count()
+    loss_before = list(loss_log)
+    loss_log.clear()
     ms_total = timed(build_resident, args.steps, True)
     launches = _lib.launch_count() - launches0
+    loss_timed = list(loss_log)
     ms_e2e = timed(build_e2e, args.steps, True)
     # Per-launch CUDA events around the contraction cost ~0.15 ms each on this driver (measured:
     # +10 % step time), so the kernel's launch duration is taken from an instrumented REPEAT of
@@ -722,6 +814,17 @@ def run_b200_arm(args, wl):
         strong = {"scaling": "strong", "global_batch": 16, "frames_per_gpu_per_step": Bs,
                   "steps": n_strong, "ms_per_step": ms_s / n_strong, "value": 16 * n_strong / (ms_s * 1e-3),
                   "unit": UNIT}
+    sharded = None
+    if world > 1 and not args.no_extras:
+        # N3 evidence in the driver's own multi-GPU runs: config 5 sharded over these N GPUs
+        del trainer, model
+        dev_x.clear()
+        dev_y.clear()
+        torch.cuda.empty_cache()
+        try:
+            sharded = sharded_rollout(dev, world, rank)
+        except Exception as exc:  # noqa: BLE001
+            sharded = {"error": f"{type(exc).__name__}: {exc}"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -737,10 +840,16 @@ def run_b200_arm(args, wl):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
+        "loss": {"first_untimed_step": loss_before[0] if loss_before else None,
+                 "timed_first": loss_timed[0] if loss_timed else None,
+                 "timed_last": loss_timed[-1] if loss_timed else None,
+                 "all_finite": bool(np.isfinite(loss_before + loss_timed).all()),
+                 "note": "rank-0 LpLoss.rel summed over its frames, every step read back by the host"},
         "clocks": clocks,
         "roofline": roofline,
         "edge_first": edge_first,
         "strong_scaling": strong,
+        "sharded_rollout": sharded,
         "edges_per_s": value * edges_per_frame,
         "flops": {
             "algorithmic_train_flop_per_frame": 4 * A * unit_flop,
@@ -815,7 +924,7 @@ def run_b200_arm(args, wl):
             }
         except Exception as exc:  # the headline stands even if an extra fails: say so in the line
             line["extras_error"] = f"{type(exc).__name__}: {exc}"
-    print(json.dumps(line), flush=True)
+    emit_line(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -830,6 +939,8 @@ def main():
                     help="frames per GPU per step; 16 = the reference's default batch_size 128 "
                          "(graph_kernel.py:318) spread over the 8 GPUs of one box")
     ap.add_argument("--pool", type=int, default=4, help="distinct batches cycled through")
+    ap.add_argument("--lr", type=float, default=1e-4,
+                    help="Adam learning rate (see config.optimizer for why not the reference's 0.01)")
     ap.add_argument("--cpu-seconds-per-step", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timer", action="store_true", help="(diagnostic) no per-launch events")
@@ -845,6 +956,7 @@ def main():
 
     from molecular_dynamics_neural_operator_b200 import synthetic as syn
 
+    LR_NOTE["lr"] = args.lr
     wl = syn.WORKLOADS[args.workload]
     if args.impl == "reference":
         # edges/frame of the synthetic workload, from the same generator (SciPy on one frame)

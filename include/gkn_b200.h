@@ -219,6 +219,12 @@ int gkn_segment_matvec(const float* rows, const int32_t* perm, const int32_t* se
                        const float* M1, const float* nin, const float* M2, const float* bias,
                        float* out, float* agg_out, int64_t N, int32_t W, int32_t relu,
                        void* stream);
+/* Dataset feeder (reference dataset.py:194-201, a Python loop per edge there):
+ * edge_attr[e, :] = [pos[edge_index[0,e], :], pos[edge_index[1,e], :]] for a batch of graphs whose
+ * node ids index the rows of pos (float32 [M,3]; edge_index int64 [2,E]; edge_attr float32 [E,6]).
+ * status (int32[1], may be NULL) gets bit 0 set if a node id lies outside [0, M). */
+int gkn_edge_attr_gather(const float* pos, const int64_t* edge_index, int64_t E, int64_t M,
+                         float* edge_attr, int32_t* status, void* stream);
 /* g[n,:] = gy[n,:] * (relu ? (y[n,:] > 0) : 1);  gn[n,:] = g[n,:] * inv_cnt[n] */
 int gkn_relu_grad_scale(const float* gy, const float* y, const float* inv_cnt, float* g, float* gn,
                         int64_t N, int32_t W, int32_t relu, void* stream);

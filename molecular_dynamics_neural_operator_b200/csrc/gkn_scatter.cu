@@ -920,3 +920,51 @@ extern "C" int gkn_segment_matvec(const float* rows, const int32_t* perm, const 
     GKN_CHECK_LAUNCH("segment_matvec launch");
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// edge_attr[e] = [pos[row e], pos[col e]]   (dataset feeder: reference dataset.py:194-201 builds this
+// with a Python loop per edge).  One thread per edge: two gathered 12-byte reads from the (small,
+// cache-resident) coordinate table, three 8-byte stores into the 24-byte record.
+// ------------------------------------------------------------------------------------------------
+namespace gkn {
+namespace {
+__global__ void __launch_bounds__(256)
+edge_attr_gather_kernel(const float* __restrict__ pos, const int64_t* __restrict__ edge_index,
+                        int64_t E, int64_t M, float* __restrict__ edge_attr,
+                        int32_t* __restrict__ status) {
+    for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < E;
+         e += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t i = __ldg(edge_index + e), j = __ldg(edge_index + E + e);
+        float2* out = reinterpret_cast<float2*>(edge_attr + e * 6);
+        if (i < 0 || i >= M || j < 0 || j >= M) {
+            if (status != nullptr) atomicOr(status, 1);  // out-of-range node id: record, write zeros
+            out[0] = out[1] = out[2] = make_float2(0.f, 0.f);
+            continue;
+        }
+        const float ax = __ldg(pos + 3 * i), ay = __ldg(pos + 3 * i + 1), az = __ldg(pos + 3 * i + 2);
+        const float bx = __ldg(pos + 3 * j), by = __ldg(pos + 3 * j + 1), bz = __ldg(pos + 3 * j + 2);
+        out[0] = make_float2(ax, ay);
+        out[1] = make_float2(az, bx);
+        out[2] = make_float2(by, bz);
+    }
+}
+}  // namespace
+}  // namespace gkn
+
+extern "C" int gkn_edge_attr_gather(const float* pos, const int64_t* edge_index, int64_t E, int64_t M,
+                                    float* edge_attr, int32_t* status, void* stream) {
+    using namespace gkn;
+    if (E == 0) return 0;
+    if (E < 0 || M <= 0 || pos == nullptr || edge_index == nullptr || edge_attr == nullptr) {
+        return set_error("gkn_edge_attr_gather: bad size or NULL pointer argument");
+    }
+    int sms = 0;
+    int rc = device_sm_count(&sms);
+    if (rc) return rc;
+    int64_t blocks = (E + 255) / 256;
+    if (blocks > int64_t(sms) * 16) blocks = int64_t(sms) * 16;
+    edge_attr_gather_kernel<<<dim3(unsigned(blocks)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        pos, edge_index, E, M, edge_attr, status);
+    GKN_CHECK_LAUNCH("edge_attr_gather launch");
+    return 0;
+}

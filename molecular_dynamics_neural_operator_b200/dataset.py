@@ -154,3 +154,59 @@ class ContactMapDataset(torch.utils.data.Dataset):
             edge_attr=torch.from_numpy(edge_attr.reshape(-1, 6)).to(torch.float32),
             edge_index=torch.from_numpy(edge_index).to(torch.long),
         )
+
+    # ------------------------------------------------------------------------------------------
+    # Device-side feeder: a whole batch at once, on the GPU
+    # ------------------------------------------------------------------------------------------
+    def to_device(self, device) -> "ContactMapDataset":
+        """Keep the trajectory ([F, R, 3] float32) and the residue ids resident on ``device`` so
+        that ``device_batch`` never touches the host for coordinates."""
+        self._dev = torch.device(device)
+        self._pos_dev = torch.from_numpy(self.edge_attrs.astype("float32", copy=False)).to(self._dev)
+        self._aa_dev = self.x_aminoacid.to(self._dev)
+        return self
+
+    def device_batch(self, indices, graph: str = "stored", threshold: float = 8.0,
+                     prepare: bool = True) -> PairData:
+        """The collated batch ``collate([self[i] for i in indices])`` built on the GPU
+        (call ``to_device`` first): windows and targets are slices of the resident trajectory and
+        the edge attributes come from one gather kernel (gkn_edge_attr_gather) instead of the
+        reference's Python loop per edge (dataset.py:194-201).
+
+        graph="stored": edges from the file's pre-computed ``contact_map`` (dataset.py:189), as in
+                        the reference; the ragged lists are concatenated on the host and copied.
+        graph="radius": edges rebuilt on the fly from window frame ``idx`` of ``point_cloud`` by
+                        the radius-graph kernel (threshold in the units of the coordinates; self
+                        loops included, (row, col) order) - no contact maps needed on disk.
+        Both use frame ``idx`` (the FIRST window frame) for the edge attributes, dataset.py:197."""
+        import numpy as np
+
+        from . import ops  # noqa: PLC0415
+
+        if not hasattr(self, "_pos_dev"):
+            raise RuntimeError("device_batch: call to_device(device) first")
+        idx = torch.as_tensor(list(indices), dtype=torch.long, device=self._dev)
+        B, W, R = idx.numel(), self.window_size, self._pos_dev.size(1)
+        if B == 0 or int(idx.max()) >= len(self) or int(idx.min()) < 0:
+            raise IndexError("device_batch: empty batch or index out of range")
+        win = idx[:, None] + torch.arange(W, device=self._dev)[None, :]
+        x_position = self._pos_dev[win.reshape(-1)]                      # [B*W, R, 3]
+        y = self._pos_dev[idx + W + self.horizon - 1].reshape(B * R, 3)
+        first = self._pos_dev[idx]                                       # [B, R, 3]
+        plan = None
+        if graph == "radius":
+            edge_index, edge_attr, row_ptr = ops.radius_graph(first, threshold, return_row_ptr=True)
+            if prepare:
+                plan = ops.plan_from_csr(edge_index, row_ptr, B * R, validate=False)
+        elif graph == "stored":
+            lists = [np.asarray(self.edge_indices[int(i)]).reshape(2, -1) + k * R
+                     for k, i in enumerate(idx.tolist())]
+            edge_index = torch.from_numpy(np.concatenate(lists, axis=1).astype(np.int64)).to(self._dev)
+            edge_attr = ops.edge_attr_gather(first.reshape(B * R, 3), edge_index)
+        else:
+            raise ValueError("graph must be 'stored' or 'radius'")
+        data = PairData(x_aminoacid=self._aa_dev.repeat(B), x_position=x_position, y=y,
+                        edge_attr=edge_attr, edge_index=edge_index)
+        if plan is not None:
+            data._gkn_plan = plan
+        return data

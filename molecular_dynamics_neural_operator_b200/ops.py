@@ -189,6 +189,28 @@ def radius_graph(pos: torch.Tensor, threshold: float, return_row_ptr: bool = Fal
     return edge_index, edge_attr
 
 
+def edge_attr_gather(pos: torch.Tensor, edge_index: torch.Tensor, validate: bool = True) -> torch.Tensor:
+    """edge_attr [E, 6] = [pos[row], pos[col]] for node coordinates pos float32 [M, 3] (a batch of
+    graphs: M = total nodes, edge_index already offset) - gkn_edge_attr_gather, the feeder's
+    replacement for the reference's per-edge Python loop (dataset.py:194-201)."""
+    lib = _lib.load()
+    _require_cuda(pos, "pos")
+    pos = pos.reshape(-1, 3).contiguous()
+    ei = edge_index.contiguous()
+    if ei.dim() != 2 or ei.size(0) != 2 or ei.dtype != torch.int64:
+        raise ValueError("edge_index must be int64 [2, E]")
+    E, M = int(ei.size(1)), int(pos.size(0))
+    out = torch.empty((E, 6), dtype=torch.float32, device=pos.device)
+    status = torch.zeros(1, dtype=torch.int32, device=pos.device)
+    with torch.cuda.device(pos.device):
+        _lib.check(lib.gkn_edge_attr_gather(_p(pos, torch.float32, "pos"), _p(ei, torch.int64, "edge_index"),
+                                            E, M, _p(out), _p(status), _stream()),
+                   "gkn_edge_attr_gather")
+    if validate and int(status.item()) != 0:
+        raise ValueError(f"edge_index contains node ids outside [0, {M})")
+    return out
+
+
 def _contract(kind: str, h, w3, idx, node, precision: str) -> torch.Tensor:
     _require_cuda(h, "h")
     lib = _lib.load()

@@ -84,3 +84,50 @@ def test_dataset_fed_batch_with_arbitrary_contact_maps_matches_oracle(tmp_path):
     ref = orc.kernelnn_forward(sd, data, 2, W, R)
     err = float((out.detach().cpu().double() - ref).abs().max() / ref.abs().max())
     assert err <= 1e-5  # nodes R-2, R-1 never receive messages: mean over zero edges -> 0
+
+
+def test_device_feeder_equals_collated_getitem_and_reference_loop(tmp_path):
+    """ContactMapDataset.device_batch (trajectory resident on the GPU, edge attributes from
+    gkn_edge_attr_gather) is bit-identical to collate([ds[i] ...]), i.e. to the reference's
+    per-edge Python loop (dataset.py:180-204); with graph='radius' the edges are the radius-graph
+    kernel's, bit-identical to the reference's construct_pairdata on the first window frame."""
+    import numpy as np
+
+    from molecular_dynamics_neural_operator_b200.dataset import ContactMapDataset, collate
+    from molecular_dynamics_neural_operator_b200 import ops
+    from oracle import gkn_oracle as orc
+
+    rng = np.random.default_rng(1)
+    F, R, W, H = 12, 9, 3, 2
+    pc = rng.normal(size=(F, 3, R)).astype(np.float32) * 3
+    cms = np.empty(F, dtype=object)
+    for f in range(F):
+        e = int(rng.integers(5, 30))
+        cms[f] = np.concatenate([rng.integers(0, R, e), rng.integers(0, R, e)]).astype(np.int64)
+    np.savez(tmp_path / "t.npz", contact_map=cms, point_cloud=pc, rmsd=np.zeros(F, np.float32),
+             amino_acids=rng.integers(0, 20, R).astype(np.int64))
+    ds = ContactMapDataset(str(tmp_path / "t.npz"), window_size=W, horizon=H).to_device("cuda")
+    idx = [4, 0, 7, 7]
+    ref = collate([ds[i] for i in idx])
+    got = ds.device_batch(idx, graph="stored")
+    for f in ("x_aminoacid", "x_position", "y", "edge_attr", "edge_index"):
+        assert torch.equal(getattr(got, f).cpu(), getattr(ref, f)), f
+    # on-the-fly graphs from the coordinates
+    thr = 4.0
+    got = ds.device_batch(idx, graph="radius", threshold=thr)
+    pos = np.transpose(pc, [0, 2, 1])
+    eis, eas = [], []
+    for k, i in enumerate(idx):
+        ei, ea = orc.construct_pairdata_arrays(pos[i:i + 1], thr)
+        eis.append(ei + k * R)
+        eas.append(ea)
+    assert np.array_equal(got.edge_index.cpu().numpy(), np.concatenate(eis, axis=1))
+    assert np.array_equal(got.edge_attr.cpu().numpy(), np.concatenate(eas, axis=0))
+    assert got._gkn_plan.num_nodes == len(idx) * R
+    # the gather kernel rejects ids outside the batch
+    bad = got.edge_index.clone()
+    bad[0, 0] = len(idx) * R
+    with pytest.raises(ValueError):
+        ops.edge_attr_gather(got.x_position[:1].reshape(-1, 3), bad)
+    with pytest.raises(IndexError):
+        ds.device_batch([len(ds)])
