@@ -219,6 +219,21 @@ int gkn_segment_matvec(const float* rows, const int32_t* perm, const int32_t* se
                        const float* M1, const float* nin, const float* M2, const float* bias,
                        float* out, float* agg_out, int64_t N, int32_t W, int32_t relu,
                        void* stream);
+/* ---- sharded large-frame rollout: the exchange step fused with the node update ----------------
+ * Source-range sharding (sharded.py) leaves rank p with partial sums S_p [2, N, W] fp32 (messages
+ * and x_j) at every destination.  Rank r computes, for ITS nodes [n0, n1),
+ *     x'[n] = act( inv_cnt[n] * sum_p S_p[0,n] + (inv_cnt[n] * sum_p S_p[1,n]) @ B3 + x[n] @ root + bias )
+ * (PyG mean + NNConv_old.update, graph_kernel.py:194-209) reading the rows of every peer's S_p
+ * through mapped peer pointers and writing x'[n] into every rank's x' buffer: reduce-scatter,
+ * compute and all-gather in one kernel over NVLink.  partial_ptrs / xout_ptrs: HOST arrays of
+ * `world` device addresses (this rank's own buffers included, in rank order; e.g. the buffer_ptrs
+ * of a torch symmetric-memory handle).  The caller synchronises the ranks before (all S_p written)
+ * and after (all x' rows landed) the launch.  W in {32, 64, 128}, world <= 16. */
+int gkn_shard_reduce_update(const uint64_t* partial_ptrs, const uint64_t* xout_ptrs, int32_t world,
+                            const float* x, const float* inv_cnt, const float* B3,
+                            const float* root, const float* bias, int64_t n0, int64_t n1,
+                            int64_t N, int32_t W, int32_t relu, void* stream);
+
 /* Dataset feeder (reference dataset.py:194-201, a Python loop per edge there):
  * edge_attr[e, :] = [pos[edge_index[0,e], :], pos[edge_index[1,e], :]] for a batch of graphs whose
  * node ids index the rows of pos (float32 [M,3]; edge_index int64 [2,E]; edge_attr float32 [E,6]).

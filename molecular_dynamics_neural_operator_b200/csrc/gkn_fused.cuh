@@ -24,6 +24,51 @@ __device__ __forceinline__ Item load_item(const Item* items, int64_t v) {
     return it;
 }
 
+// Software pipeline over a CTA's item queue.  An item record is a global load (an L2 round trip);
+// loading "the next one" at the top of an iteration and branching on its kind in the following
+// iteration stalls a role for that whole latency whenever an iteration is short, and anything
+// derived from the record by further loads (the row pointers of a D item) adds a second, dependent
+// latency.  ncu's source page showed the single-thread roles 60 % stalled on exactly these loads.
+// So records are loaded kItemDepth items ahead and rotated through registers; derived loads are
+// issued for the record that becomes current in the NEXT iteration, from a record that arrived
+// iterations ago - nothing a role branches on is younger than one full iteration.
+constexpr int kItemDepth = 3;
+
+struct ItemPipe {
+    Item q[kItemDepth];
+    const Item* items;
+    int64_t v_next, v_end, vstep;
+
+    __device__ __forceinline__ static Item nop() {
+        Item it;
+        it.a = make_int4(2 /* no-op kind in both kernels */, 0, 0, 0);
+        it.b = make_int4(-1, 0, -1, 0);
+        return it;
+    }
+    __device__ __forceinline__ Item fetch() {
+        const Item it = v_next < v_end ? load_item(items, v_next) : nop();
+        v_next += vstep;
+        return it;
+    }
+    __device__ __forceinline__ void init(const Item* it, int64_t v0, int64_t v1, int64_t step) {
+        items = it;
+        v_next = v0;
+        v_end = v1;
+        vstep = step;
+#pragma unroll
+        for (int i = 0; i < kItemDepth; ++i) q[i] = fetch();
+    }
+    // current record; afterwards q[0] is the record of the next iteration (already resident)
+    __device__ __forceinline__ Item pop() {
+        const Item it = q[0];
+#pragma unroll
+        for (int i = 0; i + 1 < kItemDepth; ++i) q[i] = q[i + 1];
+        q[kItemDepth - 1] = fetch();
+        return it;
+    }
+    __device__ __forceinline__ const Item& peek() const { return q[0]; }
+};
+
 __device__ __forceinline__ int32_t ld_acquire(const int32_t* p) {
     int32_t v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");

@@ -57,6 +57,7 @@ enum { IT_P = 0, IT_C = 1, IT_NOP = 2 };
 //      the unit's source node.  wait (before the loads of U): flags[wait_idx] >= wait_target
 using fused::Item;
 using fused::load_item;
+using fused::ItemPipe;
 using fused::wait_counter;
 using fused::fence_proxy_async_global;
 using fused::sts128;
@@ -163,10 +164,10 @@ node_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
         };
         const uint64_t pol_stream = l2_policy_evict_first();
         if (lane == 0) {
-            Item nx = v0 < v1 ? load_item(p.items, v0) : Item{};
+            ItemPipe pipe;
+            pipe.init(p.items, v0, v1, vstep);
             for (int64_t v = v0; v < v1; v += vstep) {
-                const Item it = nx;
-                if (v + vstep < v1) nx = load_item(p.items, v + vstep);
+                const Item it = pipe.pop();
                 if (it.a.x == IT_P) {
 #pragma unroll
                     for (int f = 0; f < C::kPFills; ++f) {
@@ -231,10 +232,10 @@ node_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
         };
         uint32_t n_acc = 0;
         if (lane == 0) {
-            Item nx = v0 < v1 ? load_item(p.items, v0) : Item{};
+            ItemPipe pipe;
+            pipe.init(p.items, v0, v1, vstep);
             for (int64_t v = v0; v < v1; v += vstep) {
-                const Item it = nx;
-                if (v + vstep < v1) nx = load_item(p.items, v + vstep);
+                const Item it = pipe.pop();
                 if (it.a.x != IT_P && it.a.x != IT_C) continue;
                 const uint32_t as = n_acc % kAcc;
                 const uint32_t aphase = (n_acc / kAcc) & 1u;
@@ -305,10 +306,10 @@ node_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
                 pending = -1;
             }
         };
-        Item nx = v0 < v1 ? load_item(p.items, v0) : Item{};
+        ItemPipe pipe;
+        pipe.init(p.items, v0, v1, vstep);
         for (int64_t v = v0; v < v1; v += vstep) {
-            const Item it = nx;
-            if (v + vstep < v1) nx = load_item(p.items, v + vstep);
+            const Item it = pipe.pop();
             if (it.a.x != IT_P && it.a.x != IT_C) continue;
             const uint32_t as = n_acc % kAcc;
             const uint32_t aphase = (n_acc / kAcc) & 1u;

@@ -36,6 +36,7 @@ using fused::fence_proxy_async_global;
 using fused::Item;
 using fused::lds128;
 using fused::load_item;
+using fused::ItemPipe;
 using fused::pack_bf16;
 using fused::red_release_add;
 using fused::sts128;
@@ -147,10 +148,9 @@ node_fused_bwd_kernel(const __grid_constant__ CUtensorMap tmap_hs,
 
     // the padded row range of a D item's node: two loads from a table that consecutive items of a
     // CTA walk almost sequentially (L1 hits after the first touch of a line)
-    auto decode_d = [&](int32_t n) {
-        const int32_t b = __ldg(p.pptr + n);
-        return make_dunit(b, __ldg(p.pptr + n + 1) - b);
-    };
+    // only the two loads: the arithmetic on them (make_dunit) is done where the unit is used, one
+    // iteration later - a dependent instruction right here would stall on the loads at once
+    auto decode_d = [&](int32_t n) { return make_int2(__ldg(p.pptr + n), __ldg(p.pptr + n + 1)); };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -198,15 +198,15 @@ node_fused_bwd_kernel(const __grid_constant__ CUtensorMap tmap_hs,
         uint32_t n_x = 0;  // node blocks consumed so far
         const uint64_t pol_stream = l2_policy_evict_first();
         if (lane == 0) {
-            Item nx = v0 < v1 ? load_item(p.items, v0) : Item{};
-            DUnit un = (v0 < v1 && nx.a.x == IT_D) ? decode_d(nx.a.y) : DUnit{};
+            ItemPipe pipe;
+            pipe.init(p.items, v0, v1, vstep);
+            int2 un = pipe.peek().a.x == IT_D ? decode_d(pipe.peek().a.y) : make_int2(0, 0);
             for (int64_t v = v0; v < v1; v += vstep) {
-                const Item it = nx;
-                const DUnit u = un;
-                if (v + vstep < v1) {
-                    nx = load_item(p.items, v + vstep);
-                    if (nx.a.x == IT_D) un = decode_d(nx.a.y);
-                }
+                const DUnit u = make_dunit(un.x, un.y - un.x);
+                const Item it = pipe.pop();
+                // row pointers of the NEXT item (its record arrived iterations ago): in flight
+                // while this item is processed
+                if (pipe.peek().a.x == IT_D) un = decode_d(pipe.peek().a.y);
                 if (it.a.x == IT_D) {
                     for (int kb = 0; kb < u.nkb; ++kb) {
                         mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -269,15 +269,15 @@ node_fused_bwd_kernel(const __grid_constant__ CUtensorMap tmap_hs,
         };
         uint32_t n_d = 0, n_x = 0;
         if (lane == 0) {
-            Item nx = v0 < v1 ? load_item(p.items, v0) : Item{};
-            DUnit un = (v0 < v1 && nx.a.x == IT_D) ? decode_d(nx.a.y) : DUnit{};
+            ItemPipe pipe;
+            pipe.init(p.items, v0, v1, vstep);
+            int2 un = pipe.peek().a.x == IT_D ? decode_d(pipe.peek().a.y) : make_int2(0, 0);
             for (int64_t v = v0; v < v1; v += vstep) {
-                const Item it = nx;
-                const DUnit u = un;
-                if (v + vstep < v1) {
-                    nx = load_item(p.items, v + vstep);
-                    if (nx.a.x == IT_D) un = decode_d(nx.a.y);
-                }
+                const DUnit u = make_dunit(un.x, un.y - un.x);
+                const Item it = pipe.pop();
+                // row pointers of the NEXT item (its record arrived iterations ago): in flight
+                // while this item is processed
+                if (pipe.peek().a.x == IT_D) un = decode_d(pipe.peek().a.y);
                 if (it.a.x == IT_D) {
                     // every D item takes a turn on the accumulator slots - also the one of an empty
                     // group (no MMAs: the commit fires at once and the epilogue stores zeros)
@@ -390,15 +390,15 @@ node_fused_bwd_kernel(const __grid_constant__ CUtensorMap tmap_hs,
             }
             __syncwarp();
         };
-        Item nx = v0 < v1 ? load_item(p.items, v0) : Item{};
-        DUnit un = (v0 < v1 && nx.a.x == IT_D) ? decode_d(nx.a.y) : DUnit{};
+        ItemPipe pipe;
+        pipe.init(p.items, v0, v1, vstep);
+        int2 un = pipe.peek().a.x == IT_D ? decode_d(pipe.peek().a.y) : make_int2(0, 0);
         for (int64_t v = v0; v < v1; v += vstep) {
-            const Item it = nx;
-            const DUnit u = un;
-            if (v + vstep < v1) {
-                nx = load_item(p.items, v + vstep);
-                if (nx.a.x == IT_D) un = decode_d(nx.a.y);
-            }
+            const DUnit u = make_dunit(un.x, un.y - un.x);
+            const Item it = pipe.pop();
+            // row pointers of the NEXT item (its record arrived iterations ago): in flight
+            // while this item is processed
+            if (pipe.peek().a.x == IT_D) un = decode_d(pipe.peek().a.y);
             if (it.a.x == IT_D) {
                 const uint32_t ds = n_d % kDSlots, dphase = (n_d / kDSlots) & 1u;
                 ++n_d;

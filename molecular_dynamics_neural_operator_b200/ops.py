@@ -436,15 +436,18 @@ def edge_layer0(ea, w1, b1, out_dtype) -> torch.Tensor:
 
 
 def segment_matvec(rows, perm, seg_ptr, gidx, gnode, scale, M1, nin, M2, bias, relu: bool,
-                   want_agg: bool = False):
+                   want_agg: bool = False, out=None, agg_out=None):
     """out[n] = act(scale*sum rows[p] + (scale*sum gnode[gidx[p]]) @ M1 + nin[n] @ M2 + bias).
-    See gkn_segment_matvec in gkn_b200.h.  Returns (out, agg or None)."""
+    See gkn_segment_matvec in gkn_b200.h.  Returns (out, agg or None); ``out`` / ``agg_out``:
+    caller-provided fp32 [N, W] buffers to write into."""
     lib = _lib.load()
     ref = nin if nin is not None else gnode  # M1 = M2 = nin = None: plain segment sums
     N, W = int(ref.size(0)), int(ref.size(1))
     f32, i32 = torch.float32, torch.int32
-    out = torch.empty((N, W), dtype=f32, device=ref.device)
-    agg = torch.empty((N, W), dtype=f32, device=ref.device) if want_agg else None
+    if out is None:
+        out = torch.empty((N, W), dtype=f32, device=ref.device)
+    agg = agg_out if agg_out is not None else (
+        torch.empty((N, W), dtype=f32, device=ref.device) if want_agg else None)
     with torch.cuda.device(ref.device):
         _lib.check(
             lib.gkn_segment_matvec(
@@ -997,3 +1000,32 @@ def sum_partials(part: torch.Tensor, addend: torch.Tensor | None, out: torch.Ten
                                         _p(out, torch.float32, "out"), _stream()),
                    "gkn_sum_partials")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Sharded rollout: exchange + node update + broadcast in one kernel over peer memory
+# ------------------------------------------------------------------------------------------------
+def shard_reduce_update(partial_ptrs, xout_ptrs, x, inv_cnt, B3, root, bias, n0: int, n1: int,
+                        relu: bool) -> None:
+    """For the nodes [n0, n1) this rank owns: sum the partial rows of every rank (``partial_ptrs``:
+    device addresses of the ranks' [2, N, W] fp32 buffers, in rank order), apply the node update
+    and store the new rows into every rank's x' buffer (``xout_ptrs``) - gkn_shard_reduce_update.
+    The caller synchronises the ranks before and after."""
+    import ctypes
+
+    lib = _lib.load()
+    world = len(partial_ptrs)
+    if len(xout_ptrs) != world:
+        raise ValueError("shard_reduce_update: one partial buffer and one x' buffer per rank")
+    N, W = int(x.size(0)), int(x.size(1))
+    arr = ctypes.c_uint64 * world
+    pa, xa = arr(*[int(v) for v in partial_ptrs]), arr(*[int(v) for v in xout_ptrs])
+    f32 = torch.float32
+    with torch.cuda.device(x.device):
+        _lib.check(
+            lib.gkn_shard_reduce_update(
+                ctypes.cast(pa, c_void_p), ctypes.cast(xa, c_void_p), world, _p(x, f32, "x"),
+                _p(inv_cnt, f32, "inv_cnt"), _p(B3, f32, "B3"), _p(root, f32, "root"),
+                _p(bias, f32, "bias"), int(n0), int(n1), N, W, int(bool(relu)), _stream()),
+            "gkn_shard_reduce_update",
+        )

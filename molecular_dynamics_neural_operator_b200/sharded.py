@@ -163,10 +163,10 @@ def shard_frame_by_source(edge_index: torch.Tensor, edge_attr: torch.Tensor, num
                        inv_cnt)
 
 
-def _node_partial_sums(x, shard: SourceShard, hs, w3r, msg):
+def _node_partial_sums(x, shard: SourceShard, hs, w3r, msg, out=None):
     """One application's local work: U for the owned nodes, messages of their outgoing edges, and
     the partial sums of those messages (and of x_j, for the b3 term) at every destination.
-    Returns [2, N, w] fp32."""
+    Returns [2, N, w] fp32 (written into ``out`` when given, e.g. a symmetric-memory buffer)."""
     N, W = x.shape
     K = hs.size(1)
     lay, plan = shard.lay, shard.plan
@@ -176,6 +176,10 @@ def _node_partial_sums(x, shard: SourceShard, hs, w3r, msg):
         ops.node_msg(hs, U.view(c1 - c0, W, K), lay, lay.unit_first[shard.n0 + c0],
                      lay.unit_first[shard.n0 + c1], shard.n0 + c0, msg)
         del U
+    if out is not None:
+        ops.segment_matvec(msg, lay.qpos, plan.dst_ptr, lay.src_pad, x, None, None, None, None,
+                           None, False, out=out[0], agg_out=out[1])
+        return out
     r, agg = ops.segment_matvec(msg, lay.qpos, plan.dst_ptr, lay.src_pad, x, None, None, None, None,
                                 None, False, want_agg=True)
     return torch.stack([r, agg])
@@ -224,6 +228,63 @@ def _node_shard_setup(shard: SourceShard, net, W: int):
     return hs, w3r, B3, msg
 
 
+# The exchange of the node-first sharding.  "peer" (default when torch's symmetric memory can be set
+# up for the group): partial sums live in symmetric-memory buffers and ONE kernel per rank reduces
+# the rows of its node range straight out of every peer's buffer, applies the node update and
+# stores the new rows into every peer's x' buffer (gkn_shard_reduce_update) - reduce-scatter,
+# compute and all-gather fused over NVLink.  "nccl": ncclAllReduce of the partial sums, then the
+# node update on every rank (round 1).  GKN_SHARD_EXCHANGE=nccl selects the latter.
+import os as _os
+
+_PEER_CACHE: dict = {}
+
+
+class PeerExchange:
+    """Symmetric-memory buffers of one (N, W, group): partial sums [2, N, W] and two x' buffers
+    (double buffered: a fast rank may already be storing x of application a+1 into its peers while
+    a slow one still reads x of application a)."""
+
+    def __init__(self, N: int, W: int, device, group):
+        import torch.distributed._symmetric_memory as symm
+
+        g = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(g), dist.get_world_size(g)
+        self.N, self.W = N, W
+        self.part = symm.empty((2, N, W), dtype=torch.float32, device=device)
+        self.h_part = symm.rendezvous(self.part, g)
+        self.xbuf, self.h_x = [], []
+        for _ in range(2):
+            t = symm.empty((N, W), dtype=torch.float32, device=device)
+            self.xbuf.append(t)
+            self.h_x.append(symm.rendezvous(t, g))
+        rows = (N + self.world - 1) // self.world
+        self.n0, self.n1 = min(N, self.rank * rows), min(N, (self.rank + 1) * rows)
+        self.part_ptrs = list(self.h_part.buffer_ptrs)
+        self.x_ptrs = [list(h.buffer_ptrs) for h in self.h_x]
+
+    def barrier(self):
+        self.h_part.barrier()
+
+
+def peer_exchange(N: int, W: int, device, group):
+    """The cached PeerExchange of (N, W, group), or None when symmetric memory is unavailable (then
+    the NCCL all-reduce is used).  Collective: every rank of the group must call it."""
+    if _os.environ.get("GKN_SHARD_EXCHANGE", "peer") != "peer":
+        return None
+    key = (N, W, str(device), id(group))
+    if key not in _PEER_CACHE:
+        try:
+            _PEER_CACHE.clear()  # one frame size at a time
+            _PEER_CACHE[key] = PeerExchange(N, W, device, group)
+        except Exception as exc:  # noqa: BLE001  (no symmetric memory on this system / backend)
+            import warnings
+
+            warnings.warn(f"peer-memory exchange unavailable ({type(exc).__name__}: {exc}); "
+                          "using the NCCL all-reduce")
+            _PEER_CACHE[key] = None
+    return _PEER_CACHE[key]
+
+
 @torch.no_grad()
 def sharded_stack_forward_node(x0, shard: SourceShard, net, root1, bias1, root2, bias2, schedule,
                                relu: bool, group=None) -> torch.Tensor:
@@ -233,32 +294,58 @@ def sharded_stack_forward_node(x0, shard: SourceShard, net, root1, bias1, root2,
     hs, w3r, B3, msg = _node_shard_setup(shard, net, W)
     roots, biases = (root1, root2), (bias1, bias2)
     x = x0.contiguous()
-    for c in schedule:
+    px = peer_exchange(N, W, x.device, group) if dist.get_world_size(group) > 1 else None
+    for a, c in enumerate(schedule):
+        # with the peer exchange the partial rows are written where the peers can read them
         if hs is not None:
-            sums = _node_partial_sums(x, shard, hs, w3r, msg)
+            sums = _node_partial_sums(x, shard, hs, w3r, msg, out=px.part if px is not None else None)
+        elif px is not None:
+            sums = px.part.zero_()
         else:
             sums = torch.zeros((2, N, W), dtype=torch.float32, device=x.device)
-        dist.all_reduce(sums, group=group)
-        x = _node_update(x, sums, shard.inv_cnt, B3, roots[c], biases[c], relu)
-    return x
+        if px is None:
+            dist.all_reduce(sums, group=group)
+            x = _node_update(x, sums, shard.inv_cnt, B3, roots[c], biases[c], relu)
+            continue
+        px.barrier()                 # every rank's partial sums are in place
+        ops.shard_reduce_update(px.part_ptrs, px.x_ptrs[a & 1], x, shard.inv_cnt, B3,
+                                roots[c].contiguous(), biases[c].contiguous(), px.n0, px.n1, relu)
+        px.barrier()                 # every row of x' has landed everywhere
+        x = px.xbuf[a & 1]
+    return x.clone() if px is not None else x
 
 
 @torch.no_grad()
 def emulate_world_node(x0, edge_index, edge_attr, net, root1, bias1, root2, bias2, schedule,
-                       relu: bool, world: int, row_ptr=None) -> torch.Tensor:
-    """All ranks of sharded_stack_forward_node in turn on one GPU; the all-reduce is a sum."""
+                       relu: bool, world: int, row_ptr=None, fused_exchange: bool = False) -> torch.Tensor:
+    """All ranks of sharded_stack_forward_node in turn on one GPU; the all-reduce is a sum, or
+    (``fused_exchange``) the peer-memory kernel run once per emulated rank."""
     N, W = x0.shape
     shards = [shard_frame_by_source(edge_index, edge_attr, N, r, world, row_ptr)
               for r in range(world)]
     setups = [_node_shard_setup(s, net, W) for s in shards]
     roots, biases = (root1, root2), (bias1, bias2)
     x = x0.contiguous()
+    rows = (N + world - 1) // world
     for c in schedule:
-        sums = torch.zeros((2, N, W), dtype=torch.float32, device=x.device)
-        for s, (hs, w3r, B3, msg) in zip(shards, setups):
-            if hs is not None:
-                sums += _node_partial_sums(x, s, hs, w3r, msg)
-        x = _node_update(x, sums, shards[0].inv_cnt, setups[0][2], roots[c], biases[c], relu)
+        parts = [(_node_partial_sums(x, s, hs, w3r, msg) if hs is not None else
+                  torch.zeros((2, N, W), dtype=torch.float32, device=x.device))
+                 for s, (hs, w3r, B3, msg) in zip(shards, setups)]
+        if fused_exchange:
+            # what every rank's gkn_shard_reduce_update launch does, one emulated rank after the
+            # other: "peer" buffers are the other ranks' tensors on this same GPU
+            xouts = [torch.empty_like(x) for _ in range(world)]
+            for r in range(world):
+                ops.shard_reduce_update([p.data_ptr() for p in parts], [t.data_ptr() for t in xouts],
+                                        x, shards[0].inv_cnt, setups[0][2], roots[c].contiguous(),
+                                        biases[c].contiguous(), min(N, r * rows),
+                                        min(N, (r + 1) * rows), relu)
+            for t in xouts[1:]:
+                assert torch.equal(t, xouts[0])  # every rank ends up with the same x'
+            x = xouts[0]
+        else:
+            sums = torch.stack(parts).sum(0)
+            x = _node_update(x, sums, shards[0].inv_cnt, setups[0][2], roots[c], biases[c], relu)
     return x
 
 

@@ -71,10 +71,47 @@ def test_emulated_source_range_shards_match_the_unsharded_node_first_stack(world
         out = emulate_world_node(x0, ei, ea, *args, sched, True, world, row_ptr=rp)
         assert out.shape == ref.shape
         assert float((out - ref).abs().max() / ref.abs().max()) <= NODE_SHARD_TOL
+    # the exchange fused with the node update (gkn_shard_reduce_update, one launch per emulated
+    # rank reading every "peer" buffer): same bound, and every rank holds the same x'
+    out = emulate_world_node(x0, ei, ea, *args, sched, True, world, row_ptr=row_ptr,
+                             fused_exchange=True)
+    assert float((out - ref).abs().max() / ref.abs().max()) <= NODE_SHARD_TOL
 
 
-def _worker(rank, world, port, out, K=128):
+@pytest.mark.parametrize("W,N,world", [(32, 77, 3), (64, 1000, 8), (128, 513, 2), (64, 5, 8)])
+def test_fused_exchange_kernel_matches_fp32_restatement(W, N, world):
+    """gkn_shard_reduce_update against its definition in torch fp32: sum of the ranks' partial
+    rows in rank order, mean scale, two w x w products, bias, ReLU; rows outside [n0, n1) of the
+    output buffers untouched; ragged last range; ranks that own no node."""
+    from molecular_dynamics_neural_operator_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(W + N)
+    parts = [torch.randn(2, N, W, device="cuda", generator=g) for _ in range(world)]
+    x = torch.randn(N, W, device="cuda", generator=g)
+    inv = torch.rand(N, device="cuda", generator=g) + 0.1
+    B3, root = (torch.randn(W, W, device="cuda", generator=g) / 8 for _ in range(2))
+    bias = torch.randn(W, device="cuda", generator=g)
+    S = torch.zeros(2, N, W, device="cuda")
+    for p_ in parts:
+        S += p_
+    ref = torch.relu(inv[:, None] * S[0] + (inv[:, None] * S[1]) @ B3 + x @ root + bias)
+    xouts = [torch.full((N, W), float("nan"), device="cuda") for _ in range(world)]
+    rows = (N + world - 1) // world
+    for r in range(world):
+        n0, n1 = min(N, r * rows), min(N, (r + 1) * rows)
+        ops.shard_reduce_update([t.data_ptr() for t in parts], [t.data_ptr() for t in xouts], x, inv,
+                                B3, root, bias, n0, n1, True)
+        if r == 0 and n1 < N:
+            assert bool(torch.isnan(xouts[0][n1:]).all())  # only the owned rows are written
+    for t in xouts:
+        assert torch.equal(t, xouts[0])
+    assert float((xouts[0] - ref).abs().max() / ref.abs().max()) < 1e-5
+
+
+def _worker(rank, world, port, out, K=128, exchange="peer"):
     from types import SimpleNamespace
+
+    os.environ["GKN_SHARD_EXCHANGE"] = exchange
 
     import torch.distributed as dist
 
@@ -102,10 +139,13 @@ def _worker(rank, world, port, out, K=128):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-@pytest.mark.parametrize("K,tol", [(128, 1e-6), (256, NODE_SHARD_TOL)], ids=["edge_first", "node_first"])
-def test_two_process_nccl_run_matches_single_gpu(K, tol):
+@pytest.mark.parametrize("K,tol,exchange", [(128, 1e-6, "nccl"), (256, NODE_SHARD_TOL, "nccl"),
+                                            (256, NODE_SHARD_TOL, "peer")],
+                         ids=["edge_first", "node_first_nccl", "node_first_peer_memory"])
+def test_two_process_nccl_run_matches_single_gpu(K, tol, exchange):
     """K = 128: destination-range shards of the edge-first kernels (all-gather); K = 256: source-
-    range shards of the node-first kernels (all-reduce of partial sums, fp32 re-association)."""
+    range shards of the node-first kernels - exchange by NCCL all-reduce of the partial sums, or by
+    the fused peer-memory kernel (symmetric memory over NVLink)."""
     import torch.multiprocessing as mp
 
     with socket.socket() as s:
@@ -113,5 +153,5 @@ def test_two_process_nccl_run_matches_single_gpu(K, tol):
         port = s.getsockname()[1]
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(2, port, out, K), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, out, K, exchange), nprocs=2, join=True)
     assert out[0] <= tol and out[1] <= tol
