@@ -224,7 +224,7 @@ def run_reference_arm(args, wl, edges_per_frame):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    ref = CpuReference(wl, threads)
+    ref = CpuReference(wl, threads, lr=args.lr)
     n_atoms = ref.pick_atoms(args.cpu_seconds_per_step, edges_per_frame)
     traj = syn.trajectory(wl, wl.window + 2 + args.steps + args.warmup, seed=0)
     aa = syn.residue_ids(wl)
@@ -246,7 +246,8 @@ def run_reference_arm(args, wl, edges_per_frame):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": bench_config(wl, args.frames_per_gpu, edges_per_frame, reference=True),
+        "config": bench_config(wl, args.frames_per_gpu, edges_per_frame),
+        "arm_details": arm_details(True),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -255,14 +256,34 @@ def run_reference_arm(args, wl, edges_per_frame):
     print(json.dumps(line), flush=True)
 
 
-def bench_config(wl, frames_per_gpu, edges_per_frame, reference=False):
+def bench_config(wl, frames_per_gpu, edges_nominal):
+    """The workload both arms are quoted on - the SAME dictionary in the B200 line and in the
+    `--impl reference` line (`edges_nominal`: edges of frame 0 of the seeded trajectory, which the
+    GPU kernel and SciPy agree on bit for bit).  What differs between the arms is under
+    `arm_details`."""
+    return {
+        "workload": (f"{wl.name}: {wl.num_atoms}-atom frames, {wl.cutoff} A radius graph "
+                     f"(~{int(edges_nominal)} directed edges/frame incl. self loops), KernelNN "
+                     f"width {wl.width} kernel_width {wl.ker_width} depth {wl.depth} "
+                     f"({2 * wl.depth} NNConv applications), window {wl.window}; step = graph "
+                     f"build + fwd + LpLoss + bwd + Adam(lr={LR_NOTE['lr']}, weight_decay=5e-4)"),
+        "frames_per_gpu_per_step": frames_per_gpu,
+        "batch_note": "reference default batch_size is 128 (graph_kernel.py:318) = 16 frames per GPU "
+                      "on 8 GPUs; per-GPU work is fixed as N grows (weak scaling)",
+        "lr_note": "the reference's default lr 0.01 (graph_kernel.py:319) sends THIS random-init "
+                   "model on THESE synthetic coordinates to inf after the first update (loss 1.1e8 "
+                   "-> inf -> NaN: 12 tied applications amplify every weight change), lr 1e-3 kills "
+                   "every ReLU; at 1e-4 the loss falls steadily (1.1e8 -> 29 in 60 steps), so the "
+                   "timed steps carry finite activations and gradients.  Throughput does not depend "
+                   "on lr",
+        "l2_policy": "per-step working set (h_e alone ~0.12 GB per frame) exceeds the 126 MB L2; "
+                     "each step uses a different batch of frames",
+    }
+
+
+def arm_details(reference: bool):
     if reference:
         return {
-            "workload": (f"{wl.name}: {wl.num_atoms}-atom frames, {wl.cutoff} A radius graph "
-                         f"(~{int(edges_per_frame)} directed edges/frame incl. self loops), KernelNN "
-                         f"width {wl.width} kernel_width {wl.ker_width} depth {wl.depth} "
-                         f"({2 * wl.depth} NNConv applications), window {wl.window}; step = graph "
-                         f"build + fwd + LpLoss + bwd + Adam"),
             "formulation": "the reference's own: SciPy distance_matrix graph, per-edge [E,w,w] kernel "
                            "materialised by the edge MLP every application, fp32, PyTorch CPU "
                            "(oracle/gkn_oracle.py restating graph_kernel.py:194-209, :277-309, :362-393)",
@@ -271,28 +292,13 @@ def bench_config(wl, frames_per_gpu, edges_per_frame, reference=False):
             "parallelism": "one process, all host threads (torch intra-op)",
         }
     return {
-        "workload": (f"{wl.name}: {wl.num_atoms}-atom frames, {wl.cutoff} A radius graph "
-                     f"(~{int(edges_per_frame)} directed edges/frame incl. self loops), KernelNN "
-                     f"width {wl.width} kernel_width {wl.ker_width} depth {wl.depth} "
-                     f"({2 * wl.depth} NNConv applications), window {wl.window}; step = graph "
-                     f"build + fwd + LpLoss + bwd + Adam"),
-        "frames_per_gpu_per_step": frames_per_gpu,
-        "batch_note": "reference default batch_size is 128 (graph_kernel.py:318) = 16 frames per GPU "
-                      "on 8 GPUs; per-GPU work is fixed as N grows (weak scaling)",
         "factorization": os.environ.get("GKN_FACTORIZATION", "node"),
-        "optimizer": f"Adam(lr={LR_NOTE['lr']}, weight_decay=5e-4) as graph_kernel.py:541-543.  The "
-                     "reference's default lr 0.01 (graph_kernel.py:319) sends THIS random-init model on "
-                     "THESE synthetic coordinates to inf after the first update (loss 1.1e8 -> inf -> "
-                     "NaN: 12 tied applications amplify every weight change), lr 1e-3 kills every ReLU; "
-                     "at 1e-4 the loss falls steadily (1.1e8 -> 29 in 60 steps), so the timed steps "
-                     "carry finite activations and gradients.  Throughput does not depend on lr",
+        "node_fused": os.environ.get("GKN_NODE_FUSED", "0"),
+        "node_fused_bwd": os.environ.get("GKN_NODE_FUSED_BWD", "0"),
         "untimed_steps_before_timing": "max(8, warmup) resident + max(3, warmup) host-fed + 2 resident; "
                                        "Python cyclic GC disabled inside the timed loops",
         "parallelism": "frames sharded over GPUs, bucketed NCCL gradient all-reduce",
-        "l2_policy": "per-step working set (h_e alone ~0.12 GB per frame) exceeds the 126 MB L2; "
-                     "each step uses a different batch of frames",
     }
-
 
 
 # ------------------------------------------------------------------------------------------------
@@ -684,6 +690,10 @@ def run_b200_arm(args, wl):
                     "trilinear form with ~40x fewer FLOPs and is HBM-bound",
         }
 
+    with torch.no_grad():
+        ei0, _ = ops.radius_graph(torch.from_numpy(syn.trajectory(wl, 1, seed=0)).to(dev), wl.cutoff)
+    edges_nominal = int(ei0.size(1))
+    del ei0
     frames_total = B * world * args.steps
     value = frames_total / (ms_total * 1e-3)
     e2e_value = frames_total / (ms_e2e * 1e-3)
@@ -836,7 +846,8 @@ def run_b200_arm(args, wl):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": bench_config(wl, B, edges_per_frame),
+        "config": bench_config(wl, B, edges_nominal),
+        "arm_details": arm_details(False),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
@@ -870,7 +881,7 @@ def run_b200_arm(args, wl):
     }
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        ref = CpuReference(wl, threads)
+        ref = CpuReference(wl, threads, lr=args.lr)
         n_atoms = ref.pick_atoms(args.cpu_seconds_per_step, edges_per_frame)
         xw, y = syn.window_batch(traj, [0], wl.window)
         aa_np = syn.residue_ids(wl)
@@ -891,7 +902,7 @@ def run_b200_arm(args, wl):
                        f"frames/s = edge-fraction / step time"),
         }
         # the reference's own default is ONE host thread (graph_kernel.py:501): a smaller sample
-        ref1 = CpuReference(wl, 1)
+        ref1 = CpuReference(wl, 1, lr=args.lr)
         n1 = max(32, n_atoms // 3)
         ref1.step(xw, y, aa_np, max(32, n1 // 2))
         dt1, e1_, k1 = 0.0, 0, 0

@@ -856,7 +856,7 @@ def fused_bwd_grid(K: int, W: int) -> tuple[int, int]:
 
 
 def fused_bwd_items(N: int, K: int, W: int, grid: int, ring: int, slack: float = 1.0,
-                    groups: int = 1):
+                    groups: int = 1, spread: float = 0.9):
     """Host-side construction of the item list of gkn_node_fused_bwd_bf16 (numpy int32 [n, 8]).
     It depends only on (N, K, grid, ring, slack) - every node has K/128 "D" items whether or not it
     has edges - so it is built once and cached.
@@ -872,8 +872,8 @@ def fused_bwd_items(N: int, K: int, W: int, grid: int, ring: int, slack: float =
     b+slack+0.9 > X(b)."""
     import numpy as np
 
-    if ring < 1.9 + slack:
-        raise ValueError("fused_bwd_items: the dU ring must hold at least 1.9 + slack node blocks")
+    if ring < 1 + spread + slack:
+        raise ValueError("fused_bwd_items: the dU ring must hold at least 1 + spread + slack node blocks")
     C = K // 128
     NB = (N + FUSED_BLOCK - 1) // FUSED_BLOCK
     pairs = W * K // 128
@@ -900,7 +900,7 @@ def fused_bwd_items(N: int, K: int, W: int, grid: int, ring: int, slack: float =
     nXb = xc.size                                               # X items per block
     xb = np.repeat(np.arange(NB), nXb)
     xc, xq, xn = np.tile(xc, NB), np.tile(xq, NB), np.tile(xn, NB)
-    x_key = xb + slack + 0.9 * (xq + 0.5) / xn
+    x_key = xb + slack + spread * (xq + 0.5) / xn
     X = np.zeros((xb.size, 8), dtype=np.int64)
     X[:, 0], X[:, 1], X[:, 2] = IT_X, FUSED_BLOCK * xb, (xb % ring) * FUSED_BLOCK
     X[:, 3] = np.minimum(FUSED_BLOCK, N - FUSED_BLOCK * xb)
@@ -953,13 +953,11 @@ def fused_bwd_items(N: int, K: int, W: int, grid: int, ring: int, slack: float =
 
 
 def fused_bwd_schedule(N: int, K: int, W: int, device, ring: int = 3,
-                       slack: float = 1.0) -> FusedSchedule:
+                       slack: float = 1.0, spread: float = 0.9) -> FusedSchedule:
     grid, _ = fused_bwd_grid(K, W)
-    if not 1.9 + slack <= ring:
-        raise ValueError("fused_bwd_schedule: ring must be at least 1.9 + slack")
-    key = (N, K, W, grid, ring, slack, str(device))
+    key = (N, K, W, grid, ring, slack, spread, str(device))
     if key not in _BWD_SCHED_CACHE:
-        items, nflags = fused_bwd_items(N, K, W, grid, ring, slack)
+        items, nflags = fused_bwd_items(N, K, W, grid, ring, slack, spread=spread)
         t = torch.from_numpy(items).to(device)
         _BWD_SCHED_CACHE[key] = FusedSchedule(t, int(t.size(0)), nflags, ring * FUSED_BLOCK, ring,
                                               grid)

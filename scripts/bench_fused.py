@@ -134,12 +134,19 @@ if hasattr(ops, "node_fused_bwd"):
     if want("bwd_du_only"):
         emit("bwd_du_only", timed(lambda i: ops.node_du_mn(hs, gs_all[i % A], lay, 0, N, dut)))
     grid, parts = ops.fused_bwd_grid(K, W)
-    for ring, slack, mode in ((3, 0.5, "all"), (3, 1.0, "all"), (4, 1.0, "all"), (4, 2.0, "all"),
-                              (3, 1.0, "D_only"), (3, 1.0, "D_only_nosig"), (3, 1.0, "X_only")):
-        name = f"bwd_fused_ring{ring}_slack{slack}" + ("" if mode == "all" else "_" + mode)
+    import os as _os
+    grid_spec = _os.environ.get("BWD_GRID")
+    combos = ([tuple(float(v) for v in c.split(":")) + ("all",) for c in grid_spec.split(",")]
+              if grid_spec else
+              [(3, 0.5, 0.9, "all"), (3, 1.0, 0.9, "all"), (4, 1.0, 0.9, "all"), (4, 2.0, 0.9, "all"),
+               (3, 1.0, 0.9, "D_only"), (3, 1.0, 0.9, "D_only_nosig"), (3, 1.0, 0.9, "X_only")])
+    for ring, slack, spread, mode in combos:
+        ring = int(ring)
+        name = f"bwd_fused_ring{ring}_slack{slack}" + ("" if spread == 0.9 else f"_spread{spread}") + \
+            ("" if mode == "all" else "_" + mode)
         if not want(name):
             continue
-        s = ops.fused_bwd_schedule(N, K, W, hs.device, ring=ring, slack=slack)
+        s = ops.fused_bwd_schedule(N, K, W, hs.device, ring=ring, slack=slack, spread=spread)
         if mode != "all":
             t = s.items.clone()
             t[t[:, 0] == (ops.IT_D if mode == "X_only" else ops.IT_X), 0] = ops.IT_NOP
