@@ -46,20 +46,24 @@ constexpr int kM = 128;
 constexpr int kKB = 64;
 constexpr int kUmmaK = 16;
 constexpr int kW = 64;             // node feature width served by this kernel
-constexpr int kThreads = 6 * 32;   // TMA producer, MMA issuer, 4 epilogue warps
-// Eight 24 KB stages - all the shared memory there is: the D items stream h from HBM, the kernel is
-// bound by the bytes it keeps in flight (measured: 6 stages 0.75 ms, 8 stages of the stand-alone
-// dU kernel 0.58 ms for the same items), so the epilogue makes do with one group of four warps, one
-// x tile and one dx accumulator.  A D k-block (two 8 KB boxes of hs + one of gs) takes one stage; a 128-column
-// pair of an X item takes two consecutive stages, each holding one 64-column half (dU box 16 KB +
-// W3k box 8 KB).  The pair must not wrap around the ring (the weight-gradient product addresses
-// both dU boxes through one descriptor), so it starts on an even stage: when the ring position is
-// odd, producer and issuer both pass over one stage (an empty hand-shake on its barriers).
+// TWO independent in-order item streams share one CTA (twelve warps):
+//   D stream  warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue   (items of kind D)
+//   X stream  warp 6 TMA producer, warp 7 MMA issuer, warps 8-11 epilogue  (items of kind X)
+// Every warp walks the CTA's whole queue and skips the other kind.  With ONE producer and ONE
+// issuer per CTA (the first version) a consumer item that was not ready held up the producer items
+// queued behind it together with their HBM loads, and every node block cost a pipeline drain:
+// producer items alone 0.76 ms, consumer items alone 0.51 ms, both 1.00 ms.  Now the only coupling
+// between the streams is the two counters per node block.
+constexpr int kThreads = 12 * 32;
+// D stream: five 24 KB stages (one k-block each: two 8 KB boxes of hs + one of gs).  X stream: two
+// 24 KB stages = one 128-column pair in flight (each stage one 64-column half: dU box 16 KB + W3k
+// box 8 KB; the weight-gradient product addresses both dU boxes through one descriptor).
 constexpr int kStageBytes = 24 * 1024;
-constexpr int kStages = 8;
+constexpr int kStages = 5;    // D ring
+constexpr int kXStages = 2;   // X ring
 constexpr int kXbBytes = kM * kW * 2;          // 16 KB: x tile of a node block
 constexpr int kDKbBytes = 24 * 1024;           // D k-block: hs 2 x 8 KB + gs 8 KB
-static_assert(kDKbBytes == kStageBytes && kStages % 2 == 0, "see the stage layout above");
+static_assert(kDKbBytes == kStageBytes, "see the stage layout above");
 constexpr int kMnBlockBytes = 64 * kKB * 2;    // 8 KB: MN-major box of 64 K-rows x 64 elements
 constexpr int kDuBoxBytes = kM * kKB * 2;      // 16 KB: 128 node rows x 64 columns of dU
 constexpr int kMaxPairs = 4;                   // 128-column pairs of dU per CTA
@@ -67,7 +71,8 @@ constexpr int kPairCols = 128;
 // TMEM columns: [0, 256) dW3k^T accumulators (4 pairs x 64), [256, 320) dx, [320, 512) three D slots
 constexpr uint32_t kTmemDw = 0, kTmemDx = 256, kTmemD = 320;
 constexpr int kDSlots = 3;
-constexpr int kSmemBytes = kStages * kStageBytes + kXbBytes + 1024 + 256 + 4 * 4096;
+constexpr int kSmemBytes =
+    (kStages + kXStages) * kStageBytes + kXbBytes + 1024 + 256 + 2 * 4 * 4096;
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory per CTA");
 
 enum { IT_D = 0, IT_X = 1, IT_NOP = 2 };
@@ -122,7 +127,8 @@ node_fused_bwd_kernel(const __grid_constant__ CUtensorMap tmap_hs,
                       const __grid_constant__ CUtensorMap tmap_x, const BwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t xb_base = smem_base + kStages * kStageBytes;
+    const uint32_t xs_base = smem_base + kStages * kStageBytes;          // X ring
+    const uint32_t xb_base = xs_base + kXStages * kStageBytes;           // x tile of a node block
     const uint32_t bar_base = xb_base + kXbBytes;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
@@ -133,7 +139,9 @@ node_fused_bwd_kernel(const __grid_constant__ CUtensorMap tmap_hs,
     const uint32_t gfull_bar = xfull_bar + 16u;                                   // dx accumulator
     const uint32_t gempty_bar = xfull_bar + 24u;
     const uint32_t wdone_bar = xfull_bar + 32u;
-    const uint32_t tmem_ptr_smem = xfull_bar + 40u;
+    auto pfull_bar = [&](int s) { return xfull_bar + 40u + 8u * s; };             // X ring
+    auto pempty_bar = [&](int s) { return xfull_bar + 40u + 8u * (kXStages + s); };
+    const uint32_t tmem_ptr_smem = xfull_bar + 40u + 8u * 2 * kXStages;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -166,6 +174,10 @@ node_fused_bwd_kernel(const __grid_constant__ CUtensorMap tmap_hs,
         mbar_init(gfull_bar, 1);
         mbar_init(gempty_bar, 4);
         mbar_init(wdone_bar, 1);
+        for (int s = 0; s < kXStages; ++s) {
+            mbar_init(pfull_bar(s), 1);
+            mbar_init(pempty_bar(s), 1);
+        }
         fence_mbar_init();
     }
     if (warp == 0 && lane == 0) {
@@ -185,19 +197,48 @@ node_fused_bwd_kernel(const __grid_constant__ CUtensorMap tmap_hs,
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
-    if (warp == 0) {
-        // ===================== TMA producer =====================
-        int stage = 0;
-        uint32_t phase = 0;
-        auto advance = [&]() {
-            if (++stage == kStages) {
-                stage = 0;
-                phase ^= 1u;
+    // staging tiles of the two epilogue groups and a helper they share
+    auto store_tile_f32 = [&](uint32_t stage_smem, uint32_t tcol, uint8_t* gbase, int rows_here,
+                              bool accumulate) {
+        // 128 x 64 fp32 accumulator -> global rows of 256 B, through the per-warp swizzled tile
+#pragma unroll
+        for (int piece = 0; piece < 2; ++piece) {
+            float f[32];
+            tmem_ld32(tcol + piece * 32, f);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                sts128(stage_smem + lane * 128 + ((c ^ (lane & 7)) << 4),
+                       make_uint4(__float_as_uint(f[4 * c]), __float_as_uint(f[4 * c + 1]),
+                                  __float_as_uint(f[4 * c + 2]), __float_as_uint(f[4 * c + 3])));
             }
-        };
-        uint32_t n_x = 0;  // node blocks consumed so far
-        const uint64_t pol_stream = l2_policy_evict_first();
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int r = j * 4 + (lane >> 3), c = lane & 7;
+                uint4 t = lds128(stage_smem + r * 128 + ((c ^ (r & 7)) << 4));
+                if (r < rows_here) {
+                    float4* gp = reinterpret_cast<float4*>(gbase + r * (kW * 4) + piece * 128 + c * 16);
+                    if (accumulate) {
+                        const float4 o = *gp;
+                        t.x = __float_as_uint(__uint_as_float(t.x) + o.x);
+                        t.y = __float_as_uint(__uint_as_float(t.y) + o.y);
+                        t.z = __float_as_uint(__uint_as_float(t.z) + o.z);
+                        t.w = __float_as_uint(__uint_as_float(t.w) + o.w);
+                    }
+                    *reinterpret_cast<uint4*>(gp) = t;
+                }
+            }
+            __syncwarp();
+        }
+    };
+
+    if (warp == 0) {
+        // ===================== D stream: TMA producer =====================
         if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint64_t pol_stream = l2_policy_evict_first();
             ItemPipe pipe;
             pipe.init(p.items, v0, v1, vstep);
             int2 un = pipe.peek().a.x == IT_D ? decode_d(pipe.peek().a.y) : make_int2(0, 0);
@@ -207,168 +248,79 @@ node_fused_bwd_kernel(const __grid_constant__ CUtensorMap tmap_hs,
                 // row pointers of the NEXT item (its record arrived iterations ago): in flight
                 // while this item is processed
                 if (pipe.peek().a.x == IT_D) un = decode_d(pipe.peek().a.y);
-                if (it.a.x == IT_D) {
-                    for (int kb = 0; kb < u.nkb; ++kb) {
-                        mbar_wait(empty_bar(stage), phase ^ 1u);
-                        const uint32_t st = smem_base + stage * kStageBytes;
-                        mbar_arrive_expect_tx(full_bar(stage), kDKbBytes);
-                        const int32_t r = u.row0 + kb * kKB;
-                        if (p.tune & 1) {
-                            tma_load_2d(st, &tmap_hs, full_bar(stage), it.a.z * kM, r);
-                            tma_load_2d(st + kMnBlockBytes, &tmap_hs, full_bar(stage), it.a.z * kM + 64, r);
-                        } else {
-                            tma_load_2d_hint(st, &tmap_hs, full_bar(stage), it.a.z * kM, r, pol_stream);
-                            tma_load_2d_hint(st + kMnBlockBytes, &tmap_hs, full_bar(stage),
-                                             it.a.z * kM + 64, r, pol_stream);
-                        }
-                        tma_load_2d(st + 2 * kMnBlockBytes, &tmap_gs, full_bar(stage), 0, r);
-                        advance();
+                if (it.a.x != IT_D) continue;
+                for (int kb = 0; kb < u.nkb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t st = smem_base + stage * kStageBytes;
+                    mbar_arrive_expect_tx(full_bar(stage), kDKbBytes);
+                    const int32_t r = u.row0 + kb * kKB;
+                    if (p.tune & 1) {
+                        tma_load_2d(st, &tmap_hs, full_bar(stage), it.a.z * kM, r);
+                        tma_load_2d(st + kMnBlockBytes, &tmap_hs, full_bar(stage), it.a.z * kM + 64, r);
+                    } else {
+                        tma_load_2d_hint(st, &tmap_hs, full_bar(stage), it.a.z * kM, r, pol_stream);
+                        tma_load_2d_hint(st + kMnBlockBytes, &tmap_hs, full_bar(stage),
+                                         it.a.z * kM + 64, r, pol_stream);
                     }
-                } else if (it.a.x == IT_X) {
-                    const int q = it.b.w & 0xff;
-                    const bool first = (it.b.w >> 8) & 1, last = (it.b.w >> 9) & 1;
-                    if (first && do_dw) {
-                        mbar_wait(xempty_bar, (n_x & 1u) ^ 1u);
-                        mbar_arrive_expect_tx(xfull_bar, kXbBytes);
-                        tma_load_2d(xb_base, &tmap_x, xfull_bar, 0, it.a.y);
-                    }
-                    if (last) ++n_x;
-                    if (it.b.x >= 0) {
-                        wait_counter(p.flags + it.b.x, it.b.y);
-                        fence_proxy_async_global();
-                    }
-                    if (stage & 1) {  // a pair starts on an even stage
-                        mbar_wait(empty_bar(stage), phase ^ 1u);
-                        mbar_arrive(full_bar(stage));
-                        advance();
-                    }
-                    const int32_t c0 = (p0 + q) * kPairCols;
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        mbar_wait(empty_bar(stage), phase ^ 1u);
-                        const uint32_t st = smem_base + stage * kStageBytes;
-                        mbar_arrive_expect_tx(full_bar(stage), kDuBoxBytes + kMnBlockBytes);
-                        tma_load_2d(st, &tmap_du, full_bar(stage), c0 + j * 64, it.a.z);
-                        tma_load_2d(st + kDuBoxBytes, &tmap_w3k, full_bar(stage), c0 + j * 64, 0);
-                        advance();
+                    tma_load_2d(st + 2 * kMnBlockBytes, &tmap_gs, full_bar(stage), 0, r);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1u;
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        constexpr uint32_t idesc_mn = umma_idesc_bf16(kM, kW, 1, 1);  // D and dW3k^T products
-        constexpr uint32_t idesc_k = umma_idesc_bf16(kM, kW, 0, 0);   // dx product
-        int stage = 0;
-        uint32_t phase = 0;
-        auto advance = [&]() {
-            if (++stage == kStages) {
-                stage = 0;
-                phase ^= 1u;
-            }
-        };
-        uint32_t n_d = 0, n_x = 0;
+        // ===================== D stream: MMA issuer =====================
         if (lane == 0) {
+            constexpr uint32_t idesc_mn = umma_idesc_bf16(kM, kW, 1, 1);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t n_d = 0;
             ItemPipe pipe;
             pipe.init(p.items, v0, v1, vstep);
             int2 un = pipe.peek().a.x == IT_D ? decode_d(pipe.peek().a.y) : make_int2(0, 0);
             for (int64_t v = v0; v < v1; v += vstep) {
                 const DUnit u = make_dunit(un.x, un.y - un.x);
                 const Item it = pipe.pop();
-                // row pointers of the NEXT item (its record arrived iterations ago): in flight
-                // while this item is processed
                 if (pipe.peek().a.x == IT_D) un = decode_d(pipe.peek().a.y);
-                if (it.a.x == IT_D) {
-                    // every D item takes a turn on the accumulator slots - also the one of an empty
-                    // group (no MMAs: the commit fires at once and the epilogue stores zeros)
-                    const uint32_t ds = n_d % kDSlots, dphase = (n_d / kDSlots) & 1u;
-                    ++n_d;
-                    mbar_wait(dempty_bar(ds), dphase ^ 1u);
-                    tc_fence_after();
-                    const uint32_t tmem_d = tmem_base + kTmemD + ds * kW;
-                    for (int kb = 0; kb < u.nkb; ++kb) {
-                        mbar_wait(full_bar(stage), phase);
-                        tc_fence_after();
-                        const uint32_t st = smem_base + stage * kStageBytes;
-                        const uint64_t adesc = umma_smem_desc(st, kMnBlockBytes, 1024, kSwizzle128B);
-                        const uint64_t bdesc =
-                            umma_smem_desc(st + 2 * kMnBlockBytes, kMnBlockBytes, 1024, kSwizzle128B);
-                        const int steps = kb == u.nkb - 1 ? u.last_steps : kKB / kUmmaK;
-                        for (int k = 0; k < steps; ++k) {
-                            // MN-major operands: a K-step of 16 rows advances the start by 2 KB
-                            umma_bf16_ss(tmem_d, adesc + 128ull * k, bdesc + 128ull * k, idesc_mn,
-                                         (kb | k) != 0 ? 1u : 0u);
-                        }
-                        umma_commit(empty_bar(stage));
-                        advance();
-                    }
-                    umma_commit(dfull_bar(ds));
-                } else if (it.a.x == IT_X) {
-                    const int q = it.b.w & 0xff;
-                    const bool first = (it.b.w >> 8) & 1, last = (it.b.w >> 9) & 1;
-                    const uint32_t xphase = n_x & 1u;
-                    const bool first_block = n_x == 0;
-                    if (first) {
-                        mbar_wait(gempty_bar, xphase ^ 1u);  // the dx accumulator has been drained
-                        if (do_dw) mbar_wait(xfull_bar, xphase);
-                        tc_fence_after();
-                    }
-                    const uint32_t tmem_x = tmem_base + kTmemDx;
-                    const uint64_t xdesc = umma_smem_desc(xb_base, kMnBlockBytes, 1024, kSwizzle128B);
-                    if (stage & 1) {  // the producer passed over this stage
-                        mbar_wait(full_bar(stage), phase);
-                        umma_commit(empty_bar(stage));
-                        advance();
-                    }
-                    const uint32_t st = smem_base + stage * kStageBytes;  // even: st + 24 KB is next
+                if (it.a.x != IT_D) continue;
+                // every D item takes a turn on the accumulator slots - also the one of an empty
+                // group (no MMAs: the commit fires at once and the epilogue stores zeros)
+                const uint32_t ds = n_d % kDSlots, dphase = (n_d / kDSlots) & 1u;
+                ++n_d;
+                mbar_wait(dempty_bar(ds), dphase ^ 1u);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + kTmemD + ds * kW;
+                for (int kb = 0; kb < u.nkb; ++kb) {
                     mbar_wait(full_bar(stage), phase);
-                    mbar_wait(full_bar(stage + 1), phase);
                     tc_fence_after();
-                    if (do_dw) {
-                        // dW3k^T[128 cols x 64 i] += dU_tile^T . x_tile  (reduction: 128 nodes);
-                        // the two 64-column boxes of dU are one stage (24 KB) apart
-                        const uint64_t adesc = umma_smem_desc(st, kStageBytes, 1024, kSwizzle128B);
-#pragma unroll
-                        for (int k = 0; k < kM / kUmmaK; ++k) {
-                            umma_bf16_ss(tmem_base + kTmemDw + q * kW, adesc + 128ull * k,
-                                         xdesc + 128ull * k, idesc_mn, (!first_block || k != 0) ? 1u : 0u);
-                        }
-                    }
-                    if (do_dx) {
-                        // dx[128 nodes x 64 i] += dU_tile . W3k_tile^T  (reduction: 128 columns)
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            const uint64_t adesc =
-                                umma_smem_desc(st + j * kStageBytes, 16, 1024, kSwizzle128B);
-                            const uint64_t bdesc = umma_smem_desc(st + j * kStageBytes + kDuBoxBytes, 16,
-                                                                  1024, kSwizzle128B);
-#pragma unroll
-                            for (int k = 0; k < kKB / kUmmaK; ++k) {
-                                umma_bf16_ss(tmem_x, adesc + 2ull * k, bdesc + 2ull * k, idesc_k,
-                                             (!first || (j | k) != 0) ? 1u : 0u);
-                            }
-                        }
+                    const uint32_t st = smem_base + stage * kStageBytes;
+                    const uint64_t adesc = umma_smem_desc(st, kMnBlockBytes, 1024, kSwizzle128B);
+                    const uint64_t bdesc =
+                        umma_smem_desc(st + 2 * kMnBlockBytes, kMnBlockBytes, 1024, kSwizzle128B);
+                    const int steps = kb == u.nkb - 1 ? u.last_steps : kKB / kUmmaK;
+                    for (int k = 0; k < steps; ++k) {
+                        // MN-major operands: a K-step of 16 rows advances the start by 2 KB
+                        umma_bf16_ss(tmem_d, adesc + 128ull * k, bdesc + 128ull * k, idesc_mn,
+                                     (kb | k) != 0 ? 1u : 0u);
                     }
                     umma_commit(empty_bar(stage));
-                    advance();
-                    umma_commit(empty_bar(stage));
-                    advance();
-                    if (last) {
-                        if (do_dw) umma_commit(xempty_bar);
-                        umma_commit(gfull_bar);
-                        ++n_x;
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1u;
                     }
                 }
+                umma_commit(dfull_bar(ds));
             }
-            umma_commit(wdone_bar);
         }
-    } else {
-        // ===================== epilogue (warps 2..5): thread = accumulator row =====================
+    } else if (warp < 6) {
+        // ===================== D stream: epilogue (warps 2..5) =====================
         const int q4 = warp & 3;           // TMEM lane quarter this warp may access
         const uint32_t lane_addr = uint32_t(q4 * 32) << 16;
         const uint32_t stage_smem = bar_base + 256 + q4 * 4096;
         const int64_t du_pitch = int64_t(kW) * p.K;  // elements per row of the dU buffer
-        uint32_t n_d = 0, n_x = 0;
+        uint32_t n_d = 0;
         // The counter update of a D item (a release, then the add) is deferred until this warp next
         // has to wait or is about to store the next item: a release right behind the stores waits
         // for their whole round trip.  It is never held across a blocking wait.
@@ -380,151 +332,207 @@ node_fused_bwd_kernel(const __grid_constant__ CUtensorMap tmap_hs,
                 pending = -1;
             }
         };
-        auto wait_full = [&](uint32_t bar, uint32_t parity) {
-            uint32_t ready = 0;
-            if (lane == 0) ready = mbar_try_wait(bar, parity);
-            ready = __shfl_sync(0xffffffffu, ready, 0);
-            if (!ready) {
-                flush();
-                if (lane == 0) mbar_wait_backoff(bar, parity, 32);
-            }
-            __syncwarp();
-        };
         ItemPipe pipe;
         pipe.init(p.items, v0, v1, vstep);
         int2 un = pipe.peek().a.x == IT_D ? decode_d(pipe.peek().a.y) : make_int2(0, 0);
         for (int64_t v = v0; v < v1; v += vstep) {
             const DUnit u = make_dunit(un.x, un.y - un.x);
             const Item it = pipe.pop();
-            // row pointers of the NEXT item (its record arrived iterations ago): in flight
-            // while this item is processed
             if (pipe.peek().a.x == IT_D) un = decode_d(pipe.peek().a.y);
-            if (it.a.x == IT_D) {
-                const uint32_t ds = n_d % kDSlots, dphase = (n_d / kDSlots) & 1u;
-                ++n_d;
-                __nv_bfloat16* out = p.du + int64_t(it.a.w) * du_pitch + int64_t(it.a.z) * kM * kW;
-                if (it.b.x >= 0) {  // ring slot free?
-                    flush();
-                    if (lane == 0) wait_counter(p.flags + it.b.x, it.b.y);
-                    __syncwarp();
-                }
-                wait_full(dfull_bar(ds), dphase);
-                tc_fence_after();
-                uint32_t w[32];
-                if (u.nkb == 0) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) w[j] = 0u;
-                } else {
-                    const uint32_t tcol = tmem_base + lane_addr + kTmemD + ds * kW;
-                    float f0[32], f1[32];
-                    tmem_ld32(tcol, f0);
-                    tmem_ld32(tcol + 32, f1);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        w[j] = pack_bf16(f0[2 * j], f0[2 * j + 1]);
-                        w[16 + j] = pack_bf16(f1[2 * j], f1[2 * j + 1]);
-                    }
-                }
-                tc_fence_before();
+            if (it.a.x != IT_D) continue;
+            const uint32_t ds = n_d % kDSlots, dphase = (n_d / kDSlots) & 1u;
+            ++n_d;
+            __nv_bfloat16* out = p.du + int64_t(it.a.w) * du_pitch + int64_t(it.a.z) * kM * kW;
+            if (it.b.x >= 0) {  // ring slot free?
+                flush();
+                if (lane == 0) wait_counter(p.flags + it.b.x, it.b.y);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(dempty_bar(ds));
-                flush();  // the previous item's counter, before this item's stores
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    sts128(stage_smem + lane * 128 + ((c ^ (lane & 7)) << 4),
-                           make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
-                }
-                __syncwarp();
-                // rows of dU[n][chunk] are 128 B and consecutive: 512 contiguous bytes per store
-                uint8_t* gbase = reinterpret_cast<uint8_t*>(out + q4 * 32 * kW);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int r = j * 4 + (lane >> 3), c = lane & 7;
-                    const uint4 t = lds128(stage_smem + r * 128 + ((c ^ (r & 7)) << 4));
-                    *reinterpret_cast<uint4*>(gbase + r * 128 + c * 16) = t;
-                }
-                __syncwarp();
-                pending = it.b.z;
-            } else if (it.a.x == IT_X) {
-                if (!((it.b.w >> 9) & 1)) continue;  // only the last pair of a block ends in an epilogue
-                const uint32_t xphase = n_x & 1u;
-                ++n_x;
-                wait_full(gfull_bar, xphase);
-                tc_fence_after();
-                // every MMA of the block has completed: this CTA is done with the block's dU
-                if (it.b.z >= 0 && lane == 0) atomicAdd(p.flags + it.b.z, 1);
-                if (do_dx) {
-                    const uint32_t tcol = tmem_base + lane_addr + kTmemDx;
-                    const int rows_here = it.a.w - q4 * 32;
-                    uint8_t* gbase = reinterpret_cast<uint8_t*>(
-                        p.dx_part + (int64_t(blockIdx.x) * p.N + it.a.y + q4 * 32) * kW);
-#pragma unroll
-                    for (int piece = 0; piece < 2; ++piece) {
-                        float f[32];
-                        tmem_ld32(tcol + piece * 32, f);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            sts128(stage_smem + lane * 128 + ((c ^ (lane & 7)) << 4),
-                                   make_uint4(__float_as_uint(f[4 * c]), __float_as_uint(f[4 * c + 1]),
-                                              __float_as_uint(f[4 * c + 2]), __float_as_uint(f[4 * c + 3])));
-                        }
-                        __syncwarp();
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int r = j * 4 + (lane >> 3), c = lane & 7;
-                            const uint4 t = lds128(stage_smem + r * 128 + ((c ^ (r & 7)) << 4));
-                            if (r < rows_here) {
-                                *reinterpret_cast<uint4*>(gbase + r * (kW * 4) + piece * 128 + c * 16) = t;
-                            }
-                        }
-                        __syncwarp();
-                    }
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(gempty_bar);
             }
+            uint32_t ready = 0;
+            if (lane == 0) ready = mbar_try_wait(dfull_bar(ds), dphase);
+            ready = __shfl_sync(0xffffffffu, ready, 0);
+            if (!ready) {
+                flush();
+                if (lane == 0) mbar_wait_backoff(dfull_bar(ds), dphase, 32);
+            }
+            __syncwarp();
+            tc_fence_after();
+            uint32_t w[32];
+            if (u.nkb == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) w[j] = 0u;
+            } else {
+                const uint32_t tcol = tmem_base + lane_addr + kTmemD + ds * kW;
+                float f0[32], f1[32];
+                tmem_ld32(tcol, f0);
+                tmem_ld32(tcol + 32, f1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    w[j] = pack_bf16(f0[2 * j], f0[2 * j + 1]);
+                    w[16 + j] = pack_bf16(f1[2 * j], f1[2 * j + 1]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dempty_bar(ds));
+            flush();  // the previous item's counter, before this item's stores
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                sts128(stage_smem + lane * 128 + ((c ^ (lane & 7)) << 4),
+                       make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
+            }
+            __syncwarp();
+            // rows of dU[n][chunk] are 128 B and consecutive: 512 contiguous bytes per store
+            uint8_t* gbase = reinterpret_cast<uint8_t*>(out + q4 * 32 * kW);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int r = j * 4 + (lane >> 3), c = lane & 7;
+                const uint4 t = lds128(stage_smem + r * 128 + ((c ^ (r & 7)) << 4));
+                *reinterpret_cast<uint4*>(gbase + r * 128 + c * 16) = t;
+            }
+            __syncwarp();
+            pending = it.b.z;
         }
         flush();
+    } else if (warp == 6) {
+        // ===================== X stream: TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t n_x = 0;  // node blocks started so far
+            ItemPipe pipe;
+            pipe.init(p.items, v0, v1, vstep);
+            for (int64_t v = v0; v < v1; v += vstep) {
+                const Item it = pipe.pop();
+                if (it.a.x != IT_X) continue;
+                const int q = it.b.w & 0xff;
+                const bool first = (it.b.w >> 8) & 1;
+                if (first && do_dw) {
+                    mbar_wait(xempty_bar, (n_x & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(xfull_bar, kXbBytes);
+                    tma_load_2d(xb_base, &tmap_x, xfull_bar, 0, it.a.y);
+                }
+                if (first) ++n_x;
+                if (it.b.x >= 0) {
+                    wait_counter(p.flags + it.b.x, it.b.y);
+                    fence_proxy_async_global();
+                }
+                const int32_t c0 = (p0 + q) * kPairCols;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {  // the X ring has exactly two stages: j is the stage
+                    mbar_wait(pempty_bar(stage), phase ^ 1u);
+                    const uint32_t st = xs_base + stage * kStageBytes;
+                    mbar_arrive_expect_tx(pfull_bar(stage), kDuBoxBytes + kMnBlockBytes);
+                    tma_load_2d(st, &tmap_du, pfull_bar(stage), c0 + j * 64, it.a.z);
+                    tma_load_2d(st + kDuBoxBytes, &tmap_w3k, pfull_bar(stage), c0 + j * 64, 0);
+                    if (++stage == kXStages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 7) {
+        // ===================== X stream: MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc_mn = umma_idesc_bf16(kM, kW, 1, 1);  // dW3k^T product
+            constexpr uint32_t idesc_k = umma_idesc_bf16(kM, kW, 0, 0);   // dx product
+            uint32_t phase = 0;
+            uint32_t n_x = 0;
+            ItemPipe pipe;
+            pipe.init(p.items, v0, v1, vstep);
+            for (int64_t v = v0; v < v1; v += vstep) {
+                const Item it = pipe.pop();
+                if (it.a.x != IT_X) continue;
+                const int q = it.b.w & 0xff;
+                const bool first = (it.b.w >> 8) & 1, last = (it.b.w >> 9) & 1;
+                const uint32_t xphase = n_x & 1u;
+                const bool first_block = n_x == 0;
+                if (first) {
+                    mbar_wait(gempty_bar, xphase ^ 1u);  // the dx accumulator has been drained
+                    if (do_dw) mbar_wait(xfull_bar, xphase);
+                    tc_fence_after();
+                }
+                const uint32_t tmem_x = tmem_base + kTmemDx;
+                const uint64_t xdesc = umma_smem_desc(xb_base, kMnBlockBytes, 1024, kSwizzle128B);
+                const uint32_t st = xs_base;  // a pair fills the whole X ring: stage 0 then stage 1
+                mbar_wait(pfull_bar(0), phase);
+                mbar_wait(pfull_bar(1), phase);
+                tc_fence_after();
+                if (do_dw) {
+                    // dW3k^T[128 cols x 64 i] += dU_tile^T . x_tile  (reduction: 128 nodes); the
+                    // two 64-column boxes of dU are one stage (24 KB) apart
+                    const uint64_t adesc = umma_smem_desc(st, kStageBytes, 1024, kSwizzle128B);
+#pragma unroll
+                    for (int k = 0; k < kM / kUmmaK; ++k) {
+                        umma_bf16_ss(tmem_base + kTmemDw + q * kW, adesc + 128ull * k,
+                                     xdesc + 128ull * k, idesc_mn, (!first_block || k != 0) ? 1u : 0u);
+                    }
+                }
+                if (do_dx) {
+                    // dx[128 nodes x 64 i] += dU_tile . W3k_tile^T  (reduction: 128 columns)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const uint64_t adesc = umma_smem_desc(st + j * kStageBytes, 16, 1024, kSwizzle128B);
+                        const uint64_t bdesc =
+                            umma_smem_desc(st + j * kStageBytes + kDuBoxBytes, 16, 1024, kSwizzle128B);
+#pragma unroll
+                        for (int k = 0; k < kKB / kUmmaK; ++k) {
+                            umma_bf16_ss(tmem_x, adesc + 2ull * k, bdesc + 2ull * k, idesc_k,
+                                         (!first || (j | k) != 0) ? 1u : 0u);
+                        }
+                    }
+                }
+                umma_commit(pempty_bar(0));
+                umma_commit(pempty_bar(1));
+                phase ^= 1u;
+                if (last) {
+                    if (do_dw) umma_commit(xempty_bar);
+                    umma_commit(gfull_bar);
+                    ++n_x;
+                }
+            }
+            umma_commit(wdone_bar);
+        }
+    } else {
+        // ===================== X stream: epilogue (warps 8..11) =====================
+        const int q4 = warp & 3;
+        const uint32_t lane_addr = uint32_t(q4 * 32) << 16;
+        const uint32_t stage_smem = bar_base + 256 + (4 + q4) * 4096;
+        uint32_t n_x = 0;
+        ItemPipe pipe;
+        pipe.init(p.items, v0, v1, vstep);
+        for (int64_t v = v0; v < v1; v += vstep) {
+            const Item it = pipe.pop();
+            if (it.a.x != IT_X || !((it.b.w >> 9) & 1)) continue;  // only a block's last pair
+            const uint32_t xphase = n_x & 1u;
+            ++n_x;
+            if (lane == 0) mbar_wait_backoff(gfull_bar, xphase, 32);
+            __syncwarp();
+            tc_fence_after();
+            // every MMA of the block has completed: this CTA is done with the block's dU
+            if (it.b.z >= 0 && lane == 0) atomicAdd(p.flags + it.b.z, 1);
+            if (do_dx) {
+                store_tile_f32(stage_smem, tmem_base + lane_addr + kTmemDx,
+                               reinterpret_cast<uint8_t*>(
+                                   p.dx_part + (int64_t(blockIdx.x) * p.N + it.a.y + q4 * 32) * kW),
+                               it.a.w - q4 * 32, false);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(gempty_bar);
+        }
         // ---- the weight-gradient accumulators of this CTA's column slice leave TMEM once
         if (do_dw && np > 0) {
             if (lane == 0) mbar_wait(wdone_bar, 0);
             __syncwarp();
             tc_fence_after();
             for (int q = 0; q < np; ++q) {
-                const uint32_t tcol = tmem_base + lane_addr + kTmemDw + q * kW;
-                uint8_t* gbase = reinterpret_cast<uint8_t*>(
-                    p.dwT + (int64_t(p0 + q) * kPairCols + q4 * 32) * kW);
-#pragma unroll
-                for (int piece = 0; piece < 2; ++piece) {
-                    float f[32];
-                    tmem_ld32(tcol + piece * 32, f);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        sts128(stage_smem + lane * 128 + ((c ^ (lane & 7)) << 4),
-                               make_uint4(__float_as_uint(f[4 * c]), __float_as_uint(f[4 * c + 1]),
-                                          __float_as_uint(f[4 * c + 2]), __float_as_uint(f[4 * c + 3])));
-                    }
-                    __syncwarp();
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int r = j * 4 + (lane >> 3), c = lane & 7;
-                        uint4 t = lds128(stage_smem + r * 128 + ((c ^ (r & 7)) << 4));
-                        float4* gp = reinterpret_cast<float4*>(gbase + r * (kW * 4) + piece * 128 + c * 16);
-                        if (p.accumulate_dw) {
-                            const float4 o = *gp;
-                            t.x = __float_as_uint(__uint_as_float(t.x) + o.x);
-                            t.y = __float_as_uint(__uint_as_float(t.y) + o.y);
-                            t.z = __float_as_uint(__uint_as_float(t.z) + o.z);
-                            t.w = __float_as_uint(__uint_as_float(t.w) + o.w);
-                        }
-                        *reinterpret_cast<uint4*>(gp) = t;
-                    }
-                    __syncwarp();
-                }
+                store_tile_f32(stage_smem, tmem_base + lane_addr + kTmemDw + q * kW,
+                               reinterpret_cast<uint8_t*>(
+                                   p.dwT + (int64_t(p0 + q) * kPairCols + q4 * 32) * kW),
+                               32, p.accumulate_dw != 0);
             }
         }
     }
