@@ -291,10 +291,15 @@ def arm_details(reference: bool):
                                "scaled to whole frames by edge count",
             "parallelism": "one process, all host threads (torch intra-op)",
         }
+    from molecular_dynamics_neural_operator_b200 import functional as GF
+
     return {
-        "factorization": os.environ.get("GKN_FACTORIZATION", "node"),
-        "node_fused": os.environ.get("GKN_NODE_FUSED", "0"),
-        "node_fused_bwd": os.environ.get("GKN_NODE_FUSED_BWD", "0"),
+        "factorization": GF.FACTORIZATION,
+        "node_forward": ("fused producer/consumer kernel" if GF.NODE_FUSED else
+                         "own tcgen05 GEMM for U + grouped message kernel" if GF.NODE_U_GEMM else
+                         "library GEMM for U + grouped message kernel (gkn_node_msg_bf16)"),
+        "node_backward": ("fused dU producer / (dW3, dx) consumer kernel (gkn_node_fused_bwd_bf16)"
+                          if GF.NODE_FUSED_BWD else "gkn_node_du_mn_bf16 + two library GEMMs"),
         "untimed_steps_before_timing": "max(8, warmup) resident + max(3, warmup) host-fed + 2 resident; "
                                        "Python cyclic GC disabled inside the timed loops",
         "parallelism": "frames sharded over GPUs, bucketed NCCL gradient all-reduce",

@@ -36,13 +36,14 @@ namespace {
 constexpr int kM = 128;           // accumulator rows per item
 constexpr int kKB = 64;           // reduction elements per k-block (one 128-byte swizzle row)
 constexpr int kUmmaK = 16;
-// Two groups of four epilogue warps drain the two accumulator slots alternately: the epilogue of a
-// producer tile is a latency chain (TMEM load, convert, staging, stores, GPU-scope fence before the
-// counter moves) and one group alone paced the kernel (3 us per tile measured).
-constexpr int kEpiGroups = 2;
-constexpr int kThreads = (2 + 4 * kEpiGroups) * 32;  // TMA producer, MMA issuer, epilogue warps
-constexpr int kAcc = 2;           // TMEM accumulator slots
-constexpr int kAccCols = 256;     // columns per slot (P tiles use all, C tiles the first W)
+// TWO independent in-order item streams share one CTA (twelve warps):
+//   P stream  warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue    (producer tiles of U)
+//   C stream  warp 6 TMA producer, warp 7 MMA issuer, warps 8-11 epilogue   (message units)
+// Every warp walks the CTA's whole queue and skips the other kind; the only coupling between the
+// streams is the per-node-block counters.  (With one producer thread and one issuer thread for
+// both kinds, an item that was not ready held up the items of the other kind queued behind it.)
+constexpr int kThreads = 12 * 32;
+constexpr int kPAccCols = 256;    // TMEM: one P accumulator [0, 256), then the C accumulators
 constexpr int kABytes = kM * kKB * 2;        // 16 KB: one K-major A box (128 rows x 64)
 constexpr int kMnBlockBytes = 64 * kKB * 2;  // 8 KB: one MN-major box (64 K-rows x 64 MN elements)
 constexpr int kPCols = 256;       // columns of U per P tile
@@ -65,24 +66,22 @@ using fused::lds128;
 using fused::pack_bf16;
 using fused::red_release_add;
 
-// Shared-memory pipeline.  w <= 64: eight 24 KB stages; a message k-block (hs 16 KB + U[n] 4/8 KB)
-// takes one stage, a producer fill (x tile 16 KB + four 8 KB boxes of W3) takes two consecutive
-// ones - every item uses an even number of stages, so a fill always starts on an even stage and
-// never wraps around the ring.  w = 128: four 48 KB stages, one k-block (32 KB) or fill per stage.
-// (Coarser 48 KB stages for everything measured 12 % slower on the message items.)
+// Shared memory.  P stream: one 48 KB fill buffer (x tile 16 KB + four 8 KB boxes of W3) - the
+// tensor-core work of a tile is tiny, the stream is paced by its epilogue.  C stream: a ring of
+// stages holding one k-block each (hs 16 KB + U[n] W x 128 B): six 24 KB stages at w <= 64, four
+// 32 KB stages at w = 128.
 template <int W>
 struct FCfg {
     static constexpr int kWp = W < 64 ? 64 : W;             // reduction width of P (x zero-padded)
     static constexpr int kPFills = kWp / kKB;               // fills per P tile
-    static constexpr bool kFine = W <= 64;
-    static constexpr int kStageBytes = kFine ? 24 * 1024 : 48 * 1024;
-    static constexpr int kStages = kFine ? 8 : 4;
-    static constexpr int kPStages = kFine ? 2 : 1;          // stages per P fill
+    static constexpr int kPBytes = kABytes + 4 * kMnBlockBytes;   // 48 KB
     static constexpr int kCBBytes = W * kKB * 2;            // U[n] k-block: W rows x 64
     static constexpr int kCKbBytes = kABytes + kCBBytes;    // one C k-block
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kEpiGroups * 4 * 4096;
+    static constexpr int kStageBytes = W <= 64 ? 24 * 1024 : 32 * 1024;
+    static constexpr int kStages = W <= 64 ? 6 : 4;
+    static constexpr int kCSlots = 256 / W > 4 ? 4 : 256 / W;    // C accumulators in TMEM
+    static constexpr int kSmemBytes = kPBytes + kStages * kStageBytes + 1024 + 256 + 2 * 4 * 4096;
     static_assert(kCKbBytes <= kStageBytes, "a C k-block must fit one stage");
-    static_assert(kPStages * kStageBytes >= kABytes + 4 * kMnBlockBytes, "a P fill must fit");
     static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory per CTA");
 };
 
@@ -93,8 +92,7 @@ struct FusedParams {
     __nv_bfloat16* __restrict__ u;  // [u_rows, W*K]
     float* __restrict__ msg;        // [E_pad, W]
     int32_t K;
-    int32_t tune;  // GKN_FUSED_TUNE bits (experiments): 1 = plain (unhinted) loads of hs,
-                   // 2 = one epilogue group drains both accumulator slots
+    int32_t tune;  // GKN_FUSED_TUNE bit 0 (experiment): plain (unhinted) loads of hs
 };
 
 // tmap_x : x bf16 [N, Wp]            box 64 x 128   (A of P, K-major)
@@ -110,14 +108,20 @@ node_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
     using C = FCfg<W>;
     constexpr int kStages = C::kStages;
     constexpr int kStageBytes = C::kStageBytes;
+    constexpr int kCSlots = C::kCSlots;
     extern __shared__ uint8_t smem_raw[];
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_base = smem_base + kStages * kStageBytes;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // P fill buffer
+    const uint32_t cs_base = smem_base + C::kPBytes;                     // C ring
+    const uint32_t bar_base = cs_base + kStages * kStageBytes;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
-    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + kAcc + s); };
-    const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * kStages + 2 * kAcc);
+    auto cfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+    auto cempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + kCSlots + s); };
+    const uint32_t pfull_bar = bar_base + 8u * (2 * kStages + 2 * kCSlots);   // P fill buffer
+    const uint32_t pempty_bar = pfull_bar + 8u;
+    const uint32_t tfull_bar = pfull_bar + 16u;                                // P accumulator
+    const uint32_t tempty_bar = pfull_bar + 24u;
+    const uint32_t tmem_ptr_smem = pfull_bar + 32u;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -128,11 +132,14 @@ node_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
-        for (int s = 0; s < kAcc; ++s) {
-            mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), 4);  // the four warps of the group that drains the slot
+        for (int s = 0; s < kCSlots; ++s) {
+            mbar_init(cfull_bar(s), 1);
+            mbar_init(cempty_bar(s), 4);
         }
-        static_assert(kAcc % kEpiGroups == 0, "accumulator slots are owned by epilogue groups");
+        mbar_init(pfull_bar, 1);
+        mbar_init(pempty_bar, 1);
+        mbar_init(tfull_bar, 1);
+        mbar_init(tempty_bar, 4);
         fence_mbar_init();
     }
     if (warp == 0 && lane == 0) {
@@ -142,7 +149,7 @@ node_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
         tma_prefetch_desc(&tmap_u);
     }
     if (warp == 1) {
-        tmem_alloc(tmem_ptr_smem, kAcc * kAccCols);
+        tmem_alloc(tmem_ptr_smem, 512);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -151,153 +158,89 @@ node_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
-    const int nkb = p.K / kKB;  // k-blocks of a C item (a multiple of 4)
+    const int nkb = p.K / kKB;  // k-blocks of a C item
+
+    // 32 rows x 128 B of this warp's staging tile -> global, 8 lanes per row (whole 128 B lines)
+    auto store_rows = [&](uint32_t stage_smem, const uint32_t (&w)[32], uint8_t* gdst, int64_t pitch,
+                          int rows_here) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            sts128(stage_smem + lane * 128 + ((c ^ (lane & 7)) << 4),
+                   make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int r = j * 4 + (lane >> 3), c = lane & 7;
+            const uint4 t = lds128(stage_smem + r * 128 + ((c ^ (r & 7)) << 4));
+            if (r < rows_here) *reinterpret_cast<uint4*>(gdst + r * pitch + c * 16) = t;
+        }
+        __syncwarp();
+    };
+
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        int stage = 0;
-        uint32_t phase = 0;
-        auto advance = [&]() {
-            if (++stage == kStages) {
-                stage = 0;
-                phase ^= 1u;
-            }
-        };
-        const uint64_t pol_stream = l2_policy_evict_first();
+        // ===================== P stream: TMA producer =====================
         if (lane == 0) {
+            uint32_t n_fill = 0;
             ItemPipe pipe;
             pipe.init(p.items, v0, v1, vstep);
             for (int64_t v = v0; v < v1; v += vstep) {
                 const Item it = pipe.pop();
-                if (it.a.x == IT_P) {
+                if (it.a.x != IT_P) continue;
 #pragma unroll
-                    for (int f = 0; f < C::kPFills; ++f) {
-                        // x tile + first box(es) of W3 in the first stage, the rest in the next
-                        const uint32_t sa = smem_base + stage * kStageBytes;
-                        constexpr int kFirst = C::kFine ? 1 : 4;  // W3 boxes in the first stage
-                        mbar_wait(empty_bar(stage), phase ^ 1u);
-                        mbar_arrive_expect_tx(full_bar(stage), kABytes + kFirst * kMnBlockBytes);
-                        tma_load_2d(sa, &tmap_x, full_bar(stage), f * kKB, it.a.y);
+                for (int f = 0; f < C::kPFills; ++f, ++n_fill) {
+                    mbar_wait(pempty_bar, (n_fill & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(pfull_bar, C::kPBytes);
+                    tma_load_2d(smem_base, &tmap_x, pfull_bar, f * kKB, it.a.y);
 #pragma unroll
-                        for (int j = 0; j < kFirst; ++j) {
-                            tma_load_2d(sa + kABytes + j * kMnBlockBytes, &tmap_w3, full_bar(stage),
-                                        it.a.z + j * 64, f * kKB);
-                        }
-                        advance();
-                        if constexpr (C::kFine) {
-                            mbar_wait(empty_bar(stage), phase ^ 1u);
-                            mbar_arrive_expect_tx(full_bar(stage), 3 * kMnBlockBytes);
-#pragma unroll
-                            for (int j = 1; j < 4; ++j) {
-                                tma_load_2d(sa + kABytes + j * kMnBlockBytes, &tmap_w3,
-                                            full_bar(stage), it.a.z + j * 64, f * kKB);
-                            }
-                            advance();
-                        }
-                    }
-                } else if (it.a.x == IT_C) {
-                    bool ready = it.b.x < 0;
-                    for (int kb = 0; kb < nkb; ++kb) {
-                        mbar_wait(empty_bar(stage), phase ^ 1u);
-                        const uint32_t sa = smem_base + stage * kStageBytes;
-                        mbar_arrive_expect_tx(full_bar(stage), C::kCKbBytes);
-                        // the edge hidden state does not depend on this launch: its load goes out
-                        // before the counter is polled
-                        if (p.tune & 1) {
-                            tma_load_2d(sa, &tmap_hs, full_bar(stage), kb * kKB, it.a.y);
-                        } else {
-                            tma_load_2d_hint(sa, &tmap_hs, full_bar(stage), kb * kKB, it.a.y, pol_stream);
-                        }
-                        if (!ready) {
-                            wait_counter(p.flags + it.b.x, it.b.y);
-                            fence_proxy_async_global();
-                            ready = true;
-                        }
-                        tma_load_2d(sa + kABytes, &tmap_u, full_bar(stage), kb * kKB, it.a.w * W);
-                        advance();
+                    for (int j = 0; j < 4; ++j) {
+                        tma_load_2d(smem_base + kABytes + j * kMnBlockBytes, &tmap_w3, pfull_bar,
+                                    it.a.z + j * 64, f * kKB);
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        constexpr uint32_t idesc_p = umma_idesc_bf16(kM, kPCols, 0, 1);
-        constexpr uint32_t idesc_c = umma_idesc_bf16(kM, W, 0, 0);
-        int stage = 0;
-        uint32_t phase = 0;
-        auto advance = [&]() {
-            if (++stage == kStages) {
-                stage = 0;
-                phase ^= 1u;
-            }
-        };
-        uint32_t n_acc = 0;
+        // ===================== P stream: MMA issuer =====================
         if (lane == 0) {
+            constexpr uint32_t idesc_p = umma_idesc_bf16(kM, kPCols, 0, 1);
+            uint32_t n_fill = 0, n_p = 0;
             ItemPipe pipe;
             pipe.init(p.items, v0, v1, vstep);
             for (int64_t v = v0; v < v1; v += vstep) {
                 const Item it = pipe.pop();
-                if (it.a.x != IT_P && it.a.x != IT_C) continue;
-                const uint32_t as = n_acc % kAcc;
-                const uint32_t aphase = (n_acc / kAcc) & 1u;
-                ++n_acc;
-                mbar_wait(tempty_bar(as), aphase ^ 1u);
+                if (it.a.x != IT_P) continue;
+                mbar_wait(tempty_bar, (n_p & 1u) ^ 1u);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + as * kAccCols;
-                if (it.a.x == IT_P) {
 #pragma unroll
-                    for (int f = 0; f < C::kPFills; ++f) {
-                        const uint32_t sa = smem_base + stage * kStageBytes;
-                        const int s0 = stage;
-                        const uint32_t ph0 = phase;
-                        mbar_wait(full_bar(s0), ph0);
-                        if constexpr (C::kFine) mbar_wait(full_bar(s0 + 1), ph0);  // never wraps
-                        tc_fence_after();
-                        const uint64_t adesc = umma_smem_desc(sa, 16, 1024, kSwizzle128B);
-                        const uint64_t bdesc =
-                            umma_smem_desc(sa + kABytes, kMnBlockBytes, 1024, kSwizzle128B);
+                for (int f = 0; f < C::kPFills; ++f, ++n_fill) {
+                    mbar_wait(pfull_bar, n_fill & 1u);
+                    tc_fence_after();
+                    const uint64_t adesc = umma_smem_desc(smem_base, 16, 1024, kSwizzle128B);
+                    const uint64_t bdesc =
+                        umma_smem_desc(smem_base + kABytes, kMnBlockBytes, 1024, kSwizzle128B);
 #pragma unroll
-                        for (int k = 0; k < kKB / kUmmaK; ++k) {
-                            // K-major A: 16 elements = 32 B; MN-major B: 16 K-rows = 2048 B
-                            umma_bf16_ss(tmem_d, adesc + 2ull * k, bdesc + 128ull * k, idesc_p,
-                                         (f | k) != 0 ? 1u : 0u);
-                        }
-                        umma_commit(empty_bar(stage));
-                        advance();
-                        if constexpr (C::kFine) {
-                            umma_commit(empty_bar(stage));
-                            advance();
-                        }
+                    for (int k = 0; k < kKB / kUmmaK; ++k) {
+                        // K-major A: 16 elements = 32 B; MN-major B: 16 K-rows = 2048 B
+                        umma_bf16_ss(tmem_base, adesc + 2ull * k, bdesc + 128ull * k, idesc_p,
+                                     (f | k) != 0 ? 1u : 0u);
                     }
-                } else {
-                    for (int kb = 0; kb < nkb; ++kb) {
-                        mbar_wait(full_bar(stage), phase);
-                        tc_fence_after();
-                        const uint32_t sa = smem_base + stage * kStageBytes;
-                        const uint64_t adesc = umma_smem_desc(sa, 16, 1024, kSwizzle128B);
-                        const uint64_t bdesc = umma_smem_desc(sa + kABytes, 16, 1024, kSwizzle128B);
-#pragma unroll
-                        for (int k = 0; k < kKB / kUmmaK; ++k) {
-                            umma_bf16_ss(tmem_d, adesc + 2ull * k, bdesc + 2ull * k, idesc_c,
-                                         (kb | k) != 0 ? 1u : 0u);
-                        }
-                        umma_commit(empty_bar(stage));
-                        advance();
-                    }
+                    umma_commit(pempty_bar);
                 }
-                umma_commit(tfull_bar(as));
+                umma_commit(tfull_bar);
+                ++n_p;
             }
         }
-    } else {
-        // ===================== epilogue (warps 2..): thread = accumulator row =====================
+    } else if (warp < 6) {
+        // ===================== P stream: epilogue (warps 2..5) =====================
         const int q = warp & 3;           // TMEM lane quarter this warp may access
-        const int grp = (warp - 2) >> 2;  // epilogue group = accumulator slot it drains
         const uint32_t lane_addr = uint32_t(q * 32) << 16;
-        const uint32_t stage_smem = bar_base + 256 + (grp * 4 + q) * 4096;  // per-warp staging tile
-        const int64_t u_pitch = int64_t(W) * p.K * 2;                        // bytes per row of U
-        uint32_t n_acc = 0;
+        const uint32_t stage_smem = bar_base + 256 + q * 4096;  // per-warp 32 x 128 B staging tile
+        const int64_t u_pitch = int64_t(W) * p.K * 2;           // bytes per row of U
+        uint32_t n_p = 0;
         // The counter of a producer tile moves with release semantics after the tile's stores, and
         // a release right behind the stores waits for their full round trip.  So the update of
-        // tile t is issued when this warp next has to wait anyway or is about to store item t+1.
+        // tile t is issued when this warp next has to wait anyway or is about to store tile t+1.
         int32_t pending = -1;
         auto flush = [&]() {
             if (pending >= 0) {
@@ -310,97 +253,166 @@ node_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
         pipe.init(p.items, v0, v1, vstep);
         for (int64_t v = v0; v < v1; v += vstep) {
             const Item it = pipe.pop();
-            if (it.a.x != IT_P && it.a.x != IT_C) continue;
-            const uint32_t as = n_acc % kAcc;
-            const uint32_t aphase = (n_acc / kAcc) & 1u;
-            ++n_acc;
-            if (p.tune & 2) {
-                if (grp != 0) continue;
-            } else if (int(as % kEpiGroups) != grp) {
-                continue;  // the other group's item
-            }
-            const bool is_p = it.a.x == IT_P;
+            if (it.a.x != IT_P) continue;
+            const uint32_t tphase = n_p & 1u;
+            ++n_p;
             // never block with a counter update outstanding: somebody may be waiting for it
             uint32_t ready = 0;
-            if (lane == 0) ready = mbar_try_wait(tfull_bar(as), aphase);
+            if (lane == 0) ready = mbar_try_wait(tfull_bar, tphase);
             ready = __shfl_sync(0xffffffffu, ready, 0);
-            if (!ready || (is_p && it.b.x >= 0)) flush();
+            if (!ready || it.b.x >= 0) flush();
             if (lane == 0) {
-                if (!ready) mbar_wait(tfull_bar(as), aphase);
+                if (!ready) mbar_wait_backoff(tfull_bar, tphase, 32);
                 // ring mode: the slot this tile overwrites must have been consumed
-                if (is_p && it.b.x >= 0) wait_counter(p.flags + it.b.x, it.b.y);
+                if (it.b.x >= 0) wait_counter(p.flags + it.b.x, it.b.y);
             }
+            __syncwarp();
+            tc_fence_after();
+            const uint32_t tcol = tmem_base + lane_addr;
+            uint8_t* gbase = reinterpret_cast<uint8_t*>(p.u) + int64_t(it.a.w + q * 32) * u_pitch +
+                             int64_t(it.a.z) * 2;
+            const int rows_here = it.b.w - q * 32;
+#pragma unroll 1
+            for (int piece = 0; piece < kPCols / 64; ++piece) {
+                uint32_t w[32];
+                float f0[32], f1[32];
+                tmem_ld32(tcol + piece * 64, f0);
+                tmem_ld32(tcol + piece * 64 + 32, f1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    w[j] = pack_bf16(f0[2 * j], f0[2 * j + 1]);
+                    w[16 + j] = pack_bf16(f1[2 * j], f1[2 * j + 1]);
+                }
+                if (piece == kPCols / 64 - 1) {  // accumulator fully read: hand it back now
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar);
+                }
+                if (piece == 0) flush();  // the previous tile's counter, before this tile's stores
+                store_rows(stage_smem, w, gbase + piece * 128, u_pitch, rows_here);
+            }
+            pending = it.b.z;
+        }
+        flush();
+    } else if (warp == 6) {
+        // ===================== C stream: TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint64_t pol_stream = l2_policy_evict_first();
+            ItemPipe pipe;
+            pipe.init(p.items, v0, v1, vstep);
+            for (int64_t v = v0; v < v1; v += vstep) {
+                const Item it = pipe.pop();
+                if (it.a.x != IT_C) continue;
+                bool ready = it.b.x < 0;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t sa = cs_base + stage * kStageBytes;
+                    mbar_arrive_expect_tx(full_bar(stage), C::kCKbBytes);
+                    // the edge hidden state does not depend on this launch: its load goes out
+                    // before the counter is polled
+                    if (p.tune & 1) {
+                        tma_load_2d(sa, &tmap_hs, full_bar(stage), kb * kKB, it.a.y);
+                    } else {
+                        tma_load_2d_hint(sa, &tmap_hs, full_bar(stage), kb * kKB, it.a.y, pol_stream);
+                    }
+                    if (!ready) {
+                        wait_counter(p.flags + it.b.x, it.b.y);
+                        fence_proxy_async_global();
+                        ready = true;
+                    }
+                    tma_load_2d(sa + kABytes, &tmap_u, full_bar(stage), kb * kKB, it.a.w * W);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 7) {
+        // ===================== C stream: MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc_c = umma_idesc_bf16(kM, W, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t n_c = 0;
+            ItemPipe pipe;
+            pipe.init(p.items, v0, v1, vstep);
+            for (int64_t v = v0; v < v1; v += vstep) {
+                const Item it = pipe.pop();
+                if (it.a.x != IT_C) continue;
+                const uint32_t cs = n_c % kCSlots, cphase = (n_c / kCSlots) & 1u;
+                ++n_c;
+                mbar_wait(cempty_bar(cs), cphase ^ 1u);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + kPAccCols + cs * W;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = cs_base + stage * kStageBytes;
+                    const uint64_t adesc = umma_smem_desc(sa, 16, 1024, kSwizzle128B);
+                    const uint64_t bdesc = umma_smem_desc(sa + kABytes, 16, 1024, kSwizzle128B);
+#pragma unroll
+                    for (int k = 0; k < kKB / kUmmaK; ++k) {
+                        umma_bf16_ss(tmem_d, adesc + 2ull * k, bdesc + 2ull * k, idesc_c,
+                                     (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(stage));
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                umma_commit(cfull_bar(cs));
+            }
+        }
+    } else {
+        // ===================== C stream: epilogue (warps 8..11) =====================
+        const int q = warp & 3;
+        const uint32_t lane_addr = uint32_t(q * 32) << 16;
+        const uint32_t stage_smem = bar_base + 256 + (4 + q) * 4096;
+        uint32_t n_c = 0;
+        ItemPipe pipe;
+        pipe.init(p.items, v0, v1, vstep);
+        for (int64_t v = v0; v < v1; v += vstep) {
+            const Item it = pipe.pop();
+            if (it.a.x != IT_C) continue;
+            const uint32_t cs = n_c % kCSlots, cphase = (n_c / kCSlots) & 1u;
+            ++n_c;
+            if (lane == 0) mbar_wait_backoff(cfull_bar(cs), cphase, 32);
             __syncwarp();
             tc_fence_after();
             // a consumer's counter only says "U[n] has been read" (every MMA of the item is
             // complete): no data is published, so it moves at once and without a release
-            if (!is_p && it.b.z >= 0 && lane == 0) atomicAdd(p.flags + it.b.z, 1);
-            const uint32_t tcol = tmem_base + lane_addr + as * kAccCols;
-            const int rows_here = (is_p ? it.b.w : it.a.z) - q * 32;
-            uint8_t* gbase;
-            int64_t pitch;
-            int pieces;  // 128-byte output pieces per row
-            if (is_p) {
-                gbase = reinterpret_cast<uint8_t*>(p.u) + int64_t(it.a.w + q * 32) * u_pitch +
-                        int64_t(it.a.z) * 2;
-                pitch = u_pitch;
-                pieces = kPCols / 64;
-            } else {
-                gbase = reinterpret_cast<uint8_t*>(p.msg + int64_t(it.a.y + q * 32) * W);
-                pitch = W * 4;
-                pieces = W / 32;
-            }
-            for (int piece = 0; piece < pieces; ++piece) {
+            if (it.b.z >= 0 && lane == 0) atomicAdd(p.flags + it.b.z, 1);
+            const uint32_t tcol = tmem_base + lane_addr + kPAccCols + cs * W;
+            uint8_t* gbase = reinterpret_cast<uint8_t*>(p.msg + int64_t(it.a.y + q * 32) * W);
+            const int rows_here = it.a.z - q * 32;
+#pragma unroll
+            for (int piece = 0; piece < W / 32; ++piece) {
                 uint32_t w[32];
-                if (is_p) {
-                    float f0[32], f1[32];
-                    tmem_ld32(tcol + piece * 64, f0);
-                    tmem_ld32(tcol + piece * 64 + 32, f1);
-                    tmem_ld_wait();
+                float f[32];
+                tmem_ld32(tcol + piece * 32, f);
+                tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        w[j] = pack_bf16(f0[2 * j], f0[2 * j + 1]);
-                        w[16 + j] = pack_bf16(f1[2 * j], f1[2 * j + 1]);
-                    }
-                } else {
-                    float f[32];
-                    tmem_ld32(tcol + piece * 32, f);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(f[j]);
-                }
-                if (piece == pieces - 1) {  // accumulator fully read: hand the slot back now
+                for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(f[j]);
+                if (piece == W / 32 - 1) {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty_bar(as));
+                    if (lane == 0) mbar_arrive(cempty_bar(cs));
                 }
-                if (piece == 0) flush();  // the previous item's counter, before this item's stores
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    sts128(stage_smem + lane * 128 + ((c ^ (lane & 7)) << 4),
-                           make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
-                }
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int r = j * 4 + (lane >> 3), c = lane & 7;
-                    const uint4 t = lds128(stage_smem + r * 128 + ((c ^ (r & 7)) << 4));
-                    if (r < rows_here) {
-                        *reinterpret_cast<uint4*>(gbase + r * pitch + piece * 128 + c * 16) = t;
-                    }
-                }
-                __syncwarp();
+                store_rows(stage_smem, w, gbase + piece * 128, W * 4, rows_here);
             }
-            if (is_p) pending = it.b.z;
         }
-        flush();
     }
 
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kAcc * kAccCols);
+        tmem_dealloc(tmem_base, 512);
     }
 }
 
