@@ -476,8 +476,10 @@ def sharded_rollout(dev, world, rank, steps=3, window=2, name="synthetic_100k"):
     t = torch.tensor([ev0.elapsed_time(ev1) / steps, diff], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, diff = float(t[0]), float(t[1])
-    res = {"workload": name, "mode": f"rollout, one frame sharded over {world} GPUs "
-                                     "(source ranges, all-reduce of partial node sums)",
+    from molecular_dynamics_neural_operator_b200.sharded import exchange_in_use
+
+    res = {"workload": name, "mode": f"rollout, one frame sharded over {world} GPUs by source-node "
+                                     f"ranges; exchange per application: {exchange_in_use()}",
            "steps": steps, "ms_per_rollout_step": ms, "steps_per_s": 1e3 / ms, "atoms": wl.num_atoms,
            "edges_per_step": edges[-1], "rel_fro_vs_unsharded_forward": diff,
            "agrees_with_unsharded": diff < 2.0 ** -7}

@@ -285,6 +285,13 @@ def peer_exchange(N: int, W: int, device, group):
     return _PEER_CACHE[key]
 
 
+def exchange_in_use() -> str:
+    """Which exchange the last sharded node-first forward used on this rank."""
+    live = [v for v in _PEER_CACHE.values() if v is not None]
+    return ("fused peer-memory kernel (gkn_shard_reduce_update over symmetric memory)" if live
+            else "ncclAllReduce of the partial sums + replicated node update")
+
+
 @torch.no_grad()
 def sharded_stack_forward_node(x0, shard: SourceShard, net, root1, bias1, root2, bias2, schedule,
                                relu: bool, group=None) -> torch.Tensor:
