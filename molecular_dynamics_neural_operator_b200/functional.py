@@ -253,6 +253,7 @@ _FUSED_SLACK = float(os.environ.get("GKN_NODE_FUSED_SLACK", "1.5"))
 # library GEMMs (bench shape, one B200): 35.8 vs 37.1 ms per step.
 NODE_FUSED_BWD = os.environ.get("GKN_NODE_FUSED_BWD", "1") == "1"
 _FUSED_BWD_RING = int(os.environ.get("GKN_NODE_FUSED_BWD_RING", "3"))
+_FUSED_BWD_MIN_DEGREE = int(os.environ.get("GKN_NODE_FUSED_BWD_MIN_DEGREE", "64"))
 
 
 def node_path_supported(W: int, K: int, E: int, precision: str, needs_grad: bool = True) -> bool:
@@ -374,7 +375,11 @@ class _GKNStackNode(torch.autograd.Function):
         elif not need_edge:
             gs_one = torch.empty((lay.e_pad, W), dtype=bf, device=dev)
         gs_all = torch.empty((A, lay.e_pad, W), dtype=bf, device=dev) if need_edge else None
-        fused_bwd = NODE_FUSED_BWD and NODE_MN and W == 64
+        # the fused kernel pays 148 dx partials (38 KB) per node and one work item per (node, 128
+        # k-rows): it wins on graphs of BBA-like degree (119 edges per node: 0.80 vs 0.94 ms) and
+        # loses a few per cent at ~30 edges per node (10k-atom frames: 125 vs 120 ms per step)
+        fused_bwd = (NODE_FUSED_BWD and NODE_MN and W == 64
+                     and lay.e_pad >= _FUSED_BWD_MIN_DEGREE * N)
         if fused_bwd:
             try:
                 bsched = ops.fused_bwd_schedule(N, K, W, dev, ring=_FUSED_BWD_RING)

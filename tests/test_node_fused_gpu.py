@@ -140,6 +140,7 @@ def test_stack_variants_match_library_gemm_form(monkeypatch, needs_grad, fwd_mod
         monkeypatch.setattr(GF, "NODE_FUSED", variant and fwd_mode == "1")
         monkeypatch.setattr(GF, "NODE_U_GEMM", variant and fwd_mode == "gemm")
         monkeypatch.setattr(GF, "NODE_FUSED_BWD", variant and fused_bwd)
+        monkeypatch.setattr(GF, "_FUSED_BWD_MIN_DEGREE", 0)  # take it whatever the degree
         t = {k: v.cuda().requires_grad_(needs_grad) for k, v in base.items()}
         with torch.set_grad_enabled(needs_grad):
             out = GF._GKNStackNode.apply(

@@ -368,6 +368,7 @@ def test_node_first_stack_matches_oracle(emulated, monkeypatch, N, E, K, depth, 
     monkeypatch.setattr(GF, "NODE_FUSED", fwd_mode == "1")
     monkeypatch.setattr(GF, "NODE_U_GEMM", fwd_mode == "gemm")
     monkeypatch.setattr(GF, "NODE_FUSED_BWD", fused_bwd)
+    monkeypatch.setattr(GF, "_FUSED_BWD_MIN_DEGREE", 0)  # take it whatever the degree
     ei, p, depth = _stack_case(N, E, K, depth, seed=11 * N + depth, isolated=isolated)
     out, t = _run_node_stack(ei, p, depth, N, relu=False)
     ref, tr = _run_oracle_stack(ei, p, depth, relu=False)

@@ -228,6 +228,23 @@ def test_node_first_is_the_default_for_the_bench_shape():
     finally:
         ops.KERNEL_TIMER.disable()
     fwd = got.get("node_fused_fwd", got.get("node_msg"))
-    bwd = got.get("node_fused_bwd", got.get("node_du"))
-    assert fwd["count"] == 2 and bwd["count"] == 2
-    assert got["node_dh"]["count"] == 1
+    assert fwd["count"] == 2 and got["node_dh"]["count"] == 1
+    # 67 edges per node: the fused backward (one launch per application, no library GEMM)
+    assert GF.NODE_FUSED_BWD and got["node_fused_bwd"]["count"] == 2 and "node_du" not in got
+
+
+def test_low_degree_graphs_keep_the_three_kernel_backward():
+    """Below ~64 edges per node the fused backward's per-node overheads outweigh its savings
+    (DESIGN.md section 6): such graphs take gkn_node_du_mn_bf16 + the two dense products."""
+    from molecular_dynamics_neural_operator_b200 import functional as GF
+    from molecular_dynamics_neural_operator_b200 import ops
+
+    ei, p, depth = _stack_case(200, 3000, 256, 1, seed=4)  # 15 edges per node
+    ops.KERNEL_TIMER.enable()
+    try:
+        out, t = _gpu_stack(GF._GKNStackNode, ei, p, depth, 200, relu=True)
+        out.sum().backward()
+        got = ops.KERNEL_TIMER.collect()
+    finally:
+        ops.KERNEL_TIMER.disable()
+    assert got["node_du"]["count"] == 2 and "node_fused_bwd" not in got
