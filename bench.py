@@ -747,6 +747,14 @@ def run_b200_arm(args, wl):
                                    f"inflate the step: {ms_instr / args.steps:.1f} ms vs "
                                    f"{ms_total / args.steps:.1f} ms clean)",
                     "peak_source": f"{peaks['source']} HBM copy bandwidth"}
+        if top == "node_fused_bwd":
+            roofline["note"] = (
+                "one launch per application does the work of three kernels of round 1 "
+                "(gkn_node_du_mn_bf16 + the library GEMMs dx = dU W3^T and dW3 += x^T dU: 0.94 ms, "
+                "5.4 GB of DRAM traffic, node_du alone at 83 % of the copy bandwidth by its own byte "
+                "model); bytes_per_launch counts h and the message gradients in and the per-CTA dx "
+                "partials out - dU never reaches HBM.  Fewer bytes in less time, at a lower "
+                "fraction of the bandwidth: the kernel is latency-bound (ncu: DRAM 52 %, L2 39 %)")
     elif timer["count"]:
         flop_per_launch = 2.0 * (edges_per_frame * B) * wl.ker_width * wl.width ** 2
         avg_ms = timer["ms"] / timer["count"]
