@@ -227,10 +227,13 @@ int gkn_segment_matvec(const float* rows, const int32_t* perm, const int32_t* se
  * through mapped peer pointers and writing x'[n] into every rank's x' buffer: reduce-scatter,
  * compute and all-gather in one kernel over NVLink.  partial_ptrs / xout_ptrs: HOST arrays of
  * `world` device addresses (this rank's own buffers included, in rank order; e.g. the buffer_ptrs
- * of a torch symmetric-memory handle).  The caller synchronises the ranks before (all S_p written)
- * and after (all x' rows landed) the launch.  W in {32, 64, 128}, world <= 16. */
-int gkn_shard_reduce_update(const uint64_t* partial_ptrs, const uint64_t* xout_ptrs, int32_t world,
-                            const float* x, const float* inv_cnt, const float* B3,
+ * of a torch symmetric-memory handle).  mc_partial / mc_xout: the MULTICAST addresses of the two
+ * symmetric buffers (NVLS), or 0: with them the sum over the ranks is one multimem.ld_reduce per 16
+ * bytes, computed in the NVSwitch, and the new row is one multimem.st replicated by the switch.
+ * The caller synchronises the ranks before (all S_p written) and after (all x' rows landed) the
+ * launch.  W in {32, 64, 128}, world <= 16. */
+int gkn_shard_reduce_update(const uint64_t* partial_ptrs, const uint64_t* xout_ptrs,
+                            uint64_t mc_partial, uint64_t mc_xout, int32_t world, const float* x, const float* inv_cnt, const float* B3,
                             const float* root, const float* bias, int64_t n0, int64_t n1,
                             int64_t N, int32_t W, int32_t relu, void* stream);
 

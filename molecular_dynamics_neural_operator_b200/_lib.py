@@ -71,7 +71,8 @@ SIGNATURES = {
     ),
     "gkn_shard_reduce_update": (
         c_int,
-        [P, P, c_int32, P, P, P, P, P, c_int64, c_int64, c_int64, c_int32, c_int32, P],
+        [P, P, ctypes.c_uint64, ctypes.c_uint64, c_int32, P, P, P, P, P, c_int64, c_int64, c_int64,
+         c_int32, c_int32, P],
     ),
     "gkn_edge_attr_gather": (c_int, [P, P, c_int64, c_int64, P, P, P]),
     "gkn_relu_grad_scale": (c_int, [P, P, P, P, P, c_int64, c_int32, c_int32, P]),

@@ -15,6 +15,10 @@
 //   - stores the new feature row into the x' buffer of EVERY rank (st.global on peer pointers).
 // A reduce-scatter, the compute, and an all-gather in one pass: per rank 2 N w 4 bytes in and
 // N w 4 bytes out cross NVLink once, nothing is staged, and no rank computes a node twice.
+// With the multicast addresses of the two symmetric buffers (NVLS: NVSwitch multicast objects) the
+// sum over the ranks is done BY THE SWITCH - one multimem.ld_reduce per 16 bytes instead of one
+// load per peer - and the new row is written once with multimem.st and replicated by the switch:
+// the bytes a rank moves over its links drop from (world-1)/world x 3 N w 4 to 3 N w 4 / world.
 // The caller brackets the launch with two barriers of the symmetric-memory handle (all partials
 // written before / all x' rows landed after).
 #include "gkn_internal.h"
@@ -32,6 +36,8 @@ constexpr int kNB = 4;  // nodes per warp round
 struct PeerPtrs {
     const float* part[kMaxWorld];  // S_p [2, N, w]
     float* xout[kMaxWorld];        // x' [N, w] on rank p
+    const float* mc_part;          // multicast address of the S buffers (or NULL: peer loads)
+    float* mc_xout;                // multicast address of the x' buffers (or NULL: peer stores)
 };
 
 __device__ __forceinline__ float4 f4add(float4 a, float4 b) {
@@ -72,6 +78,32 @@ __device__ __forceinline__ float4 ld_peer(const float* p) {
     return v;
 }
 
+// sum over all ranks' copies of 16 bytes, computed in the NVSwitch
+__device__ __forceinline__ float4 ld_reduce_mc(const float* p) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p)
+                 : "memory");
+    return v;
+}
+
+// one store, replicated into every rank's copy by the NVSwitch
+template <int CPL>
+__device__ __forceinline__ void st_mc(float* p, const float (&v)[CPL]) {
+    if constexpr (CPL == 4) {
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p),
+                     "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3])
+                     : "memory");
+    } else if constexpr (CPL == 2) {
+        asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v[0]),
+                     "f"(v[1])
+                     : "memory");
+    } else {
+        asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v[0]) : "memory");
+    }
+}
+
 template <int W>
 __global__ void __launch_bounds__(kWarps * 32)
 shard_reduce_update_kernel(const PeerPtrs pp, int world, const float* __restrict__ x,
@@ -99,9 +131,14 @@ shard_reduce_update_kernel(const PeerPtrs pp, int world, const float* __restrict
             const int64_t n = base + nb;
             if (n >= n1) continue;
             float4 ar = make_float4(0.f, 0.f, 0.f, 0.f), ag = ar;
-            for (int p = 0; p < world; ++p) {  // rank order: a fixed summation order
-                ar = f4add(ar, ld_peer(pp.part[p] + n * W + col));
-                ag = f4add(ag, ld_peer(pp.part[p] + (N + n) * W + col));
+            if (pp.mc_part != nullptr) {  // the switch adds the ranks' rows
+                ar = ld_reduce_mc(pp.mc_part + n * W + col);
+                ag = ld_reduce_mc(pp.mc_part + (N + n) * W + col);
+            } else {
+                for (int p = 0; p < world; ++p) {  // rank order: a fixed summation order
+                    ar = f4add(ar, ld_peer(pp.part[p] + n * W + col));
+                    ag = f4add(ag, ld_peer(pp.part[p] + (N + n) * W + col));
+                }
             }
             const float sc = inv_cnt[n];
             *reinterpret_cast<float4*>(&s_r[wib][nb][col]) = make_float4(ar.x * sc, ar.y * sc, ar.z * sc, ar.w * sc);
@@ -143,7 +180,11 @@ shard_reduce_update_kernel(const PeerPtrs pp, int world, const float* __restrict
                 float v[CPL];
 #pragma unroll
                 for (int k = 0; k < CPL; ++k) v[k] = relu ? fmaxf(o[nb][k], 0.f) : o[nb][k];
-                for (int p = 0; p < world; ++p) st_vec<CPL>(pp.xout[p] + (base + nb) * W + c0, v);
+                if (pp.mc_xout != nullptr) {
+                    st_mc<CPL>(pp.mc_xout + (base + nb) * W + c0, v);
+                } else {
+                    for (int p = 0; p < world; ++p) st_vec<CPL>(pp.xout[p] + (base + nb) * W + c0, v);
+                }
             }
         }
         __syncwarp();
@@ -155,7 +196,8 @@ shard_reduce_update_kernel(const PeerPtrs pp, int world, const float* __restrict
 }  // namespace gkn
 
 extern "C" int gkn_shard_reduce_update(const uint64_t* partial_ptrs, const uint64_t* xout_ptrs,
-                                       int32_t world, const float* x, const float* inv_cnt,
+                                       uint64_t mc_partial, uint64_t mc_xout, int32_t world,
+                                       const float* x, const float* inv_cnt,
                                        const float* B3, const float* root, const float* bias,
                                        int64_t n0, int64_t n1, int64_t N, int32_t W, int32_t relu,
                                        void* stream) {
@@ -170,6 +212,8 @@ extern "C" int gkn_shard_reduce_update(const uint64_t* partial_ptrs, const uint6
     }
     if (n0 < 0 || n1 > N) return set_error("gkn_shard_reduce_update: node range outside [0, N)");
     PeerPtrs pp{};
+    pp.mc_part = reinterpret_cast<const float*>(mc_partial);
+    pp.mc_xout = reinterpret_cast<float*>(mc_xout);
     for (int p = 0; p < world; ++p) {
         if (partial_ptrs[p] == 0 || xout_ptrs[p] == 0) {
             return set_error("gkn_shard_reduce_update: NULL peer buffer");

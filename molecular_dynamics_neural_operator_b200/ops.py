@@ -1004,11 +1004,13 @@ def sum_partials(part: torch.Tensor, addend: torch.Tensor | None, out: torch.Ten
 # Sharded rollout: exchange + node update + broadcast in one kernel over peer memory
 # ------------------------------------------------------------------------------------------------
 def shard_reduce_update(partial_ptrs, xout_ptrs, x, inv_cnt, B3, root, bias, n0: int, n1: int,
-                        relu: bool) -> None:
+                        relu: bool, mc_partial: int = 0, mc_xout: int = 0) -> None:
     """For the nodes [n0, n1) this rank owns: sum the partial rows of every rank (``partial_ptrs``:
     device addresses of the ranks' [2, N, W] fp32 buffers, in rank order), apply the node update
     and store the new rows into every rank's x' buffer (``xout_ptrs``) - gkn_shard_reduce_update.
-    The caller synchronises the ranks before and after."""
+    ``mc_partial`` / ``mc_xout``: multicast addresses of the two symmetric buffers (NVLS) - the
+    NVSwitch then does the sum and replicates the stores.  The caller synchronises the ranks
+    before and after."""
     import ctypes
 
     lib = _lib.load()
@@ -1022,7 +1024,8 @@ def shard_reduce_update(partial_ptrs, xout_ptrs, x, inv_cnt, B3, root, bias, n0:
     with torch.cuda.device(x.device):
         _lib.check(
             lib.gkn_shard_reduce_update(
-                ctypes.cast(pa, c_void_p), ctypes.cast(xa, c_void_p), world, _p(x, f32, "x"),
+                ctypes.cast(pa, c_void_p), ctypes.cast(xa, c_void_p), int(mc_partial), int(mc_xout),
+                world, _p(x, f32, "x"),
                 _p(inv_cnt, f32, "inv_cnt"), _p(B3, f32, "B3"), _p(root, f32, "root"),
                 _p(bias, f32, "bias"), int(n0), int(n1), N, W, int(bool(relu)), _stream()),
             "gkn_shard_reduce_update",

@@ -228,8 +228,10 @@ def _node_shard_setup(shard: SourceShard, net, W: int):
     return hs, w3r, B3, msg
 
 
-# The exchange of the node-first sharding.  "peer" (default when torch's symmetric memory can be set
-# up for the group): partial sums live in symmetric-memory buffers and ONE kernel per rank reduces
+# The exchange of the node-first sharding (GKN_SHARD_EXCHANGE).  "multimem" (default): as "peer" below
+# but through the NVLS multicast addresses of the symmetric buffers - the NVSwitch adds the ranks'
+# rows (multimem.ld_reduce) and replicates the new rows (multimem.st); falls back to "peer" when the
+# fabric offers no multicast.  "peer" (when torch's symmetric memory can be set up for the group): partial sums live in symmetric-memory buffers and ONE kernel per rank reduces
 # the rows of its node range straight out of every peer's buffer, applies the node update and
 # stores the new rows into every peer's x' buffer (gkn_shard_reduce_update) - reduce-scatter,
 # compute and all-gather fused over NVLink.  "nccl": ncclAllReduce of the partial sums, then the
@@ -261,6 +263,13 @@ class PeerExchange:
         self.n0, self.n1 = min(N, self.rank * rows), min(N, (self.rank + 1) * rows)
         self.part_ptrs = list(self.h_part.buffer_ptrs)
         self.x_ptrs = [list(h.buffer_ptrs) for h in self.h_x]
+        # NVLS: multicast addresses (0 when the fabric offers none).  GKN_SHARD_EXCHANGE=peer keeps
+        # the explicit per-peer loads / stores
+        use_mc = _os.environ.get("GKN_SHARD_EXCHANGE", "multimem") == "multimem"
+        self.mc_part = int(getattr(self.h_part, "multicast_ptr", 0) or 0) if use_mc else 0
+        self.mc_x = [int(getattr(h, "multicast_ptr", 0) or 0) if use_mc else 0 for h in self.h_x]
+        if not (self.mc_part and all(self.mc_x)):
+            self.mc_part, self.mc_x = 0, [0, 0]
 
     def barrier(self):
         self.h_part.barrier()
@@ -269,7 +278,7 @@ class PeerExchange:
 def peer_exchange(N: int, W: int, device, group):
     """The cached PeerExchange of (N, W, group), or None when symmetric memory is unavailable (then
     the NCCL all-reduce is used).  Collective: every rank of the group must call it."""
-    if _os.environ.get("GKN_SHARD_EXCHANGE", "peer") != "peer":
+    if _os.environ.get("GKN_SHARD_EXCHANGE", "multimem") not in ("peer", "multimem"):
         return None
     key = (N, W, str(device), id(group))
     if key not in _PEER_CACHE:
@@ -288,8 +297,12 @@ def peer_exchange(N: int, W: int, device, group):
 def exchange_in_use() -> str:
     """Which exchange the last sharded node-first forward used on this rank."""
     live = [v for v in _PEER_CACHE.values() if v is not None]
-    return ("fused peer-memory kernel (gkn_shard_reduce_update over symmetric memory)" if live
-            else "ncclAllReduce of the partial sums + replicated node update")
+    if not live:
+        return "ncclAllReduce of the partial sums + replicated node update"
+    if live[0].mc_part:
+        return ("fused kernel over NVLS multicast (gkn_shard_reduce_update: multimem.ld_reduce / "
+                "multimem.st on symmetric memory)")
+    return "fused peer-memory kernel (gkn_shard_reduce_update over symmetric memory)"
 
 
 @torch.no_grad()
@@ -316,7 +329,8 @@ def sharded_stack_forward_node(x0, shard: SourceShard, net, root1, bias1, root2,
             continue
         px.barrier()                 # every rank's partial sums are in place
         ops.shard_reduce_update(px.part_ptrs, px.x_ptrs[a & 1], x, shard.inv_cnt, B3,
-                                roots[c].contiguous(), biases[c].contiguous(), px.n0, px.n1, relu)
+                                roots[c].contiguous(), biases[c].contiguous(), px.n0, px.n1, relu,
+                                mc_partial=px.mc_part, mc_xout=px.mc_x[a & 1])
         px.barrier()                 # every row of x' has landed everywhere
         x = px.xbuf[a & 1]
     return x.clone() if px is not None else x

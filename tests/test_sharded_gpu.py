@@ -140,12 +140,15 @@ def _worker(rank, world, port, out, K=128, exchange="peer"):
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 @pytest.mark.parametrize("K,tol,exchange", [(128, 1e-6, "nccl"), (256, NODE_SHARD_TOL, "nccl"),
-                                            (256, NODE_SHARD_TOL, "peer")],
-                         ids=["edge_first", "node_first_nccl", "node_first_peer_memory"])
+                                            (256, NODE_SHARD_TOL, "peer"),
+                                            (256, NODE_SHARD_TOL, "multimem")],
+                         ids=["edge_first", "node_first_nccl", "node_first_peer_memory",
+                              "node_first_nvls_multimem"])
 def test_two_process_nccl_run_matches_single_gpu(K, tol, exchange):
     """K = 128: destination-range shards of the edge-first kernels (all-gather); K = 256: source-
     range shards of the node-first kernels - exchange by NCCL all-reduce of the partial sums, or by
-    the fused peer-memory kernel (symmetric memory over NVLink)."""
+    the fused kernel over symmetric memory (explicit peer loads / stores, or NVLS multicast:
+    multimem.ld_reduce and multimem.st through the NVSwitch)."""
     import torch.multiprocessing as mp
 
     with socket.socket() as s:
