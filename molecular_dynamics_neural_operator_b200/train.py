@@ -172,6 +172,21 @@ def shard_frames(num_frames: int, rank: int, world: int) -> range:
     return range(rank, num_frames, world)
 
 
+def shard_frames_by_edges(edge_counts, world: int) -> list[list[int]]:
+    """Frames of one global batch dealt to ``world`` ranks so that the per-rank EDGE totals are as
+    equal as a greedy longest-first assignment makes them (the cost of a frame is linear in its
+    edge count; PyG's DataParallel balances by node count).  Returns the frame indices per rank,
+    each list in increasing order.  Deterministic: ties go to the lower frame index / rank."""
+    order = sorted(range(len(edge_counts)), key=lambda i: (-int(edge_counts[i]), i))
+    loads = [0] * world
+    out: list[list[int]] = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda k: (loads[k], len(out[k]), k))
+        out[r].append(i)
+        loads[r] += int(edge_counts[i])
+    return [sorted(v) for v in out]
+
+
 def broadcast_parameters(model: torch.nn.Module, src: int = 0, process_group=None) -> None:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1:
         for p in model.parameters():

@@ -598,3 +598,50 @@ def test_fused_backward_emulated_execution_matches_dense_products():
     emu_node_du_mn(hs, gs, lay, 0, N, dut)
     assert fro(dx_part.sum(0), dut.float() @ w3k.float().t()) < 1e-6
     assert fro(dwT, dut.float().t() @ xb.float()) < 1e-6
+
+
+# ---- randomised schedules: no deadlock, same numbers ----------------------------------------------
+def test_random_fused_schedules_execute_without_deadlock():
+    """Seeded sweep over graph size, grid size, ring and slack for both fused kernels: the in-order
+    multi-CTA emulator must drain every list (it raises on a wait that can never be satisfied)
+    and reproduce the unfused numbers."""
+    rng = np.random.default_rng(7)
+    for trial in range(6):
+        N = int(rng.integers(3, 420))
+        E = int(rng.integers(N, 12 * N))
+        grid = int(rng.choice([1, 2, 5, 13, 148]))
+        K, W = 256, 64
+        plan = cpu_plan(random_graph(N, E, seed=trial), N)
+        lay = ops.node_layout(plan)
+        g = torch.Generator().manual_seed(trial)
+        hs = torch.randn(lay.e_pad, K, generator=g).bfloat16()
+        xb = torch.randn(N, W, generator=g).bfloat16()
+        # forward
+        ring = int(rng.choice([0, 3, 4]))
+        slack = float(rng.choice([0.25, 1.0]))
+        w3r = (torch.randn(W, W * K, generator=g) / 8).bfloat16()
+        sched = ops.fused_fwd_schedule(lay, W, K, ring=ring, slack=slack, grid=grid)
+        u = torch.zeros(sched.u_rows, W * K, dtype=torch.bfloat16)
+        msg = torch.zeros(lay.e_pad, W)
+        emu_node_fused_fwd(xb, w3r, hs, u, sched, torch.zeros(sched.num_flags, dtype=torch.int32),
+                           msg, N, lay.e_pad, K, W, seed=trial)
+        ref = torch.zeros_like(msg)
+        emu_node_msg(hs, (xb.float() @ w3r.float()).bfloat16().view(N, W, K), lay, 0, lay.num_units,
+                     0, ref)
+        assert torch.equal(msg, ref), (trial, "forward")
+        # backward
+        bring = int(rng.choice([3, 4]))
+        items, nflags = ops.fused_bwd_items(N, K, W, grid, bring, 1.0)
+        bs = ops.FusedSchedule(torch.from_numpy(items), len(items), nflags, bring * 128, bring, grid)
+        gs = torch.randn(lay.e_pad, W, generator=g).bfloat16()
+        gs[lay.dst_pad < 0] = 0
+        w3k = (torch.randn(W, K * W, generator=g) / 8).bfloat16()
+        parts = min(grid, W * K // 128)
+        dx_part = torch.zeros(grid, N, W)
+        dwT = torch.zeros(K * W, W)
+        emu_node_fused_bwd(hs, gs, lay, xb, w3k, torch.zeros(bring * 128, K * W, dtype=torch.bfloat16),
+                           bs, torch.zeros(nflags, dtype=torch.int32), dx_part, dwT, False, seed=trial)
+        dut = torch.zeros(N, K * W, dtype=torch.bfloat16)
+        emu_node_du_mn(hs, gs, lay, 0, N, dut)
+        assert fro(dx_part[:parts].sum(0), dut.float() @ w3k.float().t()) < 1e-6, (trial, "dx")
+        assert fro(dwT, dut.float().t() @ xb.float()) < 1e-6, (trial, "dw")

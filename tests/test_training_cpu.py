@@ -9,7 +9,8 @@ import pytest
 import torch
 
 from molecular_dynamics_neural_operator_b200.train import (Trainer, fit, load_checkpoint,
-                                                            train_epoch, validate)
+                                                            shard_frames_by_edges, train_epoch,
+                                                            validate)
 
 
 class Tiny(torch.nn.Module):
@@ -104,3 +105,19 @@ def test_reducer_rejects_second_backward_without_finish():
     tr.loss_fn(model(b).view(4, -1), b.y.view(4, -1)).backward()
     with pytest.raises(RuntimeError, match="second backward"):
         tr.loss_fn(model(b).view(4, -1), b.y.view(4, -1)).backward()
+
+
+def test_frames_are_dealt_by_edge_count():
+    counts = [60000, 100, 59000, 61000, 200, 58000, 300, 60500]
+    parts = shard_frames_by_edges(counts, 4)
+    assert sorted(i for p in parts for i in p) == list(range(8))      # every frame exactly once
+    loads = [sum(counts[i] for i in p) for p in parts]
+    assert max(loads) - min(loads) <= max(counts)                     # longest-first bound
+    # round-robin (frames r, r + world, ...) would put 60000 + 200 next to 59000 + 300 ... and
+    # 61000 + 60500 on one rank; by edges the two extra large frames are the only imbalance left
+    even = [57000, 61000, 59500, 60500, 58000, 62000, 60000, 59000]
+    loads = [sum(even[i] for i in p) for p in shard_frames_by_edges(even, 4)]
+    assert max(loads) - min(loads) <= 1000 and all(len(p) == 2 for p in shard_frames_by_edges(even, 4))
+    assert shard_frames_by_edges(counts, 4) == parts                  # deterministic
+    assert shard_frames_by_edges([5, 5, 5, 5], 2) == [[0, 2], [1, 3]]
+    assert shard_frames_by_edges([], 3) == [[], [], []]
