@@ -101,7 +101,9 @@ int gkn_contract_dx_f32(const float* h, const float* w3, const int32_t* dst, con
  * FLOP.  Edge buffers use the "padded source-sorted" layout: the edges of source node n occupy
  * rows [pptr[n], pptr[n]+deg[n]), groups padded to a multiple of 16 rows (E_pad rows in total).
  * `units`: int32 [U,4] = (source node, first row, rows to store (<= 128), 0), one per 128-row
- * tile of a group, ordered by node.  W = 64, K % 256 == 0.  Node-indexed operands may be passed in
+ * tile of a group, ordered by node.  K % 256 == 0; W in {32, 64, 128} for msg, gather and the
+ * *_mn forms of du / dh, W = 64 for gkn_node_du_bf16 / gkn_node_dh_bf16 and the transposed gather
+ * output.  Node-indexed operands may be passed in
  * chunks of nodes [node_base, node_base + chunk_nodes) covering the units of the launch.
  *   msg : msg[q,o] = sum_k hs[q,k] * u[src q][o,k]          hs bf16 [E_pad,K], u bf16 [chunk,W,K],
  *         msg float32 [E_pad,W] (forward message, before the mean)
@@ -113,8 +115,9 @@ int gkn_contract_dx_f32(const float* h, const float* w3, const int32_t* dst, con
  *         `units` table is int32 [U*(K/256),4] = (source node, first row, rows, 256-column chunk)
  *         in (node, chunk, tile) order, so the tiles of a group that share a chunk of the node's U
  *         are adjacent (L2 reuse); unit_begin/unit_end count tiles as in msg.
- *   gather: gs[q,:] = bf16(g[idx[q],:]) (zero where idx[q] < 0), gsT its transpose; either output
- *         may be NULL. */
+ *   gather: gs[q,:W] = bf16(g[idx[q],:]) (zero where idx[q] < 0), gsT its transpose; either output
+ *         may be NULL.  gs rows hold max(W,64) values (one 128-byte row at least: at W = 32 the
+ *         upper 32 columns are written as zeros); the *_mn kernels read gs with that row length. */
 int gkn_node_msg_bf16(const void* hs_bf16, const void* u_bf16, const int32_t* units,
                       int64_t unit_begin, int64_t unit_end, int64_t E_pad, int64_t chunk_nodes,
                       int32_t node_base, float* msg, int32_t K, int32_t W, void* stream);
@@ -126,8 +129,10 @@ int gkn_node_dh_bf16(const void* gs_bf16, const void* ut_bf16, const int32_t* un
                      int32_t node_base, int32_t A, void* dh_bf16, int32_t K, int32_t W,
                      void* stream);
 /* The same two products with operands read in place as MN-major tensor-core operands: du from
- * hs [E_pad,K] and gs [E_pad,W] (no transposed copies), dh from u [A,chunk,W,K] (the forward's
- * [o,k]-ordered U, so it can be saved instead of recomputed in [k,o] order). */
+ * hs [E_pad,K] and gs [E_pad,max(W,64)] (no transposed copies; dut [nodes,K,W]), dh from
+ * gs [A,E_pad,max(W,64)] and u [A,chunk,W,K] (the forward's [o,k]-ordered U, so it can be saved
+ * instead of recomputed in [k,o] order).  W in {32, 64, 128}: this is the backward of
+ * graph_kernel.py:200-202 for every width the reference's configurations use. */
 int gkn_node_du_mn_bf16(const void* hs_bf16, const void* gs_bf16, const int32_t* pptr,
                         int64_t node_begin, int64_t node_end, int64_t E_pad, void* dut_bf16,
                         int32_t K, int32_t W, void* stream);

@@ -45,7 +45,7 @@ constexpr int kUmmaK = 16;
 constexpr int kEpiGroups = 1;
 constexpr int kThreads = (2 + 4 * kEpiGroups) * 32;
 constexpr int kABytes = kM * kKB * 2;  // 16 KB
-constexpr int kW = 64;       // node feature width of the backward kernels (MODE_MSG: 32/64/128)
+constexpr int kW = 64;       // node feature width of the K-major backward kernels (MODE_DU / MODE_DH)
 
 // *_MN: the same products with operands read straight from their natural row-major buffers as
 // MN-major UMMA operands (no transposed copies of h / gm, no [k,o]-ordered copy of U):
@@ -57,9 +57,15 @@ __host__ __device__ constexpr bool mode_is_dh(int m) { return m == MODE_DH || m 
 __host__ __device__ constexpr bool mode_is_du(int m) { return m == MODE_DU || m == MODE_DU_MN; }
 constexpr int kMnBlockBytes = 64 * kKB * 2;  // one MN-major TMA box: 64 K-rows x 64 MN elements
 
+// Row length of the padded-order gradient buffer gs: 128-byte rows at least, so that one row is a
+// whole swizzle row of an MN-major box.  At w = 32 the upper 32 columns are zeros (written by
+// gkn_node_gather_bf16); the dU product then runs 64 accumulator columns wide and stores 32.
+__host__ __device__ constexpr int gs_width(int W) { return W < 64 ? 64 : W; }
+
 template <int MODE, int W>
 struct NCfg {
-    static constexpr int kBN = mode_is_dh(MODE) ? 256 : W;      // accumulator columns
+    // accumulator columns
+    static constexpr int kBN = mode_is_dh(MODE) ? 256 : (MODE == MODE_DU_MN ? gs_width(W) : W);
     static constexpr int kBBytes = kBN * kKB * 2;               // 4 .. 32 KB
     static constexpr int kStageBytes = kABytes + kBBytes;       // 20 .. 48 KB
     static constexpr int kStages = 192 * 1024 / kStageBytes > 8 ? 8 : 192 * 1024 / kStageBytes;
@@ -69,6 +75,13 @@ struct NCfg {
     static constexpr int kABoxes = kAMn ? kM / 64 : 1;          // TMA boxes per k-block
     static constexpr int kBBoxes = kBMn ? kBN / 64 : 1;
     static constexpr int kTmemCols = kAcc * kBN;                // 512 / 256
+    // MODE_DH_MN: reduction = the w output channels of every application, in k-blocks of 64 (two
+    // per application at w = 128; at w = 32 one k-block of two UMMA steps whose B boxes are 32 rows)
+    static constexpr int kKbPerApp = MODE == MODE_DH_MN && W > 64 ? W / 64 : 1;
+    static constexpr int kFullSteps = MODE == MODE_DH_MN && W < 64 ? W / kUmmaK : kKB / kUmmaK;
+    static constexpr int kBBoxRows = MODE == MODE_DH_MN && W < 64 ? W : 64;
+    static constexpr int kTxBytes =
+        kBMn ? kABytes + kBBoxes * kBBoxRows * 128 : kStageBytes;  // bytes TMA delivers per stage
     static constexpr int kSmemBytes =
         kStages * kStageBytes + 1024 + 256 + kEpiGroups * 4 * 4096 /*output staging*/;
     static_assert(kAcc % kEpiGroups == 0, "accumulator stages are owned by epilogue groups");
@@ -112,9 +125,9 @@ __device__ __forceinline__ Unit decode_unit(const NodeParams& p, int64_t v) {
         const int4 t = __ldg(p.units + v);  // (group, first row, rows, column chunk)
         u.group = t.x; u.row0 = t.y; u.rows = t.z; u.chunk = t.w;
         u.a_c0 = 0; u.a_c1 = t.y; u.da_c0 = 0; u.da_c1 = p.a_rows_per_app;
-        u.b_c0 = u.chunk * 256; u.b_c1 = (t.x - p.node_base) * kW;
+        u.b_c0 = u.chunk * 256; u.b_c1 = (t.x - p.node_base) * W;
         u.db_c0 = 0; u.db_c1 = p.b_rows_per_app;
-        u.nkb = p.A; u.last_steps = kKB / kUmmaK;
+        u.nkb = p.A * NCfg<MODE, W>::kKbPerApp; u.last_steps = NCfg<MODE, W>::kFullSteps;
     } else if constexpr (MODE == MODE_DU_MN) {
         const int32_t chunks = p.K / kM;
         const int32_t g = p.node_base + int32_t(v / chunks);
@@ -170,7 +183,8 @@ template <int MODE, int W>
 __global__ void __launch_bounds__(kThreads, 1)
 node_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                  const __grid_constant__ CUtensorMap tmap_b, const NodeParams p) {
-    static_assert(MODE == MODE_MSG || W == kW, "the backward kernels serve w = 64");
+    static_assert(MODE == MODE_MSG || MODE == MODE_DU_MN || MODE == MODE_DH_MN || W == kW,
+                  "the K-major backward kernels serve w = 64");
     using C = NCfg<MODE, W>;
     constexpr int kStages = C::kStages;
     constexpr int kStageBytes = C::kStageBytes;
@@ -238,22 +252,25 @@ node_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 for (int kb = 0; kb < u.nkb; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sa = smem_base + stage * kStageBytes;
-                    mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
+                    mbar_arrive_expect_tx(full_bar(stage), C::kTxBytes);
+                    // k-block -> (application / plain index, 64-channel half inside it)
+                    const int ka = kb / C::kKbPerApp, half = (kb % C::kKbPerApp) * kKB;
+                    const int a_c0 = u.a_c0 + ka * u.da_c0 + half, a_c1 = u.a_c1 + ka * u.da_c1;
+                    const int b_c0 = u.b_c0 + ka * u.db_c0, b_c1 = u.b_c1 + ka * u.db_c1 + half;
 #pragma unroll
                     for (int j = 0; j < C::kABoxes; ++j) {
                         if (p.hints & 1) {
                             tma_load_2d_hint(sa + j * kMnBlockBytes, &tmap_a, full_bar(stage),
-                                             u.a_c0 + kb * u.da_c0 + j * 64, u.a_c1 + kb * u.da_c1,
-                                             pol_stream);
+                                             a_c0 + j * 64, a_c1, pol_stream);
                         } else {
                             tma_load_2d(sa + j * kMnBlockBytes, &tmap_a, full_bar(stage),
-                                        u.a_c0 + kb * u.da_c0 + j * 64, u.a_c1 + kb * u.da_c1);
+                                        a_c0 + j * 64, a_c1);
                         }
                     }
 #pragma unroll
                     for (int j = 0; j < C::kBBoxes; ++j) {
                         tma_load_2d(sa + kABytes + j * kMnBlockBytes, &tmap_b, full_bar(stage),
-                                    u.b_c0 + kb * u.db_c0 + j * 64, u.b_c1 + kb * u.db_c1);
+                                    b_c0 + j * 64, b_c1);
                     }
                     if (++stage == kStages) {
                         stage = 0;
@@ -291,7 +308,7 @@ node_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const uint32_t sa = smem_base + stage * kStageBytes;
                     const uint64_t adesc = umma_smem_desc(sa, a_lbo, 1024, kSwizzle128B);
                     const uint64_t bdesc = umma_smem_desc(sa + kABytes, b_lbo, 1024, kSwizzle128B);
-                    const int steps = kb == u.nkb - 1 ? u.last_steps : kKB / kUmmaK;
+                    const int steps = kb == u.nkb - 1 ? u.last_steps : C::kFullSteps;
                     for (int k = 0; k < steps; ++k) {
                         umma_bf16_ss(tmem_d, adesc + a_step * uint64_t(k), bdesc + b_step * uint64_t(k),
                                      idesc, (kb | k) != 0 ? 1u : 0u);
@@ -322,9 +339,9 @@ node_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 if (mode_is_du(MODE) && grp == 0) {
                     uint4* dst = reinterpret_cast<uint4*>(
                         static_cast<__nv_bfloat16*>(p.out) +
-                        (int64_t(u.group - p.node_base) * p.K + u.chunk * kM + row) * kW);
+                        (int64_t(u.group - p.node_base) * p.K + u.chunk * kM + row) * W);
 #pragma unroll
-                    for (int j = 0; j < kW / 8; ++j) dst[j] = make_uint4(0u, 0u, 0u, 0u);
+                    for (int j = 0; j < W / 8; ++j) dst[j] = make_uint4(0u, 0u, 0u, 0u);
                 }
                 continue;
             }
@@ -354,8 +371,8 @@ node_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             } else {
                 gbase = reinterpret_cast<uint8_t*>(
                     static_cast<__nv_bfloat16*>(p.out) +
-                    (int64_t(u.group - p.node_base) * p.K + u.chunk * kM + q * 32) * kW);
-                pitch = kW * 2;
+                    (int64_t(u.group - p.node_base) * p.K + u.chunk * kM + q * 32) * W);
+                pitch = W * 2;
             }
             constexpr int kColsPerPiece = MODE == MODE_MSG ? 32 : 64;  // 128 bytes of output
 #pragma unroll
@@ -388,7 +405,8 @@ node_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 for (int j = 0; j < 8; ++j) {
                     const int r = j * 4 + (lane >> 3), c = lane & 7;
                     const uint4 t = lds128(stage_smem + r * 128 + ((c ^ (r & 7)) << 4));
-                    if (r < rows_here) {
+                    // (MODE_DU_MN at w = 32: the accumulator is 64 columns wide, 32 are output)
+                    if (r < rows_here && (!mode_is_du(MODE) || W >= 64 || c * 8 < W)) {
                         uint4* gp = reinterpret_cast<uint4*>(gbase + r * pitch + piece * 128 + c * 16);
                         if (p.hints & 2) {
                             __stcs(gp, t);
@@ -465,44 +483,51 @@ int check_common(const char* name, int32_t K, int32_t W, int64_t E_pad, bool any
     return 0;
 }
 
-// Gs[q, :] = bf16(g[idx[q], :]) (zero row where idx[q] < 0) and its transpose GsT[:, q]
+// Gs[q, :] = bf16(g[idx[q], :]) (zero row where idx[q] < 0; rows of gs_width(W) values, columns
+// >= W zero) and, at w = 64, its transpose GsT[:, q]
+template <int W>
 __global__ void __launch_bounds__(256)
 node_gather_kernel(const float* __restrict__ g, const int32_t* __restrict__ idx, int64_t E_pad,
                    __nv_bfloat16* __restrict__ gs, __nv_bfloat16* __restrict__ gsT) {
-    __shared__ __nv_bfloat16 tile[64][kW + 8];
+    constexpr int Wp = gs_width(W);
+    constexpr int kTpr = Wp / 4;          // threads per row (4 columns each)
+    constexpr int kRpp = 256 / kTpr;      // rows per pass
+    __shared__ __nv_bfloat16 tile[W == kW ? 64 : 1][Wp + 8];
     const int t = threadIdx.x;
     for (int64_t q0 = int64_t(blockIdx.x) * 64; q0 < E_pad; q0 += int64_t(gridDim.x) * 64) {
-        __syncthreads();
+        if constexpr (W == kW) __syncthreads();
 #pragma unroll
-        for (int pass = 0; pass < 4; ++pass) {
-            const int r = pass * 16 + (t >> 4);
-            const int c = (t & 15) * 4;
+        for (int pass = 0; pass < 64 / kRpp; ++pass) {
+            const int r = pass * kRpp + t / kTpr;
+            const int c = (t % kTpr) * 4;
             const int64_t qq = q0 + r;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (qq < E_pad) {
+            if (qq < E_pad && c < W) {
                 const int32_t n = __ldg(idx + qq);
-                if (n >= 0) v = __ldg(reinterpret_cast<const float4*>(g + int64_t(n) * kW + c));
+                if (n >= 0) v = __ldg(reinterpret_cast<const float4*>(g + int64_t(n) * W + c));
             }
             const uint2 pk = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
-            *reinterpret_cast<uint2*>(&tile[r][c]) = pk;
-            if (gs != nullptr && qq < E_pad) *reinterpret_cast<uint2*>(gs + qq * kW + c) = pk;
+            if constexpr (W == kW) *reinterpret_cast<uint2*>(&tile[r][c]) = pk;
+            if (gs != nullptr && qq < E_pad) *reinterpret_cast<uint2*>(gs + qq * Wp + c) = pk;
         }
-        __syncthreads();
-        if (gsT != nullptr) {
-            // thread -> channel o = t / 4, 16 consecutive positions (E_pad is a multiple of 16)
-            const int o = t >> 2;
-            const int qb = (t & 3) * 16;
-            if (q0 + qb < E_pad) {
-                uint32_t w[8];
+        if constexpr (W == kW) {
+            __syncthreads();
+            if (gsT != nullptr) {
+                // thread -> channel o = t / 4, 16 consecutive positions (E_pad is a multiple of 16)
+                const int o = t >> 2;
+                const int qb = (t & 3) * 16;
+                if (q0 + qb < E_pad) {
+                    uint32_t w[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint16_t lo = *reinterpret_cast<const uint16_t*>(&tile[qb + 2 * j][o]);
-                    const uint16_t hi = *reinterpret_cast<const uint16_t*>(&tile[qb + 2 * j + 1][o]);
-                    w[j] = uint32_t(lo) | (uint32_t(hi) << 16);
+                    for (int j = 0; j < 8; ++j) {
+                        const uint16_t lo = *reinterpret_cast<const uint16_t*>(&tile[qb + 2 * j][o]);
+                        const uint16_t hi = *reinterpret_cast<const uint16_t*>(&tile[qb + 2 * j + 1][o]);
+                        w[j] = uint32_t(lo) | (uint32_t(hi) << 16);
+                    }
+                    uint4* dst = reinterpret_cast<uint4*>(gsT + int64_t(o) * E_pad + q0 + qb);
+                    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
                 }
-                uint4* dst = reinterpret_cast<uint4*>(gsT + int64_t(o) * E_pad + q0 + qb);
-                dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
             }
         }
     }
@@ -614,13 +639,13 @@ extern "C" int gkn_node_du_mn_bf16(const void* hs_bf16, const void* gs_bf16, con
     if (hs_bf16 == nullptr || gs_bf16 == nullptr || pptr == nullptr || dut_bf16 == nullptr) {
         return set_error("gkn_node_du_mn_bf16: NULL pointer argument");
     }
-    int rc = check_common("gkn_node_du_mn_bf16", K, W, E_pad);
+    int rc = check_common("gkn_node_du_mn_bf16", K, W, E_pad, true);
     if (rc) return rc;
     if (E_pad == 0) return set_error("gkn_node_du_mn_bf16: empty edge set");
     CUtensorMap ta, tb;
     rc = make_tensor_map_bf16_2d(&ta, hs_bf16, uint64_t(K), uint64_t(E_pad), 64, kKB);
     if (rc) return rc;
-    rc = make_tensor_map_bf16_2d(&tb, gs_bf16, uint64_t(kW), uint64_t(E_pad), 64, kKB);
+    rc = make_tensor_map_bf16_2d(&tb, gs_bf16, uint64_t(gs_width(W)), uint64_t(E_pad), 64, kKB);
     if (rc) return rc;
     NodeParams p{};
     p.pptr = pptr;
@@ -629,7 +654,12 @@ extern "C" int gkn_node_du_mn_bf16(const void* hs_bf16, const void* gs_bf16, con
     p.v_end = (node_end - node_begin) * (K / kM);
     p.K = K;
     p.node_base = int32_t(node_begin);
-    return launch_node_gemm<MODE_DU_MN>(ta, tb, p, static_cast<cudaStream_t>(stream));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (W) {
+        case 32: return launch_node_gemm<MODE_DU_MN, 32>(ta, tb, p, st);
+        case 64: return launch_node_gemm<MODE_DU_MN, 64>(ta, tb, p, st);
+        default: return launch_node_gemm<MODE_DU_MN, 128>(ta, tb, p, st);
+    }
 }
 
 extern "C" int gkn_node_dh_mn_bf16(const void* gs_bf16, const void* u_bf16, const int32_t* units,
@@ -641,17 +671,17 @@ extern "C" int gkn_node_dh_mn_bf16(const void* gs_bf16, const void* u_bf16, cons
     if (gs_bf16 == nullptr || u_bf16 == nullptr || units == nullptr || dh_bf16 == nullptr) {
         return set_error("gkn_node_dh_mn_bf16: NULL pointer argument");
     }
-    int rc = check_common("gkn_node_dh_mn_bf16", K, W, E_pad);
+    int rc = check_common("gkn_node_dh_mn_bf16", K, W, E_pad, true);
     if (rc) return rc;
     if (A <= 0) return set_error("gkn_node_dh_mn_bf16: A must be positive");
-    const int64_t a_rows = int64_t(A) * E_pad, b_rows = int64_t(A) * chunk_nodes * kW;
+    const int64_t a_rows = int64_t(A) * E_pad, b_rows = int64_t(A) * chunk_nodes * W;
     if (chunk_nodes <= 0 || a_rows >= (int64_t(1) << 31) || b_rows >= (int64_t(1) << 31)) {
         return set_error("gkn_node_dh_mn_bf16: operand too large for one launch (use smaller node chunks)");
     }
     CUtensorMap ta, tb;
-    rc = make_tensor_map_bf16_2d(&ta, gs_bf16, uint64_t(kW), uint64_t(a_rows), kKB, kM);
+    rc = make_tensor_map_bf16_2d(&ta, gs_bf16, uint64_t(gs_width(W)), uint64_t(a_rows), kKB, kM);
     if (rc) return rc;
-    rc = make_tensor_map_bf16_2d(&tb, u_bf16, uint64_t(K), uint64_t(b_rows), 64, kKB);
+    rc = make_tensor_map_bf16_2d(&tb, u_bf16, uint64_t(K), uint64_t(b_rows), 64, W < 64 ? W : kKB);
     if (rc) return rc;
     NodeParams p{};
     p.units = reinterpret_cast<const int4*>(units);
@@ -661,9 +691,14 @@ extern "C" int gkn_node_dh_mn_bf16(const void* gs_bf16, const void* u_bf16, cons
     p.K = K;
     p.A = A;
     p.a_rows_per_app = int32_t(E_pad);
-    p.b_rows_per_app = int32_t(chunk_nodes * kW);
+    p.b_rows_per_app = int32_t(chunk_nodes * W);
     p.node_base = node_base;
-    return launch_node_gemm<MODE_DH_MN>(ta, tb, p, static_cast<cudaStream_t>(stream));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (W) {
+        case 32: return launch_node_gemm<MODE_DH_MN, 32>(ta, tb, p, st);
+        case 64: return launch_node_gemm<MODE_DH_MN, 64>(ta, tb, p, st);
+        default: return launch_node_gemm<MODE_DH_MN, 128>(ta, tb, p, st);
+    }
 }
 
 extern "C" int gkn_node_gather_bf16(const float* g, const int32_t* idx, int64_t E_pad,
@@ -673,15 +708,25 @@ extern "C" int gkn_node_gather_bf16(const float* g, const int32_t* idx, int64_t 
     if (g == nullptr || idx == nullptr || (gs_bf16 == nullptr && gsT_bf16 == nullptr)) {
         return set_error("gkn_node_gather_bf16: NULL pointer argument");
     }
-    int rc = check_common("gkn_node_gather_bf16", 256, W, E_pad);
+    int rc = check_common("gkn_node_gather_bf16", 256, W, E_pad, true);
     if (rc) return rc;
+    if (W != kW && gsT_bf16 != nullptr) {
+        return set_error("gkn_node_gather_bf16: the transposed copy exists at w = 64 only");
+    }
     int sms = 0;
     rc = device_sm_count(&sms);
     if (rc) return rc;
     int64_t blocks = (E_pad + 63) / 64;
     if (blocks > int64_t(sms) * 8) blocks = int64_t(sms) * 8;
-    node_gather_kernel<<<dim3(unsigned(blocks)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        g, idx, E_pad, static_cast<__nv_bfloat16*>(gs_bf16), static_cast<__nv_bfloat16*>(gsT_bf16));
+    const dim3 grid{unsigned(blocks)};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    auto* gs = static_cast<__nv_bfloat16*>(gs_bf16);
+    auto* gsT = static_cast<__nv_bfloat16*>(gsT_bf16);
+    switch (W) {
+        case 32: node_gather_kernel<32><<<grid, 256, 0, st>>>(g, idx, E_pad, gs, gsT); break;
+        case 64: node_gather_kernel<64><<<grid, 256, 0, st>>>(g, idx, E_pad, gs, gsT); break;
+        default: node_gather_kernel<128><<<grid, 256, 0, st>>>(g, idx, E_pad, gs, gsT); break;
+    }
     GKN_CHECK_LAUNCH("node_gather launch");
     return 0;
 }

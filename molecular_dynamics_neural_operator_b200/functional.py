@@ -2,7 +2,7 @@
 the whole stack of NNConv applications that share it (reference graph_kernel.py:271-273, :299-302).
 
 Two implementations of the same function sit behind ``gkn_stack``:
-``_GKNStackNode`` (default in bf16 mode at w = 64, and for forward-only calls at w = 32/128) contracts
+``_GKNStackNode`` (default in bf16 mode at w = 32, 64 and 128) contracts
 W3 with the NODE features first and does the per-edge work as tcgen05 grouped GEMMs - see the
 section "Node-first factorisation" below and DESIGN.md section 1b; ``_GKNStack`` is the edge-first
 fused contraction described next (``GKN_FACTORIZATION=edge``, fp32 mode, other shapes).
@@ -209,7 +209,7 @@ class _GKNStack(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------
-# Node-first factorisation (default in bf16 mode at w = 64): the same trilinear form, with W3
+# Node-first factorisation (default in bf16 mode): the same trilinear form, with W3
 # contracted against the NODE features first (csrc/gkn_node_gemm.cu).  Every application is then
 #   U = x W3r (dense GEMM, [N, w] x [w, w*K])  ->  msg = grouped GEMM(h, U[src])  ->  node update
 # and its backward is  dU = grouped GEMM(h^T, gm)  ->  dx = dU W3^T,  dW3 += x^T dU  (dense GEMMs);
@@ -257,10 +257,10 @@ _FUSED_BWD_MIN_DEGREE = int(os.environ.get("GKN_NODE_FUSED_BWD_MIN_DEGREE", "64"
 
 
 def node_path_supported(W: int, K: int, E: int, precision: str, needs_grad: bool = True) -> bool:
-    """Training: w = 64 (the dU / dh kernels); forward only (rollout): w in {32, 64, 128}."""
+    """w in {32, 64, 128} (the K-major backward kernels of GKN_NODE_MN=0 serve w = 64 only)."""
     if precision != "bf16" or K % 256 != 0 or E <= 0:
         return False
-    return W == 64 or (not needs_grad and W in (32, 128))
+    return W == 64 or (W in (32, 128) and (NODE_MN or not needs_grad))
 
 
 def _node_chunks(N: int, per_node_bytes: int, budget: int | None = None):
@@ -373,8 +373,9 @@ class _GKNStackNode(torch.autograd.Function):
             hsT = hs.t().contiguous()  # [K, E_pad]: edges become the reduction dimension of dU
             gsT = torch.empty((W, lay.e_pad), dtype=bf, device=dev)
         elif not need_edge:
-            gs_one = torch.empty((lay.e_pad, W), dtype=bf, device=dev)
-        gs_all = torch.empty((A, lay.e_pad, W), dtype=bf, device=dev) if need_edge else None
+            gs_one = torch.empty((lay.e_pad, ops.gs_width(W)), dtype=bf, device=dev)
+        gs_all = (torch.empty((A, lay.e_pad, ops.gs_width(W)), dtype=bf, device=dev)
+                  if need_edge else None)
         # the fused kernel pays 148 dx partials (38 KB) per node and one work item per (node, 128
         # k-rows): it wins on graphs of BBA-like degree (119 edges per node: 0.80 vs 0.94 ms) and
         # loses a few per cent at ~30 edges per node (10k-atom frames: 125 vs 120 ms per step)

@@ -626,11 +626,20 @@ def node_dh(gs, ut, lay: NodeLayout, unit_begin: int, unit_end: int, node_base: 
         )
 
 
+def gs_width(W: int) -> int:
+    """Row length of the padded-order bf16 gradient buffer gs: at least one 128-byte swizzle row
+    (w = 32: 64 values, the upper half zeros - written by ``node_gather``)."""
+    return max(int(W), 64)
+
+
 def node_du_mn(hs, gs, lay: NodeLayout, node_begin: int, node_end: int, dut: torch.Tensor) -> None:
-    """node_du from the row-major hs [E_pad, K] and gs [E_pad, W] (gkn_node_du_mn_bf16)."""
+    """node_du from the row-major hs [E_pad, K] and gs [E_pad, gs_width(W)] into dut
+    [nodes, K * W] (gkn_node_du_mn_bf16; w in {32, 64, 128})."""
     lib = _lib.load()
     K = int(hs.size(1))
-    W = int(gs.size(1))
+    W = int(dut.size(1)) // K
+    if gs.size(1) != gs_width(W):
+        raise ValueError(f"gs must have {gs_width(W)} columns at w = {W}")
     with torch.cuda.device(hs.device), _timed("node_du"):
         _lib.check(
             lib.gkn_node_du_mn_bf16(_p(hs, torch.bfloat16, "hs"), _p(gs, torch.bfloat16, "gs"),
@@ -642,10 +651,13 @@ def node_du_mn(hs, gs, lay: NodeLayout, node_begin: int, node_end: int, dut: tor
 
 def node_dh_mn(gs, u, lay: NodeLayout, unit_begin: int, unit_end: int, node_base: int,
                dh: torch.Tensor) -> None:
-    """node_dh from u bf16 [A, chunk_nodes, W, K] (the forward's U) (gkn_node_dh_mn_bf16)."""
+    """node_dh from gs [A, E_pad, gs_width(W)] and u bf16 [A, chunk_nodes, W, K] (the forward's U)
+    (gkn_node_dh_mn_bf16; w in {32, 64, 128})."""
     lib = _lib.load()
-    A, W = int(gs.size(0)), int(gs.size(2))
+    A, W = int(gs.size(0)), int(u.size(2))
     K = int(dh.size(1))
+    if gs.size(2) != gs_width(W):
+        raise ValueError(f"gs must have {gs_width(W)} columns at w = {W}")
     with torch.cuda.device(gs.device), _timed("node_dh"):
         _lib.check(
             lib.gkn_node_dh_mn_bf16(_p(gs, torch.bfloat16, "gs"), _p(u, torch.bfloat16, "u"),
@@ -657,9 +669,12 @@ def node_dh_mn(gs, u, lay: NodeLayout, unit_begin: int, unit_end: int, node_base
 
 
 def node_gather(g, lay: NodeLayout, gs: torch.Tensor | None, gsT: torch.Tensor | None) -> None:
-    """gs[q, :] = bf16(g[dst_pad[q], :]) (zero in pad rows) and/or its transpose gsT [W, E_pad]."""
+    """gs[q, :W] = bf16(g[dst_pad[q], :]) (zero in pad rows and in columns >= W; gs has
+    gs_width(W) columns) and/or, at w = 64, its transpose gsT [W, E_pad]."""
     lib = _lib.load()
     W = int(g.size(1))
+    if gs is not None and gs.size(1) != gs_width(W):
+        raise ValueError(f"gs must have {gs_width(W)} columns at w = {W}")
     with torch.cuda.device(g.device):
         _lib.check(
             lib.gkn_node_gather_bf16(_p(g, torch.float32, "g"), _p(lay.dst_pad, torch.int32, "idx"),

@@ -104,18 +104,23 @@ def emu_node_dh(gs, ut, lay, u0, u1, node_base, dh):
 
 
 def emu_node_du_mn(hs, gs, lay, n0, n1, dut):
-    emu_node_du(hs.t(), gs.t(), lay, n0, n1, dut)
+    W = dut.size(1) // hs.size(1)  # gs rows are ops.gs_width(W) long, columns >= W are zeros
+    assert gs.size(1) == ops.gs_width(W)
+    emu_node_du(hs.t(), gs[:, :W].t(), lay, n0, n1, dut)
 
 
 def emu_node_dh_mn(gs, u, lay, u0, u1, node_base, dh):
-    emu_node_dh(gs, u.transpose(2, 3), lay, u0, u1, node_base, dh)
+    W = u.size(2)
+    assert gs.size(2) == ops.gs_width(W)
+    emu_node_dh(gs[:, :, :W], u.transpose(2, 3), lay, u0, u1, node_base, dh)
 
 
 def emu_node_gather(g, lay, gs, gsT):
     idx = lay.dst_pad.long()
     rows = torch.where((idx >= 0)[:, None], g[idx.clamp(min=0)], torch.zeros(1)).to(torch.bfloat16)
     if gs is not None:
-        gs.copy_(rows)
+        gs.zero_()
+        gs[:, :g.size(1)].copy_(rows)
     if gsT is not None:
         gsT.copy_(rows.t())
 
@@ -301,8 +306,7 @@ def test_padded_source_sorted_layout_invariants(N, E, isolated):
 
 
 # ---- autograd algebra -------------------------------------------------------------------------
-def _stack_case(N, E, K, depth, seed, isolated=()):
-    W = 64
+def _stack_case(N, E, K, depth, seed, isolated=(), W=64):
     ei = random_graph(N, E, seed, isolated)
     g = torch.Generator().manual_seed(seed + 1)
     net = orc.make_net_params(6, K, W, seed=seed, dtype=torch.float32)
@@ -383,6 +387,28 @@ def test_node_first_stack_matches_oracle(emulated, monkeypatch, N, E, K, depth, 
         assert fro(t[k].grad, tr[k].grad) < tol, k
 
 
+@pytest.mark.parametrize("W", [32, 128])
+@pytest.mark.parametrize("save_u", [True, False], ids=["saved_u", "recomputed_u"])
+def test_node_first_stack_at_other_widths_matches_oracle(emulated, monkeypatch, W, save_u):
+    """Training on the node-first path at w = 32 (config 1) and w = 128: the padded gs buffer
+    (ops.gs_width) and the per-width dU / dh kernels' host contract, against the fp64 oracle."""
+    monkeypatch.setattr(GF, "_MLP_BWD_CHUNK_ROWS", 64)
+    monkeypatch.setattr(GF, "_SAVE_U_BYTES", (1 << 40) if save_u else 0)
+    monkeypatch.setattr(GF, "_NODE_CHUNK_BYTES", W * 256 * 2 * 3)  # node ranges of 3 nodes
+    N, E, K, depth = 7, 260, 256, 2
+    assert GF.node_path_supported(W, K, E, "bf16")
+    ei, p, depth = _stack_case(N, E, K, depth, seed=W, W=W)
+    out, t = _run_node_stack(ei, p, depth, N, relu=False)
+    ref, tr = _run_oracle_stack(ei, p, depth, relu=False)
+    assert fro(out, ref) < 2.0 ** -5
+    gout = torch.randn(out.shape, generator=torch.Generator().manual_seed(5))
+    out.backward(gout)
+    ref.backward(gout.double())
+    for k in p:
+        tol = 2.0 ** -2 if k.startswith(("net.layers.0", "net.layers.2", "ea")) else 2.0 ** -5
+        assert fro(t[k].grad, tr[k].grad) < tol, k
+
+
 def test_node_first_stack_with_relu_matches_oracle(emulated):
     """With F.relu after every application (graph_kernel.py:299-302): outputs within the stack
     bound; gradients are compared where the bf16 and fp64 activation masks agree."""
@@ -437,9 +463,11 @@ def test_only_the_node_features_need_a_gradient(emulated):
 
 def test_node_path_selection():
     assert GF.node_path_supported(64, 1024, 10, "bf16")
-    assert not GF.node_path_supported(32, 1024, 10, "bf16")
+    assert GF.node_path_supported(32, 1024, 10, "bf16")      # config 1 trains on this path
+    assert GF.node_path_supported(128, 1024, 10, "bf16")
     assert GF.node_path_supported(32, 1024, 10, "bf16", needs_grad=False)
     assert GF.node_path_supported(128, 1024, 10, "bf16", needs_grad=False)
+    assert not GF.node_path_supported(16, 1024, 10, "bf16")
     assert not GF.node_path_supported(16, 1024, 10, "bf16", needs_grad=False)
     assert not GF.node_path_supported(64, 1024, 10, "fp32")
     assert not GF.node_path_supported(64, 1000, 10, "bf16")

@@ -12,8 +12,8 @@ import torch
 
 from tests.helpers import rel_err
 from tests.test_node_path_cpu import (_run_oracle_stack, _stack_case, cpu_plan, emu_node_dh,
-                                      emu_node_du, emu_node_gather, emu_node_msg, fro,
-                                      random_graph)
+                                      emu_node_dh_mn, emu_node_du, emu_node_du_mn,
+                                      emu_node_gather, emu_node_msg, fro, random_graph)
 
 pytestmark = pytest.mark.gpu
 
@@ -109,6 +109,66 @@ def test_grouped_gemm_kernels_match_fp32_restatement(case, K):
     assert rel_err(dh2.float(), dh.float()) <= BF16_OUT_TOL
 
 
+@pytest.mark.parametrize("case", list(_graphs()), ids=lambda c: c[0])
+@pytest.mark.parametrize("width,K", [(32, 256), (32, 1024), (128, 256), (128, 1024)])
+def test_backward_kernels_at_other_widths_match_fp32_restatement(case, width, K):
+    """gkn_node_gather_bf16 / gkn_node_du_mn_bf16 / gkn_node_dh_mn_bf16 at w = 32 (gs rows padded
+    to 64 values, dU accumulated 64 wide and stored 32 wide, two UMMA K-steps per application in
+    the dh pass) and w = 128 (two k-blocks per application in the dh pass)."""
+    import copy
+
+    from molecular_dynamics_neural_operator_b200 import ops
+
+    _, ei, N = case
+    plan = _plan_on_gpu(ei, N)
+    lay = ops.node_layout(plan)
+    cl = copy.copy(ops.node_layout(cpu_plan(ei, N)))
+    cl.dst_pad = lay.dst_pad.cpu()
+    gen = torch.Generator().manual_seed(K + N + width)
+    bf = torch.bfloat16
+    E_pad, Wp, A = lay.e_pad, ops.gs_width(width), 3
+    hs = torch.randn(E_pad, K, generator=gen).to(bf)
+    gs_in = torch.randn(A, N, width, generator=gen)
+    u = (torch.randn(A, N, width, K, generator=gen) / 8).to(bf)
+
+    gs_all = torch.full((A, E_pad, Wp), float("nan"), dtype=bf, device="cuda")
+    rgs_all = torch.empty(A, E_pad, Wp, dtype=bf)
+    for a in range(A):
+        ops.node_gather(gs_in[a].cuda(), lay, gs_all[a], None)
+        emu_node_gather(gs_in[a], cl, rgs_all[a], None)
+    assert torch.equal(gs_all.cpu(), rgs_all)
+    with pytest.raises(RuntimeError, match="w = 64 only"):
+        ops.node_gather(gs_in[0].cuda(), lay, gs_all[0],
+                        torch.empty(width, E_pad, dtype=bf, device="cuda"))
+
+    dut = torch.full((N, K * width), float("nan"), dtype=bf, device="cuda")
+    ops.node_du_mn(hs.cuda(), gs_all[0], lay, 0, N, dut)
+    rdut = torch.zeros(N, K * width, dtype=bf)
+    emu_node_du_mn(hs, rgs_all[0], cl, 0, N, rdut)
+    assert rel_err(dut.float(), rdut.float()) <= BF16_OUT_TOL
+    # node ranges give the same rows
+    parts = torch.full((N, K * width), float("nan"), dtype=bf, device="cuda")
+    for n0 in range(0, N, 17):
+        n1 = min(N, n0 + 17)
+        ops.node_du_mn(hs.cuda(), gs_all[0], lay, n0, n1, parts[n0:n1])
+    assert torch.equal(parts, dut)
+
+    dh = torch.full((E_pad, K), float("nan"), dtype=bf, device="cuda")
+    ops.node_dh_mn(gs_all, u.cuda(), lay, 0, lay.num_units, 0, dh)
+    rdh = torch.zeros(E_pad, K, dtype=bf)
+    emu_node_dh_mn(rgs_all, u, cl, 0, cl.num_units, 0, rdh)
+    assert rel_err(dh.float(), rdh.float()) <= BF16_OUT_TOL
+    pad = (lay.dst_pad < 0).cpu()
+    assert float(dh.float().cpu()[pad].abs().max() if pad.any() else 0.0) == 0.0
+    # ... and in node ranges (the last range ends at the end of the U buffer: w = 32 boxes there)
+    dh_parts = torch.full((E_pad, K), float("nan"), dtype=bf, device="cuda")
+    for n0 in range(0, N, 17):
+        n1 = min(N, n0 + 17)
+        ops.node_dh_mn(gs_all, u[:, n0:n1].contiguous().cuda(), lay, lay.unit_first[n0],
+                       lay.unit_first[n1], n0, dh_parts)
+    assert torch.equal(dh_parts, dh)
+
+
 def test_grouped_gemm_node_range_chunks_cover_the_same_result():
     from molecular_dynamics_neural_operator_b200 import ops
 
@@ -177,6 +237,40 @@ def test_node_first_stack_matches_edge_first_stack_and_oracle(monkeypatch, N, E,
     for k in p:
         # upstream of the edge MLP's own ReLUs the error is mask flips: 2^-4 on these graphs of
         # thousands of edges (tests/test_layer_gpu.py header; 2^-2 is kept for < 300 edges only)
+        tol = 2.0 ** -4 if k.startswith(("net.layers.0", "net.layers.2", "ea")) else 2.0 ** -5
+        assert fro(tn[k].grad.cpu(), tr[k].grad) < tol, k
+        assert fro(tn[k].grad.cpu(), te[k].grad.cpu()) < tol, k
+
+
+@pytest.mark.parametrize("width", [32, 128])
+@pytest.mark.parametrize("save_u", [True, False], ids=["saved_u", "recomputed_u"])
+def test_node_first_training_at_other_widths_matches_edge_first_and_oracle(monkeypatch, width, save_u):
+    """Config 1 (w = 32) and w = 128 train on the node-first path: outputs and every gradient
+    against the fp64 oracle and the edge-first stack (no activation between applications)."""
+    from molecular_dynamics_neural_operator_b200 import functional as GF
+    from molecular_dynamics_neural_operator_b200 import ops
+
+    N, E, K, depth = 120, 8000, 1024, 2
+    monkeypatch.setattr(GF, "_SAVE_U_BYTES", (1 << 40) if save_u else 0)
+    monkeypatch.setattr(GF, "_NODE_CHUNK_BYTES", width * K * 2 * 7)
+    monkeypatch.setattr(GF, "_NODE_DH_CHUNK_BYTES", 2 * depth * width * K * 2 * 5)
+    assert GF.node_path_supported(width, K, E, "bf16", needs_grad=True)
+    ei, p, depth = _stack_case(N, E, K, depth, seed=width, W=width)
+    ops.KERNEL_TIMER.enable()
+    try:
+        out_n, tn = _gpu_stack(GF._GKNStackNode, ei, p, depth, N, relu=False)
+        gout = torch.randn(out_n.shape, generator=torch.Generator().manual_seed(5))
+        out_n.backward(gout.cuda())
+        got = ops.KERNEL_TIMER.collect()
+    finally:
+        ops.KERNEL_TIMER.disable()
+    assert got["node_du"]["count"] >= 2 * depth and got["node_dh"]["count"] >= 1
+    out_e, te = _gpu_stack(GF._GKNStack, ei, p, depth, N, relu=False)
+    out_e.backward(gout.cuda())
+    ref, tr = _run_oracle_stack(ei, p, depth, relu=False)
+    ref.backward(gout.double())
+    assert fro(out_n.cpu(), ref) < 2.0 ** -5
+    for k in p:
         tol = 2.0 ** -4 if k.startswith(("net.layers.0", "net.layers.2", "ea")) else 2.0 ** -5
         assert fro(tn[k].grad.cpu(), tr[k].grad) < tol, k
         assert fro(tn[k].grad.cpu(), te[k].grad.cpu()) < tol, k
