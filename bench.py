@@ -716,7 +716,9 @@ def run_b200_arm(args, wl):
     node_bytes = {  # algorithmic bytes per launch
         "node_msg": 2.0 * E_b * K_ + 2.0 * N_b * w_ * K_ + 4.0 * E_b * w_,
         "node_du": 2.0 * E_b * K_ + 2.0 * E_b * w_ + 2.0 * N_b * K_ * w_,
-        "node_dh": 2.0 * A_ * E_b * w_ + 2.0 * A_ * N_b * K_ * w_ + 2.0 * E_b * K_,
+        # (+ one bit per element of h when the ReLU backward of layers.2 rides in its epilogue)
+        "node_dh": 2.0 * A_ * E_b * max(w_, 64) + 2.0 * A_ * N_b * K_ * w_ + 2.0 * E_b * K_
+                   + (E_b * K_ / 8.0 if GF.DH_FUSED_MASK and GF.NODE_MN and K_ <= 1024 else 0.0),
         # fused kernels: U / dU cross the L2 only.  fwd: h in, messages out, U written once for the
         # dh pass; bwd: h and the message gradients in, per-CTA dx partials out
         "node_fused_fwd": 2.0 * E_b * K_ + 4.0 * E_b * w_ + 2.0 * N_b * w_ * K_,

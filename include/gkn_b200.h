@@ -140,6 +140,22 @@ int gkn_node_dh_mn_bf16(const void* gs_bf16, const void* u_bf16, const int32_t* 
                         int64_t unit_begin, int64_t unit_end, int64_t E_pad, int64_t chunk_nodes,
                         int32_t node_base, int32_t A, void* dh_bf16, int32_t K, int32_t W,
                         void* stream);
+/* gkn_node_dh_mn_bf16 with the backward of DenseNet layers.2's ReLU (graph_kernel.py:239-242) fused
+ * into its epilogue: dz[q,k] = dh[q,k] where the layer's output hs[q,k] is positive, zero
+ * elsewhere, and colsum[k] (+)= sum_q dz[q,k] over the rows of the launch (the gradient of
+ * layers.2.bias; accumulate != 0 adds to colsum, which is how node-range launches are chained).
+ * The activation pattern comes as one bit per element: act_bits uint32 [E_pad, K/32], bit k%32 of
+ * word k/32 set where hs[q,k] > 0 - written once per step by gkn_relu_bits_bf16 (hs bf16
+ * [rows, K], K % 32 == 0), so the epilogue reads 32 bytes per row instead of 512.  The sums are
+ * taken per CTA in a fixed order and folded in CTA order (no atomics; deterministic).
+ * workspace: float [SM count, K] scratch.  K <= 1024. */
+int gkn_relu_bits_bf16(const void* act_bf16, int64_t rows, int32_t K, uint32_t* bits, void* stream);
+int gkn_node_dh_mn_relu_bf16(const void* gs_bf16, const void* u_bf16, const int32_t* units,
+                             int64_t unit_begin, int64_t unit_end, int64_t E_pad,
+                             int64_t chunk_nodes, int32_t node_base, int32_t A,
+                             const uint32_t* act_bits, void* dz_bf16, float* colsum,
+                             int32_t accumulate, void* workspace, int64_t workspace_bytes,
+                             int32_t K, int32_t W, void* stream);
 int gkn_node_gather_bf16(const float* g, const int32_t* idx, int64_t E_pad, void* gs_bf16,
                          void* gsT_bf16, int32_t W, void* stream);
 

@@ -99,14 +99,18 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tmap_h,
     const int64_t ngroups = gridDim.x / CG;
 
     // Contiguous unit range of this CTA (pair); unit = (tile group, column chunk), a tile group
-    // being CG consecutive 128-edge tiles.  With many tile groups per CTA the ranges are
-    // group-aligned: all CTAs then walk the W3 column chunks in phase, so a chunk fetched by one
-    // CTA is an L2 hit for the others (matters when W3 is large, e.g. 32 MB at w=128), at a tail
-    // cost < 1/64.  Otherwise units are split evenly (no tile-quantisation tail).
+    // being CG consecutive 128-edge tiles.  The forward's ranges are always tile-group aligned: a
+    // message row is then summed over ALL its column chunks by one epilogue thread and stored once
+    // - no partial sums combined through global atomics, no zero-fill of msg beforehand, and the
+    // result does not depend on the grid (quantisation tail <= one tile group per CTA: 2 % at the
+    // bench shape).  With many tile groups per CTA the same alignment also keeps all CTAs walking
+    // the W3 column chunks in phase, so a chunk fetched by one CTA is an L2 hit for the others
+    // (matters when W3 is large, e.g. 32 MB at w=128); otherwise the dx units, whose outputs are
+    // disjoint per chunk, are split evenly.
     const int64_t num_tgroups = (p.num_tiles + CG - 1) / CG;
     const int64_t total_units = num_tgroups * kChunks;
     int64_t u0, u1;
-    if (num_tgroups >= ngroups * 64) {
+    if (MODE == MODE_FWD || num_tgroups >= ngroups * 64) {
         u0 = ((num_tgroups * group) / ngroups) * kChunks;
         u1 = ((num_tgroups * (group + 1)) / ngroups) * kChunks;
     } else {
@@ -238,7 +242,6 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tmap_h,
         float acc[MODE == MODE_FWD ? W : 1];  // FWD: msg row accumulator
         float gvec[MODE == MODE_DX ? W : 1];  // DX : message-gradient row
         int32_t cur_tile = -1;
-        int chunks_in_tile = 0;
         int64_t e = 0;
         int32_t nidx = 0;
         bool valid = false;
@@ -246,16 +249,11 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tmap_h,
         auto flush_fwd = [&]() {
             if constexpr (MODE == MODE_FWD) {
                 if (cur_tile < 0 || !valid) return;
-                float* dst = p.out + e * W;
-                if (chunks_in_tile == kChunks) {
+                float* dst = p.out + e * W;  // all kChunks chunks of the tile were summed here
 #pragma unroll
-                    for (int o = 0; o < W; o += 4) {
-                        *reinterpret_cast<float4*>(dst + o) =
-                            make_float4(acc[o], acc[o + 1], acc[o + 2], acc[o + 3]);
-                    }
-                } else {
-#pragma unroll
-                    for (int o = 0; o < W; ++o) atomicAdd(dst + o, acc[o]);
+                for (int o = 0; o < W; o += 4) {
+                    *reinterpret_cast<float4*>(dst + o) =
+                        make_float4(acc[o], acc[o + 1], acc[o + 2], acc[o + 3]);
                 }
             }
         };
@@ -267,7 +265,6 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tmap_h,
             if (tile != cur_tile) {
                 flush_fwd();
                 cur_tile = tile;
-                chunks_in_tile = 0;
                 e = int64_t(tile) * kBlockM + row;
                 valid = e < p.E;
                 nidx = valid ? p.idx[e] : 0;
@@ -286,8 +283,6 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tmap_h,
                     }
                 }
             }
-            ++chunks_in_tile;
-
             // FWD: neighbour features for the i-values of this chunk, fetched before the wait.
             // DX : one dot product per i-value of this chunk.
             float xv[kIPerChunk];
@@ -376,9 +371,7 @@ int launch_contract(const CUtensorMap& tmap_h, const CUtensorMap& tmap_w, const 
     constexpr int smem = Cfg<CG>::kSmemBytes;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (err != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(contract_tc)", err);
-    // grid <= number of tile groups: every CTA (pair) then owns at least one tile group's worth of
-    // units, so a tile is shared by at most two of them and its two partial sums combine
-    // order-independently.
+    // grid <= number of tile groups: every CTA (pair) owns at least one tile group
     const int64_t num_tgroups = (p.num_tiles + CG - 1) / CG;
     int64_t groups = max_ctas / CG;
     if (groups > num_tgroups) groups = num_tgroups;
@@ -447,11 +440,6 @@ int contract_dispatch(const void* h_bf16, const void* w3_bf16, const int32_t* id
     int sms = 0;
     rc = device_sm_count(&sms);
     if (rc) return rc;
-    if (MODE == MODE_FWD) {
-        // tiles split across two CTAs are combined with reductions onto zero
-        cudaError_t err = cudaMemsetAsync(out, 0, size_t(E) * W * sizeof(float), stream);
-        if (err != cudaSuccess) return set_cuda_error("cudaMemsetAsync(msg)", err);
-    }
 #define GKN_LAUNCH(WW)                                                                  \
     return cg == 2 ? launch_contract<WW, MODE, 2>(tmap_h, tmap_w, p, sms, stream)       \
                    : launch_contract<WW, MODE, 1>(tmap_h, tmap_w, p, sms, stream)

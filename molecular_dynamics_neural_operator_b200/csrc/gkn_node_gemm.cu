@@ -56,6 +56,7 @@ enum { MODE_MSG = 0, MODE_DU = 1, MODE_DH = 2, MODE_DU_MN = 3, MODE_DH_MN = 4 };
 __host__ __device__ constexpr bool mode_is_dh(int m) { return m == MODE_DH || m == MODE_DH_MN; }
 __host__ __device__ constexpr bool mode_is_du(int m) { return m == MODE_DU || m == MODE_DU_MN; }
 constexpr int kMnBlockBytes = 64 * kKB * 2;  // one MN-major TMA box: 64 K-rows x 64 MN elements
+constexpr int kMaskMaxK = 1024;              // widest edge MLP the fused-mask dh epilogue serves
 
 // Row length of the padded-order gradient buffer gs: 128-byte rows at least, so that one row is a
 // whole swizzle row of an MN-major box.  At w = 32 the upper 32 columns are zeros (written by
@@ -82,8 +83,11 @@ struct NCfg {
     static constexpr int kBBoxRows = MODE == MODE_DH_MN && W < 64 ? W : 64;
     static constexpr int kTxBytes =
         kBMn ? kABytes + kBBoxes * kBBoxRows * 128 : kStageBytes;  // bytes TMA delivers per stage
+    // MODE_DH_MN with the ReLU mask of DenseNet layers.2 fused (NodeParams::act): per-warp column
+    // sums of the masked output (the bias gradient), kMaskMaxK columns x 4 epilogue warps
+    static constexpr int kColsumBytes = MODE == MODE_DH_MN ? 4 * kMaskMaxK * 4 : 0;
     static constexpr int kSmemBytes =
-        kStages * kStageBytes + 1024 + 256 + kEpiGroups * 4 * 4096 /*output staging*/;
+        kStages * kStageBytes + 1024 + 256 + kEpiGroups * 4 * 4096 /*output staging*/ + kColsumBytes;
     static_assert(kAcc % kEpiGroups == 0, "accumulator stages are owned by epilogue groups");
     static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory per CTA");
 };
@@ -102,6 +106,9 @@ struct NodeParams {
     int32_t node_base;                  // first node of the U / Ut / dUt chunk
     int32_t hints;                      // bit 0: A operand loaded with L2 evict_first; bit 1:
                                         // streaming (.cs) output stores  (GKN_NODE_HINTS)
+    const uint32_t* __restrict__ act_bits;  // DH_MN: [E_pad, K/32] bit c%32 of word c/32 = (hs[q,c] > 0);
+                                        // the output is zeroed where the bit is clear (or NULL)
+    float* __restrict__ colsum_part;    // DH_MN with act: per-CTA column sums [gridDim.x, K]
 };
 
 struct Unit {
@@ -330,8 +337,35 @@ node_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const int row = q * 32 + lane;
         const uint32_t lane_addr = uint32_t(q * 32) << 16;
         const uint32_t stage_smem = bar_base + 256 + (grp * 4 + q) * 4096;  // per-warp staging tile
+        // fused ReLU mask (MODE_DH_MN): this warp's column sums of what it stores
+        bool masked = false;
+        float* csum_smem = nullptr;
+        if constexpr (MODE == MODE_DH_MN) {
+            masked = p.act_bits != nullptr;
+            csum_smem = reinterpret_cast<float*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 256 +
+                                                 kEpiGroups * 4 * 4096) + q * kMaskMaxK;
+            if (masked) {
+                for (int c = lane; c < p.K; c += 32) csum_smem[c] = 0.f;
+                __syncwarp();
+            }
+        }
         uint32_t it = 0;
         Unit un = v0 < v1 ? decode_unit<MODE, W>(p, v0) : Unit{};
+        [[maybe_unused]] uint32_t mb_next[8];
+        [[maybe_unused]] auto load_bits = [&](const Unit& t, uint32_t (&m)[8]) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) m[j] = 0u;
+            if (row < t.rows) {
+                const uint4* bp = reinterpret_cast<const uint4*>(
+                    p.act_bits + int64_t(t.row0 + row) * (p.K / 32) + t.chunk * 8);
+                const uint4 lo = __ldg(bp), hi = __ldg(bp + 1);
+                m[0] = lo.x; m[1] = lo.y; m[2] = lo.z; m[3] = lo.w;
+                m[4] = hi.x; m[5] = hi.y; m[6] = hi.z; m[7] = hi.w;
+            }
+        };
+        if constexpr (MODE == MODE_DH_MN) {
+            if (masked && v0 < v1) load_bits(un, mb_next);
+        }
         for (int64_t v = v0; v < v1; v += vstep) {
             const Unit u = un;
             if (v + vstep < v1) un = decode_unit<MODE, W>(p, v + vstep);
@@ -349,6 +383,18 @@ node_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             const uint32_t aphase = (it / kAcc) & 1u;
             ++it;
             if (int(as % kEpiGroups) != grp) continue;  // the other group's unit (kAcc is even)
+            // fused ReLU backward: this thread's row has 256 mask bits per unit (8 words), fetched
+            // one unit ahead - under a saturated HBM a load issued at its point of use would sit
+            // several microseconds inside the store loop (measured: 2.4 -> 4.2 ms per launch with
+            // the bf16 activations themselves loaded here, even with L2 prefetch)
+            [[maybe_unused]] uint32_t mb[8];
+            if constexpr (MODE == MODE_DH_MN) {
+                if (masked) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) mb[j] = mb_next[j];
+                    if (v + vstep < v1) load_bits(un, mb_next);
+                }
+            }
             if (lane == 0) mbar_wait(tfull_bar(as), aphase);
             __syncwarp();
             tc_fence_after();
@@ -394,6 +440,17 @@ node_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         w[j] = pack_bf16(f0[2 * j], f0[2 * j + 1]);
                         w[16 + j] = pack_bf16(f1[2 * j], f1[2 * j + 1]);
                     }
+                    if constexpr (MODE == MODE_DH_MN) {
+                        if (masked) {
+                            // word j of the piece = columns 2j, 2j+1: bits (2j, 2j+1) of the
+                            // piece's two mask words widen to halfword masks
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const uint32_t two = (mb[piece * 2 + (j >> 4)] >> (2 * (j & 15))) & 3u;
+                                w[j] &= (two & 1u) * 0xffffu + (two >> 1) * 0xffff0000u;
+                            }
+                        }
+                    }
                 }
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
@@ -401,12 +458,26 @@ node_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                            make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
                 }
                 __syncwarp();
+                float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int r = j * 4 + (lane >> 3), c = lane & 7;
                     const uint4 t = lds128(stage_smem + r * 128 + ((c ^ (r & 7)) << 4));
                     // (MODE_DU_MN at w = 32: the accumulator is 64 columns wide, 32 are output)
                     if (r < rows_here && (!mode_is_du(MODE) || W >= 64 || c * 8 < W)) {
+                        if constexpr (MODE == MODE_DH_MN) {
+                            if (masked) {
+                                // column sums of the masked values (the bias gradient)
+                                cs[0] += __uint_as_float(t.x << 16);
+                                cs[1] += __uint_as_float(t.x & 0xffff0000u);
+                                cs[2] += __uint_as_float(t.y << 16);
+                                cs[3] += __uint_as_float(t.y & 0xffff0000u);
+                                cs[4] += __uint_as_float(t.z << 16);
+                                cs[5] += __uint_as_float(t.z & 0xffff0000u);
+                                cs[6] += __uint_as_float(t.w << 16);
+                                cs[7] += __uint_as_float(t.w & 0xffff0000u);
+                            }
+                        }
                         uint4* gp = reinterpret_cast<uint4*>(gbase + r * pitch + piece * 128 + c * 16);
                         if (p.hints & 2) {
                             __stcs(gp, t);
@@ -415,11 +486,38 @@ node_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         }
                     }
                 }
+                if constexpr (MODE == MODE_DH_MN) {
+                    if (masked) {
+                        // lanes l, l+8, l+16, l+24 hold the same 8 columns: fixed-order fold
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 8);
+                            cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 16);
+                        }
+                        if (lane < 8) {
+                            float* dst = csum_smem + u.chunk * 256 + piece * 64 + lane * 8;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) dst[i] += cs[i];
+                        }
+                    }
+                }
                 __syncwarp();
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(as));
+        }
+        if constexpr (MODE == MODE_DH_MN) {
+            if (masked) {
+                // the four warps' sums, folded in warp order: one row of the per-CTA partials
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const float* all = csum_smem - q * kMaskMaxK;
+                float* dst = p.colsum_part + int64_t(blockIdx.x) * p.K;
+                for (int c = threadIdx.x - 64; c < p.K; c += 128) {
+                    dst[c] = ((all[c] + all[kMaskMaxK + c]) + all[2 * kMaskMaxK + c]) +
+                             all[3 * kMaskMaxK + c];
+                }
+            }
         }
     }
 
@@ -531,6 +629,97 @@ node_gather_kernel(const float* __restrict__ g, const int32_t* __restrict__ idx,
             }
         }
     }
+}
+
+// bits[q, c / 32] bit (c % 32) = act[q, c] > 0 (bf16 pattern positive as a signed halfword: +0, -0
+// and negatives clear, +inf set).  One 32-bit word = 64 contiguous bytes of act per thread.
+__global__ void __launch_bounds__(256)
+relu_bits_kernel(const uint4* __restrict__ act, int64_t words, uint32_t* __restrict__ bits) {
+    for (int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x; i < words;
+         i += int64_t(gridDim.x) * 256) {
+        uint32_t out = 0u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint4 v = __ldcs(act + i * 4 + j);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t lo = int16_t(w[k] & 0xffffu) > 0, hi = int16_t(w[k] >> 16) > 0;
+                out |= (lo | (hi << 1)) << (j * 8 + k * 2);
+            }
+        }
+        bits[i] = out;
+    }
+}
+
+// colsum[c] (+)= sum_b part[b, c] in block order (the per-CTA partials of the masked dh epilogue)
+__global__ void __launch_bounds__(256)
+dh_colsum_fold_kernel(const float* __restrict__ part, int nblocks, int K, float* __restrict__ colsum,
+                      int accumulate) {
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= K) return;
+    float s = accumulate ? colsum[c] : 0.f;
+    for (int b = 0; b < nblocks; ++b) s += part[int64_t(b) * K + c];
+    colsum[c] = s;
+}
+
+int node_dh_mn_impl(const char* name, const void* gs_bf16, const void* u_bf16, const int32_t* units,
+                    int64_t unit_begin, int64_t unit_end, int64_t E_pad, int64_t chunk_nodes,
+                    int32_t node_base, int32_t A, const uint32_t* act_bits, void* dh_bf16,
+                    float* colsum, int32_t accumulate, void* workspace, int64_t workspace_bytes,
+                    int32_t K, int32_t W, cudaStream_t st) {
+    static thread_local char buf[200];
+    auto fail = [&](const char* what) {
+        snprintf(buf, sizeof(buf), "%s: %s", name, what);
+        return set_error(buf);
+    };
+    if (unit_end <= unit_begin) return 0;
+    if (gs_bf16 == nullptr || u_bf16 == nullptr || units == nullptr || dh_bf16 == nullptr) {
+        return fail("NULL pointer argument");
+    }
+    int rc = check_common(name, K, W, E_pad, true);
+    if (rc) return rc;
+    if (A <= 0) return fail("A must be positive");
+    const int64_t a_rows = int64_t(A) * E_pad, b_rows = int64_t(A) * chunk_nodes * W;
+    if (chunk_nodes <= 0 || a_rows >= (int64_t(1) << 31) || b_rows >= (int64_t(1) << 31)) {
+        return fail("operand too large for one launch (use smaller node chunks)");
+    }
+    int sms = 0;
+    rc = device_sm_count(&sms);
+    if (rc) return rc;
+    NodeParams p{};
+    p.v_begin = unit_begin * (K / 256);
+    p.v_end = unit_end * (K / 256);
+    const int64_t grid = p.v_end - p.v_begin < sms ? p.v_end - p.v_begin : sms;
+    if (act_bits != nullptr) {
+        if (K > kMaskMaxK) return fail("the fused activation mask serves K <= 1024");
+        if (colsum == nullptr || workspace == nullptr) return fail("NULL colsum / workspace");
+        if (workspace_bytes < grid * K * int64_t(sizeof(float))) return fail("workspace too small");
+    }
+    CUtensorMap ta, tb;
+    rc = make_tensor_map_bf16_2d(&ta, gs_bf16, uint64_t(gs_width(W)), uint64_t(a_rows), kKB, kM);
+    if (rc) return rc;
+    rc = make_tensor_map_bf16_2d(&tb, u_bf16, uint64_t(K), uint64_t(b_rows), 64, W < 64 ? W : kKB);
+    if (rc) return rc;
+    p.units = reinterpret_cast<const int4*>(units);
+    p.out = dh_bf16;
+    p.K = K;
+    p.A = A;
+    p.a_rows_per_app = int32_t(E_pad);
+    p.b_rows_per_app = int32_t(chunk_nodes * W);
+    p.node_base = node_base;
+    p.act_bits = act_bits;
+    p.colsum_part = static_cast<float*>(workspace);
+    switch (W) {
+        case 32: rc = launch_node_gemm<MODE_DH_MN, 32>(ta, tb, p, st); break;
+        case 64: rc = launch_node_gemm<MODE_DH_MN, 64>(ta, tb, p, st); break;
+        default: rc = launch_node_gemm<MODE_DH_MN, 128>(ta, tb, p, st); break;
+    }
+    if (rc || act_bits == nullptr) return rc;
+    dh_colsum_fold_kernel<<<(K + 255) / 256, 256, 0, st>>>(p.colsum_part, int(grid), K, colsum,
+                                                          accumulate);
+    GKN_CHECK_LAUNCH("dh_colsum_fold launch");
+    return 0;
 }
 
 }  // namespace
@@ -666,39 +855,45 @@ extern "C" int gkn_node_dh_mn_bf16(const void* gs_bf16, const void* u_bf16, cons
                                    int64_t unit_begin, int64_t unit_end, int64_t E_pad,
                                    int64_t chunk_nodes, int32_t node_base, int32_t A,
                                    void* dh_bf16, int32_t K, int32_t W, void* stream) {
+    return gkn::node_dh_mn_impl("gkn_node_dh_mn_bf16", gs_bf16, u_bf16, units, unit_begin, unit_end,
+                                E_pad, chunk_nodes, node_base, A, nullptr, dh_bf16, nullptr, 0,
+                                nullptr, 0, K, W, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gkn_relu_bits_bf16(const void* act_bf16, int64_t rows, int32_t K, uint32_t* bits,
+                                  void* stream) {
     using namespace gkn;
-    if (unit_end <= unit_begin) return 0;
-    if (gs_bf16 == nullptr || u_bf16 == nullptr || units == nullptr || dh_bf16 == nullptr) {
-        return set_error("gkn_node_dh_mn_bf16: NULL pointer argument");
+    if (rows == 0) return 0;
+    if (act_bf16 == nullptr || bits == nullptr) return set_error("gkn_relu_bits_bf16: NULL pointer");
+    if (rows < 0 || K <= 0 || K % 32 != 0) {
+        return set_error("gkn_relu_bits_bf16: K must be a positive multiple of 32");
     }
-    int rc = check_common("gkn_node_dh_mn_bf16", K, W, E_pad, true);
+    int sms = 0;
+    int rc = device_sm_count(&sms);
     if (rc) return rc;
-    if (A <= 0) return set_error("gkn_node_dh_mn_bf16: A must be positive");
-    const int64_t a_rows = int64_t(A) * E_pad, b_rows = int64_t(A) * chunk_nodes * W;
-    if (chunk_nodes <= 0 || a_rows >= (int64_t(1) << 31) || b_rows >= (int64_t(1) << 31)) {
-        return set_error("gkn_node_dh_mn_bf16: operand too large for one launch (use smaller node chunks)");
+    const int64_t words = rows * (K / 32);
+    int64_t blocks = (words + 255) / 256;
+    if (blocks > int64_t(sms) * 16) blocks = int64_t(sms) * 16;
+    relu_bits_kernel<<<dim3(unsigned(blocks)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(act_bf16), words, bits);
+    GKN_CHECK_LAUNCH("relu_bits launch");
+    return 0;
+}
+
+extern "C" int gkn_node_dh_mn_relu_bf16(const void* gs_bf16, const void* u_bf16,
+                                        const int32_t* units, int64_t unit_begin, int64_t unit_end,
+                                        int64_t E_pad, int64_t chunk_nodes, int32_t node_base,
+                                        int32_t A, const uint32_t* act_bits, void* dz_bf16,
+                                        float* colsum, int32_t accumulate, void* workspace,
+                                        int64_t workspace_bytes, int32_t K, int32_t W,
+                                        void* stream) {
+    if (act_bits == nullptr) {
+        return gkn::set_error("gkn_node_dh_mn_relu_bf16: NULL activation mask");
     }
-    CUtensorMap ta, tb;
-    rc = make_tensor_map_bf16_2d(&ta, gs_bf16, uint64_t(gs_width(W)), uint64_t(a_rows), kKB, kM);
-    if (rc) return rc;
-    rc = make_tensor_map_bf16_2d(&tb, u_bf16, uint64_t(K), uint64_t(b_rows), 64, W < 64 ? W : kKB);
-    if (rc) return rc;
-    NodeParams p{};
-    p.units = reinterpret_cast<const int4*>(units);
-    p.out = dh_bf16;
-    p.v_begin = unit_begin * (K / 256);
-    p.v_end = unit_end * (K / 256);
-    p.K = K;
-    p.A = A;
-    p.a_rows_per_app = int32_t(E_pad);
-    p.b_rows_per_app = int32_t(chunk_nodes * W);
-    p.node_base = node_base;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    switch (W) {
-        case 32: return launch_node_gemm<MODE_DH_MN, 32>(ta, tb, p, st);
-        case 64: return launch_node_gemm<MODE_DH_MN, 64>(ta, tb, p, st);
-        default: return launch_node_gemm<MODE_DH_MN, 128>(ta, tb, p, st);
-    }
+    return gkn::node_dh_mn_impl("gkn_node_dh_mn_relu_bf16", gs_bf16, u_bf16, units, unit_begin,
+                                unit_end, E_pad, chunk_nodes, node_base, A, act_bits, dz_bf16,
+                                colsum, accumulate, workspace, workspace_bytes, K, W,
+                                static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int gkn_node_gather_bf16(const float* g, const int32_t* idx, int64_t E_pad,

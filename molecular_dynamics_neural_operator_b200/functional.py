@@ -226,6 +226,10 @@ _MLP_BWD_CHUNK_ROWS = int(os.environ.get("GKN_MLP_BWD_CHUNK_ROWS", "65536"))
 # MN-major operand variants of the dU / dh kernels: h, gm and U are read in place (no transposed
 # copy of h, no [k,o]-ordered recomputation of U).  GKN_NODE_MN=0 selects the K-major kernels.
 NODE_MN = os.environ.get("GKN_NODE_MN", "1") == "1"
+# the dh kernel applies the ReLU backward of layers.2 in its epilogue (gkn_node_dh_mn_relu_bf16)
+# from a one-bit-per-element copy of the activation pattern (gkn_relu_bits_bf16): 2 GB read once
+# instead of a 6 GB elementwise pass per step; GKN_DH_FUSED_MASK=0 keeps the separate mask pass
+DH_FUSED_MASK = os.environ.get("GKN_DH_FUSED_MASK", "1") == "1"
 _MLP_SIDE_GEMM = os.environ.get("GKN_MLP_SIDE_GEMM", "1") == "1"
 # U of every application ([A, N, w*K] bf16) is kept for the dh pass when it fits this budget
 # (6.3 GB for 8 BBA frames); otherwise it is recomputed node range by node range in backward
@@ -463,8 +467,14 @@ class _GKNStackNode(torch.autograd.Function):
             dw3 = dw3k.reshape(W, K, W).permute(0, 2, 1).reshape(W * W, K)
             # dh_e for all applications at once, node range by node range (U^T recomputed)
             dh = torch.empty((lay.e_pad, K), dtype=bf, device=dev)
+            # the ReLU backward of layers.2 and its bias gradient ride in the dh epilogue
+            mask_kw, db2_fused = {}, None
+            if NODE_MN and DH_FUSED_MASK and K <= 1024:
+                db2_fused = torch.zeros(K, dtype=torch.float32, device=dev)
+                mask_kw = dict(act_bits=ops.relu_bits(hs), colsum=db2_fused)
             if u_all is not None:
-                ops.node_dh_mn(gs_all, u_all.view(A, N, W, K), lay, 0, lay.num_units, 0, dh)
+                ops.node_dh_mn(gs_all, u_all.view(A, N, W, K), lay, 0, lay.num_units, 0, dh,
+                               **mask_kw)
             else:
                 for n0, n1 in _node_chunks(N, A * W * K * 2, _NODE_DH_CHUNK_BYTES):
                     ut = torch.empty((A, n1 - n0, K * W), dtype=bf, device=dev)
@@ -472,13 +482,14 @@ class _GKNStackNode(torch.autograd.Function):
                         torch.mm(xbs[a][n0:n1], w3r if NODE_MN else w3kq, out=ut[a])
                     if NODE_MN:
                         ops.node_dh_mn(gs_all, ut.view(A, n1 - n0, W, K), lay, lay.unit_first[n0],
-                                       lay.unit_first[n1], n0, dh)
+                                       lay.unit_first[n1], n0, dh, accumulate=True, **mask_kw)
                     else:
                         ops.node_dh(gs_all, ut.view(A, n1 - n0, K, W), lay, lay.unit_first[n0],
                                     lay.unit_first[n1], n0, dh)
                     del ut
             del gs_all, u_all
-            dw2, db2, dw1, db1, dea_s = _mlp_grads(dh, ea_s, h1, hs, w1, w2, need_ea)
+            dw2, db2, dw1, db1, dea_s = _mlp_grads(dh, ea_s, h1, hs, w1, w2, need_ea,
+                                                   db2_masked=db2_fused)
             if need_ea:
                 dea = dea_s.index_select(0, lay.qpos_long)
         return (gx if need_x0 else None, dea, dw1, db1, dw2, db2, dw3, db3, droot[0], dbias[0],
@@ -486,13 +497,15 @@ class _GKNStackNode(torch.autograd.Function):
                 None, None, None, None)
 
 
-def _mlp_grads(dh, ea, h1, h, w1, w2, need_ea: bool):
-    """Backward of edge-MLP layers .0-.3 from dh_e (bf16 [rows, K]); rows in bounded chunks."""
+def _mlp_grads(dh, ea, h1, h, w1, w2, need_ea: bool, db2_masked=None):
+    """Backward of edge-MLP layers .0-.3 from dh_e (bf16 [rows, K]); rows in bounded chunks.
+    ``db2_masked``: dh already is dz2 (masked by layers.2's activation, ops.node_dh_mn with
+    ``act``) and this is its column sum."""
     E, K = h.shape
     kin = ea.size(1)
     f32 = dict(dtype=torch.float32, device=h.device)
     dw2 = torch.zeros((K, K), **f32)
-    db2 = torch.zeros(K, **f32)
+    db2 = torch.zeros(K, **f32) if db2_masked is None else db2_masked
     cs1 = torch.zeros((1 + kin, K), **f32)
     dea = torch.empty_like(ea) if need_ea else None
     w2q = w2.to(torch.bfloat16)
@@ -507,7 +520,10 @@ def _mlp_grads(dh, ea, h1, h, w1, w2, need_ea: bool):
         side_acc = torch.zeros((K, 16), **f32)
     for e0 in range(0, E, _MLP_BWD_CHUNK_ROWS):
         e1 = min(E, e0 + _MLP_BWD_CHUNK_ROWS)
-        dz2q = ops.mask_cast_colsum(dh[e0:e1], h[e0:e1], db2, torch.bfloat16)
+        if db2_masked is None:
+            dz2q = ops.mask_cast_colsum(dh[e0:e1], h[e0:e1], db2, torch.bfloat16)
+        else:
+            dz2q = dh[e0:e1]
         dw2 = _addmm32(dw2, dz2q.t(), h1[e0:e1])
         if need_ea:
             dz1 = _mm32(dz2q, w2q)

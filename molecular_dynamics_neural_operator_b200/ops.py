@@ -649,22 +649,51 @@ def node_du_mn(hs, gs, lay: NodeLayout, node_begin: int, node_end: int, dut: tor
         )
 
 
+def relu_bits(act: torch.Tensor) -> torch.Tensor:
+    """One bit per element of a bf16 activation matrix [rows, K]: int32 [rows, K // 32], bit k % 32
+    of word k // 32 set where act[q, k] > 0 (gkn_relu_bits_bf16)."""
+    lib = _lib.load()
+    rows, K = int(act.size(0)), int(act.size(1))
+    bits = torch.empty((rows, K // 32), dtype=torch.int32, device=act.device)
+    with torch.cuda.device(act.device), _timed("relu_bits"):
+        _lib.check(lib.gkn_relu_bits_bf16(_p(act, torch.bfloat16, "act"), rows, K,
+                                          _p(bits, torch.int32, "bits"), _stream()),
+                   "gkn_relu_bits_bf16")
+    return bits
+
+
 def node_dh_mn(gs, u, lay: NodeLayout, unit_begin: int, unit_end: int, node_base: int,
-               dh: torch.Tensor) -> None:
+               dh: torch.Tensor, act_bits: torch.Tensor | None = None,
+               colsum: torch.Tensor | None = None, accumulate: bool = False) -> None:
     """node_dh from gs [A, E_pad, gs_width(W)] and u bf16 [A, chunk_nodes, W, K] (the forward's U)
-    (gkn_node_dh_mn_bf16; w in {32, 64, 128})."""
+    (gkn_node_dh_mn_bf16; w in {32, 64, 128}).
+
+    With ``act_bits`` (``relu_bits(hs)``: int32 [E_pad, K // 32]) the ReLU backward of DenseNet
+    layers.2 is applied in the epilogue: ``dh`` receives dz2 = dh * (hs > 0) and ``colsum`` (fp32
+    [K]) its column sums over the launch's rows (gkn_node_dh_mn_relu_bf16; ``accumulate`` adds to
+    ``colsum``)."""
     lib = _lib.load()
     A, W = int(gs.size(0)), int(u.size(2))
     K = int(dh.size(1))
     if gs.size(2) != gs_width(W):
         raise ValueError(f"gs must have {gs_width(W)} columns at w = {W}")
+    common = (_p(gs, torch.bfloat16, "gs"), _p(u, torch.bfloat16, "u"),
+              _p(lay.dh_units(K // 256), torch.int32, "units"), unit_begin, unit_end, lay.e_pad,
+              int(u.size(1)), node_base, A)
     with torch.cuda.device(gs.device), _timed("node_dh"):
+        if act_bits is None:
+            _lib.check(lib.gkn_node_dh_mn_bf16(*common, _p(dh, torch.bfloat16, "dh"), K, W,
+                                               _stream()), "gkn_node_dh_mn_bf16")
+            return
+        if tuple(act_bits.shape) != (dh.size(0), K // 32) or colsum is None or colsum.numel() != K:
+            raise ValueError("act_bits must be [E_pad, K // 32] and colsum have K entries")
+        ws = torch.empty((device_sm_count(), K), dtype=torch.float32, device=gs.device)
         _lib.check(
-            lib.gkn_node_dh_mn_bf16(_p(gs, torch.bfloat16, "gs"), _p(u, torch.bfloat16, "u"),
-                                    _p(lay.dh_units(K // 256), torch.int32, "units"), unit_begin, unit_end,
-                                    lay.e_pad, int(u.size(1)), node_base, A,
-                                    _p(dh, torch.bfloat16, "dh"), K, W, _stream()),
-            "gkn_node_dh_mn_bf16",
+            lib.gkn_node_dh_mn_relu_bf16(*common, _p(act_bits, torch.int32, "act_bits"),
+                                         _p(dh, torch.bfloat16, "dh"),
+                                         _p(colsum, torch.float32, "colsum"), int(accumulate),
+                                         _p(ws), ws.numel() * 4, K, W, _stream()),
+            "gkn_node_dh_mn_relu_bf16",
         )
 
 

@@ -109,10 +109,24 @@ def emu_node_du_mn(hs, gs, lay, n0, n1, dut):
     emu_node_du(hs.t(), gs[:, :W].t(), lay, n0, n1, dut)
 
 
-def emu_node_dh_mn(gs, u, lay, u0, u1, node_base, dh):
+def emu_relu_bits(act):
+    pos = (act > 0).view(act.size(0), -1, 32).long()
+    words = (pos << torch.arange(32)).sum(-1)
+    return torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32)
+
+
+def emu_node_dh_mn(gs, u, lay, u0, u1, node_base, dh, act_bits=None, colsum=None, accumulate=False):
     W = u.size(2)
     assert gs.size(2) == ops.gs_width(W)
     emu_node_dh(gs[:, :, :W], u.transpose(2, 3), lay, u0, u1, node_base, dh)
+    if act_bits is not None:  # ReLU backward of layers.2 + bias gradient over this call's rows
+        keep = ((act_bits.long()[:, :, None] >> torch.arange(32)) & 1).bool().view(dh.shape)
+        tot = torch.zeros(dh.size(1))
+        for _, row0, rows, _ in lay.units[u0:u1].tolist():
+            sl = slice(row0, row0 + rows)
+            dh[sl] = torch.where(keep[sl], dh[sl], torch.zeros((), dtype=dh.dtype))
+            tot += dh[sl].float().sum(0)
+        colsum.copy_(colsum + tot if accumulate else tot)
 
 
 def emu_node_gather(g, lay, gs, gsT):
@@ -250,6 +264,7 @@ def install_emulation(setattr_fn):
                      ("mask_cast_colsum", emu_mask_cast_colsum), ("node_msg", emu_node_msg),
                      ("node_du", emu_node_du), ("node_dh", emu_node_dh),
                      ("node_du_mn", emu_node_du_mn), ("node_dh_mn", emu_node_dh_mn),
+                     ("relu_bits", emu_relu_bits),
                      ("node_gather", emu_node_gather), ("node_fused_fwd", emu_node_fused_fwd),
                      ("node_u_gemm", emu_node_u_gemm),
                      ("node_fused_bwd", emu_node_fused_bwd), ("sum_partials", emu_sum_partials),
@@ -407,6 +422,24 @@ def test_node_first_stack_at_other_widths_matches_oracle(emulated, monkeypatch, 
     for k in p:
         tol = 2.0 ** -2 if k.startswith(("net.layers.0", "net.layers.2", "ea")) else 2.0 ** -5
         assert fro(t[k].grad, tr[k].grad) < tol, k
+
+
+@pytest.mark.parametrize("save_u", [True, False], ids=["saved_u", "recomputed_u"])
+def test_relu_backward_fused_into_the_dh_pass_changes_nothing(emulated, monkeypatch, save_u):
+    """GKN_DH_FUSED_MASK: dz2 and the layers.2 bias gradient from the dh epilogue (node ranges
+    chained through ``accumulate``) against the separate mask pass."""
+    monkeypatch.setattr(GF, "_SAVE_U_BYTES", (1 << 40) if save_u else 0)
+    monkeypatch.setattr(GF, "_NODE_DH_CHUNK_BYTES", 2 * 2 * 64 * 256 * 2 * 3)  # 3 nodes per range
+    N, E, K, depth = 8, 300, 256, 2
+    ei, p, depth = _stack_case(N, E, K, depth, seed=21)
+    grads = []
+    for fused in (True, False):
+        monkeypatch.setattr(GF, "DH_FUSED_MASK", fused)
+        out, t = _run_node_stack(ei, p, depth, N, relu=True)
+        out.backward(torch.ones_like(out))
+        grads.append(t)
+    for k in p:
+        assert fro(grads[0][k].grad, grads[1][k].grad) < 1e-6, k
 
 
 def test_node_first_stack_with_relu_matches_oracle(emulated):

@@ -13,7 +13,8 @@ import torch
 from tests.helpers import rel_err
 from tests.test_node_path_cpu import (_run_oracle_stack, _stack_case, cpu_plan, emu_node_dh,
                                       emu_node_dh_mn, emu_node_du, emu_node_du_mn,
-                                      emu_node_gather, emu_node_msg, fro, random_graph)
+                                      emu_node_gather, emu_node_msg, emu_relu_bits, fro,
+                                      random_graph)
 
 pytestmark = pytest.mark.gpu
 
@@ -167,6 +168,57 @@ def test_backward_kernels_at_other_widths_match_fp32_restatement(case, width, K)
         ops.node_dh_mn(gs_all, u[:, n0:n1].contiguous().cuda(), lay, lay.unit_first[n0],
                        lay.unit_first[n1], n0, dh_parts)
     assert torch.equal(dh_parts, dh)
+
+
+@pytest.mark.parametrize("case", list(_graphs()), ids=lambda c: c[0])
+@pytest.mark.parametrize("width,K", [(64, 1024), (64, 256), (32, 512), (128, 1024)])
+def test_dh_pass_with_fused_relu_backward(case, width, K):
+    """gkn_relu_bits_bf16 + gkn_node_dh_mn_relu_bf16: the bit pattern of act > 0 (bit-exact
+    against the CPU restatement), the same dh values where the activation is positive, zeros
+    elsewhere (bit-exact against masking the plain kernel's output), column sums within fp32
+    summation-order error of a float64 sum, node-range launches chained through ``accumulate``,
+    and run-to-run identical (no atomics)."""
+    from molecular_dynamics_neural_operator_b200 import ops
+
+    _, ei, N = case
+    plan = _plan_on_gpu(ei, N)
+    lay = ops.node_layout(plan)
+    gen = torch.Generator().manual_seed(K + N + width)
+    bf = torch.bfloat16
+    E_pad, Wp, A = lay.e_pad, ops.gs_width(width), 2
+    gs_all = torch.zeros(A, E_pad, Wp, dtype=bf, device="cuda")
+    for a in range(A):
+        ops.node_gather(torch.randn(N, width, generator=gen).cuda(), lay, gs_all[a], None)
+    u = (torch.randn(A, N, width, K, generator=gen) / 8).to(bf).cuda()
+    act = torch.relu(torch.randn(E_pad, K, generator=gen)).to(bf).cuda()  # about half zeros
+    act[0, :8] = torch.tensor([0.0, -0.0, 1e-30, -1.0, float("inf"), 2.0, 0.0, 3.0]).to(bf)
+
+    bits = ops.relu_bits(act)
+    assert torch.equal(bits.cpu(), emu_relu_bits(act.cpu()))
+    plain = torch.empty(E_pad, K, dtype=bf, device="cuda")
+    ops.node_dh_mn(gs_all, u, lay, 0, lay.num_units, 0, plain)
+    want = torch.where(act > 0, plain, torch.zeros((), dtype=bf, device="cuda"))
+    got = torch.full((E_pad, K), float("nan"), dtype=bf, device="cuda")
+    colsum = torch.full((K,), float("nan"), device="cuda")
+    ops.node_dh_mn(gs_all, u, lay, 0, lay.num_units, 0, got, act_bits=bits, colsum=colsum)
+    assert torch.equal(got, want)
+    ref = want.double().sum(0)
+    scale = want.double().abs().sum(0).max()
+    assert float((colsum.double() - ref).abs().max()) <= 1e-5 * float(scale)
+
+    again = torch.empty_like(got)
+    colsum2 = torch.empty_like(colsum)
+    ops.node_dh_mn(gs_all, u, lay, 0, lay.num_units, 0, again, act_bits=bits, colsum=colsum2)
+    assert torch.equal(again, got) and torch.equal(colsum2, colsum)
+
+    parts = torch.full((E_pad, K), float("nan"), dtype=bf, device="cuda")
+    csum = torch.zeros(K, device="cuda")
+    for n0 in range(0, N, 17):
+        n1 = min(N, n0 + 17)
+        ops.node_dh_mn(gs_all, u[:, n0:n1].contiguous(), lay, lay.unit_first[n0],
+                       lay.unit_first[n1], n0, parts, act_bits=bits, colsum=csum, accumulate=True)
+    assert torch.equal(parts, got)
+    assert float((csum.double() - ref).abs().max()) <= 1e-5 * float(scale)
 
 
 def test_grouped_gemm_node_range_chunks_cover_the_same_result():
