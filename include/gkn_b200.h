@@ -258,6 +258,23 @@ int gkn_shard_reduce_update(const uint64_t* partial_ptrs, const uint64_t* xout_p
                             const float* root, const float* bias, int64_t n0, int64_t n1,
                             int64_t N, int32_t W, int32_t relu, void* stream);
 
+/* Node encoder's LSTM (graph_kernel.py:278-285: nn.LSTM(3, 3) called window step by window step
+ * with the state carried over, i.e. one sequence of T steps over R independent rows, zero initial
+ * state).  fp32; PyTorch parameter layout: w_ih [4D, D], w_hh [4D, D], b_ih, b_hh [4D], gate rows in
+ * (input, forget, cell, output) order; D = 3.
+ *   fwd: x [T,R,D] -> out [T,R,D] (h_t); gates [T,R,4D] (activated) and cells [T,R,D] (c_t) are
+ *        saved for the backward (both NULL: inference).
+ *   bwd: dout [T,R,D] -> dx [T,R,D] (may be NULL) and dw_part [gkn_lstm_blocks(R), 4D*D*2 + 4D]:
+ *        per-block sums of (dW_ih, dW_hh, db) - the caller adds the blocks; db is the gradient of
+ *        both bias vectors.  One thread per row, fixed summation order, no atomics. */
+int gkn_lstm_blocks(int64_t R);
+int gkn_lstm_fwd(const float* x, const float* w_ih, const float* w_hh, const float* b_ih,
+                 const float* b_hh, float* out, float* gates, float* cells, int64_t T, int64_t R,
+                 int32_t D, void* stream);
+int gkn_lstm_bwd(const float* x, const float* w_ih, const float* w_hh, const float* out,
+                 const float* gates, const float* cells, const float* dout, float* dx,
+                 float* dw_part, int64_t T, int64_t R, int32_t D, void* stream);
+
 /* Dataset feeder (reference dataset.py:194-201, a Python loop per edge there):
  * edge_attr[e, :] = [pos[edge_index[0,e], :], pos[edge_index[1,e], :]] for a batch of graphs whose
  * node ids index the rows of pos (float32 [M,3]; edge_index int64 [2,E]; edge_attr float32 [E,6]).

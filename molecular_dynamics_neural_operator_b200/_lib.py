@@ -47,6 +47,9 @@ SIGNATURES = {
         c_int,
         [P, P, P, c_int64, c_int64, c_int64, c_int64, c_int32, c_int32, P, c_int32, c_int32, P],
     ),
+    "gkn_lstm_blocks": (c_int, [c_int64]),
+    "gkn_lstm_fwd": (c_int, [P, P, P, P, P, P, P, P, c_int64, c_int64, c_int32, P]),
+    "gkn_lstm_bwd": (c_int, [P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int32, P]),
     "gkn_relu_bits_bf16": (c_int, [P, c_int64, c_int32, P, P]),
     "gkn_node_dh_mn_relu_bf16": (
         c_int, [P, P, P, c_int64, c_int64, c_int64, c_int64, c_int32, c_int32, P, P, P, c_int32, P,

@@ -563,3 +563,43 @@ def gkn_stack(x0, edge_attr_sorted, net, root1, bias1, root2, bias2, plan: Graph
     return fn.apply(x0, edge_attr_sorted, l0.weight, l0.bias, l2.weight, l2.bias, l4.weight,
                            l4.bias, root1, bias1, root2, bias2, plan, tuple(schedule), bool(relu),
                            precision)
+
+
+# ------------------------------------------------------------------------------------------------
+# Node encoder's LSTM (reference graph_kernel.py:278-285) - csrc/gkn_lstm.cu
+# ------------------------------------------------------------------------------------------------
+# GKN_LSTM=0 leaves nn.LSTM to cuDNN / the native torch kernels
+OWN_LSTM = os.environ.get("GKN_LSTM", "1") == "1"
+
+
+class _LSTMSeq(torch.autograd.Function):
+    """``nn.LSTM(3, 3)`` over one [T, R, 3] sequence with zero initial state: all h_t."""
+
+    @staticmethod
+    def forward(ctx, x, w_ih, w_hh, b_ih, b_hh):
+        x, w_ih, w_hh, b_ih, b_hh = (t.detach().contiguous() for t in (x, w_ih, w_hh, b_ih, b_hh))
+        save = any(ctx.needs_input_grad)
+        out, gates, cells = ops.lstm_fwd(x, w_ih, w_hh, b_ih, b_hh, save)
+        if save:
+            ctx.save_for_backward(x, w_ih, w_hh, out, gates, cells)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w_ih, w_hh, out, gates, cells = ctx.saved_tensors
+        dx, dw_ih, dw_hh, db = ops.lstm_bwd(x, w_ih, w_hh, out, gates, cells,
+                                            dout.contiguous().float(), ctx.needs_input_grad[0])
+        return dx, dw_ih, dw_hh, db, db.clone()
+
+
+def lstm_supported(lstm: torch.nn.LSTM, x: torch.Tensor) -> bool:
+    return (OWN_LSTM and x.is_cuda and x.dtype == torch.float32 and lstm.input_size == 3
+            and lstm.hidden_size == 3 and lstm.num_layers == 1 and not lstm.bidirectional
+            and lstm.bias and not lstm.batch_first and lstm.proj_size == 0)
+
+
+def lstm_sequence(lstm: torch.nn.LSTM, x: torch.Tensor) -> torch.Tensor:
+    """All hidden states of ``lstm`` over x [T, R, 3] from a zero initial state."""
+    return _LSTMSeq.apply(x, lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0,
+                          lstm.bias_hh_l0)
+

@@ -206,8 +206,14 @@ class KernelNN(torch.nn.Module):
         # concatenated sequence of length W*B, whose last B outputs are the loop's final `x`.
         # fp32 mode uses the native kernels: cuDNN would run this 3 -> 3 LSTM and its backward in
         # TF32 (cudnn.allow_tf32 defaults to True), which breaks the 1e-5 parity bar.
-        with torch.backends.cudnn.flags(enabled=self.precision != "fp32"):
-            seq, hidden = self.lstm(x.reshape(-1, self.num_residues, 3), hidden)
+        xs = x.reshape(-1, self.num_residues, 3)
+        if GF.lstm_supported(self.lstm, xs):
+            # csrc/gkn_lstm.cu: one row per thread, fp32 (cuDNN's generic path costs ~1.1 ms of a
+            # 35 ms training step on this 3 -> 3 recurrence)
+            seq = GF.lstm_sequence(self.lstm, xs)
+        else:
+            with torch.backends.cudnn.flags(enabled=self.precision != "fp32"):
+                seq, hidden = self.lstm(xs, hidden)
         x = seq[-n_batch:]
         x = self.lstm_fc(x)
         emb = self.emb(data.x_aminoacid)

@@ -714,6 +714,51 @@ def node_gather(g, lay: NodeLayout, gs: torch.Tensor | None, gsT: torch.Tensor |
 
 
 # ------------------------------------------------------------------------------------------------
+# Node encoder's LSTM (csrc/gkn_lstm.cu; reference graph_kernel.py:278-285)
+# ------------------------------------------------------------------------------------------------
+def lstm_fwd(x, w_ih, w_hh, b_ih, b_hh, save: bool):
+    """h_t of nn.LSTM(D, D) (zero initial state) over x [T, R, D]; with ``save`` also the activated
+    gates [T, R, 4D] and cell states [T, R, D] the backward needs (gkn_lstm_fwd)."""
+    lib = _lib.load()
+    T, R, D = (int(v) for v in x.shape)
+    f32 = dict(dtype=torch.float32, device=x.device)
+    out = torch.empty((T, R, D), **f32)
+    gates = torch.empty((T, R, 4 * D), **f32) if save else None
+    cells = torch.empty((T, R, D), **f32) if save else None
+    with torch.cuda.device(x.device), _timed("lstm"):
+        _lib.check(
+            lib.gkn_lstm_fwd(_p(x, torch.float32, "x"), _p(w_ih, torch.float32, "w_ih"),
+                             _p(w_hh, torch.float32, "w_hh"), _p(b_ih, torch.float32, "b_ih"),
+                             _p(b_hh, torch.float32, "b_hh"), _p(out), _p(gates), _p(cells), T, R,
+                             D, _stream()),
+            "gkn_lstm_fwd",
+        )
+    return out, gates, cells
+
+
+def lstm_bwd(x, w_ih, w_hh, out, gates, cells, dout, need_dx: bool):
+    """Gradients of ``lstm_fwd``: (dx or None, dW_ih, dW_hh, db) with db the gradient of both bias
+    vectors (gkn_lstm_bwd; per-block partial sums folded here)."""
+    lib = _lib.load()
+    T, R, D = (int(v) for v in x.shape)
+    f32 = dict(dtype=torch.float32, device=x.device)
+    blocks = int(lib.gkn_lstm_blocks(R))
+    part = torch.empty((blocks, 8 * D * D + 4 * D), **f32)
+    dx = torch.empty((T, R, D), **f32) if need_dx else None
+    with torch.cuda.device(x.device), _timed("lstm"):
+        _lib.check(
+            lib.gkn_lstm_bwd(_p(x, torch.float32, "x"), _p(w_ih, torch.float32, "w_ih"),
+                             _p(w_hh, torch.float32, "w_hh"), _p(out, torch.float32, "out"),
+                             _p(gates, torch.float32, "gates"), _p(cells, torch.float32, "cells"),
+                             _p(dout, torch.float32, "dout"), _p(dx), _p(part), T, R, D, _stream()),
+            "gkn_lstm_bwd",
+        )
+    tot = part.sum(0)
+    g = 4 * D * D
+    return dx, tot[:g].view(4 * D, D), tot[g:2 * g].view(4 * D, D), tot[2 * g:]
+
+
+# ------------------------------------------------------------------------------------------------
 # Fused producer/consumer forward of the node-first path (csrc/gkn_node_fused.cu)
 # ------------------------------------------------------------------------------------------------
 FUSED_BLOCK = 128     # nodes per block of U (the M tile of the producer GEMM)
