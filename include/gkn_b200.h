@@ -281,6 +281,14 @@ int gkn_lstm_bwd(const float* x, const float* w_ih, const float* w_hh, const flo
  * status (int32[1], may be NULL) gets bit 0 set if a node id lies outside [0, M). */
 int gkn_edge_attr_gather(const float* pos, const int64_t* edge_index, int64_t E, int64_t M,
                          float* edge_attr, int32_t* status, void* stream);
+/* out[i,o] = sum_r x[r,i] * g[r,o] (float32, [W,W] from rows x W operands) and, when gsum != NULL,
+ * gsum[o] = sum_r g[r,o]: the gradients of NNConv_old.root / .bias (graph_kernel.py:204-209) over
+ * the node rows of all applications stacked, and of layers.4.bias (agg^T G).  Two launches, per-CTA
+ * partial sums folded in CTA order (deterministic).  W in {16, 32, 64, 128};
+ * workspace >= gkn_xty_workspace_bytes(W). */
+int64_t gkn_xty_workspace_bytes(int32_t W);
+int gkn_xty_f32(const float* x, const float* g, int64_t rows, int32_t W, float* out, float* gsum,
+                void* workspace, int64_t workspace_bytes, void* stream);
 /* g[n,:] = gy[n,:] * (relu ? (y[n,:] > 0) : 1);  gn[n,:] = g[n,:] * inv_cnt[n] */
 int gkn_relu_grad_scale(const float* gy, const float* y, const float* inv_cnt, float* g, float* gn,
                         int64_t N, int32_t W, int32_t relu, void* stream);

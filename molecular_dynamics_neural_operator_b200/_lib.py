@@ -82,6 +82,8 @@ SIGNATURES = {
          c_int32, c_int32, P],
     ),
     "gkn_edge_attr_gather": (c_int, [P, P, c_int64, c_int64, P, P, P]),
+    "gkn_xty_workspace_bytes": (c_int64, [c_int32]),
+    "gkn_xty_f32": (c_int, [P, P, c_int64, c_int32, P, P, P, c_int64, P]),
     "gkn_relu_grad_scale": (c_int, [P, P, P, P, P, c_int64, c_int32, c_int32, P]),
     "gkn_edge_outer_sum": (
         c_int,

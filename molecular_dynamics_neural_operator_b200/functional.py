@@ -191,16 +191,14 @@ class _GKNStack(torch.autograd.Function):
         for c in (0, 1):
             idx = [a for a in range(A) if schedule[a] == c]
             if idx:
-                # batched over applications (a [w, A*N] @ [A*N, w] product would run on one CTA)
-                droot[c] = torch.bmm(X[idx].transpose(1, 2), G[idx]).sum(0)
-                dbias[c] = G[idx].sum((0, 1))
+                droot[c], dbias[c] = ops.xty(X[idx].reshape(-1, W), G[idx].reshape(-1, W), True)
             else:
                 droot[c] = torch.zeros_like(roots[c])
                 dbias[c] = torch.zeros(W, dtype=torch.float32, device=gout.device)
         dw3 = db3 = dw2 = db2 = dw1 = db1 = dea = None
         if need_edge:
             # db3[i*W+o] = sum_e x_j[e,i] gn[dst e,o] = sum_n (mean-scaled agg)[n,i] g[n,o]
-            db3 = torch.bmm(torch.stack(list(aggs)).transpose(1, 2), G).sum(0).reshape(-1)
+            db3 = ops.xty(torch.stack(list(aggs)).reshape(-1, W), G.reshape(-1, W))[0].reshape(-1)
             dw3, dw2, db2, dw1, db1, dea = _edge_grads(
                 X, torch.stack(gns), plan, ea, h1, h, w1, w2, w3q, need_ea, precision)
         return (gx if need_x0 else None, dea, dw1, db1, dw2, db2, dw3, db3, droot[0], dbias[0],
@@ -456,14 +454,13 @@ class _GKNStackNode(torch.autograd.Function):
         for c in (0, 1):
             idx = [a for a in range(A) if schedule[a] == c]
             if idx:
-                droot[c] = torch.bmm(X[idx].transpose(1, 2), G[idx]).sum(0)
-                dbias[c] = G[idx].sum((0, 1))
+                droot[c], dbias[c] = ops.xty(X[idx].reshape(-1, W), G[idx].reshape(-1, W), True)
             else:
                 droot[c] = torch.zeros_like(roots[c])
                 dbias[c] = torch.zeros(W, dtype=torch.float32, device=dev)
         dw3 = db3 = dw2 = db2 = dw1 = db1 = dea = None
         if need_edge:
-            db3 = torch.bmm(torch.stack(list(aggs)).transpose(1, 2), G).sum(0).reshape(-1)
+            db3 = ops.xty(torch.stack(list(aggs)).reshape(-1, W), G.reshape(-1, W))[0].reshape(-1)
             dw3 = dw3k.reshape(W, K, W).permute(0, 2, 1).reshape(W * W, K)
             # dh_e for all applications at once, node range by node range (U^T recomputed)
             dh = torch.empty((lay.e_pad, K), dtype=bf, device=dev)

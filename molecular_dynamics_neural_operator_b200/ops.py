@@ -697,6 +697,26 @@ def node_dh_mn(gs, u, lay: NodeLayout, unit_begin: int, unit_end: int, node_base
         )
 
 
+def xty(x: torch.Tensor, g: torch.Tensor, colsum: bool = False):
+    """(x^T g [W, W], column sums of g [W] or None) for float32 x, g [rows, W] (gkn_xty_f32)."""
+    lib = _lib.load()
+    rows, W = int(x.size(0)), int(x.size(1))
+    if g.shape != x.shape:
+        raise ValueError("x and g must have the same shape")
+    _require_cuda(x, "x")
+    if W not in (16, 32, 64, 128):  # widths the reference never instantiates: library product
+        return x.t() @ g, (g.sum(0) if colsum else None)
+    f32 = dict(dtype=torch.float32, device=x.device)
+    out = torch.empty((W, W), **f32)
+    gsum = torch.empty(W, **f32) if colsum else None
+    with torch.cuda.device(x.device), _timed("xty"):
+        nbytes = int(lib.gkn_xty_workspace_bytes(W))
+        ws = torch.empty(nbytes // 4, **f32)
+        _lib.check(lib.gkn_xty_f32(_p(x, torch.float32, "x"), _p(g, torch.float32, "g"), rows, W,
+                                   _p(out), _p(gsum), _p(ws), nbytes, _stream()), "gkn_xty_f32")
+    return out, gsum
+
+
 def node_gather(g, lay: NodeLayout, gs: torch.Tensor | None, gsT: torch.Tensor | None) -> None:
     """gs[q, :W] = bf16(g[dst_pad[q], :]) (zero in pad rows and in columns >= W; gs has
     gs_width(W) columns) and/or, at w = 64, its transpose gsT [W, E_pad]."""

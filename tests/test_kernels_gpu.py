@@ -4,6 +4,8 @@ import numpy as np
 import pytest
 import torch
 
+from tests.helpers import rel_err
+
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
@@ -264,3 +266,20 @@ def test_fused_edge_gradient_rejects_low_degree_graphs():
     xs = torch.zeros(2, N, W, device=DEV)
     with pytest.raises(ValueError, match="more than 8 destination"):
         ops.edge_grad_dh(xs, xs, plan, torch.zeros(K, W * W, dtype=torch.bfloat16, device=DEV))
+
+
+@pytest.mark.parametrize("rows,W", [(1, 64), (31, 32), (8064 * 6, 64), (5000, 128), (100000, 32), (700, 16), (90, 48)])
+def test_xty_matches_float64_product(rows, W):
+    """gkn_xty_f32 (root / bias / b3 gradients): fp32 accumulation in a fixed order against a
+    float64 product, 1e-5 of the largest entry; run-to-run identical."""
+    from molecular_dynamics_neural_operator_b200 import ops
+
+    gen = torch.Generator().manual_seed(rows + W)
+    x = torch.randn(rows, W, generator=gen).cuda()
+    g = torch.randn(rows, W, generator=gen).cuda()
+    out, gsum = ops.xty(x, g, colsum=True)
+    ref = x.double().t() @ g.double()
+    assert rel_err(out, ref) <= 1e-5
+    assert rel_err(gsum, g.double().sum(0)) <= 1e-5
+    out2, none = ops.xty(x, g)
+    assert none is None and torch.equal(out2, out)

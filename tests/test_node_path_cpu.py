@@ -250,6 +250,10 @@ def emu_node_fused_bwd(hs, gs, lay, xb, w3k, du, sched, flags, dx_part, dwT, acc
                 dwT[sl] = acc[c]
 
 
+def emu_xty(x, g, colsum=False):
+    return x.t() @ g, (g.sum(0) if colsum else None)
+
+
 def emu_sum_partials(part, addend, out):
     tot = part.sum(0).reshape(out.shape)
     out.copy_(tot if addend is None else addend + tot)
@@ -264,7 +268,7 @@ def install_emulation(setattr_fn):
                      ("mask_cast_colsum", emu_mask_cast_colsum), ("node_msg", emu_node_msg),
                      ("node_du", emu_node_du), ("node_dh", emu_node_dh),
                      ("node_du_mn", emu_node_du_mn), ("node_dh_mn", emu_node_dh_mn),
-                     ("relu_bits", emu_relu_bits),
+                     ("relu_bits", emu_relu_bits), ("xty", emu_xty),
                      ("node_gather", emu_node_gather), ("node_fused_fwd", emu_node_fused_fwd),
                      ("node_u_gemm", emu_node_u_gemm),
                      ("node_fused_bwd", emu_node_fused_bwd), ("sum_partials", emu_sum_partials),
