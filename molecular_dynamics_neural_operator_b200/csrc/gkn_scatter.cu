@@ -627,6 +627,7 @@ __global__ void __launch_bounds__(256)
 edge_layer0_kernel(const float* __restrict__ ea, const float* __restrict__ w1,
                    const float* __restrict__ b1, OUT* __restrict__ out, int64_t E, int K) {
     const int64_t stride = gridDim.x;
+    const bool vec_in = (reinterpret_cast<uintptr_t>(ea) & 15) == 0;
     for (int c = threadIdx.x * 4; c < K; c += 256 * 4) {
         float w[4][KIN], b[4];
 #pragma unroll
@@ -635,27 +636,51 @@ edge_layer0_kernel(const float* __restrict__ ea, const float* __restrict__ w1,
 #pragma unroll
             for (int j = 0; j < KIN; ++j) w[k][j] = w1[(c + k) * KIN + j];
         }
-        for (int64_t e = blockIdx.x; e < E; e += stride) {
-            float x[KIN];
+        // four edges per trip: their 4 * KIN inputs arrive as float4 loads (the same addresses
+        // for every thread of the block: broadcast), 16 * KIN independent FMAs, four row stores
+        constexpr int kEdges = 4;
+        for (int64_t e0 = int64_t(blockIdx.x) * kEdges; e0 < E; e0 += stride * kEdges) {
+            float x[kEdges][KIN];
+            if (vec_in && e0 + kEdges <= E && (KIN * kEdges) % 4 == 0) {
+                const float4* xp = reinterpret_cast<const float4*>(ea + e0 * KIN);
+                float flat[kEdges * KIN];
 #pragma unroll
-            for (int j = 0; j < KIN; ++j) x[j] = __ldg(ea + e * KIN + j);
-            float o[4];
+                for (int q = 0; q < kEdges * KIN / 4; ++q) {
+                    const float4 v = __ldg(xp + q);
+                    flat[4 * q] = v.x; flat[4 * q + 1] = v.y; flat[4 * q + 2] = v.z; flat[4 * q + 3] = v.w;
+                }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                float acc = b[k];
+                for (int i = 0; i < kEdges; ++i)
 #pragma unroll
-                for (int j = 0; j < KIN; ++j) acc = fmaf(x[j], w[k][j], acc);
-                o[k] = fmaxf(acc, 0.f);
-            }
-            if constexpr (sizeof(OUT) == 2) {
-                __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]);
-                __nv_bfloat162 hi = __floats2bfloat162_rn(o[2], o[3]);
-                uint2 pk;
-                pk.x = *reinterpret_cast<uint32_t*>(&lo);
-                pk.y = *reinterpret_cast<uint32_t*>(&hi);
-                *reinterpret_cast<uint2*>(out + e * K + c) = pk;
+                    for (int j = 0; j < KIN; ++j) x[i][j] = flat[i * KIN + j];
             } else {
-                *reinterpret_cast<float4*>(out + e * K + c) = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+                for (int i = 0; i < kEdges; ++i)
+#pragma unroll
+                    for (int j = 0; j < KIN; ++j) x[i][j] = e0 + i < E ? __ldg(ea + (e0 + i) * KIN + j) : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < kEdges; ++i) {
+                if (e0 + i >= E) break;
+                float o[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float acc = b[k];
+#pragma unroll
+                    for (int j = 0; j < KIN; ++j) acc = fmaf(x[i][j], w[k][j], acc);
+                    o[k] = fmaxf(acc, 0.f);
+                }
+                OUT* dst = out + (e0 + i) * K + c;
+                if constexpr (sizeof(OUT) == 2) {
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]);
+                    __nv_bfloat162 hi = __floats2bfloat162_rn(o[2], o[3]);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                    *reinterpret_cast<uint2*>(dst) = pk;
+                } else {
+                    *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+                }
             }
         }
     }

@@ -202,13 +202,16 @@ def test_edge_layer0(dt):
     from molecular_dynamics_neural_operator_b200 import ops
 
     g = torch.Generator().manual_seed(6)
-    for E, K in [(1, 64), (777, 128), (5000, 1024)]:
-        ea = torch.randn(E, 6, generator=g) * 5
+    for E, K in [(1, 64), (2, 64), (3, 64), (777, 128), (5000, 1024)]:
+        ea = torch.randn(E + 1, 6, generator=g) * 5
         w1, b1 = torch.randn(K, 6, generator=g), torch.randn(K, generator=g)
-        out = ops.edge_layer0(ea.to(DEV), w1.to(DEV), b1.to(DEV), dt)
-        ref = torch.relu(ea.double() @ w1.double().t() + b1.double())
-        tol = 1e-5 if dt == torch.float32 else 2.0 ** -8
-        assert ((out.cpu().double() - ref).abs() / (ref.abs() + 1)).max().item() <= tol
+        dev = ea.to(DEV)
+        # rows [0, E): 16-byte aligned input (four edges per float4 group); rows [1, E + 1): not
+        for view, rows in ((dev[:E], ea[:E]), (dev[1:], ea[1:])):
+            out = ops.edge_layer0(view, w1.to(DEV), b1.to(DEV), dt)
+            ref = torch.relu(rows.double() @ w1.double().t() + b1.double())
+            tol = 1e-5 if dt == torch.float32 else 2.0 ** -8
+            assert ((out.cpu().double() - ref).abs() / (ref.abs() + 1)).max().item() <= tol
 
 
 def test_mask_cast_colsum_bf16_input_in_place():
