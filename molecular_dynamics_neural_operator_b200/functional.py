@@ -220,7 +220,10 @@ FACTORIZATION = os.environ.get("GKN_FACTORIZATION", "node")
 _NODE_CHUNK_BYTES = int(os.environ.get("GKN_NODE_CHUNK_MB", "4096")) << 20
 # ... and, when U is recomputed for the dh pass (A * w*K values per node), of this many
 _NODE_DH_CHUNK_BYTES = int(os.environ.get("GKN_NODE_DH_CHUNK_MB", "8192")) << 20
-_MLP_BWD_CHUNK_ROWS = int(os.environ.get("GKN_MLP_BWD_CHUNK_ROWS", "65536"))
+# rows per chunk of the edge-MLP backward (bounds its dz1 temporary: 512 MB at K = 1024).  Measured
+# at the bench shape (1.03 M padded edges): 32768 rows 34.06, 65536 33.33, 131072 33.03, 262144
+# 32.75 ms per step - a chunk is far larger than the L2 either way, fewer and larger GEMMs win
+_MLP_BWD_CHUNK_ROWS = int(os.environ.get("GKN_MLP_BWD_CHUNK_ROWS", "262144"))
 # MN-major operand variants of the dU / dh kernels: h, gm and U are read in place (no transposed
 # copy of h, no [k,o]-ordered recomputation of U).  GKN_NODE_MN=0 selects the K-major kernels.
 NODE_MN = os.environ.get("GKN_NODE_MN", "1") == "1"
