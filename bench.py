@@ -373,7 +373,8 @@ def quick_train(dev, name, frames, steps, warm=3):
     ev1.record()
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1) / steps
-    node = GF.FACTORIZATION == "node" and GF.node_path_supported(wl.width, wl.ker_width, edges, "bf16")
+    node = GF.FACTORIZATION == "node" and GF.node_path_supported(
+        wl.width, wl.ker_width, edges, "bf16", True, frames * wl.num_atoms)
     res = {"workload": name, "frames_per_step": frames, "steps": steps, "ms_per_step": ms,
            "frames_per_s": frames / (ms * 1e-3), "edges_per_frame": edges / frames,
            "edges_per_s": edges / (ms * 1e-3), "width": wl.width, "depth": wl.depth,

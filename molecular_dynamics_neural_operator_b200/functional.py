@@ -261,11 +261,27 @@ _FUSED_BWD_RING = int(os.environ.get("GKN_NODE_FUSED_BWD_RING", "3"))
 _FUSED_BWD_MIN_DEGREE = int(os.environ.get("GKN_NODE_FUSED_BWD_MIN_DEGREE", "64"))
 
 
-def node_path_supported(W: int, K: int, E: int, precision: str, needs_grad: bool = True) -> bool:
-    """w in {32, 64, 128} (the K-major backward kernels of GKN_NODE_MN=0 serve w = 64 only)."""
+# Training at w = 32 on graphs of low degree stays on the edge-first kernels: there the per-edge
+# contraction is only 2*K*32*32 FLOP (1.4 ns per edge on the tensor cores) while the node-first
+# path moves U = N*32*K bf16 per application through HBM - 0.3 + 20/degree ns per edge.  Measured
+# on config 1 (28 residues x batch 128, 14 edges per node): 6.2 ms per step edge-first, 9.4 ms
+# node-first; the node-first kernels win from about 20 edges per node (model) upwards.
+_NODE_MIN_DEGREE_W32 = float(os.environ.get("GKN_NODE_MIN_DEGREE_W32", "24"))
+
+
+def node_path_supported(W: int, K: int, E: int, precision: str, needs_grad: bool = True,
+                        num_nodes: int | None = None) -> bool:
+    """w in {32, 64, 128} (the K-major backward kernels of GKN_NODE_MN=0 serve w = 64 only);
+    ``num_nodes`` lets the w = 32 training case choose by degree (see above)."""
     if precision != "bf16" or K % 256 != 0 or E <= 0:
         return False
-    return W == 64 or (W in (32, 128) and (NODE_MN or not needs_grad))
+    if W == 64:
+        return True
+    if W not in (32, 128) or (needs_grad and not NODE_MN):
+        return False
+    if W == 32 and needs_grad and num_nodes and E < _NODE_MIN_DEGREE_W32 * num_nodes:
+        return False
+    return True
 
 
 def _node_chunks(N: int, per_node_bytes: int, budget: int | None = None):
@@ -558,7 +574,8 @@ def gkn_stack(x0, edge_attr_sorted, net, root1, bias1, root2, bias2, plan: Graph
                root1, bias1, root2, bias2)
     needs_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
     if FACTORIZATION == "node" and node_path_supported(x0.size(1), l4.weight.size(1),
-                                                       plan.num_edges, precision, needs_grad):
+                                                       plan.num_edges, precision, needs_grad,
+                                                       plan.num_nodes):
         fn = _GKNStackNode
     return fn.apply(x0, edge_attr_sorted, l0.weight, l0.bias, l2.weight, l2.bias, l4.weight,
                            l4.bias, root1, bias1, root2, bias2, plan, tuple(schedule), bool(relu),

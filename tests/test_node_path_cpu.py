@@ -500,7 +500,13 @@ def test_only_the_node_features_need_a_gradient(emulated):
 
 def test_node_path_selection():
     assert GF.node_path_supported(64, 1024, 10, "bf16")
-    assert GF.node_path_supported(32, 1024, 10, "bf16")      # config 1 trains on this path
+    assert GF.node_path_supported(32, 1024, 10, "bf16")
+    # w = 32 training chooses by degree: config 1 (14 edges per node) stays edge-first, denser
+    # graphs and forward-only calls go node-first
+    assert not GF.node_path_supported(32, 1024, 50776, "bf16", num_nodes=3584)
+    assert GF.node_path_supported(32, 1024, 50776, "bf16", needs_grad=False, num_nodes=3584)
+    assert GF.node_path_supported(32, 1024, 60000, "bf16", num_nodes=504)
+    assert GF.node_path_supported(128, 1024, 50776, "bf16", num_nodes=3584)
     assert GF.node_path_supported(128, 1024, 10, "bf16")
     assert GF.node_path_supported(32, 1024, 10, "bf16", needs_grad=False)
     assert GF.node_path_supported(128, 1024, 10, "bf16", needs_grad=False)
