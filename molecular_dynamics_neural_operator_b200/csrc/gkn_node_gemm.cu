@@ -592,8 +592,9 @@ node_gather_kernel(const float* __restrict__ g, const int32_t* __restrict__ idx,
     constexpr int kRpp = 256 / kTpr;      // rows per pass
     __shared__ __nv_bfloat16 tile[W == kW ? 64 : 1][Wp + 8];
     const int t = threadIdx.x;
+    const bool transpose = W == kW && gsT != nullptr;  // (uniform) the smem tile and its barriers
     for (int64_t q0 = int64_t(blockIdx.x) * 64; q0 < E_pad; q0 += int64_t(gridDim.x) * 64) {
-        if constexpr (W == kW) __syncthreads();
+        if (transpose) __syncthreads();
 #pragma unroll
         for (int pass = 0; pass < 64 / kRpp; ++pass) {
             const int r = pass * kRpp + t / kTpr;
@@ -605,12 +606,12 @@ node_gather_kernel(const float* __restrict__ g, const int32_t* __restrict__ idx,
                 if (n >= 0) v = __ldg(reinterpret_cast<const float4*>(g + int64_t(n) * W + c));
             }
             const uint2 pk = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
-            if constexpr (W == kW) *reinterpret_cast<uint2*>(&tile[r][c]) = pk;
+            if (transpose) *reinterpret_cast<uint2*>(&tile[W == kW ? r : 0][c]) = pk;
             if (gs != nullptr && qq < E_pad) *reinterpret_cast<uint2*>(gs + qq * Wp + c) = pk;
         }
         if constexpr (W == kW) {
-            __syncthreads();
-            if (gsT != nullptr) {
+            if (transpose) {
+                __syncthreads();
                 // thread -> channel o = t / 4, 16 consecutive positions (E_pad is a multiple of 16)
                 const int o = t >> 2;
                 const int qb = (t & 3) * 16;
