@@ -81,12 +81,13 @@ class ClockSampler:
 
     QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+             "clocks_event_reasons.sw_power_cap,power.draw")
 
     def __init__(self, gpu_index: int):
         self.gpu_index = gpu_index
         self.proc = None
         self.lines: list[str] = []
+        self.marks: list[tuple[str, int]] = []   # (timed loop, index of its first sample)
         self.thread = None
 
     def start(self):
@@ -105,6 +106,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self, name: str):
+        """Samples from here on belong to the timed loop `name` (per-loop medians in the JSON line:
+        a loop that ran through a power-cap dip shows up as such)."""
+        self.marks.append((name, len(self.lines)))
+
     def stop(self):
         if self.proc is None:
             return None
@@ -114,9 +120,9 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, smax, reasons = [], [], set()
+        sm, smax, reasons, watts, idx = [], [], set(), [], []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        for i, line in enumerate(self.lines):
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 6:
                 continue
@@ -125,13 +131,30 @@ class ClockSampler:
                 smax.append(float(parts[1]))
             except ValueError:
                 continue
+            idx.append(i)
+            try:
+                watts.append(float(parts[6]))
+            except (IndexError, ValueError):
+                watts.append(float("nan"))
             for n, v in zip(names, parts[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         if not sm:
             return None
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        out = {"sm_mhz": statistics.median(sm), "sm_min_mhz": min(sm), "sm_max_mhz": max(smax),
+               "reasons": sorted(reasons), "samples": len(sm)}
+        by_loop = {}
+        for k, (name, start) in enumerate(self.marks):
+            end = self.marks[k + 1][1] if k + 1 < len(self.marks) else len(self.lines)
+            sel = [j for j, i in enumerate(idx) if start <= i < end]
+            if sel:
+                w = [watts[j] for j in sel if watts[j] == watts[j]]
+                by_loop[name] = {"sm_mhz": statistics.median(sm[j] for j in sel),
+                                 "sm_min_mhz": min(sm[j] for j in sel),
+                                 "power_w": statistics.median(w) if w else None, "samples": len(sel)}
+        if by_loop:
+            out["by_loop"] = by_loop
+        return out
 
 
 def dist_info():
@@ -647,9 +670,13 @@ def run_b200_arm(args, wl):
     launches0 = _lib.launch_count()
     loss_before = list(loss_log)
     loss_log.clear()
+    if sampler:
+        sampler.mark("value")
     ms_total = timed(build_resident, args.steps, True)
     launches = _lib.launch_count() - launches0
     loss_timed = list(loss_log)
+    if sampler:
+        sampler.mark("e2e")
     ms_e2e = timed(build_e2e, args.steps, True)
     # Per-launch CUDA events around the contraction cost ~0.15 ms each on this driver (measured:
     # +10 % step time), so the kernel's launch duration is taken from an instrumented REPEAT of
@@ -658,6 +685,8 @@ def run_b200_arm(args, wl):
     ms_instr = None
     if not args.no_kernel_timer:
         ops.KERNEL_TIMER.enable("contract")
+        if sampler:
+            sampler.mark("instrumented")
         ms_instr = timed(build_resident, args.steps, True)
         timer = ops.KERNEL_TIMER.collect()
         ops.KERNEL_TIMER.disable()
