@@ -132,3 +132,35 @@ def test_checkpoint_roundtrip_uses_the_reference_layout(tmp_path):
     assert load_checkpoint(tmp_path / "best.pt", model2, Trainer(model2)) == 7
     for a, b in zip(model.parameters(), model2.parameters()):
         assert torch.equal(a, b)
+
+
+def test_clock_sampler_reports_clocks_and_power_per_timed_loop():
+    """bench.py's `clocks` object: overall median / min / max, throttle reasons, and per timed loop
+    (marks) the median clock and power - parsed from nvidia-smi's csv lines (no GPU needed)."""
+    import importlib.util
+    from pathlib import Path
+
+    spec = importlib.util.spec_from_file_location("bench_mod", Path(__file__).resolve().parents[1] / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    class _Proc:
+        def terminate(self):
+            pass
+
+        def wait(self, timeout=None):
+            return 0
+
+    s = bench.ClockSampler(0)
+    s.proc = _Proc()
+    row = "{}, 1965, Not Active, Not Active, Not Active, {}, {}"
+    s.mark("value")
+    s.lines += [row.format(1900, "Active", 760.0), row.format(1880, "Active", 770.0)]
+    s.mark("e2e")
+    s.lines += [row.format(1700, "Active", 950.0), "garbage", row.format(1740, "Not Active", "[N/A]")]
+    out = s.stop()
+    assert out["sm_mhz"] == 1810.0 and out["sm_min_mhz"] == 1700.0 and out["sm_max_mhz"] == 1965.0
+    assert out["reasons"] == ["sw_power_cap"] and out["samples"] == 4
+    assert out["by_loop"]["value"] == {"sm_mhz": 1890.0, "sm_min_mhz": 1880.0, "power_w": 765.0,
+                                       "samples": 2}
+    assert out["by_loop"]["e2e"]["sm_mhz"] == 1720.0 and out["by_loop"]["e2e"]["power_w"] == 950.0
