@@ -588,9 +588,9 @@ __global__ void __launch_bounds__(256)
 node_gather_kernel(const float* __restrict__ g, const int32_t* __restrict__ idx, int64_t E_pad,
                    __nv_bfloat16* __restrict__ gs, __nv_bfloat16* __restrict__ gsT) {
     constexpr int Wp = gs_width(W);
-    constexpr int kTpr = Wp / 4;          // threads per row (4 columns each)
+    constexpr int kTpr = Wp / 8;          // threads per row (8 columns each: one 16-byte store)
     constexpr int kRpp = 256 / kTpr;      // rows per pass
-    __shared__ __nv_bfloat16 tile[W == kW ? 64 : 1][Wp + 8];
+    __shared__ __align__(16) __nv_bfloat16 tile[W == kW ? 64 : 1][Wp + 8];
     const int t = threadIdx.x;
     const bool transpose = W == kW && gsT != nullptr;  // (uniform) the smem tile and its barriers
     for (int64_t q0 = int64_t(blockIdx.x) * 64; q0 < E_pad; q0 += int64_t(gridDim.x) * 64) {
@@ -598,16 +598,21 @@ node_gather_kernel(const float* __restrict__ g, const int32_t* __restrict__ idx,
 #pragma unroll
         for (int pass = 0; pass < 64 / kRpp; ++pass) {
             const int r = pass * kRpp + t / kTpr;
-            const int c = (t % kTpr) * 4;
+            const int c = (t % kTpr) * 8;
             const int64_t qq = q0 + r;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
             if (qq < E_pad && c < W) {
                 const int32_t n = __ldg(idx + qq);
-                if (n >= 0) v = __ldg(reinterpret_cast<const float4*>(g + int64_t(n) * W + c));
+                if (n >= 0) {
+                    const float4* src = reinterpret_cast<const float4*>(g + int64_t(n) * W + c);
+                    v0 = __ldg(src);
+                    v1 = __ldg(src + 1);
+                }
             }
-            const uint2 pk = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
-            if (transpose) *reinterpret_cast<uint2*>(&tile[W == kW ? r : 0][c]) = pk;
-            if (gs != nullptr && qq < E_pad) *reinterpret_cast<uint2*>(gs + qq * Wp + c) = pk;
+            const uint4 pk = make_uint4(pack_bf16(v0.x, v0.y), pack_bf16(v0.z, v0.w),
+                                        pack_bf16(v1.x, v1.y), pack_bf16(v1.z, v1.w));
+            if (transpose) *reinterpret_cast<uint4*>(&tile[W == kW ? r : 0][c]) = pk;
+            if (gs != nullptr && qq < E_pad) *reinterpret_cast<uint4*>(gs + qq * Wp + c) = pk;
         }
         if constexpr (W == kW) {
             if (transpose) {
